@@ -1,0 +1,254 @@
+"""ctypes binding of the CPU oracle (oracle/tfhe_oracle.c).
+
+TEST INFRASTRUCTURE ONLY -- see the header of oracle/tfhe_oracle.h.  Only tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this module.
+The product package (fhe_string_bounty_b200) never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+_SO = _HERE / "libtfhe_oracle.so"
+
+
+def build(force: bool = False) -> Path:
+    """Compile the C restatement (gcc -O3 -fopenmp).  Building the checker is not using it."""
+    src = _HERE / "tfhe_oracle.c"
+    hdr = _HERE / "tfhe_oracle.h"
+    if force or not _SO.exists() or _SO.stat().st_mtime < max(src.stat().st_mtime, hdr.stat().st_mtime):
+        subprocess.run(["make", "-C", str(_HERE), "-s", "-B"], check=True)
+    return _SO
+
+
+class Params(C.Structure):
+    _fields_ = [
+        ("lwe_dim", C.c_uint32), ("glwe_dim", C.c_uint32), ("poly_size", C.c_uint32),
+        ("pbs_base_log", C.c_uint32), ("pbs_level", C.c_uint32),
+        ("ks_base_log", C.c_uint32), ("ks_level", C.c_uint32),
+        ("grouping_factor", C.c_uint32), ("msg_mod", C.c_uint32), ("carry_mod", C.c_uint32),
+        ("lwe_std", C.c_double), ("glwe_std", C.c_double),
+    ]
+
+    @property
+    def big_dim(self) -> int:
+        return self.glwe_dim * self.poly_size
+
+    @property
+    def lut_len(self) -> int:
+        return (self.glwe_dim + 1) * self.poly_size
+
+
+class Rng(C.Structure):
+    _fields_ = [("s", C.c_uint64 * 4), ("has_spare", C.c_int), ("spare", C.c_double)]
+
+
+_lib = None
+_u64p = np.ctypeslib.ndpointer(dtype=np.uint64, flags="C_CONTIGUOUS")
+_i64p = np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")
+_u32p = np.ctypeslib.ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS")
+_f64p = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+_PP = C.POINTER(Params)
+_RP = C.POINTER(Rng)
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    build()
+    L = C.CDLL(str(_SO))
+    sig = {
+        "orc_params_message_2_carry_2_ks_pbs": (None, [_PP]),
+        "orc_params_multi_bit_message_2_carry_2_group_3_ks_pbs": (None, [_PP]),
+        "orc_params_toy": (None, [_PP]),
+        "orc_rng_seed": (None, [_RP, C.c_uint64]),
+        "orc_rng_u64": (C.c_uint64, [_RP]),
+        "orc_gen_binary_key": (None, [_RP, _u64p, C.c_size_t]),
+        "orc_lwe_encrypt": (None, [_u64p, C.c_size_t, C.c_uint64, C.c_double, _RP, _u64p]),
+        "orc_lwe_decrypt": (C.c_uint64, [_u64p, C.c_size_t, _u64p]),
+        "orc_gen_ksk": (None, [_PP, _u64p, _u64p, C.c_uint64, _u64p]),
+        "orc_gen_bsk": (None, [_PP, _u64p, _u64p, C.c_uint64, _u64p]),
+        "orc_gen_multi_bit_bsk": (None, [_PP, _u64p, _u64p, C.c_uint64, _u64p]),
+        "orc_ksk_len": (C.c_size_t, [_PP]),
+        "orc_bsk_len": (C.c_size_t, [_PP]),
+        "orc_closest_representable": (C.c_uint64, [C.c_uint64, C.c_uint32, C.c_uint32]),
+        "orc_closest_representable_u32": (C.c_uint32, [C.c_uint32, C.c_uint32, C.c_uint32]),
+        "orc_decompose": (None, [C.c_uint64, C.c_uint32, C.c_uint32, _i64p]),
+        "orc_modulus_switch": (C.c_uint64, [C.c_uint64, C.c_uint32]),
+        "orc_monomial_div": (None, [_u64p, _u64p, C.c_size_t, C.c_size_t]),
+        "orc_monomial_mul": (None, [_u64p, _u64p, C.c_size_t, C.c_size_t]),
+        "orc_monomial_mul_and_subtract": (None, [_u64p, _u64p, C.c_size_t, C.c_size_t]),
+        "orc_sample_extract0": (None, [_PP, _u64p, _u64p]),
+        "orc_keyswitch": (None, [_PP, _u64p, _u64p, _u64p]),
+        "orc_fill_accumulator": (C.c_uint64, [_PP, _u64p, _u64p]),
+        "orc_trivial_pbs": (C.c_uint64, [_PP, C.c_uint64, _u64p]),
+        "orc_encode": (C.c_uint64, [_PP, C.c_uint64]),
+        "orc_decode": (C.c_uint64, [_PP, C.c_uint64]),
+        "orc_fft_forward_integer": (None, [C.c_size_t, _u64p, _f64p, _f64p]),
+        "orc_fft_forward_torus": (None, [C.c_size_t, _u64p, _f64p, _f64p]),
+        "orc_fft_add_backward_torus": (None, [C.c_size_t, _u64p, _f64p, _f64p]),
+        "orc_fourier_bsk_new": (C.c_void_p, [_PP, _u64p]),
+        "orc_fourier_bsk_free": (None, [C.c_void_p]),
+        "orc_add_external_product_f64": (None, [_PP, C.c_void_p, C.c_size_t, _u64p, _u64p]),
+        "orc_add_external_product_exact": (None, [_PP, _u64p, _u64p, _u64p]),
+        "orc_pbs_f64": (None, [_PP, C.c_void_p, _u64p, _u64p, _u64p]),
+        "orc_pbs_exact": (None, [_PP, _u64p, _u64p, _u64p, _u64p]),
+        "orc_ks_pbs_batch": (C.c_int, [_PP, _u64p, C.c_void_p, _u64p, C.c_void_p, _u64p, _u64p, C.c_void_p, C.c_size_t, C.c_int]),
+        "orc_max_threads": (C.c_int, []),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = L
+    return L
+
+
+def params(name: str = "2_2") -> Params:
+    p = Params()
+    L = lib()
+    if name in ("2_2", "PARAM_MESSAGE_2_CARRY_2_KS_PBS"):
+        L.orc_params_message_2_carry_2_ks_pbs(C.byref(p))
+    elif name in ("multibit_2_2_g3", "PARAM_MULTI_BIT_MESSAGE_2_CARRY_2_GROUP_3_KS_PBS"):
+        L.orc_params_multi_bit_message_2_carry_2_group_3_ks_pbs(C.byref(p))
+    elif name == "toy":
+        L.orc_params_toy(C.byref(p))
+    else:
+        raise KeyError(name)
+    return p
+
+
+class ClientKey:
+    """Secret keys of shortint::ClientKey (engine/client_side.rs:13-37): GLWE key, its flattened
+    'big' LWE view, and the small LWE key.  encrypt/decrypt follow client_side.rs:58-124 and
+    client_key/mod.rs:281-302 (Big encryption key => ciphertexts under the big key, GLWE noise)."""
+
+    def __init__(self, p: Params, seed: int):
+        L = lib()
+        self.p = p
+        self.rng = Rng()
+        L.orc_rng_seed(C.byref(self.rng), seed)
+        self.glwe_sk = np.zeros(p.big_dim, dtype=np.uint64)
+        self.small_sk = np.zeros(p.lwe_dim, dtype=np.uint64)
+        L.orc_gen_binary_key(C.byref(self.rng), self.glwe_sk, p.big_dim)
+        L.orc_gen_binary_key(C.byref(self.rng), self.small_sk, p.lwe_dim)
+        self.big_sk = self.glwe_sk  # GlweSecretKey::as_lwe_secret_key
+
+    def encrypt_raw(self, plaintext: int) -> np.ndarray:
+        ct = np.zeros(self.p.big_dim + 1, dtype=np.uint64)
+        lib().orc_lwe_encrypt(self.big_sk, self.p.big_dim, plaintext & (2**64 - 1), self.p.glwe_std, C.byref(self.rng), ct)
+        return ct
+
+    def encrypt(self, msg: int) -> np.ndarray:
+        """client_side.rs:58-85: message reduced mod msg_mod*carry_mod? No: mod message modulus."""
+        m = msg % self.p.msg_mod
+        return self.encrypt_raw(lib().orc_encode(C.byref(self.p), m))
+
+    def encrypt_with_carry(self, value: int) -> np.ndarray:
+        """Encrypt any value below msg_mod*carry_mod (used to exercise every LUT box)."""
+        v = value % (self.p.msg_mod * self.p.carry_mod)
+        return self.encrypt_raw(lib().orc_encode(C.byref(self.p), v))
+
+    def encrypt_batch(self, values) -> np.ndarray:
+        return np.stack([self.encrypt_with_carry(int(v)) for v in values])
+
+    def decrypt_raw(self, ct: np.ndarray) -> int:
+        return int(lib().orc_lwe_decrypt(self.big_sk, self.p.big_dim, np.ascontiguousarray(ct)))
+
+    def decrypt_message_and_carry(self, ct: np.ndarray) -> int:
+        return int(lib().orc_decode(C.byref(self.p), self.decrypt_raw(ct)))
+
+    def decrypt(self, ct: np.ndarray) -> int:
+        return self.decrypt_message_and_carry(ct) % self.p.msg_mod
+
+    def decrypt_batch(self, cts: np.ndarray) -> np.ndarray:
+        return np.array([self.decrypt_message_and_carry(c) for c in cts], dtype=np.int64)
+
+    def decrypt_small_raw(self, ct: np.ndarray) -> int:
+        return int(lib().orc_lwe_decrypt(self.small_sk, self.p.lwe_dim, np.ascontiguousarray(ct)))
+
+
+class ServerKey:
+    """KSK + (multi-bit) BSK in the standard domain, plus the oracle's own Fourier copy
+    (shortint/engine/server_side.rs:54-160)."""
+
+    def __init__(self, ck: ClientKey, seed: int, fourier: bool = True):
+        L = lib()
+        p = ck.p
+        self.p = p
+        self.ksk = np.zeros(L.orc_ksk_len(C.byref(p)), dtype=np.uint64)
+        L.orc_gen_ksk(C.byref(p), ck.big_sk, ck.small_sk, seed, self.ksk)
+        self.bsk = np.zeros(L.orc_bsk_len(C.byref(p)), dtype=np.uint64)
+        if p.grouping_factor == 0:
+            L.orc_gen_bsk(C.byref(p), ck.small_sk, ck.glwe_sk, seed + 1, self.bsk)
+        else:
+            L.orc_gen_multi_bit_bsk(C.byref(p), ck.small_sk, ck.glwe_sk, seed + 1, self.bsk)
+        self._fourier = None
+        if fourier:
+            self._fourier = L.orc_fourier_bsk_new(C.byref(p), self.bsk)
+
+    def __del__(self):
+        if getattr(self, "_fourier", None):
+            lib().orc_fourier_bsk_free(self._fourier)
+            self._fourier = None
+
+    @property
+    def fourier(self):
+        if self._fourier is None:
+            self._fourier = lib().orc_fourier_bsk_new(C.byref(self.p), self.bsk)
+        return self._fourier
+
+    # shortint/server_key/mod.rs:383-399
+    def generate_lookup_table(self, f) -> tuple[np.ndarray, int]:
+        p = self.p
+        table = np.array([int(f(i)) for i in range(p.msg_mod * p.carry_mod)], dtype=np.uint64)
+        acc = np.zeros(p.lut_len, dtype=np.uint64)
+        degree = lib().orc_fill_accumulator(C.byref(p), table, acc)
+        return acc, int(degree)
+
+    # shortint/server_key/bivariate_pbs.rs:71-97
+    def generate_lookup_table_bivariate(self, f) -> tuple[np.ndarray, int]:
+        m = self.p.msg_mod
+        return self.generate_lookup_table(lambda x: f((x // m) % m, (x % m) % m))
+
+    def keyswitch(self, ct: np.ndarray) -> np.ndarray:
+        out = np.zeros(self.p.lwe_dim + 1, dtype=np.uint64)
+        lib().orc_keyswitch(C.byref(self.p), self.ksk, np.ascontiguousarray(ct), out)
+        return out
+
+    def pbs(self, lwe_small: np.ndarray, acc: np.ndarray, exact: bool = False) -> np.ndarray:
+        out = np.zeros(self.p.big_dim + 1, dtype=np.uint64)
+        if exact:
+            lib().orc_pbs_exact(C.byref(self.p), self.bsk, np.ascontiguousarray(lwe_small), acc, out)
+        else:
+            lib().orc_pbs_f64(C.byref(self.p), self.fourier, np.ascontiguousarray(lwe_small), acc, out)
+        return out
+
+    def ks_pbs_batch(self, cts: np.ndarray, luts: np.ndarray, lut_idx=None, threads: int = 0, want_ks: bool = False):
+        """shortint/server_key/mod.rs:783-857 over a batch (one ciphertext per OpenMP thread)."""
+        p = self.p
+        cts = np.ascontiguousarray(cts, dtype=np.uint64).reshape(-1, p.big_dim + 1)
+        luts = np.ascontiguousarray(luts, dtype=np.uint64).reshape(-1, p.lut_len)
+        batch = cts.shape[0]
+        out = np.zeros_like(cts)
+        idx_ptr = None
+        if lut_idx is not None:
+            lut_idx = np.ascontiguousarray(lut_idx, dtype=np.uint32)
+            idx_ptr = lut_idx.ctypes.data_as(C.c_void_p)
+        ks = np.zeros((batch, p.lwe_dim + 1), dtype=np.uint64) if want_ks else None
+        ks_ptr = ks.ctypes.data_as(C.c_void_p) if want_ks else None
+        used = lib().orc_ks_pbs_batch(C.byref(p), self.ksk, self.fourier, luts, idx_ptr, cts, out, ks_ptr, batch, threads)
+        self.last_threads = used
+        return (out, ks) if want_ks else out
+
+
+def decompose(x: int, base_log: int, level: int) -> list[int]:
+    d = np.zeros(level, dtype=np.int64)
+    lib().orc_decompose(x, base_log, level, d)
+    return [int(v) for v in d]
