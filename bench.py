@@ -1,0 +1,259 @@
+#!/usr/bin/env python
+"""bench.py -- batched KS-PBS throughput on B200 (BASELINE.json configs[1]) and the CPU reference arm.
+
+    python bench.py --gpus N --steps K --warmup W            # this engine (one rank per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host cores
+
+A "step" is one pass of the hot path -- keyswitch + programmable bootstrap with per-ciphertext lookup
+table -- over one batch of `--batch` independent LWE ciphertexts per GPU at PARAM_MESSAGE_2_CARRY_2_KS_PBS.
+`value` is device-timed whole-job KS-PBS/s with inputs resident in HBM; `e2e` is the same metric through the
+host-buffer C-ABI call (tfhe_b200_ks_pbs_batch) with pinned host inputs and outputs, copies inside the
+timed region.  Keys and ciphertexts are uniformly random words: the path's work is data independent
+(correctness is the job of tests/, which use real seeded keys against the oracle).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+FLOP_PER_PBS = 742 * 262144.0          # n * ((k+1)(l+1)(5 M log2 M + 6 M) + (k+1)^2 l M 8), M = 1024
+BSK_BYTES = 742 * 4 * 1024 * 16        # Fourier bootstrapping key
+KSK_BYTES = 2048 * 5 * 743 * 8
+CT_BYTES = 2049 * 8
+
+
+def _clock_sampler(stop, samples, device_index):
+    q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    while not stop.is_set():
+        try:
+            out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(device_index)],
+                                 capture_output=True, text=True, timeout=5).stdout.strip()
+            if out:
+                samples.append([s.strip() for s in out.split(",")])
+        except Exception:
+            pass
+        stop.wait(0.2)
+
+
+def _summarise_clocks(samples):
+    if not samples:
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+    sm = sorted(float(s[0]) for s in samples if s[0].replace(".", "").isdigit())
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    reasons = [n for i, n in enumerate(names) if any(len(s) > 3 + i and s[3 + i].lower().startswith("active") for s in samples)]
+    return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(samples[0][1]) if samples[0][1].replace(".", "").isdigit() else None,
+            "power_w_max": max((float(s[2]) for s in samples if s[2].replace(".", "").isdigit()), default=None),
+            "samples": len(samples), "reasons": reasons}
+
+
+def _peaks():
+    f = ROOT / "MEASURED_PEAKS.json"
+    if f.exists():
+        return json.loads(f.read_text()), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+def cpu_reference_rate(n_cts: int, threads: int = 0):
+    """Times the CPU oracle (restatement of the reference's KS-PBS, one ciphertext per OpenMP thread, the
+    structure of tfhe/benches/core_crypto/pbs_bench.rs:512-536).  Only this leg may touch oracle/."""
+    from oracle import oracle as O
+    p = O.params("2_2")
+    rng = np.random.default_rng(0xB200)
+    ksk = rng.integers(0, 2**64, size=O.lib().orc_ksk_len(p), dtype=np.uint64)
+    bsk = rng.integers(0, 2**64, size=O.lib().orc_bsk_len(p), dtype=np.uint64)
+
+    class _SK:  # ServerKey without key generation: random words give the same work
+        pass
+    import ctypes as C
+    f = O.lib().orc_fourier_bsk_new(C.byref(p), bsk)
+    luts = rng.integers(0, 2**64, size=(16, p.lut_len), dtype=np.uint64)
+    cts = rng.integers(0, 2**64, size=(n_cts, p.big_dim + 1), dtype=np.uint64)
+    idx = (np.arange(n_cts) % 16).astype(np.uint32)
+    out = np.zeros_like(cts)
+    L = O.lib()
+    cores = threads or L.orc_max_threads()
+    warm = min(n_cts, cores)
+    L.orc_ks_pbs_batch(C.byref(p), ksk, f, luts, idx.ctypes.data_as(C.c_void_p), cts[:warm], out[:warm], None, warm, cores)
+    t0 = time.perf_counter()
+    used = L.orc_ks_pbs_batch(C.byref(p), ksk, f, luts, idx.ctypes.data_as(C.c_void_p), cts, out, None, n_cts, cores)
+    dt = time.perf_counter() - t0
+    L.orc_fourier_bsk_free(f)
+    return n_cts / dt, used, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    cores = O.lib().orc_max_threads()
+    per_step = max(cores * 2, 16)
+    rates = []
+    t_all = time.perf_counter()
+    for s in range(args.warmup + args.steps):
+        r, used, dt = cpu_reference_rate(per_step)
+        if s >= args.warmup:
+            rates.append((r, dt))
+    total_t = sum(dt for _, dt in rates)
+    value = per_step * len(rates) / total_t
+    line = {
+        "impl": "reference", "metric": "batched KS-PBS throughput", "value": value, "unit": "PBS/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_t / max(len(rates), 1), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "PARAM_MESSAGE_2_CARRY_2_KS_PBS batched KS-PBS (configs[1])", "batch_per_step": per_step,
+                   "note": "reference Rust crate cannot be built here (no cargo); CPU oracle port of its algorithm, all host cores"},
+        "cpu_baseline": {"value": value, "unit": "PBS/s", "cores": cores, "kind": "port",
+                         "sample": f"{per_step} KS-PBS per step x {args.steps} steps, one ciphertext per OpenMP thread"},
+        "e2e": {"value": value, "unit": "PBS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import fhe_string_bounty_b200 as F
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    B = args.batch
+    p = F.Params(**F.PARAM_MESSAGE_2_CARRY_2_KS_PBS)
+    eng = F.Engine(p, device=local)
+    rng = np.random.default_rng(0xB200)          # same keys on every rank: keys are replicated, work is sharded
+    eng.upload_ksk(rng.integers(0, 2**64, size=p.ksk_len, dtype=np.uint64))
+    eng.upload_bsk_std(rng.integers(0, 2**64, size=p.bsk_len, dtype=np.uint64))
+    eng.upload_luts(rng.integers(0, 2**64, size=(16, p.lut_len), dtype=np.uint64))
+
+    g = torch.Generator(device="cuda").manual_seed(1234 + rank)
+    d_in = torch.randint(-2**63, 2**63 - 1, (B, p.big_len), dtype=torch.int64, device="cuda", generator=g)
+    d_idx = (torch.arange(B, device="cuda", dtype=torch.int32) % 16).contiguous()
+    d_out = torch.empty_like(d_in)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        eng.ks_pbs_batch_device(d_in, d_idx, d_out, B, stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    stop, samples = threading.Event(), []
+    sampler = threading.Thread(target=_clock_sampler, args=(stop, samples, local), daemon=True)
+    sampler.start()
+    launches0 = eng.kernel_launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ks_ms_sum = pbs_ms_sum = 0.0
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = eng.kernel_launches - launches0
+    # per-kernel durations of the dominant kernel, measured live (CUDA events on the launching stream)
+    for _ in range(min(args.steps, 5)):
+        step()
+        torch.cuda.synchronize()
+        k, q = eng.last_kernel_ms()
+        ks_ms_sum += k
+        pbs_ms_sum += q
+    n_k = min(args.steps, 5)
+    ks_ms, pbs_ms = ks_ms_sum / n_k, pbs_ms_sum / n_k
+    stop.set()
+    sampler.join(timeout=2)
+
+    # e2e through the host-buffer C-ABI entry point, pinned host memory, copies inside the timed region
+    h_in = torch.empty((B, p.big_len), dtype=torch.int64).pin_memory()
+    h_in.copy_(d_in.cpu())
+    h_idx = (torch.arange(B, dtype=torch.int32) % 16).pin_memory()
+    h_out = torch.empty((B, p.big_len), dtype=torch.int64).pin_memory()
+    e2e_steps = max(2, min(args.steps, 5))
+    eng.ks_pbs_batch(h_in, h_idx, h_out)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        eng.ks_pbs_batch(h_in, h_idx, h_out)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    if world > 1:
+        t = torch.tensor([ms, e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_s = float(t[0]), float(t[1])
+    if rank == 0:
+        peaks, peak_kind = _peaks()
+        fp64_peak = eng.probe_fp64_tflops()
+        value = B * world * args.steps / (ms * 1e-3)
+        e2e = B * world * e2e_steps / e2e_s
+        pbs_tflops = B * FLOP_PER_PBS / (pbs_ms * 1e-3) / 1e12
+        hbm_alg = (BSK_BYTES + KSK_BYTES + B * (2 * CT_BYTES + 743 * 8 * 2)) / ((pbs_ms + ks_ms) * 1e-3) / 1e9
+        cpu_rate, cpu_cores, cpu_dt = cpu_reference_rate(args.cpu_sample) if args.cpu_sample > 0 else (None, 0, 0)
+        line = {
+            "metric": "batched KS-PBS throughput", "value": value, "unit": "PBS/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "PARAM_MESSAGE_2_CARRY_2_KS_PBS batched KS-PBS (configs[1])", "batch_per_gpu": B,
+                       "luts": 16, "l2_policy": "inputs larger than L2 (cts in+out %.0f MB + keys 109 MB per step)" % (2 * B * CT_BYTES / 1e6),
+                       "sharding": "ciphertexts partitioned across ranks, keys replicated, no data-path collective"},
+            "e2e": {"value": e2e, "unit": "PBS/s", "h2d_bytes_per_step": B * (CT_BYTES + 4), "d2h_bytes_per_step": B * CT_BYTES},
+            "gpu_launches": launches,
+            "kernels": {"keyswitch_ms": ks_ms, "pbs_ms": pbs_ms},
+            "roofline": {"bound": "fp64", "kernel": "pbs_classic_kernel", "achieved": pbs_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
+                         "frac": pbs_tflops / fp64_peak if fp64_peak else None, "traffic": None,
+                         "peak_source": "FP64 FMA microbenchmark run in this process (MEASURED_PEAKS.json has no FP64 figure)",
+                         "flop_per_pbs": FLOP_PER_PBS,
+                         "hbm": {"achieved": hbm_alg, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
+                                 "frac": hbm_alg / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None, "peak_source": peak_kind}},
+            "clocks": _summarise_clocks(samples),
+        }
+        if cpu_rate is not None:
+            line["cpu_baseline"] = {"value": cpu_rate, "unit": "PBS/s", "cores": cpu_cores, "kind": "port",
+                                    "sample": f"{args.cpu_sample} KS-PBS (same parameter set, random keys), {cpu_dt:.1f} s"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    eng.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=8192, help="ciphertexts per GPU per step")
+    ap.add_argument("--cpu-sample", type=int, default=256, help="KS-PBS evaluated by the CPU baseline leg (0 = skip)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

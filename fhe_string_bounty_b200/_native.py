@@ -1,0 +1,245 @@
+"""ctypes loader for libtfhe_b200.so and a small numpy-facing wrapper around the C ABI.
+
+Nothing here computes: every method forwards to an ``extern "C"`` entry point declared in
+``include/tfhe_b200.h``.  Missing library or missing GPU raises NativeError (no fallback).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+_PKG = Path(__file__).resolve().parent
+_SO = _PKG / "libtfhe_b200.so"
+_SOURCES = ["csrc/pbs.cu", "csrc/keyswitch.cu", "csrc/leveled.cu", "csrc/c_api.cu"]
+_HEADERS = ["csrc/fft_core.cuh", "csrc/kernels.h", "../include/tfhe_b200.h"]
+
+NVCC_FLAGS = [
+    "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+    "-Xcompiler", "-fPIC", "-shared",
+]
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def build_native(force: bool = False, verbose: bool = False) -> Path:
+    """nvcc-compile every kernel for sm_100a into the in-tree libtfhe_b200.so."""
+    srcs = [_PKG / s for s in _SOURCES if (_PKG / s).exists()]
+    deps = srcs + [(_PKG / h).resolve() for h in _HEADERS]
+    if not force and _SO.exists() and all(_SO.stat().st_mtime >= d.stat().st_mtime for d in deps if d.exists()):
+        return _SO
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc, *NVCC_FLAGS, "-o", str(_SO), *map(str, srcs)]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    env = dict(os.environ)
+    env.pop("CC", None)
+    env.pop("CXX", None)
+    res = subprocess.run(cmd, capture_output=True, text=True, env=env)
+    if res.returncode != 0:
+        raise NativeError("nvcc failed:\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stderr)
+    return _SO
+
+
+class Params(C.Structure):
+    """Mirror of tfhe_b200_params (shortint ClassicPBSParameters subset)."""
+    _fields_ = [
+        ("lwe_dim", C.c_uint32), ("glwe_dim", C.c_uint32), ("poly_size", C.c_uint32),
+        ("pbs_base_log", C.c_uint32), ("pbs_level", C.c_uint32),
+        ("ks_base_log", C.c_uint32), ("ks_level", C.c_uint32),
+        ("grouping_factor", C.c_uint32), ("msg_mod", C.c_uint32), ("carry_mod", C.c_uint32),
+    ]
+
+    @property
+    def big_len(self) -> int:
+        return self.glwe_dim * self.poly_size + 1
+
+    @property
+    def small_len(self) -> int:
+        return self.lwe_dim + 1
+
+    @property
+    def lut_len(self) -> int:
+        return (self.glwe_dim + 1) * self.poly_size
+
+    @property
+    def ksk_len(self) -> int:
+        return self.glwe_dim * self.poly_size * self.ks_level * (self.lwe_dim + 1)
+
+    @property
+    def bsk_len(self) -> int:
+        k1 = self.glwe_dim + 1
+        return self.lwe_dim * self.pbs_level * k1 * k1 * self.poly_size
+
+
+# shortint/parameters/mod.rs:703-717
+PARAM_MESSAGE_2_CARRY_2_KS_PBS = dict(lwe_dim=742, glwe_dim=1, poly_size=2048, pbs_base_log=23, pbs_level=1,
+                                      ks_base_log=3, ks_level=5, grouping_factor=0, msg_mod=4, carry_mod=4)
+
+EXPORTS = {
+    "tfhe_b200_ctx_create": (C.c_int, [C.c_int, C.POINTER(Params), C.POINTER(C.c_void_p)]),
+    "tfhe_b200_ctx_destroy": (C.c_int, [C.c_void_p]),
+    "tfhe_b200_last_error": (C.c_char_p, []),
+    "tfhe_b200_upload_ksk": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "tfhe_b200_upload_bsk_std": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "tfhe_b200_upload_luts": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32]),
+    "tfhe_b200_keyswitch_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "tfhe_b200_pbs_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "tfhe_b200_ks_pbs_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "tfhe_b200_keyswitch_batch_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "tfhe_b200_pbs_batch_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "tfhe_b200_ks_pbs_batch_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "tfhe_b200_synchronize": (C.c_int, [C.c_void_p]),
+    "tfhe_b200_pbs_batch_partial": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32]),
+    "tfhe_b200_kernel_launches": (C.c_uint64, [C.c_void_p]),
+    "tfhe_b200_time_last_kernels": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "tfhe_b200_probe_fp64_tflops": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
+    "tfhe_b200_version": (C.c_char_p, []),
+}
+
+_lib = None
+
+
+def load_native():
+    """dlopen the in-tree library and type every exported symbol; raises NativeError if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not _SO.exists():
+        raise NativeError(f"{_SO} is missing: run __graft_entry__.build() (nvcc, sm_100a). There is no CPU fallback.")
+    lib = C.CDLL(str(_SO))
+    for name, (res, args) in EXPORTS.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:
+            raise NativeError(f"libtfhe_b200.so does not export {name}") from e
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        if not a.flags["C_CONTIGUOUS"]:
+            raise ValueError("array must be C-contiguous")
+        return a.ctypes.data
+    if isinstance(a, int):
+        return a
+    if hasattr(a, "data_ptr"):  # torch tensor (host pinned or device)
+        return a.data_ptr()
+    raise TypeError(type(a))
+
+
+class Engine:
+    """One tfhe_b200_ctx (one GPU).  Methods take numpy arrays (host entry points) or raw device
+    pointers / torch CUDA tensors (``*_device`` entry points)."""
+
+    def __init__(self, params: dict | Params = None, device: int = 0):
+        self.lib = load_native()
+        if params is None:
+            params = PARAM_MESSAGE_2_CARRY_2_KS_PBS
+        self.p = params if isinstance(params, Params) else Params(**params)
+        h = C.c_void_p()
+        self._check(self.lib.tfhe_b200_ctx_create(device, C.byref(self.p), C.byref(h)))
+        self.h = h
+        self.device = device
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise NativeError(self.lib.tfhe_b200_last_error().decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.tfhe_b200_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # keys -------------------------------------------------------------------------------------------
+    def upload_ksk(self, ksk: np.ndarray):
+        ksk = np.ascontiguousarray(ksk, dtype=np.uint64)
+        self._check(self.lib.tfhe_b200_upload_ksk(self.h, _ptr(ksk), ksk.size))
+
+    def upload_bsk_std(self, bsk: np.ndarray):
+        bsk = np.ascontiguousarray(bsk, dtype=np.uint64)
+        self._check(self.lib.tfhe_b200_upload_bsk_std(self.h, _ptr(bsk), bsk.size))
+
+    def upload_luts(self, luts: np.ndarray):
+        luts = np.ascontiguousarray(luts, dtype=np.uint64).reshape(-1, self.p.lut_len)
+        self._check(self.lib.tfhe_b200_upload_luts(self.h, _ptr(luts), luts.shape[0]))
+        self.n_luts = luts.shape[0]
+
+    # host-buffer hot path -------------------------------------------------------------------------------
+    def keyswitch_batch(self, cts: np.ndarray) -> np.ndarray:
+        cts = np.ascontiguousarray(cts, dtype=np.uint64).reshape(-1, self.p.big_len)
+        out = np.empty((cts.shape[0], self.p.small_len), dtype=np.uint64)
+        self._check(self.lib.tfhe_b200_keyswitch_batch(self.h, _ptr(cts), _ptr(out), cts.shape[0]))
+        return out
+
+    def pbs_batch(self, small: np.ndarray, lut_idx=None, n_iters: int | None = None) -> np.ndarray:
+        small = np.ascontiguousarray(small, dtype=np.uint64).reshape(-1, self.p.small_len)
+        out = np.empty((small.shape[0], self.p.big_len), dtype=np.uint64)
+        idx = None if lut_idx is None else np.ascontiguousarray(lut_idx, dtype=np.uint32)
+        if n_iters is None:
+            self._check(self.lib.tfhe_b200_pbs_batch(self.h, _ptr(small), _ptr(idx), _ptr(out), small.shape[0]))
+        else:
+            self._check(self.lib.tfhe_b200_pbs_batch_partial(self.h, _ptr(small), _ptr(idx), _ptr(out), small.shape[0], n_iters))
+        return out
+
+    def ks_pbs_batch(self, cts, lut_idx=None, out=None):
+        """apply_lookup_table over a batch (host buffers: numpy arrays or pinned torch tensors)."""
+        if isinstance(cts, np.ndarray):
+            cts = np.ascontiguousarray(cts, dtype=np.uint64).reshape(-1, self.p.big_len)
+            batch = cts.shape[0]
+            if out is None:
+                out = np.empty_like(cts)
+        else:
+            batch = cts.shape[0]
+        if isinstance(lut_idx, (list, tuple)):
+            lut_idx = np.asarray(lut_idx, dtype=np.uint32)
+        if isinstance(lut_idx, np.ndarray):
+            lut_idx = np.ascontiguousarray(lut_idx, dtype=np.uint32)
+        self._check(self.lib.tfhe_b200_ks_pbs_batch(self.h, _ptr(cts), _ptr(lut_idx), _ptr(out), batch))
+        return out
+
+    # device-buffer hot path ---------------------------------------------------------------------------
+    def ks_pbs_batch_device(self, d_in, d_idx, d_out, batch: int, stream: int | None = None):
+        self._check(self.lib.tfhe_b200_ks_pbs_batch_device(self.h, _ptr(d_in), _ptr(d_idx), _ptr(d_out), batch, stream))
+
+    def keyswitch_batch_device(self, d_in, d_small, batch: int, stream: int | None = None):
+        self._check(self.lib.tfhe_b200_keyswitch_batch_device(self.h, _ptr(d_in), _ptr(d_small), batch, stream))
+
+    def pbs_batch_device(self, d_small, d_idx, d_out, batch: int, stream: int | None = None):
+        self._check(self.lib.tfhe_b200_pbs_batch_device(self.h, _ptr(d_small), _ptr(d_idx), _ptr(d_out), batch, stream))
+
+    def synchronize(self):
+        self._check(self.lib.tfhe_b200_synchronize(self.h))
+
+    # instrumentation -------------------------------------------------------------------------------------
+    @property
+    def kernel_launches(self) -> int:
+        return int(self.lib.tfhe_b200_kernel_launches(self.h))
+
+    def last_kernel_ms(self) -> tuple[float, float]:
+        a, b = C.c_float(), C.c_float()
+        self._check(self.lib.tfhe_b200_time_last_kernels(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def probe_fp64_tflops(self) -> float:
+        v = C.c_double()
+        self._check(self.lib.tfhe_b200_probe_fp64_tflops(self.device, C.byref(v)))
+        return v.value

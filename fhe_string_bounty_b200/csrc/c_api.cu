@@ -1,0 +1,356 @@
+// c_api.cu -- extern "C" boundary of libtfhe_b200.so (see include/tfhe_b200.h for the reference
+// interfaces each entry point replaces).  Plain pointers and sizes only; no torch types.
+#include "../../include/tfhe_b200.h"
+#include "fft_core.cuh"
+#include "kernels.h"
+
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(const std::string &msg) {
+    g_last_error = msg;
+    return 1;
+}
+
+#define TB_CUDA(expr)                                                                              \
+    do {                                                                                           \
+        cudaError_t e__ = (expr);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return fail(std::string(#expr) + ": " + cudaGetErrorString(e__));                      \
+    } while (0)
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+struct tfhe_b200_ctx {
+    int device = 0;
+    tfhe_b200_params p{};
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    bool timed = false;
+    // keys
+    DevBuf ksk_packed, ksk_colsum, bskf, tbl, luts;
+    uint32_t n_luts = 0;
+    bool have_ksk = false, have_bsk = false;
+    // staging for the host-pointer entry points
+    DevBuf d_in, d_small, d_out, d_idx;
+    uint64_t launches = 0;
+    std::mutex mu;
+
+    size_t big_len() const { return (size_t)p.glwe_dim * p.poly_size + 1; }
+    size_t small_len() const { return (size_t)p.lwe_dim + 1; }
+    size_t lut_len() const { return (size_t)(p.glwe_dim + 1) * p.poly_size; }
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+int check_params(const tfhe_b200_params &p) {
+    if (p.poly_size != (uint32_t)tb::kN) return fail("unsupported poly_size (engine is built for N = 2048)");
+    if (p.glwe_dim != 1) return fail("unsupported glwe_dim (engine is built for k = 1)");
+    if (p.pbs_level != 1) return fail("unsupported pbs_level (engine is built for l = 1)");
+    if (p.pbs_base_log < 2 || p.pbs_base_log > 30) return fail("unsupported pbs_base_log");
+    if (p.ks_level < 1 || p.ks_base_log < 2 || p.ks_base_log > 7 || p.ks_base_log * p.ks_level > 31)
+        return fail("unsupported keyswitch decomposition");
+    if (p.lwe_dim < 1 || p.lwe_dim > 4096) return fail("unsupported lwe_dim");
+    if (p.grouping_factor != 0) return fail("multi-bit PBS is not built in this round (grouping_factor must be 0)");
+    return 0;
+}
+
+int do_keyswitch(tfhe_b200_ctx *c, const uint64_t *d_in, uint64_t *d_small, size_t batch, cudaStream_t s) {
+    if (!c->have_ksk) return fail("keyswitch key not uploaded");
+    TB_CUDA(tbk::launch_keyswitch(d_in, (const uint64_t *)c->ksk_packed.p, (const uint64_t *)c->ksk_colsum.p, d_small,
+                                  (int)batch, (int)(c->p.glwe_dim * c->p.poly_size), (int)c->p.lwe_dim,
+                                  (int)c->p.ks_base_log, (int)c->p.ks_level, s));
+    c->launches += 1;
+    return 0;
+}
+
+int do_pbs(tfhe_b200_ctx *c, const uint64_t *d_small, const uint32_t *d_idx, uint64_t *d_out, size_t batch, uint32_t n_iters,
+           cudaStream_t s) {
+    if (!c->have_bsk) return fail("bootstrap key not uploaded");
+    if (c->n_luts == 0) return fail("no lookup tables uploaded");
+    TB_CUDA(tbk::launch_pbs_classic(d_small, d_idx, (const uint64_t *)c->luts.p, c->bskf.p, c->tbl.p, d_out, (int)batch,
+                                    (int)c->p.lwe_dim, (int)c->p.pbs_base_log, (int)n_iters, s));
+    c->launches += 1;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *tfhe_b200_last_error(void) { return g_last_error.c_str(); }
+const char *tfhe_b200_version(void) { return "tfhe_b200 0.1 (sm_100a; classic KS-PBS, N=2048, k=1, l=1)"; }
+
+int tfhe_b200_ctx_create(int cuda_device, const tfhe_b200_params *params, tfhe_b200_ctx **out) {
+    if (!out) return fail("null out pointer");
+    *out = nullptr;
+    if (!params) return fail("null params");
+    if (check_params(*params)) return 1;
+    int count = 0;
+    TB_CUDA(cudaGetDeviceCount(&count));
+    if (cuda_device < 0 || cuda_device >= count) return fail("no such CUDA device (this engine has no CPU fallback)");
+    DeviceGuard g(cuda_device);
+    tfhe_b200_ctx *c = new tfhe_b200_ctx();
+    c->device = cuda_device;
+    c->p = *params;
+    TB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (auto &e : c->ev) TB_CUDA(cudaEventCreate(&e));
+    TB_CUDA(tbk::pbs_configure());
+    TB_CUDA(tbk::ks_configure((int)params->ks_level));
+    // inter-pass twiddle table
+    std::vector<double> tbl(2 * tb::kM);
+    tb_make_twiddle_table(tbl.data());
+    TB_CUDA(c->tbl.reserve(tbl.size() * sizeof(double)));
+    TB_CUDA(cudaMemcpyAsync(c->tbl.p, tbl.data(), tbl.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    TB_CUDA(cudaStreamSynchronize(c->stream));
+    *out = c;
+    return 0;
+}
+
+int tfhe_b200_ctx_destroy(tfhe_b200_ctx *c) {
+    if (!c) return 0;
+    DeviceGuard g(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (DevBuf *b : {&c->ksk_packed, &c->ksk_colsum, &c->bskf, &c->tbl, &c->luts, &c->d_in, &c->d_small, &c->d_out, &c->d_idx})
+        b->release();
+    for (auto &e : c->ev) if (e) cudaEventDestroy(e);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return 0;
+}
+
+int tfhe_b200_upload_ksk(tfhe_b200_ctx *c, const uint64_t *ksk, size_t len) {
+    if (!c || !ksk) return fail("null argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    const size_t rows = (size_t)c->p.glwe_dim * c->p.poly_size * c->p.ks_level;
+    if (len != rows * (c->p.lwe_dim + 1)) return fail("keyswitch key length does not match the parameters");
+    const int ldk = tbk::ks_padded_cols((int)c->p.lwe_dim);
+    DevBuf raw;
+    TB_CUDA(raw.reserve(len * 8));
+    TB_CUDA(c->ksk_packed.reserve(rows * ldk * 8));
+    TB_CUDA(c->ksk_colsum.reserve((size_t)ldk * 8));
+    TB_CUDA(cudaMemcpyAsync(raw.p, ksk, len * 8, cudaMemcpyHostToDevice, c->stream));
+    TB_CUDA(tbk::launch_ksk_pack((const uint64_t *)raw.p, (uint64_t *)c->ksk_packed.p, (uint64_t *)c->ksk_colsum.p, (int)rows,
+                                 (int)c->p.lwe_dim, c->stream));
+    c->launches += 2;
+    TB_CUDA(cudaStreamSynchronize(c->stream));
+    raw.release();
+    c->have_ksk = true;
+    return 0;
+}
+
+int tfhe_b200_upload_bsk_std(tfhe_b200_ctx *c, const uint64_t *bsk, size_t len) {
+    if (!c || !bsk) return fail("null argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    const size_t k1 = c->p.glwe_dim + 1;
+    const size_t n_polys = (size_t)c->p.lwe_dim * c->p.pbs_level * k1 * k1;
+    if (len != n_polys * c->p.poly_size) return fail("bootstrap key length does not match the parameters");
+    DevBuf raw;
+    TB_CUDA(raw.reserve(len * 8));
+    TB_CUDA(c->bskf.reserve(n_polys * tb::kM * sizeof(double) * 2));
+    TB_CUDA(cudaMemcpyAsync(raw.p, bsk, len * 8, cudaMemcpyHostToDevice, c->stream));
+    TB_CUDA(tbk::launch_bsk_convert((const uint64_t *)raw.p, c->bskf.p, c->tbl.p, (int)n_polys, c->stream));
+    c->launches += 1;
+    TB_CUDA(cudaStreamSynchronize(c->stream));
+    raw.release();
+    c->have_bsk = true;
+    return 0;
+}
+
+int tfhe_b200_upload_luts(tfhe_b200_ctx *c, const uint64_t *luts, uint32_t n_luts) {
+    if (!c || !luts || n_luts == 0) return fail("null or empty lookup-table set");
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    const size_t bytes = (size_t)n_luts * c->lut_len() * 8;
+    TB_CUDA(cudaStreamSynchronize(c->stream));
+    TB_CUDA(c->luts.reserve(bytes));
+    TB_CUDA(cudaMemcpyAsync(c->luts.p, luts, bytes, cudaMemcpyHostToDevice, c->stream));
+    TB_CUDA(cudaStreamSynchronize(c->stream));
+    c->n_luts = n_luts;
+    return 0;
+}
+
+int tfhe_b200_synchronize(tfhe_b200_ctx *c) {
+    if (!c) return fail("null context");
+    DeviceGuard g(c->device);
+    TB_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ---- device-buffer entry points -----------------------------------------------------------------
+
+int tfhe_b200_keyswitch_batch_device(tfhe_b200_ctx *c, const uint64_t *d_in, uint64_t *d_small, size_t batch, void *stream) {
+    if (!c || (batch && (!d_in || !d_small))) return fail("null argument");
+    DeviceGuard g(c->device);
+    return do_keyswitch(c, d_in, d_small, batch, stream ? (cudaStream_t)stream : c->stream);
+}
+
+int tfhe_b200_pbs_batch_device(tfhe_b200_ctx *c, const uint64_t *d_small, const uint32_t *d_idx, uint64_t *d_out, size_t batch,
+                               void *stream) {
+    if (!c || (batch && (!d_small || !d_out))) return fail("null argument");
+    DeviceGuard g(c->device);
+    return do_pbs(c, d_small, d_idx, d_out, batch, c->p.lwe_dim, stream ? (cudaStream_t)stream : c->stream);
+}
+
+int tfhe_b200_ks_pbs_batch_device(tfhe_b200_ctx *c, const uint64_t *d_in, const uint32_t *d_idx, uint64_t *d_out, size_t batch,
+                                  void *stream) {
+    if (!c || (batch && (!d_in || !d_out))) return fail("null argument");
+    if (batch == 0) return 0;
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    TB_CUDA(c->d_small.reserve(batch * c->small_len() * 8));
+    TB_CUDA(cudaEventRecord(c->ev[0], s));
+    if (do_keyswitch(c, d_in, (uint64_t *)c->d_small.p, batch, s)) return 1;
+    TB_CUDA(cudaEventRecord(c->ev[1], s));
+    if (do_pbs(c, (const uint64_t *)c->d_small.p, d_idx, d_out, batch, c->p.lwe_dim, s)) return 1;
+    TB_CUDA(cudaEventRecord(c->ev[2], s));
+    c->timed = true;
+    return 0;
+}
+
+// ---- host-buffer entry points ---------------------------------------------------------------------
+
+int tfhe_b200_keyswitch_batch(tfhe_b200_ctx *c, const uint64_t *in, uint64_t *out, size_t batch) {
+    if (!c || (batch && (!in || !out))) return fail("null argument");
+    if (batch == 0) return 0;
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    TB_CUDA(c->d_in.reserve(batch * c->big_len() * 8));
+    TB_CUDA(c->d_small.reserve(batch * c->small_len() * 8));
+    TB_CUDA(cudaMemcpyAsync(c->d_in.p, in, batch * c->big_len() * 8, cudaMemcpyHostToDevice, c->stream));
+    if (do_keyswitch(c, (const uint64_t *)c->d_in.p, (uint64_t *)c->d_small.p, batch, c->stream)) return 1;
+    TB_CUDA(cudaMemcpyAsync(out, c->d_small.p, batch * c->small_len() * 8, cudaMemcpyDeviceToHost, c->stream));
+    TB_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+static int pbs_host(tfhe_b200_ctx *c, const uint64_t *in, const uint32_t *idx, uint64_t *out, size_t batch, uint32_t n_iters) {
+    if (!c || (batch && (!in || !out))) return fail("null argument");
+    if (batch == 0) return 0;
+    if (n_iters > c->p.lwe_dim) return fail("n_iters exceeds lwe_dim");
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    TB_CUDA(c->d_small.reserve(batch * c->small_len() * 8));
+    TB_CUDA(c->d_out.reserve(batch * c->big_len() * 8));
+    TB_CUDA(cudaMemcpyAsync(c->d_small.p, in, batch * c->small_len() * 8, cudaMemcpyHostToDevice, c->stream));
+    const uint32_t *d_idx = nullptr;
+    if (idx) {
+        TB_CUDA(c->d_idx.reserve(batch * 4));
+        TB_CUDA(cudaMemcpyAsync(c->d_idx.p, idx, batch * 4, cudaMemcpyHostToDevice, c->stream));
+        d_idx = (const uint32_t *)c->d_idx.p;
+    }
+    if (do_pbs(c, (const uint64_t *)c->d_small.p, d_idx, (uint64_t *)c->d_out.p, batch, n_iters, c->stream)) return 1;
+    TB_CUDA(cudaMemcpyAsync(out, c->d_out.p, batch * c->big_len() * 8, cudaMemcpyDeviceToHost, c->stream));
+    TB_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int tfhe_b200_pbs_batch(tfhe_b200_ctx *c, const uint64_t *in, const uint32_t *idx, uint64_t *out, size_t batch) {
+    if (!c) return fail("null context");
+    return pbs_host(c, in, idx, out, batch, c->p.lwe_dim);
+}
+
+int tfhe_b200_pbs_batch_partial(tfhe_b200_ctx *c, const uint64_t *in, const uint32_t *idx, uint64_t *out, size_t batch,
+                                uint32_t n_iters) {
+    return pbs_host(c, in, idx, out, batch, n_iters);
+}
+
+int tfhe_b200_ks_pbs_batch(tfhe_b200_ctx *c, const uint64_t *in, const uint32_t *idx, uint64_t *out, size_t batch) {
+    if (!c || (batch && (!in || !out))) return fail("null argument");
+    if (batch == 0) return 0;
+    {
+        std::lock_guard<std::mutex> lk(c->mu);
+        DeviceGuard g(c->device);
+        TB_CUDA(c->d_in.reserve(batch * c->big_len() * 8));
+        TB_CUDA(c->d_out.reserve(batch * c->big_len() * 8));
+        TB_CUDA(cudaMemcpyAsync(c->d_in.p, in, batch * c->big_len() * 8, cudaMemcpyHostToDevice, c->stream));
+        if (idx) {
+            TB_CUDA(c->d_idx.reserve(batch * 4));
+            TB_CUDA(cudaMemcpyAsync(c->d_idx.p, idx, batch * 4, cudaMemcpyHostToDevice, c->stream));
+        }
+    }
+    if (tfhe_b200_ks_pbs_batch_device(c, (const uint64_t *)c->d_in.p, idx ? (const uint32_t *)c->d_idx.p : nullptr,
+                                      (uint64_t *)c->d_out.p, batch, nullptr))
+        return 1;
+    DeviceGuard g(c->device);
+    TB_CUDA(cudaMemcpyAsync(out, c->d_out.p, batch * c->big_len() * 8, cudaMemcpyDeviceToHost, c->stream));
+    TB_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ---- instrumentation --------------------------------------------------------------------------------
+
+uint64_t tfhe_b200_kernel_launches(const tfhe_b200_ctx *c) { return c ? c->launches : 0; }
+
+int tfhe_b200_time_last_kernels(tfhe_b200_ctx *c, float *ks_ms, float *pbs_ms) {
+    if (!c || !c->timed) return fail("no timed ks_pbs call yet");
+    DeviceGuard g(c->device);
+    TB_CUDA(cudaEventSynchronize(c->ev[2]));
+    if (ks_ms) TB_CUDA(cudaEventElapsedTime(ks_ms, c->ev[0], c->ev[1]));
+    if (pbs_ms) TB_CUDA(cudaEventElapsedTime(pbs_ms, c->ev[1], c->ev[2]));
+    return 0;
+}
+
+int tfhe_b200_probe_fp64_tflops(int cuda_device, double *tflops) {
+    if (!tflops) return fail("null argument");
+    *tflops = 0.0;
+    int count = 0;
+    TB_CUDA(cudaGetDeviceCount(&count));
+    if (cuda_device < 0 || cuda_device >= count) return fail("no such CUDA device");
+    DeviceGuard g(cuda_device);
+    cudaDeviceProp prop;
+    TB_CUDA(cudaGetDeviceProperties(&prop, cuda_device));
+    double *sink = nullptr;
+    TB_CUDA(cudaMalloc(&sink, 8));
+    cudaEvent_t a, b;
+    TB_CUDA(cudaEventCreate(&a));
+    TB_CUDA(cudaEventCreate(&b));
+    const int blocks = prop.multiProcessorCount * 8, iters = 4096;
+    TB_CUDA(tbk::launch_fp64_peak(sink, blocks, 256, nullptr));   // warm-up
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        TB_CUDA(cudaEventRecord(a));
+        TB_CUDA(tbk::launch_fp64_peak(sink, blocks, iters, nullptr));
+        TB_CUDA(cudaEventRecord(b));
+        TB_CUDA(cudaEventSynchronize(b));
+        float ms = 0;
+        TB_CUDA(cudaEventElapsedTime(&ms, a, b));
+        if (ms < best) best = ms;
+    }
+    const double flops = 2.0 * 64.0 * (double)iters * 256.0 * (double)blocks;  // 64 FMA per thread-iteration
+    *tflops = flops / (best * 1e-3) / 1e12;
+    cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(sink);
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,24 @@
+// kernels.h -- internal launcher interface between the C-ABI layer (c_api.cu) and the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+#include <cstdint>
+
+namespace tbk {
+
+// keyswitch.cu
+int ks_padded_cols(int n);
+cudaError_t ks_configure(int level);
+cudaError_t launch_ksk_pack(const uint64_t *ksk, uint64_t *packed, uint64_t *colsum, int rows, int n, cudaStream_t stream);
+cudaError_t launch_keyswitch(const uint64_t *lwe_in, const uint64_t *ksk_packed, const uint64_t *colsum, uint64_t *lwe_out,
+                             int batch, int in_dim, int n, int base_log, int level, cudaStream_t stream);
+
+// pbs.cu
+cudaError_t pbs_configure();
+cudaError_t launch_pbs_classic(const uint64_t *lwe_small, const uint32_t *lut_idx, const uint64_t *luts, const void *bskf,
+                               const void *tbl, uint64_t *out, int batch, int n, int base_log, int n_iters,
+                               cudaStream_t stream);
+cudaError_t launch_bsk_convert(const uint64_t *bsk_std, void *bskf, const void *tbl, int n_polys, cudaStream_t stream);
+cudaError_t launch_fp64_peak(double *sink, int blocks, int iters, cudaStream_t stream);
+
+}  // namespace tbk

@@ -1,0 +1,243 @@
+// pbs.cu -- programmable bootstrap for sm_100a: blind rotation (the 742-iteration CMUX loop), Fourier
+// external product, sample extraction, and the one-time standard->Fourier key conversion.
+//
+// Replaces, on the device, the CPU path
+//   core_crypto/fft_impl/fft64/crypto/bootstrap.rs:242-364  (blind_rotate_assign, bootstrap)
+//   core_crypto/fft_impl/fft64/crypto/ggsw.rs:477-598,616-697 (add_external_product_assign, update_with_fmadd)
+//   core_crypto/fft_impl/fft64/math/fft/mod.rs:197-326,496-557 (fold/twist conversions around plan.fwd/inv)
+//   core_crypto/algorithms/polynomial_algorithms.rs:315-366,425-497 (monomial div, mul-and-subtract)
+//   core_crypto/algorithms/glwe_sample_extraction.rs:91-147
+//   core_crypto/algorithms/lwe_bootstrap_key_conversion.rs:99- (std -> Fourier key)
+//
+// Mapping: one CTA (2 warps) per ciphertext, warp w owns GLWE polynomial w (k = 1).  The accumulator
+// (2 x 2048 u64 = 32 KiB) stays in shared memory for all n iterations; each lane keeps its 32 complex
+// points (64 FP64 registers) of the polynomial being transformed.  Per iteration a warp does: rotated
+// gather + subtract + 1-level signed decomposition straight into FFT registers, forward FFT, a
+// cross-warp exchange of spectra, the 2x2 complex multiply-accumulate against the Fourier GGSW
+// (coalesced 16-byte loads, L2-resident key), inverse FFT, round-to-torus and accumulate.
+#include "kernels.h"
+#include "fft_core.cuh"
+
+namespace tb {
+
+struct PbsSmem {
+    uint64_t acc[2][kN];   // GLWE accumulator (mask poly, body poly)
+    double xb[2][kM];      // per-warp exchange tile (transpose halves / spectrum exchange)
+};
+static_assert(sizeof(PbsSmem) == 48 * 1024, "smem budget: 4 CTAs per SM");
+
+// lane <-> register transpose of one 32x32 tile of doubles through the warp-private buffer
+__device__ __forceinline__ void warp_transpose(double (&v)[32], double *xb, int lane) {
+#pragma unroll
+    for (int r = 0; r < 32; ++r) xb[xpose_write_idx(lane, r)] = v[r];
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < 32; ++r) v[r] = xb[xpose_read_idx(lane, r)];
+    __syncwarp();
+}
+
+__device__ __forceinline__ void fft_forward_warp(double (&re)[32], double (&im)[32], const cplx *__restrict__ tbl,
+                                                 double *xb, int lane) {
+    pretwist_fwd(re, im);
+    radix32_dif(re, im);
+    twiddle_fwd(re, im, [&](int i) { return __ldg(tbl + i); }, lane);
+    warp_transpose(re, xb, lane);
+    warp_transpose(im, xb, lane);
+    radix32_dif(re, im);
+}
+
+__device__ __forceinline__ void fft_inverse_warp(double (&re)[32], double (&im)[32], const cplx *__restrict__ tbl,
+                                                 double *xb, int lane) {
+    radix32_dit_inv(re, im);
+    warp_transpose(re, xb, lane);
+    warp_transpose(im, xb, lane);
+    twiddle_inv(re, im, [&](int i) { return __ldg(tbl + i); }, lane);
+    radix32_dit_inv(re, im);
+    posttwist_inv(re, im);
+}
+
+// Fourier key layout: [ggsw i][output poly c][input poly (GGSW row) r][register p][thread t] complex,
+// with the 1/1024 of the inverse transform and the 2^-64 torus scale folded in (both exact).
+__device__ __forceinline__ size_t bskf_index(int i, int c, int r) { return ((size_t)(i * 2 + c) * 2 + r) * kM; }
+
+__global__ void __launch_bounds__(64, 4)
+pbs_classic_kernel(const uint64_t *__restrict__ lwe_small,  // [batch][n+1], small key
+                   const uint32_t *__restrict__ lut_idx,    // [batch] or nullptr (LUT 0)
+                   const uint64_t *__restrict__ luts,       // [n_luts][2][N]
+                   const cplx *__restrict__ bskf, const cplx *__restrict__ tbl,
+                   uint64_t *__restrict__ out,              // [batch][2N.. k*N+1]
+                   int n, int base_log, int n_iters) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    PbsSmem &sm = *reinterpret_cast<PbsSmem *>(smem_raw);
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ct = blockIdx.x;
+    uint64_t *my = sm.acc[w];
+    double *xbw = sm.xb[w];
+    const cplx *xbo_c = reinterpret_cast<const cplx *>(sm.xb[1 - w]);
+    cplx *xbw_c = reinterpret_cast<cplx *>(sm.xb[w]);
+    const uint64_t *lwe = lwe_small + (size_t)ct * (n + 1);
+
+    // bootstrap.rs:254-271: acc <- LUT * X^(-b_hat)  ==  LUT * X^(2N - b_hat)
+    {
+        const uint32_t b_hat = modulus_switch_2n(__ldg(lwe + n)) & (2 * kN - 1);
+        const uint32_t a0 = (2 * kN - b_hat) & (2 * kN - 1);
+        const uint64_t *lut = luts + ((size_t)(lut_idx ? lut_idx[ct] : 0) * 2 + w) * kN;
+        for (int j = lane; j < kN; j += 32) {
+            int src; bool neg;
+            rot_src(j, a0, src, neg);
+            const uint64_t v = __ldg(lut + src);
+            my[j] = neg ? (uint64_t)0 - v : v;
+        }
+    }
+    __syncwarp();
+
+    double re[32], im[32];
+    for (int i = 0; i < n_iters; ++i) {
+        // bootstrap.rs:279-316.  The reference skips a_i == 0; a_hat == 0 (mod 2N) makes ct1 == 0 and the
+        // external product add exactly zero, so skipping on a_hat is bit-identical.
+        const uint32_t a = modulus_switch_2n(__ldg(lwe + i)) & (2 * kN - 1);
+        if (a == 0) continue;
+
+        // ct1 = acc * X^a - acc (polynomial_algorithms.rs:425-497), rounded + decomposed at level 1
+        // (ggsw.rs:515-533), folded: point j = coeff j + i * coeff (j + N/2)  (fft/mod.rs:226-238)
+#pragma unroll
+        for (int m = 0; m < 32; ++m) {
+            const int j = lane + 32 * m;
+            const uint32_t s0 = ((uint32_t)j - a) & (2 * kN - 1);
+            const uint32_t s1 = (s0 + kM) & (2 * kN - 1);
+            uint64_t r0 = my[s0 & (kN - 1)], r1 = my[s1 & (kN - 1)];
+            r0 = (s0 >= (uint32_t)kN) ? (uint64_t)0 - r0 : r0;
+            r1 = (s1 >= (uint32_t)kN) ? (uint64_t)0 - r1 : r1;
+            re[m] = (double)signed_digit_l1(r0 - my[j], base_log);
+            im[m] = (double)signed_digit_l1(r1 - my[j + kM], base_log);
+        }
+
+        fft_forward_warp(re, im, tbl, xbw, lane);
+
+        // out_fft[c] = sum_r ggsw[r][c] * fourier_r  (ggsw.rs:547-576): warp w produces output poly w and
+        // needs the other warp's spectrum; exchanged in two halves through the 8 KiB tiles.
+        const cplx *g_own = bskf + bskf_index(i, w, w);
+        const cplx *g_oth = bskf + bskf_index(i, w, 1 - w);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+#pragma unroll
+            for (int pp = 0; pp < 16; ++pp) {
+                cplx f; f.x = re[half * 16 + pp]; f.y = im[half * 16 + pp];
+                xbw_c[pp * 32 + lane] = f;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int pp = 0; pp < 16; ++pp) {
+                const int p = half * 16 + pp;
+                const cplx fo = xbo_c[pp * 32 + lane];
+                const cplx ga = __ldg(g_own + p * 32 + lane);
+                const cplx gb = __ldg(g_oth + p * 32 + lane);
+                const double fr = re[p], fi = im[p];
+                double orr = DMUL(fr, ga.x);
+                orr = DFMA(-fi, ga.y, orr);
+                orr = DFMA(fo.x, gb.x, orr);
+                orr = DFMA(-fo.y, gb.y, orr);
+                double oi = DMUL(fr, ga.y);
+                oi = DFMA(fi, ga.x, oi);
+                oi = DFMA(fo.x, gb.y, oi);
+                oi = DFMA(fo.y, gb.x, oi);
+                re[p] = orr; im[p] = oi;
+            }
+            __syncthreads();
+        }
+
+        fft_inverse_warp(re, im, tbl, xbw, lane);
+
+        // fft/mod.rs:285-326 convert_add_backward_torus: acc += from_torus(.)
+#pragma unroll
+        for (int m = 0; m < 32; ++m) {
+            const int j = lane + 32 * m;
+            my[j] += from_torus_f64(re[m]);
+            my[j + kM] += from_torus_f64(im[m]);
+        }
+        __syncwarp();
+    }
+
+    // glwe_sample_extraction.rs:125-146 (coefficient 0): mask -> (A[0], -A[N-1], ..., -A[1]); body = B[0]
+    uint64_t *o = out + (size_t)ct * (kN + 1);
+    if (w == 0) {
+        for (int j = lane; j < kN; j += 32) o[j] = (j == 0) ? my[0] : (uint64_t)0 - my[kN - j];
+    } else if (lane == 0) {
+        o[kN] = my[0];
+    }
+}
+
+// lwe_bootstrap_key_conversion.rs:99- / fft/mod.rs:197-218 (convert_forward_torus): one warp per polynomial.
+// Input  std layout [i][level = 1][row r][col c][N]  (entities/ggsw_ciphertext.rs:185-197)
+// Output bskf layout [i][c][r][p][t]
+__global__ void __launch_bounds__(32)
+bsk_convert_kernel(const uint64_t *__restrict__ bsk_std, cplx *__restrict__ bskf, const cplx *__restrict__ tbl, int n_polys) {
+    __shared__ double xb[kM];
+    const int q = blockIdx.x, lane = threadIdx.x;
+    if (q >= n_polys) return;
+    const int i = q >> 2, r = (q >> 1) & 1, c = q & 1;
+    const uint64_t *src = bsk_std + (size_t)q * kN;
+    const double scale = 5.293955920339377e-23;  // 2^-74 = 2^-64 (torus) * 2^-10 (inverse FFT size), exact
+    double re[32], im[32];
+#pragma unroll
+    for (int m = 0; m < 32; ++m) {
+        const int j = lane + 32 * m;
+        re[m] = DMUL((double)(long long)src[j], scale);
+        im[m] = DMUL((double)(long long)src[j + kM], scale);
+    }
+    fft_forward_warp(re, im, tbl, xb, lane);
+    cplx *dst = bskf + bskf_index(i, c, r);
+#pragma unroll
+    for (int p = 0; p < 32; ++p) {
+        cplx v; v.x = re[p]; v.y = im[p];
+        dst[p * 32 + lane] = v;
+    }
+}
+
+// ---- FP64 FMA peak probe (roofline denominator; MEASURED_PEAKS.json has no FP64 figure) ----------
+__global__ void __launch_bounds__(256)
+fp64_peak_kernel(double *sink, int iters) {
+    double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            a0 = __fma_rn(a0, m, c); a1 = __fma_rn(a1, m, c); a2 = __fma_rn(a2, m, c); a3 = __fma_rn(a3, m, c);
+            a4 = __fma_rn(a4, m, c); a5 = __fma_rn(a5, m, c); a6 = __fma_rn(a6, m, c); a7 = __fma_rn(a7, m, c);
+        }
+    }
+    if (a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 == 12345.678) sink[0] = a0;
+}
+
+}  // namespace tb
+
+// ---- host launchers ---------------------------------------------------------------------------
+
+namespace tbk {
+
+cudaError_t pbs_configure() {
+    return cudaFuncSetAttribute(tb::pbs_classic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tb::PbsSmem));
+}
+
+cudaError_t launch_pbs_classic(const uint64_t *lwe_small, const uint32_t *lut_idx, const uint64_t *luts,
+                               const void *bskf, const void *tbl, uint64_t *out, int batch, int n, int base_log,
+                               int n_iters, cudaStream_t stream) {
+    if (batch <= 0) return cudaSuccess;
+    tb::pbs_classic_kernel<<<batch, 64, sizeof(tb::PbsSmem), stream>>>(
+        lwe_small, lut_idx, luts, reinterpret_cast<const tb::cplx *>(bskf), reinterpret_cast<const tb::cplx *>(tbl), out, n,
+        base_log, n_iters);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_bsk_convert(const uint64_t *bsk_std, void *bskf, const void *tbl, int n_polys, cudaStream_t stream) {
+    tb::bsk_convert_kernel<<<n_polys, 32, 0, stream>>>(bsk_std, reinterpret_cast<tb::cplx *>(bskf),
+                                                       reinterpret_cast<const tb::cplx *>(tbl), n_polys);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fp64_peak(double *sink, int blocks, int iters, cudaStream_t stream) {
+    tb::fp64_peak_kernel<<<blocks, 256, 0, stream>>>(sink, iters);
+    return cudaGetLastError();
+}
+
+}  // namespace tbk

@@ -1,0 +1,99 @@
+/*
+ * tfhe_b200.h -- C ABI of the B200-native KS-PBS engine (libtfhe_b200.so, CUDA sm_100a).
+ *
+ * The reference (tfhe-rs 0.5.0 fork, /root/reference) has NO FFI under this path: KS-PBS is a direct
+ * Rust call chain.  This boundary is introduced exactly under
+ *   shortint::ServerKey::apply_lookup_table        tfhe/src/shortint/server_key/mod.rs:457-476
+ *   ServerKey::keyswitch_programmable_bootstrap_assign                         mod.rs:783-857
+ * and follows the reference's own C-API conventions (tfhe/src/c_api/utils.rs:3-28): every function
+ * returns int, 0 = success, non-zero = failure; out-pointers are nulled first; objects are opaque
+ * heap handles freed by a matching destroy; raw key / ciphertext arrays stay caller-owned
+ * (precedent: tfhe/src/c_api/core_crypto/mod.rs:38-122).  INTEGRATION.md shows the Rust
+ * `extern "C"` block and build.rs lines a maintainer would add.
+ *
+ * Only raw LWE arrays cross the boundary; degree / noise-level metadata and the trivial-ciphertext
+ * short cut (mod.rs:788-791) stay on the host side.
+ */
+#ifndef TFHE_B200_H
+#define TFHE_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tfhe_b200_ctx tfhe_b200_ctx;
+
+/* shortint::ClassicPBSParameters / MultiBitPBSParameters (shortint/parameters/mod.rs:703-717,
+ * multi_bit.rs:173-190); grouping_factor = 0 selects the classic PBS. */
+typedef struct {
+    uint32_t lwe_dim;        /* n   (small key)            */
+    uint32_t glwe_dim;       /* k                           */
+    uint32_t poly_size;      /* N                           */
+    uint32_t pbs_base_log, pbs_level;
+    uint32_t ks_base_log, ks_level;
+    uint32_t grouping_factor;
+    uint32_t msg_mod, carry_mod;
+} tfhe_b200_params;
+
+/* Lifetime.  One context per GPU; re-entrant per context, no thread-locals (replaces the thread-local
+ * ShortintEngine scratch, shortint/engine/mod.rs:23-25,184-189, and the global FFT plan cache,
+ * core_crypto/fft_impl/fft64/math/fft/mod.rs:98-102,146-193). */
+int tfhe_b200_ctx_create(int cuda_device, const tfhe_b200_params *params, tfhe_b200_ctx **out);
+int tfhe_b200_ctx_destroy(tfhe_b200_ctx *ctx);
+const char *tfhe_b200_last_error(void);
+
+/* Keys (host pointers, copied).
+ * ksk: LweKeyswitchKey<u64> container, [k*N][ks_level (level l..1)][n+1]
+ *      (core_crypto/entities/lwe_keyswitch_key.rs:77-110,396).
+ * bsk: STANDARD-domain LweBootstrapKey<u64>, [n][pbs_level (1..l)][k+1][k+1][N]
+ *      (entities/ggsw_ciphertext.rs:185-197); converted to the engine's own Fourier layout on the
+ *      device (replaces lwe_bootstrap_key_conversion.rs:99- / FourierLweBootstrapKey::new).
+ * luts: n_luts accumulators as produced by ServerKey::generate_lookup_table
+ *      (shortint/server_key/mod.rs:383-399, engine/mod.rs:72-128), each (k+1)*N words. */
+int tfhe_b200_upload_ksk(tfhe_b200_ctx *ctx, const uint64_t *ksk, size_t len);
+int tfhe_b200_upload_bsk_std(tfhe_b200_ctx *ctx, const uint64_t *bsk, size_t len);
+int tfhe_b200_upload_luts(tfhe_b200_ctx *ctx, const uint64_t *luts, uint32_t n_luts);
+
+/* Batched hot path, HOST buffers (H2D + kernels + D2H inside the call, synchronous).
+ * lwe_big:   batch x (k*N + 1) words under the big key;  lwe_small: batch x (n + 1) words.
+ * lut_idx:   batch indices into the uploaded LUT table (NULL = LUT 0 for all).
+ * keyswitch_batch  replaces keyswitch_lwe_ciphertext            core_crypto/algorithms/lwe_keyswitch.rs:96-170
+ * pbs_batch        replaces programmable_bootstrap_lwe_ciphertext_mem_optimized
+ *                                                                algorithms/lwe_programmable_bootstrapping.rs:1067-1107
+ * ks_pbs_batch     replaces keyswitch_programmable_bootstrap_assign (non-trivial branch)
+ *                                                                shortint/server_key/mod.rs:793-856 */
+int tfhe_b200_keyswitch_batch(tfhe_b200_ctx *ctx, const uint64_t *lwe_big, uint64_t *lwe_small, size_t batch);
+int tfhe_b200_pbs_batch(tfhe_b200_ctx *ctx, const uint64_t *lwe_small, const uint32_t *lut_idx, uint64_t *lwe_big,
+                        size_t batch);
+int tfhe_b200_ks_pbs_batch(tfhe_b200_ctx *ctx, const uint64_t *lwe_big_in, const uint32_t *lut_idx,
+                           uint64_t *lwe_big_out, size_t batch);
+
+/* Same operations on DEVICE buffers of the context's GPU, enqueued on `cuda_stream` (a cudaStream_t;
+ * NULL = the context's own stream) without synchronising: used to chain tree levels and by the
+ * multi-GPU driver. */
+int tfhe_b200_keyswitch_batch_device(tfhe_b200_ctx *ctx, const uint64_t *d_lwe_big, uint64_t *d_lwe_small, size_t batch,
+                                     void *cuda_stream);
+int tfhe_b200_pbs_batch_device(tfhe_b200_ctx *ctx, const uint64_t *d_lwe_small, const uint32_t *d_lut_idx,
+                               uint64_t *d_lwe_big, size_t batch, void *cuda_stream);
+int tfhe_b200_ks_pbs_batch_device(tfhe_b200_ctx *ctx, const uint64_t *d_lwe_big_in, const uint32_t *d_lut_idx,
+                                  uint64_t *d_lwe_big_out, size_t batch, void *cuda_stream);
+int tfhe_b200_synchronize(tfhe_b200_ctx *ctx);
+
+/* Test hook: PBS that stops after `n_iters` blind-rotation iterations (n_iters = 1 gives one CMUX =
+ * one add_external_product_assign, fft64/crypto/ggsw.rs:477-598, whose output is comparable
+ * coefficient-wise with the oracle). */
+int tfhe_b200_pbs_batch_partial(tfhe_b200_ctx *ctx, const uint64_t *lwe_small, const uint32_t *lut_idx,
+                                uint64_t *lwe_big, size_t batch, uint32_t n_iters);
+
+/* Instrumentation. */
+uint64_t tfhe_b200_kernel_launches(const tfhe_b200_ctx *ctx);   /* kernels launched by this context so far */
+int tfhe_b200_time_last_kernels(tfhe_b200_ctx *ctx, float *ks_ms, float *pbs_ms); /* CUDA-event ms of the last ks_pbs call */
+int tfhe_b200_probe_fp64_tflops(int cuda_device, double *tflops);  /* dependent-FMA microbenchmark */
+const char *tfhe_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,48 @@
+"""Shared helpers for the parity tests (oracle side)."""
+import ctypes as C
+
+import numpy as np
+
+
+def oracle_partial_pbs(orc, sk, lwe_small, lut, n_iters):
+    """bootstrap.rs:254-316 restated with the oracle primitives, stopping after n_iters mask elements;
+    returns the sample-extracted LWE (same shape as a full PBS output)."""
+    L = orc.lib()
+    p = sk.p
+    N, k1 = p.poly_size, p.glwe_dim + 1
+    b_hat = L.orc_modulus_switch(int(lwe_small[p.lwe_dim]), 11)
+    acc = np.zeros(k1 * N, dtype=np.uint64)
+    for q in range(k1):
+        tmp = np.zeros(N, dtype=np.uint64)
+        L.orc_monomial_div(tmp, np.ascontiguousarray(lut[q * N:(q + 1) * N]), N, b_hat)
+        acc[q * N:(q + 1) * N] = tmp
+    for i in range(n_iters):
+        if int(lwe_small[i]) == 0:
+            continue
+        a_hat = L.orc_modulus_switch(int(lwe_small[i]), 11)
+        ct1 = np.zeros_like(acc)
+        for q in range(k1):
+            tmp = np.zeros(N, dtype=np.uint64)
+            L.orc_monomial_mul_and_subtract(tmp, np.ascontiguousarray(acc[q * N:(q + 1) * N]), N, a_hat)
+            ct1[q * N:(q + 1) * N] = tmp
+        L.orc_add_external_product_f64(C.byref(p), sk.fourier, i, acc, ct1)
+    out = np.zeros(p.big_dim + 1, dtype=np.uint64)
+    L.orc_sample_extract0(C.byref(p), acc, out)
+    return out
+
+
+def engine_params(orc_params):
+    return dict(lwe_dim=orc_params.lwe_dim, glwe_dim=orc_params.glwe_dim, poly_size=orc_params.poly_size,
+                pbs_base_log=orc_params.pbs_base_log, pbs_level=orc_params.pbs_level,
+                ks_base_log=orc_params.ks_base_log, ks_level=orc_params.ks_level,
+                grouping_factor=orc_params.grouping_factor, msg_mod=orc_params.msg_mod, carry_mod=orc_params.carry_mod)
+
+
+def phase_error(ck, cts, expected_values):
+    """|decrypted phase - expected plaintext| in u64 torus units, per ciphertext."""
+    errs = []
+    for ct, v in zip(cts, expected_values):
+        ph = ck.decrypt_raw(ct)
+        d = (ph - (int(v) << 59)) % 2**64
+        errs.append(min(d, 2**64 - d))
+    return np.array(errs, dtype=np.float64)
