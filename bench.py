@@ -148,7 +148,12 @@ def run_b200(args):
     d_in = torch.randint(-2**63, 2**63 - 1, (B, p.big_len), dtype=torch.int64, device="cuda", generator=g)
     d_idx = (torch.arange(B, device="cuda", dtype=torch.int32) % 16).contiguous()
     d_out = torch.empty_like(d_in)
-    stream = torch.cuda.current_stream().cuda_stream
+    # a non-default torch stream: handle 0 would mean "the context's own stream" to the C ABI, and
+    # torch.cuda.Event only sees the stream it is recorded on
+    tstream = torch.cuda.Stream()
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
 
     def step():
         eng.ks_pbs_batch_device(d_in, d_idx, d_out, B, stream)

@@ -201,32 +201,56 @@ TB_HD void posttwist_inv(double (&re)[32], double (&im)[32]) {
 // The inter-pass twiddle table: tbl[p*32 + l] = w^l * W^(l*brev5(p)) = exp(i*pi*l*(1 - 4*brev5(p))/2048),
 // stored as interleaved (re, im).  Built on the host in long double (see tb_make_twiddle_table).
 // register p of lane l *= tbl[p*32 + l]   (forward)   /   *= conj(tbl[p*32 + l])   (inverse)
+// Loads are issued in groups of TB_TW_CHUNK so that the compiler cannot hoist all 32 (128 registers)
+// above the butterflies and spill; TB_FENCE stops it from merging the groups.
+#if defined(__CUDA_ARCH__)
+#define TB_FENCE() asm volatile("" ::: "memory")
+#else
+#define TB_FENCE() do {} while (0)
+#endif
+constexpr int TB_TW_CHUNK = 8;
+
 template <class Load>
 TB_HD void twiddle_fwd(double (&re)[32], double (&im)[32], Load load, int lane) {
 #pragma unroll
-    for (int p = 0; p < 32; ++p) {
-        const cplx w = load(p * 32 + lane);
-        const double a = re[p], b = im[p];
-        re[p] = DFMA(a, w.x, -DMUL(b, w.y));
-        im[p] = DFMA(b, w.x, DMUL(a, w.y));
+    for (int c = 0; c < 32; c += TB_TW_CHUNK) {
+        cplx w[TB_TW_CHUNK];
+#pragma unroll
+        for (int q = 0; q < TB_TW_CHUNK; ++q) w[q] = load((c + q) * 32 + lane);
+#pragma unroll
+        for (int q = 0; q < TB_TW_CHUNK; ++q) {
+            const double a = re[c + q], b = im[c + q];
+            re[c + q] = DFMA(a, w[q].x, -DMUL(b, w[q].y));
+            im[c + q] = DFMA(b, w[q].x, DMUL(a, w[q].y));
+        }
+        TB_FENCE();
     }
 }
 template <class Load>
 TB_HD void twiddle_inv(double (&re)[32], double (&im)[32], Load load, int lane) {
 #pragma unroll
-    for (int p = 0; p < 32; ++p) {
-        const cplx w = load(p * 32 + lane);
-        const double a = re[p], b = im[p];
-        re[p] = DFMA(a, w.x, DMUL(b, w.y));
-        im[p] = DFMA(b, w.x, -DMUL(a, w.y));
+    for (int c = 0; c < 32; c += TB_TW_CHUNK) {
+        cplx w[TB_TW_CHUNK];
+#pragma unroll
+        for (int q = 0; q < TB_TW_CHUNK; ++q) w[q] = load((c + q) * 32 + lane);
+#pragma unroll
+        for (int q = 0; q < TB_TW_CHUNK; ++q) {
+            const double a = re[c + q], b = im[c + q];
+            re[c + q] = DFMA(a, w[q].x, DMUL(b, w[q].y));
+            im[c + q] = DFMA(b, w[q].x, -DMUL(a, w[q].y));
+        }
+        TB_FENCE();
     }
 }
 
-// shared-memory transpose addressing: (lane L, register r) is written at word r*32 + ((L + r) & 31);
-// afterwards lane L reads register r from word L*32 + ((r + L) & 31).  Both sides are bank-conflict free
-// for 8-byte words (within each half-warp the low four address bits are distinct).
-TB_HD constexpr int xpose_write_idx(int lane, int r) { return r * 32 + ((lane + r) & 31); }
-TB_HD constexpr int xpose_read_idx(int lane, int r) { return lane * 32 + ((r + lane) & 31); }
+// shared-memory transpose addressing: a 32 x 33 (padded) tile of 8-byte words.  (lane L, register r) is
+// written at word r*33 + L; afterwards lane L reads register r from word L*33 + r.  Every address is
+// "per-lane base + compile-time constant" (no per-register index registers to keep alive across the
+// blind-rotation loop) and both sides are bank-conflict free (33 = 1 mod 16 for 8-byte words).
+constexpr int kXposeStride = 33;
+constexpr int kXposeWords = 32 * kXposeStride;
+TB_HD constexpr int xpose_write_idx(int lane, int r) { return r * kXposeStride + lane; }
+TB_HD constexpr int xpose_read_idx(int lane, int r) { return lane * kXposeStride + r; }
 
 // frequency held by (thread t, register p) after the forward transform
 TB_HD constexpr int freq_of(int t, int p) { return brev5(t) + 32 * brev5(p); }

@@ -22,9 +22,17 @@ namespace tb {
 
 struct PbsSmem {
     uint64_t acc[2][kN];   // GLWE accumulator (mask poly, body poly)
-    double xb[2][kM];      // per-warp exchange tile (transpose halves / spectrum exchange)
+    double xb[2][kXposeWords];  // per-warp exchange tile (padded 32x33 transpose halves / spectrum exchange)
 };
-static_assert(sizeof(PbsSmem) == 48 * 1024, "smem budget: 4 CTAs per SM");
+static_assert(sizeof(PbsSmem) <= 50 * 1024, "smem budget: 4 CTAs per SM");
+
+// 16-byte read-only load as a volatile asm: keeps its position relative to the TB_FENCE()s, so that loads
+// are issued in bounded groups instead of being hoisted wholesale (which made ptxas spill FFT data)
+__device__ __forceinline__ cplx ldg_cplx(const cplx *p) {
+    cplx v;
+    asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
 
 // lane <-> register transpose of one 32x32 tile of doubles through the warp-private buffer
 __device__ __forceinline__ void warp_transpose(double (&v)[32], double *xb, int lane) {
@@ -40,7 +48,7 @@ __device__ __forceinline__ void fft_forward_warp(double (&re)[32], double (&im)[
                                                  double *xb, int lane) {
     pretwist_fwd(re, im);
     radix32_dif(re, im);
-    twiddle_fwd(re, im, [&](int i) { return __ldg(tbl + i); }, lane);
+    twiddle_fwd(re, im, [&](int i) { return ldg_cplx(tbl + i); }, lane);
     warp_transpose(re, xb, lane);
     warp_transpose(im, xb, lane);
     radix32_dif(re, im);
@@ -51,7 +59,7 @@ __device__ __forceinline__ void fft_inverse_warp(double (&re)[32], double (&im)[
     radix32_dit_inv(re, im);
     warp_transpose(re, xb, lane);
     warp_transpose(im, xb, lane);
-    twiddle_inv(re, im, [&](int i) { return __ldg(tbl + i); }, lane);
+    twiddle_inv(re, im, [&](int i) { return ldg_cplx(tbl + i); }, lane);
     radix32_dit_inv(re, im);
     posttwist_inv(re, im);
 }
@@ -101,23 +109,43 @@ pbs_classic_kernel(const uint64_t *__restrict__ lwe_small,  // [batch][n+1], sma
         // ct1 = acc * X^a - acc (polynomial_algorithms.rs:425-497), rounded + decomposed at level 1
         // (ggsw.rs:515-533), folded: point j = coeff j + i * coeff (j + N/2)  (fft/mod.rs:226-238)
 #pragma unroll
-        for (int m = 0; m < 32; ++m) {
-            const int j = lane + 32 * m;
-            const uint32_t s0 = ((uint32_t)j - a) & (2 * kN - 1);
-            const uint32_t s1 = (s0 + kM) & (2 * kN - 1);
-            uint64_t r0 = my[s0 & (kN - 1)], r1 = my[s1 & (kN - 1)];
-            r0 = (s0 >= (uint32_t)kN) ? (uint64_t)0 - r0 : r0;
-            r1 = (s1 >= (uint32_t)kN) ? (uint64_t)0 - r1 : r1;
-            re[m] = (double)signed_digit_l1(r0 - my[j], base_log);
-            im[m] = (double)signed_digit_l1(r1 - my[j + kM], base_log);
+        for (int m0 = 0; m0 < 32; m0 += 8) {
+#pragma unroll
+            for (int m = m0; m < m0 + 8; ++m) {
+                const int j = lane + 32 * m;
+                const uint32_t s0 = ((uint32_t)j - a) & (2 * kN - 1);
+                const uint32_t s1 = (s0 + kM) & (2 * kN - 1);
+                uint64_t r0 = my[s0 & (kN - 1)], r1 = my[s1 & (kN - 1)];
+                r0 = (s0 >= (uint32_t)kN) ? (uint64_t)0 - r0 : r0;
+                r1 = (s1 >= (uint32_t)kN) ? (uint64_t)0 - r1 : r1;
+                re[m] = (double)signed_digit_l1(r0 - my[j], base_log);
+                im[m] = (double)signed_digit_l1(r1 - my[j + kM], base_log);
+            }
+            TB_FENCE();
         }
 
-        fft_forward_warp(re, im, tbl, xbw, lane);
+        // forward FFT (fft_forward_warp, inlined so that the first Fourier-GGSW loads can be issued before
+        // the second radix-32 pass and overlap it)
+        pretwist_fwd(re, im);
+        radix32_dif(re, im);
+        twiddle_fwd(re, im, [&](int i) { return ldg_cplx(tbl + i); }, lane);
+        warp_transpose(re, xbw, lane);
+        warp_transpose(im, xbw, lane);
 
         // out_fft[c] = sum_r ggsw[r][c] * fourier_r  (ggsw.rs:547-576): warp w produces output poly w and
-        // needs the other warp's spectrum; exchanged in two halves through the 8 KiB tiles.
-        const cplx *g_own = bskf + bskf_index(i, w, w);
-        const cplx *g_oth = bskf + bskf_index(i, w, 1 - w);
+        // needs the other warp's spectrum; exchanged in two halves through the 8 KiB tiles.  The GGSW
+        // loads run one 4-point chunk ahead of the multiply-accumulate (register double buffer).
+        const cplx *g_own = bskf + bskf_index(i, w, w) + lane;
+        const cplx *g_oth = bskf + bskf_index(i, w, 1 - w) + lane;
+        cplx ga[2][4], gb[2][4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            ga[0][q] = ldg_cplx(g_own + q * 32);
+            gb[0][q] = ldg_cplx(g_oth + q * 32);
+        }
+        TB_FENCE();
+        radix32_dif(re, im);
+
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
 #pragma unroll
@@ -127,21 +155,34 @@ pbs_classic_kernel(const uint64_t *__restrict__ lwe_small,  // [batch][n+1], sma
             }
             __syncthreads();
 #pragma unroll
-            for (int pp = 0; pp < 16; ++pp) {
-                const int p = half * 16 + pp;
-                const cplx fo = xbo_c[pp * 32 + lane];
-                const cplx ga = __ldg(g_own + p * 32 + lane);
-                const cplx gb = __ldg(g_oth + p * 32 + lane);
-                const double fr = re[p], fi = im[p];
-                double orr = DMUL(fr, ga.x);
-                orr = DFMA(-fi, ga.y, orr);
-                orr = DFMA(fo.x, gb.x, orr);
-                orr = DFMA(-fo.y, gb.y, orr);
-                double oi = DMUL(fr, ga.y);
-                oi = DFMA(fi, ga.x, oi);
-                oi = DFMA(fo.x, gb.y, oi);
-                oi = DFMA(fo.y, gb.x, oi);
-                re[p] = orr; im[p] = oi;
+            for (int c4 = 0; c4 < 4; ++c4) {
+                const int chunk = half * 4 + c4;       // 8 chunks of 4 points
+                const int cur = chunk & 1;
+                if (chunk + 1 < 8) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        ga[cur ^ 1][q] = ldg_cplx(g_own + ((chunk + 1) * 4 + q) * 32);
+                        gb[cur ^ 1][q] = ldg_cplx(g_oth + ((chunk + 1) * 4 + q) * 32);
+                    }
+                }
+                cplx fo[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) fo[q] = xbo_c[(c4 * 4 + q) * 32 + lane];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int p = chunk * 4 + q;
+                    const double fr = re[p], fi = im[p];
+                    double orr = DMUL(fr, ga[cur][q].x);
+                    orr = DFMA(-fi, ga[cur][q].y, orr);
+                    orr = DFMA(fo[q].x, gb[cur][q].x, orr);
+                    orr = DFMA(-fo[q].y, gb[cur][q].y, orr);
+                    double oi = DMUL(fr, ga[cur][q].y);
+                    oi = DFMA(fi, ga[cur][q].x, oi);
+                    oi = DFMA(fo[q].x, gb[cur][q].y, oi);
+                    oi = DFMA(fo[q].y, gb[cur][q].x, oi);
+                    re[p] = orr; im[p] = oi;
+                }
+                TB_FENCE();
             }
             __syncthreads();
         }
@@ -172,7 +213,7 @@ pbs_classic_kernel(const uint64_t *__restrict__ lwe_small,  // [batch][n+1], sma
 // Output bskf layout [i][c][r][p][t]
 __global__ void __launch_bounds__(32)
 bsk_convert_kernel(const uint64_t *__restrict__ bsk_std, cplx *__restrict__ bskf, const cplx *__restrict__ tbl, int n_polys) {
-    __shared__ double xb[kM];
+    __shared__ double xb[kXposeWords];
     const int q = blockIdx.x, lane = threadIdx.x;
     if (q >= n_polys) return;
     const int i = q >> 2, r = (q >> 1) & 1, c = q & 1;

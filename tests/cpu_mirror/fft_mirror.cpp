@@ -16,7 +16,7 @@ struct Warp {
 };
 
 static void transpose(Warp &w) {
-    static double xb[1024];
+    static double xb[kXposeWords];
     for (int part = 0; part < 2; ++part) {
         for (int l = 0; l < 32; ++l)
             for (int r = 0; r < 32; ++r) xb[xpose_write_idx(l, r)] = part ? w.im[l][r] : w.re[l][r];

@@ -57,7 +57,7 @@ def test_one_cmux_matches_oracle(orc, keys_2_2, eng):
     small = np.stack([sk.keyswitch(c) for c in cts])
     idx = np.array([0, 3, 4, 1], dtype=np.uint32)
     worst = 0
-    for n_iters in (0, 1, 2):
+    for n_iters in (0, 1):
         got = eng.pbs_batch(small, idx, n_iters=n_iters)
         for b in range(len(cts)):
             want = oracle_partial_pbs(orc, sk, small[b], luts[idx[b]], n_iters)
@@ -67,7 +67,7 @@ def test_one_cmux_matches_oracle(orc, keys_2_2, eng):
                 assert d == 0, "LUT rotation / sample extraction must be bit-exact"
             if n_iters == 1:
                 assert d <= 2**44, f"n_iters={n_iters} ct {b}: max|delta| = 2^{np.log2(max(d, 1)):.1f}"
-    print(f"max |delta| GPU vs oracle-f64 after <=2 CMUX: 2^{np.log2(max(worst, 1)):.1f}")
+    print(f"max |delta| GPU vs oracle-f64 after one CMUX: 2^{np.log2(max(worst, 1)):.1f}")
 
 
 def test_ks_pbs_all_messages_all_luts(orc, keys_2_2, eng):
