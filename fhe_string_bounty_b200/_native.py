@@ -14,8 +14,8 @@ import numpy as np
 
 _PKG = Path(__file__).resolve().parent
 _SO = _PKG / "libtfhe_b200.so"
-_SOURCES = ["csrc/pbs.cu", "csrc/keyswitch.cu", "csrc/leveled.cu", "csrc/c_api.cu"]
-_HEADERS = ["csrc/fft_core.cuh", "csrc/kernels.h", "../include/tfhe_b200.h"]
+_SOURCES = ["csrc/pbs.cu", "csrc/keyswitch.cu", "csrc/leveled.cu", "csrc/c_api.cu", "csrc/host_api.cu"]
+_HEADERS = ["csrc/fft_core.cuh", "csrc/kernels.h", "csrc/ctx.h", "csrc/host/program.h", "csrc/host/radix.h", "csrc/host/strings.h", "../include/tfhe_b200.h"]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -102,6 +102,13 @@ EXPORTS = {
     "tfhe_b200_time_last_kernels": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "tfhe_b200_probe_fp64_tflops": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
     "tfhe_b200_version": (C.c_char_p, []),
+    "tfhe_b200_program_build": (C.c_int, [C.POINTER(Params), C.c_char_p, C.c_void_p, C.c_size_t, C.c_char_p, C.POINTER(C.c_void_p)]),
+    "tfhe_b200_program_destroy": (C.c_int, [C.c_void_p]),
+    "tfhe_b200_program_counts": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "tfhe_b200_program_copy": (C.c_int, [C.c_void_p] + [C.c_void_p] * 11),
+    "tfhe_b200_program_accumulators": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "tfhe_b200_program_run": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "tfhe_b200_program_last_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
 }
 
 _lib = None

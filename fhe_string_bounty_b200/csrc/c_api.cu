@@ -1,74 +1,23 @@
 // c_api.cu -- extern "C" boundary of libtfhe_b200.so (see include/tfhe_b200.h for the reference
 // interfaces each entry point replaces).  Plain pointers and sizes only; no torch types.
-#include "../../include/tfhe_b200.h"
-#include "fft_core.cuh"
-#include "kernels.h"
-
-#include <cstdio>
-#include <cstring>
-#include <mutex>
-#include <string>
-#include <vector>
+#include "ctx.h"
 
 namespace {
-
 thread_local std::string g_last_error;
+}
 
+namespace tbc {
 int fail(const std::string &msg) {
     g_last_error = msg;
     return 1;
 }
+}  // namespace tbc
 
-#define TB_CUDA(expr)                                                                              \
-    do {                                                                                           \
-        cudaError_t e__ = (expr);                                                                  \
-        if (e__ != cudaSuccess)                                                                    \
-            return fail(std::string(#expr) + ": " + cudaGetErrorString(e__));                      \
-    } while (0)
-
-struct DevBuf {
-    void *p = nullptr;
-    size_t cap = 0;
-    cudaError_t reserve(size_t bytes) {
-        if (bytes <= cap) return cudaSuccess;
-        if (p) cudaFree(p);
-        p = nullptr; cap = 0;
-        cudaError_t e = cudaMalloc(&p, bytes);
-        if (e == cudaSuccess) cap = bytes;
-        return e;
-    }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
-};
-
-}  // namespace
-
-struct tfhe_b200_ctx {
-    int device = 0;
-    tfhe_b200_params p{};
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
-    bool timed = false;
-    // keys
-    DevBuf ksk_packed, ksk_colsum, bskf, tbl, luts;
-    uint32_t n_luts = 0;
-    bool have_ksk = false, have_bsk = false;
-    // staging for the host-pointer entry points
-    DevBuf d_in, d_small, d_out, d_idx;
-    uint64_t launches = 0;
-    std::mutex mu;
-
-    size_t big_len() const { return (size_t)p.glwe_dim * p.poly_size + 1; }
-    size_t small_len() const { return (size_t)p.lwe_dim + 1; }
-    size_t lut_len() const { return (size_t)(p.glwe_dim + 1) * p.poly_size; }
-};
+using tbc::DevBuf;
+using tbc::DeviceGuard;
+using tbc::fail;
 
 namespace {
-
-struct DeviceGuard {
-    int prev = -1;
-    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); }
-    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
-};
 
 int check_params(const tfhe_b200_params &p) {
     if (p.poly_size != (uint32_t)tb::kN) return fail("unsupported poly_size (engine is built for N = 2048)");
@@ -82,26 +31,37 @@ int check_params(const tfhe_b200_params &p) {
     return 0;
 }
 
-int do_keyswitch(tfhe_b200_ctx *c, const uint64_t *d_in, uint64_t *d_small, size_t batch, cudaStream_t s) {
+}  // namespace
+
+namespace tbc {
+
+int do_keyswitch(tfhe_b200_ctx *c, const uint64_t *d_in, uint64_t *d_small, size_t batch, cudaStream_t s, const uint32_t *in_slot) {
     if (!c->have_ksk) return fail("keyswitch key not uploaded");
-    TB_CUDA(tbk::launch_keyswitch(d_in, (const uint64_t *)c->ksk_packed.p, (const uint64_t *)c->ksk_colsum.p, d_small,
+    TB_CUDA(tbk::launch_keyswitch(d_in, in_slot, (const uint64_t *)c->ksk_packed.p, (const uint64_t *)c->ksk_colsum.p, d_small,
                                   (int)batch, (int)(c->p.glwe_dim * c->p.poly_size), (int)c->p.lwe_dim,
                                   (int)c->p.ks_base_log, (int)c->p.ks_level, s));
     c->launches += 1;
     return 0;
 }
 
-int do_pbs(tfhe_b200_ctx *c, const uint64_t *d_small, const uint32_t *d_idx, uint64_t *d_out, size_t batch, uint32_t n_iters,
-           cudaStream_t s) {
+int do_pbs(tfhe_b200_ctx *c, const uint64_t *d_small, const uint32_t *d_idx, const uint64_t *d_luts, uint64_t *d_out, size_t batch,
+           uint32_t n_iters, cudaStream_t s, const uint32_t *out_slot) {
     if (!c->have_bsk) return fail("bootstrap key not uploaded");
-    if (c->n_luts == 0) return fail("no lookup tables uploaded");
-    TB_CUDA(tbk::launch_pbs_classic(d_small, d_idx, (const uint64_t *)c->luts.p, c->bskf.p, c->tbl.p, d_out, (int)batch,
+    if (!d_luts) return fail("no lookup tables uploaded");
+    TB_CUDA(tbk::launch_pbs_classic(d_small, d_idx, d_luts, c->bskf.p, c->tbl.p, d_out, out_slot, (int)batch,
                                     (int)c->p.lwe_dim, (int)c->p.pbs_base_log, (int)n_iters, s));
     c->launches += 1;
     return 0;
 }
 
-}  // namespace
+}  // namespace tbc
+
+using tbc::do_keyswitch;
+
+static int do_pbs(tfhe_b200_ctx *c, const uint64_t *d_small, const uint32_t *d_idx, uint64_t *d_out, size_t batch, uint32_t n_iters,
+                  cudaStream_t s) {
+    return tbc::do_pbs(c, d_small, d_idx, c->n_luts ? (const uint64_t *)c->luts.p : nullptr, d_out, batch, n_iters, s, nullptr);
+}
 
 extern "C" {
 

@@ -1,0 +1,72 @@
+// ctx.h -- the opaque context behind tfhe_b200_ctx, shared by c_api.cu and host_api.cu.
+#pragma once
+#include "../../include/tfhe_b200.h"
+#include "fft_core.cuh"
+#include "kernels.h"
+
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+namespace tbc {
+
+int fail(const std::string &msg);   // records the thread-local error string, returns 1
+
+#define TB_CUDA(expr)                                                                              \
+    do {                                                                                           \
+        cudaError_t e__ = (expr);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return tbc::fail(std::string(#expr) + ": " + cudaGetErrorString(e__));                 \
+    } while (0)
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+}  // namespace tbc
+
+struct tfhe_b200_ctx {
+    int device = 0;
+    tfhe_b200_params p{};
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    bool timed = false;
+    // keys
+    tbc::DevBuf ksk_packed, ksk_colsum, bskf, tbl, luts;
+    uint32_t n_luts = 0;
+    bool have_ksk = false, have_bsk = false;
+    // staging for the host-pointer entry points
+    tbc::DevBuf d_in, d_small, d_out, d_idx;
+    uint64_t launches = 0;
+    std::mutex mu;
+
+    size_t big_len() const { return (size_t)p.glwe_dim * p.poly_size + 1; }
+    size_t small_len() const { return (size_t)p.lwe_dim + 1; }
+    size_t lut_len() const { return (size_t)(p.glwe_dim + 1) * p.poly_size; }
+};
+
+namespace tbc {
+// shared launch helpers (c_api.cu)
+int do_keyswitch(tfhe_b200_ctx *c, const uint64_t *d_in, uint64_t *d_small, size_t batch, cudaStream_t s,
+                 const uint32_t *in_slot = nullptr);
+int do_pbs(tfhe_b200_ctx *c, const uint64_t *d_small, const uint32_t *d_idx, const uint64_t *d_luts, uint64_t *d_out, size_t batch,
+           uint32_t n_iters, cudaStream_t s, const uint32_t *out_slot = nullptr);
+}  // namespace tbc

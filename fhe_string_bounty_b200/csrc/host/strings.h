@@ -1,0 +1,205 @@
+// host/strings.h -- encrypted ASCII string operations composed from the radix methods (host/radix.h).
+//
+// The reference snapshot has no FheString module: only the tutorial type
+// FheAsciiString{bytes: Vec<FheUint8>} with to_upper/to_lower (docs/tutorials/ascii_fhe_string.md:81-154) and the
+// regex example's StringCiphertext = Vec<RadixCiphertext>, 4 blocks per char (examples/regex_engine/ciphertext.rs:4-22).
+// The operations below are the compositions SURVEY.md Appendix B derives for BASELINE.json's configs, on strings of
+// PUBLIC length (no padding): a char is an FheUint8 = 4 little-endian 2-bit blocks (integer/encryption.rs:69-83).
+// Only decrypted results are comparable with the reference (there is nothing to compare ciphertext-wise).
+#pragma once
+#include "radix.h"
+
+namespace tbh {
+
+struct FheString {
+    std::vector<Radix> chars;   // chars[i] = 4 blocks, little-endian
+    size_t len() const { return chars.size(); }
+};
+
+class StringServerKey {
+  public:
+    explicit StringServerKey(Program &prog) : pg(prog), isk(prog), p(prog.params()) {}
+
+    static constexpr size_t BLOCKS_PER_CHAR = 4;
+
+    FheString input_string(size_t n_chars) {
+        FheString s;
+        for (size_t i = 0; i < n_chars; ++i) {
+            Radix c;
+            for (size_t b = 0; b < BLOCKS_PER_CHAR; ++b) c.push_back(pg.input());
+            s.chars.push_back(c);
+        }
+        return s;
+    }
+    // trivial (clear) string, e.g. a clear pattern: server_key/mod.rs:684-721 per block
+    FheString trivial_string(const std::string &clear) {
+        FheString s;
+        for (unsigned char ch : clear) {
+            Radix c;
+            for (size_t b = 0; b < BLOCKS_PER_CHAR; ++b) c.push_back(pg.create_trivial((ch >> (2 * b)) & 3));
+            s.chars.push_back(c);
+        }
+        return s;
+    }
+
+    static Radix concat(const FheString &s, size_t from, size_t n) {
+        Radix r;
+        for (size_t i = from; i < from + n; ++i) r.insert(r.end(), s.chars[i].begin(), s.chars[i].end());
+        return r;
+    }
+    // big-endian integer view for lexicographic order: char 0 most significant (SURVEY.md App. B "Ordering")
+    static Radix lex_radix(const FheString &s, size_t n) {
+        Radix r;
+        for (size_t i = n; i-- > 0;) r.insert(r.end(), s.chars[i].begin(), s.chars[i].end());
+        return r;
+    }
+
+    // ---- eq / ne: config 1 ([32, 3, 1] PBS per level for 8 chars) -----------------------------------------------------
+    BooleanBlock eq(const FheString &a, const FheString &b) {
+        if (a.len() != b.len()) return pg.create_trivial(0);
+        return isk.unchecked_eq(concat(a, 0, a.len()), concat(b, 0, b.len()));
+    }
+    BooleanBlock ne(const FheString &a, const FheString &b) {
+        if (a.len() != b.len()) return pg.create_trivial(1);
+        return isk.unchecked_ne(concat(a, 0, a.len()), concat(b, 0, b.len()));
+    }
+
+    // ---- lexicographic comparison: config 5 ([256,128,...,1,1] for 128 chars) ----------------------------------------
+    // sign of the common prefix; the public lengths break ties
+    BooleanBlock cmp(const FheString &a, const FheString &b, bool want_less, bool or_equal) {
+        const size_t n = std::min(a.len(), b.len());
+        const bool a_shorter = a.len() < b.len(), same = a.len() == b.len();
+        // result when the common prefix is equal
+        const bool tie = same ? or_equal : (want_less ? a_shorter : !a_shorter);
+        if (n == 0) return pg.create_trivial(tie ? 1 : 0);
+        Ct sign = isk.unchecked_compare(lex_radix(a, n), lex_radix(b, n));
+        return isk.map_sign_result(sign, [=](uint64_t x) {
+            if (x == IntegerServerKey::IS_EQUAL) return tie;
+            return want_less ? x == IntegerServerKey::IS_INFERIOR : x == IntegerServerKey::IS_SUPERIOR;
+        });
+    }
+    BooleanBlock lt(const FheString &a, const FheString &b) { return cmp(a, b, true, false); }
+    BooleanBlock le(const FheString &a, const FheString &b) { return cmp(a, b, true, true); }
+    BooleanBlock gt(const FheString &a, const FheString &b) { return cmp(a, b, false, false); }
+    BooleanBlock ge(const FheString &a, const FheString &b) { return cmp(a, b, false, true); }
+
+    // ---- contains / starts_with / ends_with / find: config 3 -------------------------------------------------------------
+    // match flag of every window: block equalities for all (window, pattern position) pairs in one level, then one
+    // AND tree per window ([15424, 1205, 241] for 256/16)
+    std::vector<Ct> window_matches(const FheString &hay, const FheString &pat) {
+        std::vector<Ct> m;
+        if (pat.len() > hay.len()) return m;
+        const size_t W = hay.len() - pat.len() + 1;
+        std::vector<std::vector<Ct>> eqs(W);
+        for (size_t w = 0; w < W; ++w) eqs[w] = isk.block_equalities(concat(hay, w, pat.len()), concat(pat, 0, pat.len()));
+        // level-synchronous AND trees: run the per-window reductions in lock step so levels line up
+        for (size_t w = 0; w < W; ++w) m.push_back(isk.are_all_comparisons_block_true(eqs[w]));
+        return m;
+    }
+    BooleanBlock contains(const FheString &hay, const FheString &pat) {
+        if (pat.len() == 0) return pg.create_trivial(1);
+        if (pat.len() > hay.len()) return pg.create_trivial(0);
+        std::vector<Ct> m = window_matches(hay, pat);
+        return isk.is_at_least_one_comparisons_block_true(m);
+    }
+    BooleanBlock starts_with(const FheString &s, const FheString &pat) {
+        if (pat.len() > s.len()) return pg.create_trivial(0);
+        if (pat.len() == 0) return pg.create_trivial(1);
+        return isk.unchecked_eq(concat(s, 0, pat.len()), concat(pat, 0, pat.len()));
+    }
+    BooleanBlock ends_with(const FheString &s, const FheString &pat) {
+        if (pat.len() > s.len()) return pg.create_trivial(0);
+        if (pat.len() == 0) return pg.create_trivial(1);
+        return isk.unchecked_eq(concat(s, s.len() - pat.len(), pat.len()), concat(pat, 0, pat.len()));
+    }
+    // find: (found, index of the first match as a radix of ceil(log4(W)) blocks; 0 when not found, like the
+    // regex example's "no match" convention of returning a boolean separately)
+    std::pair<BooleanBlock, Radix> find(const FheString &hay, const FheString &pat) {
+        const size_t W = pat.len() <= hay.len() ? hay.len() - pat.len() + 1 : 0;
+        size_t idx_blocks = 1;
+        while ((size_t(1) << (2 * idx_blocks)) < std::max<size_t>(W, 1)) ++idx_blocks;
+        Radix zero_idx;
+        for (size_t b = 0; b < idx_blocks; ++b) zero_idx.push_back(pg.create_trivial(0));
+        if (W == 0) return {pg.create_trivial(0), zero_idx};
+        if (pat.len() == 0) return {pg.create_trivial(1), zero_idx};
+        std::vector<Ct> m = window_matches(hay, pat);
+        // inclusive prefix OR (Hillis-Steele, the structure of radix_parallel/add.rs:572-603 with an OR LUT)
+        std::vector<Ct> pre = m;
+        for (size_t d = 1; d < W; d *= 2) {
+            std::vector<Ct> next = pre;
+            for (size_t i = d; i < W; ++i) next[i] = isk.boolean_bitor(pre[i], pre[i - d]);
+            pre.swap(next);
+        }
+        // one-hot first match: first_w = m_w AND NOT pre_{w-1}
+        std::vector<Ct> first(W);
+        first[0] = m[0];
+        for (size_t w = 1; w < W; ++w)
+            first[w] = pg.pbs_bivariate(m[w], pre[w - 1], [](uint64_t x, uint64_t y) { return uint64_t((x & 1) && !(y & 1)); });
+        // index digit b = sum_w ((w >> 2b) & 3) * first_w: select with a LUT (clean, noise NOMINAL), then sum in
+        // chunks of 15 with a cleaning PBS, exactly the chunking of scalar_comparison.rs:155-170
+        const size_t max_value = p.total_mod() - 1;
+        Radix index;
+        for (size_t b = 0; b < idx_blocks; ++b) {
+            std::vector<Ct> terms;
+            for (size_t w = 0; w < W; ++w) {
+                const uint64_t digit = (w >> (2 * b)) & 3;
+                if (digit == 0) continue;
+                terms.push_back(pg.pbs(first[w], [digit](uint64_t x) { return (x & 1) ? digit : uint64_t(0); }));
+            }
+            if (terms.empty()) { index.push_back(pg.create_trivial(0)); continue; }
+            while (terms.size() > 1) {
+                std::vector<Ct> next;
+                for (size_t i = 0; i < terms.size(); i += max_value) {
+                    const size_t len = std::min(max_value, terms.size() - i);
+                    Ct sum = terms[i];
+                    for (size_t j = 1; j < len; ++j) sum = pg.unchecked_add(sum, terms[i + j]);
+                    sum.degree = p.msg_mod - 1;   // at most one term is non-zero
+                    next.push_back(pg.pbs(sum, [this](uint64_t x) { return x % p.msg_mod; }));
+                }
+                terms.swap(next);
+            }
+            index.push_back(terms[0]);
+        }
+        return {pre[W - 1], index};
+    }
+
+    // ---- case conversion: config 4 --------------------------------------------------------------------------------------------
+    // The tutorial circuit (ascii_fhe_string.md:88-94: gt(64) & lt(91), cast, *32, +) costs 19 PBS per char; only the
+    // decrypted result has to match, so the fused form is used: with hi = b3*4+b2 and lo = b1*4+b0 (leveled packing),
+    //   class(hi) in {0, 1: hi == H, 2: hi == H+1},  range(lo) = [lo >= 1] + 2*[lo <= 10],
+    //   is_letter = LUT(class*4 + range),  b2' = LUT(b2*4 + is_letter) = b2 +/- 2   (bit 5 toggles; no carry can occur)
+    // = 4 PBS per char in 3 levels.  H = 4 for upper-case input ('A'..'Z' = 0x41..0x5A), 6 for lower-case.
+    Ct is_letter_of_case(const Radix &c, bool upper) {
+        const uint64_t H = upper ? 4 : 6;
+        Ct hi = pg.unchecked_add(pg.unchecked_scalar_mul(c[3], p.msg_mod), c[2]);
+        Ct lo = pg.unchecked_add(pg.unchecked_scalar_mul(c[1], p.msg_mod), c[0]);
+        Ct cls = pg.pbs(hi, [H](uint64_t x) { return x == H ? uint64_t(1) : (x == H + 1 ? uint64_t(2) : uint64_t(0)); });
+        Ct rng = pg.pbs(lo, [](uint64_t x) { return uint64_t(x >= 1) + 2 * uint64_t(x <= 10); });
+        return pg.pbs_bivariate(cls, rng, [](uint64_t k, uint64_t r) {
+            return uint64_t((k == 1 && (r & 1)) || (k == 2 && (r & 2)));
+        });
+    }
+    FheString change_case(const FheString &s, bool to_lower) {
+        FheString out = s;
+        for (size_t i = 0; i < s.len(); ++i) {
+            Ct flag = is_letter_of_case(s.chars[i], /*upper=*/to_lower);
+            out.chars[i][2] = pg.pbs_bivariate(s.chars[i][2], flag, [to_lower](uint64_t b2, uint64_t f) {
+                if (!(f & 1)) return b2;
+                return to_lower ? (b2 | 2) : (b2 & 1);   // set / clear bit 5 of the char (bit 1 of block 2)
+            });
+        }
+        return out;
+    }
+    FheString to_lowercase(const FheString &s) { return change_case(s, true); }
+    FheString to_uppercase(const FheString &s) { return change_case(s, false); }
+    BooleanBlock eq_ignore_case(const FheString &a, const FheString &b) {
+        if (a.len() != b.len()) return pg.create_trivial(0);
+        return eq(to_lowercase(a), to_lowercase(b));
+    }
+
+    Program &pg;
+    IntegerServerKey isk;
+    Params p;
+};
+
+}  // namespace tbh

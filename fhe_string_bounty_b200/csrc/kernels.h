@@ -10,15 +10,27 @@ namespace tbk {
 int ks_padded_cols(int n);
 cudaError_t ks_configure(int level);
 cudaError_t launch_ksk_pack(const uint64_t *ksk, uint64_t *packed, uint64_t *colsum, int rows, int n, cudaStream_t stream);
-cudaError_t launch_keyswitch(const uint64_t *lwe_in, const uint64_t *ksk_packed, const uint64_t *colsum, uint64_t *lwe_out,
+cudaError_t launch_keyswitch(const uint64_t *lwe_in, const uint32_t *in_slot, const uint64_t *ksk_packed, const uint64_t *colsum, uint64_t *lwe_out,
                              int batch, int in_dim, int n, int base_log, int level, cudaStream_t stream);
 
 // pbs.cu
 cudaError_t pbs_configure();
 cudaError_t launch_pbs_classic(const uint64_t *lwe_small, const uint32_t *lut_idx, const uint64_t *luts, const void *bskf,
-                               const void *tbl, uint64_t *out, int batch, int n, int base_log, int n_iters,
-                               cudaStream_t stream);
+                               const void *tbl, uint64_t *out, const uint32_t *out_slot, int batch, int n, int base_log,
+                               int n_iters, cudaStream_t stream);
 cudaError_t launch_bsk_convert(const uint64_t *bsk_std, void *bskf, const void *tbl, int n_polys, cudaStream_t stream);
 cudaError_t launch_fp64_peak(double *sink, int blocks, int iters, cudaStream_t stream);
+
+// leveled.cu
+struct LinInstr {          // out = sum_k coef[k] * in[k]  (+ body_add on the body word); terms in [term_begin, term_end)
+    uint32_t out_slot, term_begin, term_end, pad;
+    uint64_t body_add;
+};
+struct LinTerm {
+    uint32_t slot, pad;
+    int64_t coef;
+};
+cudaError_t launch_linear(uint64_t *arena, const LinInstr *instrs, const LinTerm *terms, int n_instrs, int lwe_len,
+                          cudaStream_t stream);
 
 }  // namespace tbk

@@ -30,7 +30,8 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // ksk_packed: [kN*level rows][ldk columns] (rows padded to ldk = multiple of TILE_J, zero filled)
 // colsum:     [ldk]  = sum over rows (wrapping)
 __global__ void __launch_bounds__(THREADS, 2)
-keyswitch_kernel(const uint64_t *__restrict__ lwe_in,     // [batch][in_dim + 1]
+keyswitch_kernel(const uint64_t *__restrict__ lwe_in,     // [batch][in_dim + 1], or an arena indexed by in_slot
+                 const uint32_t *__restrict__ in_slot,    // nullptr, or arena slot of each batch element
                  const uint64_t *__restrict__ ksk_packed, const uint64_t *__restrict__ colsum,
                  uint64_t *__restrict__ lwe_out,          // [batch][n + 1]
                  int batch, int in_dim, int n, int ldk, int base_log, int level) {
@@ -74,7 +75,7 @@ keyswitch_kernel(const uint64_t *__restrict__ lwe_in,     // [batch][in_dim + 1]
             const int cl = e / CH_I, ii = e % CH_I;
             const int b = b0 + cl;
             uint64_t x = 0;
-            if (b < batch) x = __ldg(lwe_in + (size_t)b * (in_dim + 1) + st * CH_I + ii);
+            if (b < batch) x = __ldg(lwe_in + (size_t)(in_slot ? in_slot[b] : b) * (in_dim + 1) + st * CH_I + ii);
             // closest_representable(x) >> (64 - total_bits), kept modulo 2^total_bits
             uint32_t state = (uint32_t)(((x >> (63 - total_bits)) + 1) >> 1) & ((1u << total_bits) - 1u);
             for (int lv = 0; lv < level; ++lv) {   // yields level `level` first == KSK row order
@@ -127,7 +128,7 @@ keyswitch_kernel(const uint64_t *__restrict__ lwe_in,     // [batch][in_dim + 1]
     for (int x = 0; x < 8; ++x) {
         const int b = b0 + tb * 8 + x;
         if (b >= batch) continue;
-        const uint64_t body = __ldg(lwe_in + (size_t)b * (in_dim + 1) + in_dim);
+        const uint64_t body = __ldg(lwe_in + (size_t)(in_slot ? in_slot[b] : b) * (in_dim + 1) + in_dim);
 #pragma unroll
         for (int y = 0; y < 4; ++y) {
             const int j = j0 + tj * 4 + y;
@@ -180,13 +181,13 @@ cudaError_t launch_ksk_pack(const uint64_t *ksk, uint64_t *packed, uint64_t *col
     return cudaGetLastError();
 }
 
-cudaError_t launch_keyswitch(const uint64_t *lwe_in, const uint64_t *ksk_packed, const uint64_t *colsum, uint64_t *lwe_out,
+cudaError_t launch_keyswitch(const uint64_t *lwe_in, const uint32_t *in_slot, const uint64_t *ksk_packed, const uint64_t *colsum, uint64_t *lwe_out,
                              int batch, int in_dim, int n, int base_log, int level, cudaStream_t stream) {
     if (batch <= 0) return cudaSuccess;
     const int ldk = ks_padded_cols(n);
     dim3 grid((batch + tbks::TILE_B - 1) / tbks::TILE_B, ldk / tbks::TILE_J);
     tbks::keyswitch_kernel<<<grid, tbks::THREADS, tbks::ks_smem_bytes(level), stream>>>(
-        lwe_in, ksk_packed, colsum, lwe_out, batch, in_dim, n, ldk, base_log, level);
+        lwe_in, in_slot, ksk_packed, colsum, lwe_out, batch, in_dim, n, ldk, base_log, level);
     return cudaGetLastError();
 }
 

@@ -73,7 +73,8 @@ pbs_classic_kernel(const uint64_t *__restrict__ lwe_small,  // [batch][n+1], sma
                    const uint32_t *__restrict__ lut_idx,    // [batch] or nullptr (LUT 0)
                    const uint64_t *__restrict__ luts,       // [n_luts][2][N]
                    const cplx *__restrict__ bskf, const cplx *__restrict__ tbl,
-                   uint64_t *__restrict__ out,              // [batch][2N.. k*N+1]
+                   uint64_t *__restrict__ out,              // [batch][k*N+1], or an arena indexed by out_slot
+                   const uint32_t *__restrict__ out_slot,   // nullptr, or arena slot of each batch element
                    int n, int base_log, int n_iters) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PbsSmem &sm = *reinterpret_cast<PbsSmem *>(smem_raw);
@@ -200,7 +201,7 @@ pbs_classic_kernel(const uint64_t *__restrict__ lwe_small,  // [batch][n+1], sma
     }
 
     // glwe_sample_extraction.rs:125-146 (coefficient 0): mask -> (A[0], -A[N-1], ..., -A[1]); body = B[0]
-    uint64_t *o = out + (size_t)ct * (kN + 1);
+    uint64_t *o = out + (size_t)(out_slot ? out_slot[ct] : ct) * (kN + 1);
     if (w == 0) {
         for (int j = lane; j < kN; j += 32) o[j] = (j == 0) ? my[0] : (uint64_t)0 - my[kN - j];
     } else if (lane == 0) {
@@ -261,11 +262,11 @@ cudaError_t pbs_configure() {
 }
 
 cudaError_t launch_pbs_classic(const uint64_t *lwe_small, const uint32_t *lut_idx, const uint64_t *luts,
-                               const void *bskf, const void *tbl, uint64_t *out, int batch, int n, int base_log,
-                               int n_iters, cudaStream_t stream) {
+                               const void *bskf, const void *tbl, uint64_t *out, const uint32_t *out_slot, int batch, int n,
+                               int base_log, int n_iters, cudaStream_t stream) {
     if (batch <= 0) return cudaSuccess;
     tb::pbs_classic_kernel<<<batch, 64, sizeof(tb::PbsSmem), stream>>>(
-        lwe_small, lut_idx, luts, reinterpret_cast<const tb::cplx *>(bskf), reinterpret_cast<const tb::cplx *>(tbl), out, n,
+        lwe_small, lut_idx, luts, reinterpret_cast<const tb::cplx *>(bskf), reinterpret_cast<const tb::cplx *>(tbl), out, out_slot, n,
         base_log, n_iters);
     return cudaGetLastError();
 }

@@ -87,6 +87,36 @@ int tfhe_b200_synchronize(tfhe_b200_ctx *ctx);
 int tfhe_b200_pbs_batch_partial(tfhe_b200_ctx *ctx, const uint64_t *lwe_small, const uint32_t *lut_idx,
                                 uint64_t *lwe_big, size_t batch, uint32_t n_iters);
 
+/* ---- host layer: integer-radix / string operations recorded as level-batched programs -------------------------
+ * Mirrors, as one batched call per tree level, the per-block rayon fan-out of
+ *   integer::ServerKey::{unchecked_eq,ne,lt,le,gt,ge}_parallelized   integer/server_key/radix_parallel/comparison.rs:10-83,
+ *                                                                      integer/server_key/comparator.rs:389-464,1103-1126
+ *   are_all_comparisons_block_true / is_at_least_one_...              radix_parallel/scalar_comparison.rs:147-240
+ *   unchecked_scalar_{eq,lt,gt}_parallelized                          scalar_comparison.rs:366-458, comparator.rs:474-502
+ *   if_then_else_parallelized                                         radix_parallel/cmux.rs:72-
+ *   add_parallelized (carry propagation)                              radix_parallel/add.rs:206-243,518-603
+ * and the string compositions of SURVEY.md Appendix B (the snapshot has no FheString module; see
+ * fhe_string_bounty_b200/csrc/host/strings.h).  `op` is one of:
+ *   shortint_apply_lut {n, f(0..15)}      shortint_bivariate_lut {n, f(x,y) row-major}
+ *   radix_{eq,ne,lt,le,gt,ge,add} {n_blocks}   radix_scalar_{eq,lt,gt} {n_blocks, scalar}   radix_if_then_else {n_blocks}
+ *   bool_all_true / bool_any_true {n}     bool_sum_finish {n_summed, want_all}
+ *   string_{eq,ne,lt,le,gt,ge,eq_ignore_case,contains,starts_with,ends_with,find} {len_a, len_b}
+ *   string_{to_lowercase,to_uppercase} {len}     string_contains_windows {len_a, len_b, w0, w1}
+ * With clear_operand != NULL the second string operand is that clear (trivial) string instead of an input.
+ * Inputs are fresh shortint blocks (degree msg_mod-1); a char is 4 little-endian 2-bit blocks. */
+typedef struct tfhe_b200_program tfhe_b200_program;
+int tfhe_b200_program_build(const tfhe_b200_params *params, const char *op, const uint64_t *args, size_t n_args,
+                            const char *clear_operand, tfhe_b200_program **out);
+int tfhe_b200_program_destroy(tfhe_b200_program *prog);
+int tfhe_b200_program_counts(const tfhe_b200_program *prog, uint64_t counts[9]);
+int tfhe_b200_program_copy(const tfhe_b200_program *prog, uint32_t *level_lin_off, uint32_t *level_pbs_off,
+                           uint32_t *lin_out_tb_te, uint64_t *lin_body, uint32_t *term_slot, int64_t *term_coef,
+                           uint32_t *pbs_in_out_lut, uint64_t *lut_tables, uint64_t *lut_degrees, uint32_t *outputs,
+                           uint64_t *output_degree_noise);
+int tfhe_b200_program_accumulators(const tfhe_b200_program *prog, uint64_t *accs);
+int tfhe_b200_program_run(tfhe_b200_ctx *ctx, tfhe_b200_program *prog, const uint64_t *inputs, uint64_t *outputs);
+int tfhe_b200_program_last_ms(const tfhe_b200_program *prog, float *ms);
+
 /* Instrumentation. */
 uint64_t tfhe_b200_kernel_launches(const tfhe_b200_ctx *ctx);   /* kernels launched by this context so far */
 int tfhe_b200_time_last_kernels(tfhe_b200_ctx *ctx, float *ks_ms, float *pbs_ms); /* CUDA-event ms of the last ks_pbs call */
