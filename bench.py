@@ -122,6 +122,55 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def bench_string_ops(eng, p, rank, world, local):
+    """FheString eq / contains / find ops per second (BASELINE.json configs[0], [2]) through the host layer: host buffers in,
+    host buffers out (H2D, every tree level's launches, D2H inside the timed region).  With several ranks, eq shards the
+    chars and contains shards the 241 windows; the per-rank boolean blocks meet in one NCCL all-reduce (16 KiB)."""
+    import torch
+    import torch.distributed as dist
+    import fhe_string_bounty_b200 as F
+    from fhe_string_bounty_b200 import multi_gpu as MG
+    from fhe_string_bounty_b200.host import Program
+    params = dict(F.PARAM_MESSAGE_2_CARRY_2_KS_PBS)
+    rng = np.random.default_rng(77)              # same on every rank (the operands are replicated, the work is sharded)
+    execute = lambda prog, ins: prog.run(eng, ins)
+    dev = f"cuda:{local}"
+    out = {}
+
+    def timed(fn, reps):
+        fn()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t[0])
+        return reps / dt
+
+    a8 = rng.integers(0, 2**64, size=(32, p.big_len), dtype=np.uint64)
+    b8 = rng.integers(0, 2**64, size=(32, p.big_len), dtype=np.uint64)
+    hay = rng.integers(0, 2**64, size=(1024, p.big_len), dtype=np.uint64)
+    pat = rng.integers(0, 2**64, size=(64, p.big_len), dtype=np.uint64)
+    out["eq_8char_ops_per_s"] = timed(lambda: MG.sharded_eq(execute, params, a8, b8, 8, rank, world, dev), 20)
+    out["contains_256_16_ops_per_s"] = timed(lambda: MG.sharded_contains(execute, params, hay, pat, 256, 16, rank, world, dev), 3)
+    if world == 1:
+        find = Program("string_find", (256, 16), params=params)
+        ins = np.concatenate([hay, pat])
+        out["find_256_16_ops_per_s"] = timed(lambda: find.run(eng, ins), 3)
+        out["find_256_16_pbs"] = find.n_pbs
+        low = Program("string_to_lowercase", (1024,), params=params)
+        s1024 = rng.integers(0, 2**64, size=(4096, p.big_len), dtype=np.uint64)
+        out["to_lowercase_1024_ops_per_s"] = timed(lambda: low.run(eng, s1024), 3)
+    out["note"] = "host buffers in/out; eq shards chars, contains shards windows across ranks + one all-reduce of a 2049-word LWE"
+    return out
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -206,6 +255,10 @@ def run_b200(args):
     barrier()
     e2e_s = time.perf_counter() - t0
 
+    string_ops = None
+    if args.string_ops:
+        string_ops = bench_string_ops(eng, p, rank, world, local)
+
     if world > 1:
         t = torch.tensor([ms, e2e_s], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -236,6 +289,8 @@ def run_b200(args):
                                  "frac": hbm_alg / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None, "peak_source": peak_kind}},
             "clocks": _summarise_clocks(samples),
         }
+        if string_ops is not None:
+            line["string_ops"] = string_ops
         if cpu_rate is not None:
             line["cpu_baseline"] = {"value": cpu_rate, "unit": "PBS/s", "cores": cpu_cores, "kind": "port",
                                     "sample": f"{args.cpu_sample} KS-PBS (same parameter set, random keys), {cpu_dt:.1f} s"}
@@ -252,6 +307,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=8192, help="ciphertexts per GPU per step")
+    ap.add_argument("--string-ops", type=int, default=1, help="also time FheString eq/contains/find through the host layer (0 = skip)")
     ap.add_argument("--cpu-sample", type=int, default=256, help="KS-PBS evaluated by the CPU baseline leg (0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -108,6 +108,9 @@ class Program:
         self._check(self.lib.tfhe_b200_program_run(eng.h, self.h, inputs.ctypes.data if inputs.size else None, out.ctypes.data if out.size else None))
         return out
 
+    def pipe(self, execute, inputs):
+        return execute(self, inputs)
+
     def last_ms(self) -> float:
         v = C.c_float()
         self._check(self.lib.tfhe_b200_program_last_ms(self.h, C.byref(v)))
