@@ -48,6 +48,12 @@ int do_pbs(tfhe_b200_ctx *c, const uint64_t *d_small, const uint32_t *d_idx, con
            uint32_t n_iters, cudaStream_t s, const uint32_t *out_slot) {
     if (!c->have_bsk) return fail("bootstrap key not uploaded");
     if (!d_luts) return fail("no lookup tables uploaded");
+    if (c->pbs_kernel == 3) {
+        TB_CUDA(tbk::launch_pbs_classic_v3(d_small, d_idx, d_luts, c->bskf.p, c->tbl.p, d_out, out_slot, (int)batch, (int)c->p.lwe_dim,
+                                           (int)c->p.pbs_base_log, (int)n_iters, s));
+        c->launches += 1;
+        return 0;
+    }
     TB_CUDA(tbk::launch_pbs_classic(d_small, d_idx, d_luts, c->bskf.p, c->tbl.p, d_out, out_slot, (int)batch,
                                     (int)c->p.lwe_dim, (int)c->p.pbs_base_log, (int)n_iters, s));
     c->launches += 1;
@@ -82,7 +88,9 @@ int tfhe_b200_ctx_create(int cuda_device, const tfhe_b200_params *params, tfhe_b
     c->p = *params;
     TB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (auto &e : c->ev) TB_CUDA(cudaEventCreate(&e));
+    if (const char *e = std::getenv("TFHE_B200_PBS_KERNEL")) c->pbs_kernel = (e[0] == '2') ? 2 : 3;
     TB_CUDA(tbk::pbs_configure());
+    TB_CUDA(tbk::pbs_v3_configure());
     TB_CUDA(tbk::ks_configure((int)params->ks_level));
     // inter-pass twiddle table
     std::vector<double> tbl(2 * tb::kM);
@@ -138,7 +146,10 @@ int tfhe_b200_upload_bsk_std(tfhe_b200_ctx *c, const uint64_t *bsk, size_t len) 
     TB_CUDA(raw.reserve(len * 8));
     TB_CUDA(c->bskf.reserve(n_polys * tb::kM * sizeof(double) * 2));
     TB_CUDA(cudaMemcpyAsync(raw.p, bsk, len * 8, cudaMemcpyHostToDevice, c->stream));
-    TB_CUDA(tbk::launch_bsk_convert((const uint64_t *)raw.p, c->bskf.p, c->tbl.p, (int)n_polys, c->stream));
+    if (c->pbs_kernel == 3)
+        TB_CUDA(tbk::launch_bsk_convert_v3((const uint64_t *)raw.p, c->bskf.p, c->tbl.p, (int)n_polys, c->stream));
+    else
+        TB_CUDA(tbk::launch_bsk_convert((const uint64_t *)raw.p, c->bskf.p, c->tbl.p, (int)n_polys, c->stream));
     c->launches += 1;
     TB_CUDA(cudaStreamSynchronize(c->stream));
     raw.release();

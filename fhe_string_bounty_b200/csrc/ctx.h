@@ -5,6 +5,7 @@
 #include "kernels.h"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -53,6 +54,7 @@ struct tfhe_b200_ctx {
     tbc::DevBuf ksk_packed, ksk_colsum, bskf, tbl, luts;
     uint32_t n_luts = 0;
     bool have_ksk = false, have_bsk = false;
+    int pbs_kernel = 3;   // 3: TMEM + TMA ring (pbs_v3.cu), 2: one CTA per ciphertext (pbs.cu); env TFHE_B200_PBS_KERNEL
     // staging for the host-pointer entry points
     tbc::DevBuf d_in, d_small, d_out, d_idx;
     uint64_t launches = 0;
