@@ -118,14 +118,17 @@ pbs_classic_kernel_v3(const uint64_t *__restrict__ lwe_small, const uint32_t *__
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
     const int W = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ctl = W & 3, w = W >> 2;               // ciphertext within the CTA, polynomial
+    // warp -> (ciphertext, polynomial): the two warps of a ciphertext (coupled by pair barriers) sit on DIFFERENT
+    // schedulers (warp id % 4), so each scheduler hosts warps of two different ciphertexts, which are started half an
+    // iteration apart (see the stagger below): one is in an FP64 phase while the other is in a shared-memory phase.
+    const int ctl = W >> 1, w = W & 1;
     const int ct_raw = blockIdx.x * CTS + ctl;
     const bool live = ct_raw < batch;
     const int ct = live ? ct_raw : batch - 1;        // ragged tail: recompute the last ciphertext, skip the store
     uint64_t *my = sm.mbuf[W];
     double *tile = reinterpret_cast<double *>(sm.mbuf[W]);
     cplx *myc = reinterpret_cast<cplx *>(sm.mbuf[W]);
-    const cplx *othc = reinterpret_cast<const cplx *>(sm.mbuf[W ^ 4]);
+    const cplx *othc = reinterpret_cast<const cplx *>(sm.mbuf[W ^ 1]);
     const uint64_t *lwe = lwe_small + (size_t)ct * (n + 1);
     const int total_pieces = n_iters * PIECES_PER_ITER;
 
@@ -140,7 +143,7 @@ pbs_classic_kernel_v3(const uint64_t *__restrict__ lwe_small, const uint32_t *__
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_mine = sm.tmem_base + ((uint32_t)(ctl * 32) << 16) + (uint32_t)(w * 128);
+    const uint32_t tmem_mine = sm.tmem_base + ((uint32_t)((W & 3) * 32) << 16) + (uint32_t)((W >> 2) * 128);   // lane quarter = warp id % 4
     if (threadIdx.x == 0) {
         const int first = total_pieces < NSLOT ? total_pieces : NSLOT;
         for (int g = 0; g < first; ++g) {
@@ -184,6 +187,9 @@ pbs_classic_kernel_v3(const uint64_t *__restrict__ lwe_small, const uint32_t *__
     }
     __syncwarp();
 
+    // stagger: ciphertexts 2,3 start once ciphertexts 0,1 have finished their first forward FFT
+    if (ctl >= 2 && n_iters > 0) asm volatile("bar.sync 9, 256;" ::: "memory");
+
     for (int i = 0; i < n_iters; ++i) {
         const uint32_t a = modulus_switch_2n(__ldg(lwe + i)) & (2 * kN - 1);   // a == 0 is NOT skipped: adds exactly zero
 
@@ -212,6 +218,7 @@ pbs_classic_kernel_v3(const uint64_t *__restrict__ lwe_small, const uint32_t *__
         warp_transpose(re, tile, lane);
         warp_transpose(im, tile, lane);
         radix32_dif(re, im);
+        if (i == 0 && ctl < 2) asm volatile("bar.arrive 9, 256;" ::: "memory");
 
         // spectrum exchange between the two warps of the ciphertext (whole polynomial at once: 16 KiB buffer)
 #pragma unroll
