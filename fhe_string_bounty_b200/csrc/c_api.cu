@@ -37,6 +37,14 @@ namespace tbc {
 
 int do_keyswitch(tfhe_b200_ctx *c, const uint64_t *d_in, uint64_t *d_small, size_t batch, cudaStream_t s, const uint32_t *in_slot) {
     if (!c->have_ksk) return fail("keyswitch key not uploaded");
+    if (c->ks_kernel == 1) {
+        TB_CUDA(c->ks_digits.reserve(tbk::ks_mma_digits_bytes((int)batch, (int)(c->p.glwe_dim * c->p.poly_size), (int)c->p.ks_level)));
+        TB_CUDA(tbk::launch_keyswitch_mma(d_in, in_slot, (uint8_t *)c->ks_digits.p, (const uint8_t *)c->ksk_planes.p,
+                                          (const uint64_t *)c->ksk_colsum.p, d_small, (int)batch, (int)(c->p.glwe_dim * c->p.poly_size),
+                                          (int)c->p.lwe_dim, (int)c->p.ks_base_log, (int)c->p.ks_level, s));
+        c->launches += 2;
+        return 0;
+    }
     TB_CUDA(tbk::launch_keyswitch(d_in, in_slot, (const uint64_t *)c->ksk_packed.p, (const uint64_t *)c->ksk_colsum.p, d_small,
                                   (int)batch, (int)(c->p.glwe_dim * c->p.poly_size), (int)c->p.lwe_dim,
                                   (int)c->p.ks_base_log, (int)c->p.ks_level, s));
@@ -88,6 +96,8 @@ int tfhe_b200_ctx_create(int cuda_device, const tfhe_b200_params *params, tfhe_b
     c->p = *params;
     TB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (auto &e : c->ev) TB_CUDA(cudaEventCreate(&e));
+    if (const char *e = std::getenv("TFHE_B200_KS_KERNEL")) c->ks_kernel = (e[0] == 'i') ? 0 : 1;
+    if (!tbk::ks_mma_supported((int)params->ks_level)) c->ks_kernel = 0;
     if (const char *e = std::getenv("TFHE_B200_PBS_KERNEL")) c->pbs_kernel = (e[0] == '2') ? 2 : 3;
     TB_CUDA(tbk::pbs_configure());
     TB_CUDA(tbk::pbs_v3_configure());
@@ -106,7 +116,7 @@ int tfhe_b200_ctx_destroy(tfhe_b200_ctx *c) {
     if (!c) return 0;
     DeviceGuard g(c->device);
     cudaStreamSynchronize(c->stream);
-    for (DevBuf *b : {&c->ksk_packed, &c->ksk_colsum, &c->bskf, &c->tbl, &c->luts, &c->d_in, &c->d_small, &c->d_out, &c->d_idx})
+    for (DevBuf *b : {&c->ksk_packed, &c->ksk_colsum, &c->ksk_planes, &c->ks_digits, &c->bskf, &c->tbl, &c->luts, &c->d_in, &c->d_small, &c->d_out, &c->d_idx})
         b->release();
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -129,6 +139,11 @@ int tfhe_b200_upload_ksk(tfhe_b200_ctx *c, const uint64_t *ksk, size_t len) {
     TB_CUDA(tbk::launch_ksk_pack((const uint64_t *)raw.p, (uint64_t *)c->ksk_packed.p, (uint64_t *)c->ksk_colsum.p, (int)rows,
                                  (int)c->p.lwe_dim, c->stream));
     c->launches += 2;
+    if (c->ks_kernel == 1) {
+        TB_CUDA(c->ksk_planes.reserve(rows * (size_t)ldk * 8));
+        TB_CUDA(tbk::launch_ksk_planes((const uint64_t *)c->ksk_packed.p, (uint8_t *)c->ksk_planes.p, (int)rows, ldk, c->stream));
+        c->launches += 1;
+    }
     TB_CUDA(cudaStreamSynchronize(c->stream));
     raw.release();
     c->have_ksk = true;

@@ -13,6 +13,14 @@ cudaError_t launch_ksk_pack(const uint64_t *ksk, uint64_t *packed, uint64_t *col
 cudaError_t launch_keyswitch(const uint64_t *lwe_in, const uint32_t *in_slot, const uint64_t *ksk_packed, const uint64_t *colsum, uint64_t *lwe_out,
                              int batch, int in_dim, int n, int base_log, int level, cudaStream_t stream);
 
+// keyswitch_mma.cu
+bool ks_mma_supported(int level);
+cudaError_t launch_ksk_planes(const uint64_t *packed, uint8_t *bmat, int rows, int ldk, cudaStream_t stream);
+cudaError_t launch_keyswitch_mma(const uint64_t *lwe_in, const uint32_t *in_slot, uint8_t *digits_scratch, const uint8_t *bmat,
+                                 const uint64_t *colsum, uint64_t *lwe_out, int batch, int in_dim, int n, int base_log, int level,
+                                 cudaStream_t stream);
+size_t ks_mma_digits_bytes(int batch, int in_dim, int level);
+
 // pbs.cu
 cudaError_t pbs_configure();
 cudaError_t launch_pbs_classic(const uint64_t *lwe_small, const uint32_t *lut_idx, const uint64_t *luts, const void *bskf,
