@@ -86,14 +86,16 @@ class StringServerKey {
     // ---- contains / starts_with / ends_with / find: config 3 -------------------------------------------------------------
     // match flag of every window: block equalities for all (window, pattern position) pairs in one level, then one
     // AND tree per window ([15424, 1205, 241] for 256/16)
-    std::vector<Ct> window_matches(const FheString &hay, const FheString &pat) {
+    // windows [w0, w1) only (w1 = npos: all) -- the multi-GPU split records just a rank's share of the windows
+    std::vector<Ct> window_matches(const FheString &hay, const FheString &pat, size_t w0 = 0, size_t w1 = size_t(-1)) {
         std::vector<Ct> m;
         if (pat.len() > hay.len()) return m;
         const size_t W = hay.len() - pat.len() + 1;
-        std::vector<std::vector<Ct>> eqs(W);
-        for (size_t w = 0; w < W; ++w) eqs[w] = isk.block_equalities(concat(hay, w, pat.len()), concat(pat, 0, pat.len()));
-        // level-synchronous AND trees: run the per-window reductions in lock step so levels line up
-        for (size_t w = 0; w < W; ++w) m.push_back(isk.are_all_comparisons_block_true(eqs[w]));
+        w1 = std::min(w1, W);
+        std::vector<std::vector<Ct>> eqs;
+        for (size_t w = w0; w < w1; ++w) eqs.push_back(isk.block_equalities(concat(hay, w, pat.len()), concat(pat, 0, pat.len())));
+        // the AND trees are scheduled by readiness, so the per-window reductions line up level by level
+        for (auto &e : eqs) m.push_back(isk.are_all_comparisons_block_true(e));
         return m;
     }
     BooleanBlock contains(const FheString &hay, const FheString &pat) {

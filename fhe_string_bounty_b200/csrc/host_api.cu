@@ -136,9 +136,9 @@ bool record(tfhe_b200_program &h, const std::string &op, const uint64_t *a, size
         else if (f == "contains_windows") {
             // multi-GPU shard: match flag OR-reduced over windows [a[2], a[3]) only -> one boolean block
             if (!need(4)) return false;
-            std::vector<tbh::Ct> m = ssk.window_matches(s, t);
-            if (a[3] > m.size() || a[2] >= a[3]) { err = "contains_windows: bad window range"; return false; }
-            std::vector<tbh::Ct> mine(m.begin() + a[2], m.begin() + a[3]);
+            const size_t nwin = t.len() <= s.len() ? s.len() - t.len() + 1 : 0;
+            if (a[3] > nwin || a[2] >= a[3]) { err = "contains_windows: bad window range"; return false; }
+            std::vector<tbh::Ct> mine = ssk.window_matches(s, t, a[2], a[3]);
             pg.output(isk.is_at_least_one_comparisons_block_true(mine));
         }
         else { err = "unknown string op: " + op; return false; }

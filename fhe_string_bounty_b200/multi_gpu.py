@@ -46,7 +46,7 @@ def sharded_contains(execute, params: dict, hay: np.ndarray, pat: np.ndarray, ha
                      rank: int, world: int, device: str | None = None) -> np.ndarray:
     """contains(hay, pat) with the windows split over `world` ranks.  Every rank returns the same boolean block."""
     n_win = hay_len - pat_len + 1
-    if n_win <= 0 or pat_len == 0:
+    if n_win <= 0 or pat_len == 0 or world == 1:   # nothing to split: the plain single-GPU program
         return cached_program("string_contains", (hay_len, pat_len), params).pipe(execute, np.concatenate([hay, pat]))[0]
     active = min(world, n_win)                      # more ranks than windows: the surplus ranks contribute a zero block
     inputs = np.concatenate([hay, pat])
@@ -63,6 +63,8 @@ def sharded_contains(execute, params: dict, hay: np.ndarray, pat: np.ndarray, ha
 def sharded_eq(execute, params: dict, a: np.ndarray, b: np.ndarray, n_chars: int, rank: int, world: int,
                device: str | None = None) -> np.ndarray:
     """eq of two equal-length strings with the chars split over ranks: per-rank eq of its slice, all-reduce, x == active."""
+    if world == 1 and n_chars:
+        return execute(cached_program("string_eq", (n_chars, n_chars), params), np.concatenate([a, b]))[0]
     active = max(1, min(world, n_chars))
     if rank < active and n_chars:
         c0, c1 = shard_range(n_chars, rank, active)
