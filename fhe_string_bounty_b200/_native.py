@@ -14,8 +14,8 @@ import numpy as np
 
 _PKG = Path(__file__).resolve().parent
 _SO = _PKG / "libtfhe_b200.so"
-_SOURCES = ["csrc/pbs.cu", "csrc/pbs_v3.cu", "csrc/keyswitch.cu", "csrc/keyswitch_mma.cu", "csrc/leveled.cu", "csrc/c_api.cu", "csrc/host_api.cu"]
-_HEADERS = ["csrc/fft_core.cuh", "csrc/kernels.h", "csrc/ctx.h", "csrc/host/program.h", "csrc/host/radix.h", "csrc/host/strings.h", "../include/tfhe_b200.h"]
+_SOURCES = ["csrc/pbs.cu", "csrc/pbs_v3.cu", "csrc/pbs_multibit.cu", "csrc/keyswitch.cu", "csrc/keyswitch_mma.cu", "csrc/leveled.cu", "csrc/c_api.cu", "csrc/host_api.cu"]
+_HEADERS = ["csrc/fft_core.cuh", "csrc/ring_helpers.cuh", "csrc/kernels.h", "csrc/ctx.h", "csrc/host/program.h", "csrc/host/radix.h", "csrc/host/strings.h", "../include/tfhe_b200.h"]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -76,12 +76,17 @@ class Params(C.Structure):
     @property
     def bsk_len(self) -> int:
         k1 = self.glwe_dim + 1
-        return self.lwe_dim * self.pbs_level * k1 * k1 * self.poly_size
+        n_ggsw = self.lwe_dim if not self.grouping_factor else (self.lwe_dim // self.grouping_factor) << self.grouping_factor
+        return n_ggsw * self.pbs_level * k1 * k1 * self.poly_size
 
 
 # shortint/parameters/mod.rs:703-717
 PARAM_MESSAGE_2_CARRY_2_KS_PBS = dict(lwe_dim=742, glwe_dim=1, poly_size=2048, pbs_base_log=23, pbs_level=1,
                                       ks_base_log=3, ks_level=5, grouping_factor=0, msg_mod=4, carry_mod=4)
+
+# shortint/parameters/multi_bit.rs:173-190
+PARAM_MULTI_BIT_MESSAGE_2_CARRY_2_GROUP_3_KS_PBS = dict(lwe_dim=888, glwe_dim=1, poly_size=2048, pbs_base_log=21, pbs_level=1,
+                                                        ks_base_log=7, ks_level=2, grouping_factor=3, msg_mod=4, carry_mod=4)
 
 EXPORTS = {
     "tfhe_b200_ctx_create": (C.c_int, [C.c_int, C.POINTER(Params), C.POINTER(C.c_void_p)]),

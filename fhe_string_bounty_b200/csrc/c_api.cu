@@ -27,7 +27,8 @@ int check_params(const tfhe_b200_params &p) {
     if (p.ks_level < 1 || p.ks_base_log < 2 || p.ks_base_log > 7 || p.ks_base_log * p.ks_level > 31)
         return fail("unsupported keyswitch decomposition");
     if (p.lwe_dim < 1 || p.lwe_dim > 4096) return fail("unsupported lwe_dim");
-    if (p.grouping_factor != 0) return fail("multi-bit PBS is not built in this round (grouping_factor must be 0)");
+    if (p.grouping_factor != 0 && p.grouping_factor != 3) return fail("unsupported grouping_factor (0 = classic, 3 = multi-bit)");
+    if (p.grouping_factor == 3 && p.lwe_dim % 3 != 0) return fail("multi-bit: lwe_dim must be a multiple of the grouping factor");
     return 0;
 }
 
@@ -56,6 +57,13 @@ int do_pbs(tfhe_b200_ctx *c, const uint64_t *d_small, const uint32_t *d_idx, con
            uint32_t n_iters, cudaStream_t s, const uint32_t *out_slot) {
     if (!c->have_bsk) return fail("bootstrap key not uploaded");
     if (!d_luts) return fail("no lookup tables uploaded");
+    if (c->p.grouping_factor == 3) {
+        const uint32_t groups = c->p.lwe_dim / 3;
+        TB_CUDA(tbk::launch_pbs_multibit(d_small, d_idx, d_luts, c->bskf.p, c->tbl.p, c->roots.p, d_out, out_slot, (int)batch,
+                                         (int)c->p.lwe_dim, (int)c->p.pbs_base_log, (int)(n_iters < groups ? n_iters : groups), s));
+        c->launches += 1;
+        return 0;
+    }
     if (c->pbs_kernel == 3) {
         TB_CUDA(tbk::launch_pbs_classic_v3(d_small, d_idx, d_luts, c->bskf.p, c->tbl.p, d_out, out_slot, (int)batch, (int)c->p.lwe_dim,
                                            (int)c->p.pbs_base_log, (int)n_iters, s));
@@ -80,7 +88,7 @@ static int do_pbs(tfhe_b200_ctx *c, const uint64_t *d_small, const uint32_t *d_i
 extern "C" {
 
 const char *tfhe_b200_last_error(void) { return g_last_error.c_str(); }
-const char *tfhe_b200_version(void) { return "tfhe_b200 0.1 (sm_100a; classic KS-PBS, N=2048, k=1, l=1)"; }
+const char *tfhe_b200_version(void) { return "tfhe_b200 0.2 (sm_100a; classic + multi-bit(g=3) KS-PBS, N=2048, k=1, l=1)"; }
 
 int tfhe_b200_ctx_create(int cuda_device, const tfhe_b200_params *params, tfhe_b200_ctx **out) {
     if (!out) return fail("null out pointer");
@@ -101,6 +109,14 @@ int tfhe_b200_ctx_create(int cuda_device, const tfhe_b200_params *params, tfhe_b
     if (const char *e = std::getenv("TFHE_B200_PBS_KERNEL")) c->pbs_kernel = (e[0] == '2') ? 2 : 3;
     TB_CUDA(tbk::pbs_configure());
     TB_CUDA(tbk::pbs_v3_configure());
+    TB_CUDA(tbk::pbs_multibit_configure());
+    {   // roots[e] = exp(i*pi*e/2048): monomial spectra of the multi-bit combine
+        std::vector<double> r(2 * 4096);
+        const long double pi = 3.14159265358979323846264338327950288L;
+        for (int e = 0; e < 4096; ++e) { r[2 * e] = (double)cosl(pi * e / 2048.0L); r[2 * e + 1] = (double)sinl(pi * e / 2048.0L); }
+        TB_CUDA(c->roots.reserve(r.size() * 8));
+        TB_CUDA(cudaMemcpy(c->roots.p, r.data(), r.size() * 8, cudaMemcpyHostToDevice));
+    }
     TB_CUDA(tbk::ks_configure((int)params->ks_level));
     // inter-pass twiddle table
     std::vector<double> tbl(2 * tb::kM);
@@ -116,7 +132,7 @@ int tfhe_b200_ctx_destroy(tfhe_b200_ctx *c) {
     if (!c) return 0;
     DeviceGuard g(c->device);
     cudaStreamSynchronize(c->stream);
-    for (DevBuf *b : {&c->ksk_packed, &c->ksk_colsum, &c->ksk_planes, &c->ks_digits, &c->bskf, &c->tbl, &c->luts, &c->d_in, &c->d_small, &c->d_out, &c->d_idx})
+    for (DevBuf *b : {&c->ksk_packed, &c->ksk_colsum, &c->ksk_planes, &c->ks_digits, &c->bskf, &c->tbl, &c->roots, &c->luts, &c->d_in, &c->d_small, &c->d_out, &c->d_idx})
         b->release();
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -155,13 +171,16 @@ int tfhe_b200_upload_bsk_std(tfhe_b200_ctx *c, const uint64_t *bsk, size_t len) 
     std::lock_guard<std::mutex> lk(c->mu);
     DeviceGuard g(c->device);
     const size_t k1 = c->p.glwe_dim + 1;
-    const size_t n_polys = (size_t)c->p.lwe_dim * c->p.pbs_level * k1 * k1;
+    const size_t n_ggsw = c->p.grouping_factor ? (size_t)(c->p.lwe_dim / c->p.grouping_factor) << c->p.grouping_factor : c->p.lwe_dim;
+    const size_t n_polys = n_ggsw * c->p.pbs_level * k1 * k1;
     if (len != n_polys * c->p.poly_size) return fail("bootstrap key length does not match the parameters");
     DevBuf raw;
     TB_CUDA(raw.reserve(len * 8));
     TB_CUDA(c->bskf.reserve(n_polys * tb::kM * sizeof(double) * 2));
     TB_CUDA(cudaMemcpyAsync(raw.p, bsk, len * 8, cudaMemcpyHostToDevice, c->stream));
-    if (c->pbs_kernel == 3)
+    if (c->p.grouping_factor == 3)
+        TB_CUDA(tbk::launch_bsk_convert_multibit((const uint64_t *)raw.p, c->bskf.p, c->tbl.p, (int)n_polys, c->stream));
+    else if (c->pbs_kernel == 3)
         TB_CUDA(tbk::launch_bsk_convert_v3((const uint64_t *)raw.p, c->bskf.p, c->tbl.p, (int)n_polys, c->stream));
     else
         TB_CUDA(tbk::launch_bsk_convert((const uint64_t *)raw.p, c->bskf.p, c->tbl.p, (int)n_polys, c->stream));

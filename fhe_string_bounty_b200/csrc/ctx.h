@@ -51,7 +51,7 @@ struct tfhe_b200_ctx {
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     bool timed = false;
     // keys
-    tbc::DevBuf ksk_packed, ksk_colsum, ksk_planes, ks_digits, bskf, tbl, luts;
+    tbc::DevBuf ksk_packed, ksk_colsum, ksk_planes, ks_digits, bskf, tbl, roots, luts;
     int ks_kernel = 1;    // 1: tensor-core GEMM (keyswitch_mma.cu), 0: IMAD GEMM (keyswitch.cu); env TFHE_B200_KS_KERNEL=imad
     uint32_t n_luts = 0;
     bool have_ksk = false, have_bsk = false;

@@ -33,6 +33,12 @@ cudaError_t launch_pbs_classic_v3(const uint64_t *lwe_small, const uint32_t *lut
                                   const void *tbl, uint64_t *out, const uint32_t *out_slot, int batch, int n, int base_log,
                                   int n_iters, cudaStream_t stream);
 cudaError_t launch_bsk_convert_v3(const uint64_t *bsk_std, void *bskf3, const void *tbl, int n_polys, cudaStream_t stream);
+// pbs_multibit.cu
+cudaError_t pbs_multibit_configure();
+cudaError_t launch_pbs_multibit(const uint64_t *lwe_small, const uint32_t *lut_idx, const uint64_t *luts, const void *bskm,
+                                const void *tbl, const void *roots, uint64_t *out, const uint32_t *out_slot, int batch, int n,
+                                int base_log, int n_groups, cudaStream_t stream);
+cudaError_t launch_bsk_convert_multibit(const uint64_t *bsk_std, void *bskm, const void *tbl, int n_polys, cudaStream_t stream);
 cudaError_t launch_fp64_peak(double *sink, int blocks, int iters, cudaStream_t stream);
 
 // leveled.cu

@@ -34,3 +34,12 @@ def keys_2_2(orc):
     ck = orc.ClientKey(p, 0xB200 + 1)
     sk = orc.ServerKey(ck, 0xB300 + 1)
     return p, ck, sk
+
+
+@pytest.fixture(scope="session")
+def keys_multibit(orc):
+    """PARAM_MULTI_BIT_MESSAGE_2_CARRY_2_GROUP_3_KS_PBS keys (shortint/parameters/multi_bit.rs:173-190), seeded."""
+    p = orc.params("multibit_2_2_g3")
+    ck = orc.ClientKey(p, 0xB200 + 5)
+    sk = orc.ServerKey(ck, 0xB300 + 5)
+    return p, ck, sk
