@@ -186,7 +186,7 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     B = args.batch
-    p = F.Params(**F.PARAM_MESSAGE_2_CARRY_2_KS_PBS)
+    p = F.Params(**(F.PARAM_MULTI_BIT_MESSAGE_2_CARRY_2_GROUP_3_KS_PBS if args.params == "multibit" else F.PARAM_MESSAGE_2_CARRY_2_KS_PBS))
     eng = F.Engine(p, device=local)
     rng = np.random.default_rng(0xB200)          # same keys on every rank: keys are replicated, work is sharded
     eng.upload_ksk(rng.integers(0, 2**64, size=p.ksk_len, dtype=np.uint64))
@@ -256,7 +256,7 @@ def run_b200(args):
     e2e_s = time.perf_counter() - t0
 
     string_ops = None
-    if args.string_ops:
+    if args.string_ops and args.params == "2_2":
         string_ops = bench_string_ops(eng, p, rank, world, local)
 
     if world > 1:
@@ -275,7 +275,7 @@ def run_b200(args):
             "metric": "batched KS-PBS throughput", "value": value, "unit": "PBS/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "PARAM_MESSAGE_2_CARRY_2_KS_PBS batched KS-PBS (configs[1])", "batch_per_gpu": B,
+            "config": {"workload": ("PARAM_MESSAGE_2_CARRY_2_KS_PBS" if args.params == "2_2" else "PARAM_MULTI_BIT_MESSAGE_2_CARRY_2_GROUP_3_KS_PBS") + " batched KS-PBS (configs[1])", "batch_per_gpu": B,
                        "luts": 16, "l2_policy": "inputs larger than L2 (cts in+out %.0f MB + keys 109 MB per step)" % (2 * B * CT_BYTES / 1e6),
                        "sharding": "ciphertexts partitioned across ranks, keys replicated, no data-path collective"},
             "e2e": {"value": e2e, "unit": "PBS/s", "h2d_bytes_per_step": B * (CT_BYTES + 4), "d2h_bytes_per_step": B * CT_BYTES},
@@ -307,6 +307,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=8192, help="ciphertexts per GPU per step")
+    ap.add_argument("--params", default="2_2", choices=["2_2", "multibit"], help="2_2 = PARAM_MESSAGE_2_CARRY_2_KS_PBS (headline); multibit = ..._GROUP_3_KS_PBS")
     ap.add_argument("--string-ops", type=int, default=1, help="also time FheString eq/contains/find through the host layer (0 = skip)")
     ap.add_argument("--cpu-sample", type=int, default=256, help="KS-PBS evaluated by the CPU baseline leg (0 = skip)")
     args = ap.parse_args()
