@@ -185,12 +185,18 @@ pbs_classic_kernel_v3(const uint64_t *__restrict__ lwe_small, const uint32_t *__
         }
         __syncwarp();   // everyone is done reading the polynomial: the buffer becomes the transpose tile
 
-        pretwist_fwd(re, im);
-        radix32_dif(re, im);
-        twiddle_fwd(re, im, [&](int idx) { return sm.tbl[idx]; }, lane);
-        warp_transpose(re, tile, lane);
-        warp_transpose(im, tile, lane);
-        radix32_dif(re, im);
+        // forward FFT; the two radix-32 passes share ONE copy of the butterfly code (2-trip loop): the kernel body must stay
+        // inside the instruction cache (ncu: no_instruction stall 0.08 -> 1.0 per instruction once it does not)
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+            if (pass == 0) pretwist_fwd(re, im);
+            radix32_dif(re, im);
+            if (pass == 0) {
+                twiddle_fwd(re, im, [&](int idx) { return sm.tbl[idx]; }, lane);
+                warp_transpose(re, tile, lane);
+                warp_transpose(im, tile, lane);
+            }
+        }
         if (i == 0 && ctl < 2) asm volatile("bar.arrive 9, 256;" ::: "memory");
 
         // spectrum exchange between the two warps of the ciphertext (whole polynomial at once: 16 KiB buffer)
@@ -201,65 +207,78 @@ pbs_classic_kernel_v3(const uint64_t *__restrict__ lwe_small, const uint32_t *__
         }
         pair_barrier(1 + ctl);
 
-        // out_fft[w] = F_w * G[w][w] + F_{1-w} * G[1-w][w], GGSW pieces from the ring
-#pragma unroll 1
-        for (int c = 0; c < PIECES_PER_ITER; ++c) {
-            const int g = i * PIECES_PER_ITER + c;
-            const int slot = g % NSLOT;
-            mbar_wait(&sm.full_bar[slot], (uint32_t)(g / NSLOT) & 1u);
-            const cplx *pc = sm.ring[slot] + (w * 2) * 4 * 32 + lane;
-            cplx ga[4], gb[4], fo[4];
+        // out_fft[w] = F_w * G[w][w] + F_{1-w} * G[1-w][w], GGSW pieces from the ring.
+        // (1) probe the 8 piece barriers back to back (they completed long ago: the ring runs 1.25 iterations ahead), only
+        //     falling back to a blocking wait for a piece that is really missing;
+        // (2) per chunk: 12 independent 16-byte shared loads, then 32 FP64 instructions -- one exposed latency per chunk;
+        // (3) release each slot right after its chunk (its values have been consumed by then, so no fence is needed for load
+        //     completion).
+        {
+            const int g0 = i * PIECES_PER_ITER;
+            uint32_t ready = 0;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                ga[q] = pc[q * 32];
-                gb[q] = pc[(4 + q) * 32];
+            for (int c = 0; c < PIECES_PER_ITER; ++c) {
+                const int g = g0 + c;
+                ready |= (mbar_try_wait(&sm.full_bar[g % NSLOT], (uint32_t)(g / NSLOT) & 1u) ? 1u : 0u) << c;
             }
-            // the values are in registers: release the slot; the last of the 8 warps re-arms it NSLOT pieces ahead
-            __syncwarp();
-            if (lane == 0) {
-                __threadfence_block();
-                const unsigned int old = atomicAdd(&sm.consumed[slot], 1u);
-                if (old == WARPS - 1) {
-                    sm.consumed[slot] = 0;
-                    const int g2 = g + NSLOT;
-                    if (g2 < total_pieces) {
-                        __threadfence_block();
-                        fence_proxy_async();
-                        mbar_expect_tx(&sm.full_bar[slot], PIECE_BYTES);
-                        tma_load_1d(sm.ring[slot], bskf3 + (size_t)g2 * PIECE_CPLX, PIECE_BYTES, &sm.full_bar[slot]);
+#pragma unroll
+            for (int c = 0; c < PIECES_PER_ITER; ++c) {
+                const int g = g0 + c;
+                const int slot = g % NSLOT;
+                if (!((ready >> c) & 1u)) mbar_wait(&sm.full_bar[slot], (uint32_t)(g / NSLOT) & 1u);
+                const cplx *pc = sm.ring[slot] + (w * 2) * 4 * 32 + lane;
+                cplx ga[4], gb[4], fo[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    ga[q] = pc[q * 32];
+                    gb[q] = pc[(4 + q) * 32];
+                    fo[q] = othc[(c * 4 + q) * 32 + lane];
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int p = c * 4 + q;
+                    const double fr = re[p], fi = im[p];
+                    double orr = DMUL(fr, ga[q].x);
+                    orr = DFMA(-fi, ga[q].y, orr);
+                    orr = DFMA(fo[q].x, gb[q].x, orr);
+                    orr = DFMA(-fo[q].y, gb[q].y, orr);
+                    double oi = DMUL(fr, ga[q].y);
+                    oi = DFMA(fi, ga[q].x, oi);
+                    oi = DFMA(fo[q].x, gb[q].y, oi);
+                    oi = DFMA(fo[q].y, gb[q].x, oi);
+                    re[p] = orr; im[p] = oi;
+                }
+                // release the slot as soon as this warp is done with it (progressive release keeps the ring full for the
+                // ciphertext group that runs half an iteration ahead); the last of the 8 warps re-arms it NSLOT pieces ahead
+                __syncwarp();
+                if (lane == 0) {
+                    const unsigned int old = atomicAdd(&sm.consumed[slot], 1u);
+                    if (old == WARPS - 1) {
+                        sm.consumed[slot] = 0;
+                        const int g2 = g + NSLOT;
+                        if (g2 < total_pieces) {
+                            __threadfence_block();
+                            fence_proxy_async();
+                            mbar_expect_tx(&sm.full_bar[slot], PIECE_BYTES);
+                            tma_load_1d(sm.ring[slot], bskf3 + (size_t)g2 * PIECE_CPLX, PIECE_BYTES, &sm.full_bar[slot]);
+                        }
                     }
                 }
-            }
-            switch (c) {   // register arrays need compile-time indices: dispatch on the chunk
-#define TB3_MAC(C)                                                                                   \
-    case C: {                                                                                        \
-        _Pragma("unroll") for (int q = 0; q < 4; ++q) fo[q] = othc[((C) * 4 + q) * 32 + lane];        \
-        _Pragma("unroll") for (int q = 0; q < 4; ++q) {                                               \
-            const int p = (C) * 4 + q;                                                               \
-            const double fr = re[p], fi = im[p];                                                     \
-            double orr = DMUL(fr, ga[q].x);                                                          \
-            orr = DFMA(-fi, ga[q].y, orr);                                                           \
-            orr = DFMA(fo[q].x, gb[q].x, orr);                                                       \
-            orr = DFMA(-fo[q].y, gb[q].y, orr);                                                      \
-            double oi = DMUL(fr, ga[q].y);                                                           \
-            oi = DFMA(fi, ga[q].x, oi);                                                              \
-            oi = DFMA(fo[q].x, gb[q].y, oi);                                                         \
-            oi = DFMA(fo[q].y, gb[q].x, oi);                                                         \
-            re[p] = orr; im[p] = oi;                                                                 \
-        }                                                                                            \
-    } break;
-                TB3_MAC(0) TB3_MAC(1) TB3_MAC(2) TB3_MAC(3) TB3_MAC(4) TB3_MAC(5) TB3_MAC(6) TB3_MAC(7)
-#undef TB3_MAC
             }
         }
         pair_barrier(1 + ctl);   // the partner has read my spectrum: the buffer is the transpose tile again
 
-        radix32_dit_inv(re, im);
-        warp_transpose(re, tile, lane);
-        warp_transpose(im, tile, lane);
-        twiddle_inv(re, im, [&](int idx) { return sm.tbl[idx]; }, lane);
-        radix32_dit_inv(re, im);
-        posttwist_inv(re, im);
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+            radix32_dit_inv(re, im);
+            if (pass == 0) {
+                warp_transpose(re, tile, lane);
+                warp_transpose(im, tile, lane);
+                twiddle_inv(re, im, [&](int idx) { return sm.tbl[idx]; }, lane);
+            } else {
+                posttwist_inv(re, im);
+            }
+        }
 
         // acc += from_torus(.): master copy in TMEM, new values to registers (next gather's "own") and shared (next rotation)
 #pragma unroll
