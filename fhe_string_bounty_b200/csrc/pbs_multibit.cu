@@ -137,12 +137,17 @@ pbs_multibit_kernel(const uint64_t *__restrict__ lwe_small, const uint32_t *__re
             im[m] = (double)signed_digit_l1((uint64_t)__double_as_longlong(im[m]), base_log);
         }
 
-        pretwist_fwd(re, im);
-        radix32_dif(re, im);
-        twiddle_fwd(re, im, [&](int idx) { return sm.tbl[idx]; }, lane);
-        warp_transpose(re, tile, lane);
-        warp_transpose(im, tile, lane);
-        radix32_dif(re, im);
+        // the two radix-32 passes share one copy of the butterfly code: the kernel must fit the instruction cache
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+            if (pass == 0) pretwist_fwd(re, im);
+            radix32_dif(re, im);
+            if (pass == 0) {
+                twiddle_fwd(re, im, [&](int idx) { return sm.tbl[idx]; }, lane);
+                warp_transpose(re, tile, lane);
+                warp_transpose(im, tile, lane);
+            }
+        }
 
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
@@ -152,7 +157,7 @@ pbs_multibit_kernel(const uint64_t *__restrict__ lwe_small, const uint32_t *__re
                 myc[pp * 32 + lane] = f;
             }
             pair_barrier(1 + ctl);
-#pragma unroll
+#pragma unroll 1
             for (int c4 = 0; c4 < 4; ++c4) {
                 const int chunk = half * 4 + c4;
                 cplx Ga[4], Gb[4];
@@ -200,32 +205,45 @@ pbs_multibit_kernel(const uint64_t *__restrict__ lwe_small, const uint32_t *__re
                         }
                     }
                 }
-                // out_fft[w] = F_w * Gc[w][w] + F_{1-w} * Gc[1-w][w]
+                // out_fft[w] = F_w * Gc[w][w] + F_{1-w} * Gc[1-w][w]   (register arrays need compile-time indices: switch on c4)
+                cplx fo[4];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int p = chunk * 4 + q;
-                    const cplx fo = othc[(c4 * 4 + q) * 32 + lane];
-                    const double fr = re[p], fi = im[p];
-                    double orr = DMUL(fr, Ga[q].x);
-                    orr = DFMA(-fi, Ga[q].y, orr);
-                    orr = DFMA(fo.x, Gb[q].x, orr);
-                    orr = DFMA(-fo.y, Gb[q].y, orr);
-                    double oi = DMUL(fr, Ga[q].y);
-                    oi = DFMA(fi, Ga[q].x, oi);
-                    oi = DFMA(fo.x, Gb[q].y, oi);
-                    oi = DFMA(fo.y, Gb[q].x, oi);
-                    re[p] = orr; im[p] = oi;
+                for (int q = 0; q < 4; ++q) fo[q] = othc[(c4 * 4 + q) * 32 + lane];
+                switch (c4) {
+#define TBM_MAC(C)                                                                                   \
+    case C: {                                                                                        \
+        _Pragma("unroll") for (int q = 0; q < 4; ++q) {                                               \
+            const int p = (half * 4 + (C)) * 4 + q;                                                  \
+            const double fr = re[p], fi = im[p];                                                     \
+            double orr = DMUL(fr, Ga[q].x);                                                          \
+            orr = DFMA(-fi, Ga[q].y, orr);                                                           \
+            orr = DFMA(fo[q].x, Gb[q].x, orr);                                                       \
+            orr = DFMA(-fo[q].y, Gb[q].y, orr);                                                      \
+            double oi = DMUL(fr, Ga[q].y);                                                           \
+            oi = DFMA(fi, Ga[q].x, oi);                                                              \
+            oi = DFMA(fo[q].x, Gb[q].y, oi);                                                         \
+            oi = DFMA(fo[q].y, Gb[q].x, oi);                                                         \
+            re[p] = orr; im[p] = oi;                                                                 \
+        }                                                                                            \
+    } break;
+                    TBM_MAC(0) TBM_MAC(1) TBM_MAC(2) TBM_MAC(3)
+#undef TBM_MAC
                 }
             }
             pair_barrier(1 + ctl);
         }
 
-        radix32_dit_inv(re, im);
-        warp_transpose(re, tile, lane);
-        warp_transpose(im, tile, lane);
-        twiddle_inv(re, im, [&](int idx) { return sm.tbl[idx]; }, lane);
-        radix32_dit_inv(re, im);
-        posttwist_inv(re, im);
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+            radix32_dit_inv(re, im);
+            if (pass == 0) {
+                warp_transpose(re, tile, lane);
+                warp_transpose(im, tile, lane);
+                twiddle_inv(re, im, [&](int idx) { return sm.tbl[idx]; }, lane);
+            } else {
+                posttwist_inv(re, im);
+            }
+        }
 
         // dst = 0; dst += G (x) src  (:503): the accumulator is REPLACED by the rounded product
 #pragma unroll
