@@ -1,0 +1,67 @@
+"""Error behaviour of the C ABI on a live GPU (reference convention: non-zero return + message, c_api/utils.rs:3-28;
+nothing falls back to the CPU) and edge-case batches."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from helpers import engine_params
+
+pytestmark = pytest.mark.gpu
+
+
+def test_missing_keys_and_bad_arguments_fail_loudly(orc, keys_2_2):
+    import fhe_string_bounty_b200 as F
+    p, ck, sk = keys_2_2
+    eng = F.Engine(engine_params(p))
+    cts = ck.encrypt_batch([1, 2, 3])
+    with pytest.raises(F.NativeError, match="keyswitch key not uploaded"):
+        eng.keyswitch_batch(cts)
+    with pytest.raises(F.NativeError, match="length"):
+        eng.upload_ksk(sk.ksk[:-1])
+    with pytest.raises(F.NativeError, match="length"):
+        eng.upload_bsk_std(sk.bsk[: sk.bsk.size // 2])
+    eng.upload_ksk(sk.ksk)
+    with pytest.raises(F.NativeError, match="bootstrap key not uploaded"):
+        eng.ks_pbs_batch(cts, None)
+    eng.upload_bsk_std(sk.bsk)
+    with pytest.raises(F.NativeError, match="lookup tables"):
+        eng.ks_pbs_batch(cts, None)
+    lib = eng.lib
+    assert lib.tfhe_b200_ks_pbs_batch(eng.h, None, None, None, 3) != 0          # null buffers
+    assert lib.tfhe_b200_ks_pbs_batch(None, cts.ctypes.data, None, cts.ctypes.data, 3) != 0   # null context
+    assert lib.tfhe_b200_ks_pbs_batch(eng.h, None, None, None, 0) == 0          # empty batch is a no-op
+    acc, _ = sk.generate_lookup_table(lambda x: x)
+    eng.upload_luts(acc[None, :])
+    with pytest.raises(F.NativeError, match="n_iters"):
+        eng.pbs_batch(np.zeros((1, p.lwe_dim + 1), dtype=np.uint64), None, n_iters=p.lwe_dim + 1)
+    h = C.c_void_p()
+    q = F.Params(**engine_params(p))
+    assert lib.tfhe_b200_ctx_create(99, C.byref(q), C.byref(h)) != 0 and h.value is None   # no such device
+    eng.close()
+
+
+def test_both_keyswitch_kernels_and_both_pbs_kernels_agree(orc, keys_2_2, monkeypatch):
+    """The IMAD keyswitch and the tensor-core keyswitch are bit-identical; the v2 and v3 blind-rotation kernels decrypt to
+    the same values (their ciphertexts differ only by FFT-layout-independent rounding, which they share: identical words)."""
+    import fhe_string_bounty_b200 as F
+    p, ck, sk = keys_2_2
+    acc, _ = sk.generate_lookup_table(lambda x: (7 * x + 2) % 16)
+    cts = ck.encrypt_batch(np.arange(37) % 16)
+    outs, kss = {}, {}
+    for ks_k, pbs_k in (("imad", "2"), ("mma", "3"), ("mma", "2")):
+        monkeypatch.setenv("TFHE_B200_KS_KERNEL", ks_k)
+        monkeypatch.setenv("TFHE_B200_PBS_KERNEL", pbs_k)
+        eng = F.Engine(engine_params(p))
+        eng.upload_ksk(sk.ksk)
+        eng.upload_bsk_std(sk.bsk)
+        eng.upload_luts(acc[None, :])
+        kss[(ks_k, pbs_k)] = eng.keyswitch_batch(cts)
+        outs[(ks_k, pbs_k)] = eng.ks_pbs_batch(cts, None)
+        eng.close()
+    assert np.array_equal(kss[("imad", "2")], kss[("mma", "3")])
+    want = [(7 * int(v) + 2) % 16 for v in np.arange(37) % 16]
+    for k, o in outs.items():
+        assert list(ck.decrypt_batch(o)) == want, k
+    # same FFT arithmetic (fft_core.cuh) in both kernels => identical words, not just identical plaintexts
+    assert np.array_equal(outs[("mma", "2")], outs[("mma", "3")])
