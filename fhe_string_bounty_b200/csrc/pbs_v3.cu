@@ -20,33 +20,35 @@
 namespace tb3 {
 using namespace tb;
 
-constexpr int CTS = 4;                 // ciphertexts per CTA
-constexpr int WARPS = 2 * CTS;
-constexpr int NTHREADS = 32 * WARPS;
+// CTS = ciphertexts per CTA: 4 for throughput (8 warps share the ring); 1 for narrow tree levels (<= one ciphertext per
+// SM: the two warps own a scheduler each, so an iteration's dependency chain runs without contention)
 constexpr int PIECE_CPLX = 512;        // [out poly 2][sel 2][q 4][lane 32]
 constexpr int PIECE_BYTES = PIECE_CPLX * 16;
 constexpr int PIECES_PER_ITER = 8;
 constexpr int NSLOT = 10;
-constexpr int TMEM_COLS = 256;
 
+template <int CTS>
 struct Smem {
-    uint64_t mbuf[WARPS][kN];              // 128 KiB
+    static constexpr int WARPS = 2 * CTS;
+    uint64_t mbuf[WARPS][kN];              // 16 KiB per warp
     cplx ring[NSLOT][PIECE_CPLX];          // 80 KiB
     cplx tbl[kM];                          // 16 KiB
     unsigned long long full_bar[NSLOT];
     unsigned int consumed[NSLOT];
     uint32_t tmem_base;
 };
-static_assert(sizeof(Smem) <= 227 * 1024, "shared memory budget");
+static_assert(sizeof(Smem<4>) <= 227 * 1024, "shared memory budget");
 
 using namespace tbr;
 __device__ __forceinline__ void pair_barrier(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 
 // ---- TMEM (tcgen05) -------------------------------------------------------------------------------------------------
+template <int TMEM_COLS>
 __device__ __forceinline__ void tmem_alloc(uint32_t *smem_dst) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "n"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
 }
+template <int TMEM_COLS>
 __device__ __forceinline__ void tmem_dealloc(uint32_t addr) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "n"(TMEM_COLS) : "memory");
 }
@@ -84,12 +86,14 @@ __device__ __forceinline__ size_t bskf3_index(int i, int chunk, int c, int sel, 
     return ((((size_t)(i * PIECES_PER_ITER + chunk) * 2 + c) * 2 + sel) * 4 + q) * 32;
 }
 
-__global__ void __launch_bounds__(NTHREADS, 1)
+template <int CTS>
+__global__ void __launch_bounds__(64 * CTS, 1)
 pbs_classic_kernel_v3(const uint64_t *__restrict__ lwe_small, const uint32_t *__restrict__ lut_idx, const uint64_t *__restrict__ luts,
                       const cplx *__restrict__ bskf3, const cplx *__restrict__ tbl_g, uint64_t *__restrict__ out,
                       const uint32_t *__restrict__ out_slot, int batch, int n, int base_log, int n_iters) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
+    constexpr int WARPS = 2 * CTS, NTHREADS = 64 * CTS, TMEM_COLS = CTS > 2 ? 256 : 128;
+    Smem<CTS> &sm = *reinterpret_cast<Smem<CTS> *>(smem_raw);
     const int W = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // warp -> (ciphertext, polynomial): the two warps of a ciphertext (coupled by pair barriers) sit on DIFFERENT
     // schedulers (warp id % 4), so each scheduler hosts warps of two different ciphertexts, which are started half an
@@ -112,7 +116,7 @@ pbs_classic_kernel_v3(const uint64_t *__restrict__ lwe_small, const uint32_t *__
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_proxy_async();
     }
-    if (W == 0) tmem_alloc(&sm.tmem_base);
+    if (W == 0) tmem_alloc<TMEM_COLS>(&sm.tmem_base);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -161,7 +165,7 @@ pbs_classic_kernel_v3(const uint64_t *__restrict__ lwe_small, const uint32_t *__
     __syncwarp();
 
     // stagger: ciphertexts 2,3 start once ciphertexts 0,1 have finished their first forward FFT
-    if (ctl >= 2 && n_iters > 0) asm volatile("bar.sync 9, 256;" ::: "memory");
+    if (CTS == 4 && ctl >= 2 && n_iters > 0) asm volatile("bar.sync 9, 256;" ::: "memory");
 
     for (int i = 0; i < n_iters; ++i) {
         const uint32_t a = modulus_switch_2n(__ldg(lwe + i)) & (2 * kN - 1);   // a == 0 is NOT skipped: adds exactly zero
@@ -197,7 +201,7 @@ pbs_classic_kernel_v3(const uint64_t *__restrict__ lwe_small, const uint32_t *__
                 warp_transpose(im, tile, lane);
             }
         }
-        if (i == 0 && ctl < 2) asm volatile("bar.arrive 9, 256;" ::: "memory");
+        if (CTS == 4 && i == 0 && ctl < 2) asm volatile("bar.arrive 9, 256;" ::: "memory");
 
         // spectrum exchange between the two warps of the ciphertext (whole polynomial at once: 16 KiB buffer)
 #pragma unroll
@@ -323,7 +327,7 @@ pbs_classic_kernel_v3(const uint64_t *__restrict__ lwe_small, const uint32_t *__
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (W == 0) tmem_dealloc(sm.tmem_base);
+    if (W == 0) tmem_dealloc<TMEM_COLS>(sm.tmem_base);
 }
 
 // std -> Fourier key in the v3 ring layout (one warp per polynomial; same forward transform as the kernel above)
@@ -361,15 +365,25 @@ bsk_convert_kernel_v3(const uint64_t *__restrict__ bsk_std, cplx *__restrict__ b
 namespace tbk {
 
 cudaError_t pbs_v3_configure() {
-    return cudaFuncSetAttribute(tb3::pbs_classic_kernel_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tb3::Smem));
+    cudaError_t e = cudaFuncSetAttribute(tb3::pbs_classic_kernel_v3<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tb3::Smem<4>));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(tb3::pbs_classic_kernel_v3<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tb3::Smem<1>));
 }
 
 cudaError_t launch_pbs_classic_v3(const uint64_t *lwe_small, const uint32_t *lut_idx, const uint64_t *luts, const void *bskf3,
                                   const void *tbl, uint64_t *out, const uint32_t *out_slot, int batch, int n, int base_log,
                                   int n_iters, cudaStream_t stream) {
     if (batch <= 0) return cudaSuccess;
-    const int grid = (batch + tb3::CTS - 1) / tb3::CTS;
-    tb3::pbs_classic_kernel_v3<<<grid, tb3::NTHREADS, sizeof(tb3::Smem), stream>>>(
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    if (batch <= sms) {   // narrow level: one ciphertext per SM, latency-oriented instance
+        tb3::pbs_classic_kernel_v3<1><<<batch, 64, sizeof(tb3::Smem<1>), stream>>>(
+            lwe_small, lut_idx, luts, reinterpret_cast<const tb::cplx *>(bskf3), reinterpret_cast<const tb::cplx *>(tbl), out, out_slot,
+            batch, n, base_log, n_iters);
+        return cudaGetLastError();
+    }
+    const int grid = (batch + 3) / 4;
+    tb3::pbs_classic_kernel_v3<4><<<grid, 256, sizeof(tb3::Smem<4>), stream>>>(
         lwe_small, lut_idx, luts, reinterpret_cast<const tb::cplx *>(bskf3), reinterpret_cast<const tb::cplx *>(tbl), out, out_slot,
         batch, n, base_log, n_iters);
     return cudaGetLastError();
