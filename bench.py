@@ -271,6 +271,12 @@ def run_b200(args):
         pbs_tflops = B * FLOP_PER_PBS / (pbs_ms * 1e-3) / 1e12
         hbm_alg = (BSK_BYTES + KSK_BYTES + B * (2 * CT_BYTES + 743 * 8 * 2)) / ((pbs_ms + ks_ms) * 1e-3) / 1e9
         cpu_rate, cpu_cores, cpu_dt = cpu_reference_rate(args.cpu_sample) if args.cpu_sample > 0 else (None, 0, 0)
+        traffic = None
+        tf = ROOT / "profiles" / "r01_pbs_traffic.json"
+        if tf.exists() and args.params == "2_2":
+            t = json.loads(tf.read_text())
+            if t.get("batch") == B:        # dram__bytes_read+write of one launch from the committed ncu capture of this workload
+                traffic = t["dram_bytes"]
         line = {
             "metric": "batched KS-PBS throughput", "value": value, "unit": "PBS/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -281,8 +287,9 @@ def run_b200(args):
             "e2e": {"value": e2e, "unit": "PBS/s", "h2d_bytes_per_step": B * (CT_BYTES + 4), "d2h_bytes_per_step": B * CT_BYTES},
             "gpu_launches": launches,
             "kernels": {"keyswitch_ms": ks_ms, "pbs_ms": pbs_ms},
-            "roofline": {"bound": "fp64", "kernel": "pbs_classic_kernel", "achieved": pbs_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": pbs_tflops / fp64_peak if fp64_peak else None, "traffic": None,
+            "roofline": {"bound": "fp64", "kernel": "pbs_classic_kernel_v3" if args.params == "2_2" else "pbs_multibit_kernel", "achieved": pbs_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
+                         "frac": pbs_tflops / fp64_peak if fp64_peak else None, "traffic": traffic,
+                         "algorithmic_bytes_per_launch": BSK_BYTES + B * (743 * 8 + CT_BYTES) + 16 * 4096 * 8,
                          "peak_source": "FP64 FMA microbenchmark run in this process (MEASURED_PEAKS.json has no FP64 figure)",
                          "flop_per_pbs": FLOP_PER_PBS,
                          "hbm": {"achieved": hbm_alg, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
