@@ -165,7 +165,9 @@ pbs_classic_kernel_v3(const uint64_t *__restrict__ lwe_small, const uint32_t *__
     __syncwarp();
 
     // stagger: ciphertexts 2,3 start once ciphertexts 0,1 have finished their first forward FFT
-    if (CTS == 4 && ctl >= 2 && n_iters > 0) asm volatile("bar.sync 9, 256;" ::: "memory");
+    // stagger: ciphertext k starts when ciphertext 0 reaches the k-th quarter of its first iteration (after the gather,
+    // after the forward FFT, after the MAC), so FP64 phases and shared-memory phases of different ciphertexts overlap
+    if (CTS == 4 && ctl >= 1 && n_iters > 0) asm volatile("bar.sync %0, 128;" ::"r"(8 + ctl) : "memory");
 
     for (int i = 0; i < n_iters; ++i) {
         const uint32_t a = modulus_switch_2n(__ldg(lwe + i)) & (2 * kN - 1);   // a == 0 is NOT skipped: adds exactly zero
@@ -188,6 +190,7 @@ pbs_classic_kernel_v3(const uint64_t *__restrict__ lwe_small, const uint32_t *__
             TB_FENCE();
         }
         __syncwarp();   // everyone is done reading the polynomial: the buffer becomes the transpose tile
+        if (CTS == 4 && i == 0 && ctl == 0) asm volatile("bar.arrive 9, 128;" ::: "memory");
 
         // forward FFT; the two radix-32 passes share ONE copy of the butterfly code (2-trip loop): the kernel body must stay
         // inside the instruction cache (ncu: no_instruction stall 0.08 -> 1.0 per instruction once it does not)
@@ -201,7 +204,7 @@ pbs_classic_kernel_v3(const uint64_t *__restrict__ lwe_small, const uint32_t *__
                 warp_transpose(im, tile, lane);
             }
         }
-        if (CTS == 4 && i == 0 && ctl < 2) asm volatile("bar.arrive 9, 256;" ::: "memory");
+        if (CTS == 4 && i == 0 && ctl == 0) asm volatile("bar.arrive 10, 128;" ::: "memory");
 
         // spectrum exchange between the two warps of the ciphertext (whole polynomial at once: 16 KiB buffer)
 #pragma unroll
@@ -271,6 +274,7 @@ pbs_classic_kernel_v3(const uint64_t *__restrict__ lwe_small, const uint32_t *__
             }
         }
         pair_barrier(1 + ctl);   // the partner has read my spectrum: the buffer is the transpose tile again
+        if (CTS == 4 && i == 0 && ctl == 0) asm volatile("bar.arrive 11, 128;" ::: "memory");
 
 #pragma unroll 1
         for (int pass = 0; pass < 2; ++pass) {
