@@ -159,6 +159,12 @@ def bench_string_ops(eng, p, rank, world, local):
     pat = rng.integers(0, 2**64, size=(64, p.big_len), dtype=np.uint64)
     out["eq_8char_ops_per_s"] = timed(lambda: MG.sharded_eq(execute, params, a8, b8, 8, rank, world, dev), 20)
     out["contains_256_16_ops_per_s"] = timed(lambda: MG.sharded_contains(execute, params, hay, pat, 256, 16, rank, world, dev), 3)
+    # throughput mode: independent string pairs share each tree level's launches (each rank takes its own share of pairs)
+    n_pairs = 128
+    many = Program("string_eq_many", (8, 8, n_pairs), params=params)
+    pairs = rng.integers(0, 2**64, size=(many.n_inputs, p.big_len), dtype=np.uint64)
+    out["eq_8char_batched_ops_per_s"] = world * n_pairs * timed(lambda: many.run(eng, pairs), 3)
+    out["eq_8char_batch"] = {"pairs_per_rank": n_pairs, "pbs": many.n_pbs, "levels": many.level_widths}
     if world == 1:
         find = Program("string_find", (256, 16), params=params)
         ins = np.concatenate([hay, pat])

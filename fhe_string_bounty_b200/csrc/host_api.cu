@@ -112,6 +112,27 @@ bool record(tfhe_b200_program &h, const std::string &op, const uint64_t *a, size
         pg.output(a[1] ? pg.pbs(s, [n](uint64_t x) { return uint64_t(x == n); }) : pg.pbs(s, [](uint64_t x) { return uint64_t(x != 0); }));
         return true;
     }
+    // ---- many independent string pairs in one program (throughput mode): a = {len_a, len_b, count}; inputs are
+    //      count x (string a, string b); one boolean per pair.  op = string_eq_many / string_lt_many / string_contains_many
+    if (op.size() > 5 && op.rfind("string_", 0) == 0 && op.compare(op.size() - 5, 5, "_many") == 0) {
+        if (!need(3)) return false;
+        const std::string f = op.substr(7, op.size() - 12);
+        std::vector<std::pair<tbh::FheString, tbh::FheString>> in;
+        for (uint64_t k = 0; k < a[2]; ++k) {
+            tbh::FheString s = ssk.input_string(a[0]);
+            tbh::FheString t = ssk.input_string(a[1]);
+            in.push_back({s, t});
+        }
+        for (auto &st : in) {
+            if (f == "eq") pg.output(ssk.eq(st.first, st.second));
+            else if (f == "ne") pg.output(ssk.ne(st.first, st.second));
+            else if (f == "lt") pg.output(ssk.lt(st.first, st.second));
+            else if (f == "le") pg.output(ssk.le(st.first, st.second));
+            else if (f == "contains") pg.output(ssk.contains(st.first, st.second));
+            else { err = "unknown batched string op: " + op; return false; }
+        }
+        return true;
+    }
     // ---- strings: a = {len_a[, len_b]}; with a non-empty `clear` the second operand is a clear (trivial) string ----------------------------------
     if (op.rfind("string_", 0) == 0) {
         if (!need(1)) return false;

@@ -178,3 +178,16 @@ def test_unknown_op_and_bad_args_fail_loudly():
         Program("string_frobnicate", (3, 3))
     with pytest.raises(NativeError):
         Program("radix_eq", ())
+
+
+def test_many_independent_pairs_share_levels(orc, toy_keys):
+    """throughput mode: N independent eq's in one program = the single-op tree widened N times, same results per pair"""
+    from oracle import radix as R
+    p, ck, sk = toy_keys
+    P1 = Program("string_eq", (3, 3), params=engine_params(p))
+    PN = Program("string_eq_many", (3, 3, 5), params=engine_params(p))
+    assert PN.level_widths == [5 * w for w in P1.level_widths]
+    pairs = [(b"abc", b"abc"), (b"abc", b"abd"), (b"zzz", b"zzz"), (b"a b", b"a_b"), (b"xyz", b"xyz")]
+    ins = np.concatenate([np.concatenate([R.encrypt_string(ck, a), R.encrypt_string(ck, b)]) for a, b in pairs])
+    out = R.run_program(PN.ir(), sk, ins)
+    assert [ck.decrypt_message_and_carry(c) for c in out] == [int(a == b) for a, b in pairs]
