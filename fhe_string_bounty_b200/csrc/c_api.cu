@@ -36,11 +36,13 @@ int check_params(const tfhe_b200_params &p) {
 
 namespace tbc {
 
-int do_keyswitch(tfhe_b200_ctx *c, const uint64_t *d_in, uint64_t *d_small, size_t batch, cudaStream_t s, const uint32_t *in_slot) {
+int do_keyswitch(tfhe_b200_ctx *c, const uint64_t *d_in, uint64_t *d_small, size_t batch, cudaStream_t s, const uint32_t *in_slot,
+                 DevBuf *digits) {
+    if (!digits) digits = &c->ks_digits;
     if (!c->have_ksk) return fail("keyswitch key not uploaded");
     if (c->ks_kernel == 1) {
-        TB_CUDA(c->ks_digits.reserve(tbk::ks_mma_digits_bytes((int)batch, (int)(c->p.glwe_dim * c->p.poly_size), (int)c->p.ks_level)));
-        TB_CUDA(tbk::launch_keyswitch_mma(d_in, in_slot, (uint8_t *)c->ks_digits.p, (const uint8_t *)c->ksk_planes.p,
+        TB_CUDA(digits->reserve(tbk::ks_mma_digits_bytes((int)batch, (int)(c->p.glwe_dim * c->p.poly_size), (int)c->p.ks_level)));
+        TB_CUDA(tbk::launch_keyswitch_mma(d_in, in_slot, (uint8_t *)digits->p, (const uint8_t *)c->ksk_planes.p,
                                           (const uint64_t *)c->ksk_colsum.p, d_small, (int)batch, (int)(c->p.glwe_dim * c->p.poly_size),
                                           (int)c->p.lwe_dim, (int)c->p.ks_base_log, (int)c->p.ks_level, s));
         c->launches += 2;
@@ -104,6 +106,7 @@ int tfhe_b200_ctx_create(int cuda_device, const tfhe_b200_params *params, tfhe_b
     c->p = *params;
     TB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (auto &e : c->ev) TB_CUDA(cudaEventCreate(&e));
+    for (auto &L : c->lane) TB_CUDA(cudaStreamCreateWithFlags(&L.s, cudaStreamNonBlocking));
     if (const char *e = std::getenv("TFHE_B200_KS_KERNEL")) c->ks_kernel = (e[0] == 'i') ? 0 : 1;
     if (!tbk::ks_mma_supported((int)params->ks_level)) c->ks_kernel = 0;
     if (const char *e = std::getenv("TFHE_B200_PBS_KERNEL")) c->pbs_kernel = (e[0] == '2') ? 2 : 3;
@@ -135,6 +138,10 @@ int tfhe_b200_ctx_destroy(tfhe_b200_ctx *c) {
     for (DevBuf *b : {&c->ksk_packed, &c->ksk_colsum, &c->ksk_planes, &c->ks_digits, &c->bskf, &c->tbl, &c->roots, &c->luts, &c->d_in, &c->d_small, &c->d_out, &c->d_idx})
         b->release();
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
+    for (auto &L : c->lane) {
+        if (L.s) { cudaStreamSynchronize(L.s); cudaStreamDestroy(L.s); }
+        for (DevBuf *b : {&L.in, &L.small, &L.out, &L.idx, &L.digits}) b->release();
+    }
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return 0;
@@ -293,23 +300,37 @@ int tfhe_b200_pbs_batch_partial(tfhe_b200_ctx *c, const uint64_t *in, const uint
 int tfhe_b200_ks_pbs_batch(tfhe_b200_ctx *c, const uint64_t *in, const uint32_t *idx, uint64_t *out, size_t batch) {
     if (!c || (batch && (!in || !out))) return fail("null argument");
     if (batch == 0) return 0;
-    {
-        std::lock_guard<std::mutex> lk(c->mu);
-        DeviceGuard g(c->device);
-        TB_CUDA(c->d_in.reserve(batch * c->big_len() * 8));
-        TB_CUDA(c->d_out.reserve(batch * c->big_len() * 8));
-        TB_CUDA(cudaMemcpyAsync(c->d_in.p, in, batch * c->big_len() * 8, cudaMemcpyHostToDevice, c->stream));
-        if (idx) {
-            TB_CUDA(c->d_idx.reserve(batch * 4));
-            TB_CUDA(cudaMemcpyAsync(c->d_idx.p, idx, batch * 4, cudaMemcpyHostToDevice, c->stream));
-        }
-    }
-    if (tfhe_b200_ks_pbs_batch_device(c, (const uint64_t *)c->d_in.p, idx ? (const uint32_t *)c->d_idx.p : nullptr,
-                                      (uint64_t *)c->d_out.p, batch, nullptr))
-        return 1;
+    if (!c->have_ksk) return fail("keyswitch key not uploaded");
+    if (!c->have_bsk) return fail("bootstrap key not uploaded");
+    if (c->n_luts == 0) return fail("no lookup tables uploaded");
+    std::lock_guard<std::mutex> lk(c->mu);
     DeviceGuard g(c->device);
-    TB_CUDA(cudaMemcpyAsync(out, c->d_out.p, batch * c->big_len() * 8, cudaMemcpyDeviceToHost, c->stream));
-    TB_CUDA(cudaStreamSynchronize(c->stream));
+    // chunks of four full waves (148 SMs x 4 ciphertexts), alternating between two lanes (stream + staging buffers)
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+    const size_t chunk = std::min<size_t>(batch, (size_t)sms * 4 * 4);
+    const size_t L = c->big_len();
+    for (auto &ln : c->lane) {
+        TB_CUDA(ln.in.reserve(chunk * L * 8));
+        TB_CUDA(ln.out.reserve(chunk * L * 8));
+        TB_CUDA(ln.small.reserve(chunk * c->small_len() * 8));
+        if (idx) TB_CUDA(ln.idx.reserve(chunk * 4));
+        if (batch <= chunk) break;   // a single chunk only needs lane 0
+    }
+    size_t k = 0;
+    for (size_t off = 0; off < batch; off += chunk, ++k) {
+        tfhe_b200_ctx::Lane &ln = c->lane[k & 1];
+        const size_t n = std::min(chunk, batch - off);
+        TB_CUDA(cudaMemcpyAsync(ln.in.p, in + off * L, n * L * 8, cudaMemcpyHostToDevice, ln.s));
+        if (idx) TB_CUDA(cudaMemcpyAsync(ln.idx.p, idx + off, n * 4, cudaMemcpyHostToDevice, ln.s));
+        if (tbc::do_keyswitch(c, (const uint64_t *)ln.in.p, (uint64_t *)ln.small.p, n, ln.s, nullptr, &ln.digits)) return 1;
+        if (tbc::do_pbs(c, (const uint64_t *)ln.small.p, idx ? (const uint32_t *)ln.idx.p : nullptr, (const uint64_t *)c->luts.p,
+                        (uint64_t *)ln.out.p, n, c->p.lwe_dim, ln.s, nullptr))
+            return 1;
+        TB_CUDA(cudaMemcpyAsync(out + off * L, ln.out.p, n * L * 8, cudaMemcpyDeviceToHost, ln.s));
+    }
+    TB_CUDA(cudaStreamSynchronize(c->lane[0].s));
+    if (k > 1) TB_CUDA(cudaStreamSynchronize(c->lane[1].s));
     return 0;
 }
 

@@ -58,6 +58,10 @@ struct tfhe_b200_ctx {
     int pbs_kernel = 3;   // 3: TMEM + TMA ring (pbs_v3.cu), 2: one CTA per ciphertext (pbs.cu); env TFHE_B200_PBS_KERNEL
     // staging for the host-pointer entry points
     tbc::DevBuf d_in, d_small, d_out, d_idx;
+    // two copy/compute lanes for the host-buffer KS-PBS entry point: H2D of chunk k+1 and D2H of chunk k-1 overlap the
+    // kernels of chunk k, and the tail wave of one chunk overlaps the head of the next
+    struct Lane { cudaStream_t s = nullptr; tbc::DevBuf in, small, out, idx, digits; };
+    Lane lane[2];
     uint64_t launches = 0;
     std::mutex mu;
 
@@ -69,7 +73,7 @@ struct tfhe_b200_ctx {
 namespace tbc {
 // shared launch helpers (c_api.cu)
 int do_keyswitch(tfhe_b200_ctx *c, const uint64_t *d_in, uint64_t *d_small, size_t batch, cudaStream_t s,
-                 const uint32_t *in_slot = nullptr);
+                 const uint32_t *in_slot = nullptr, DevBuf *digits = nullptr);
 int do_pbs(tfhe_b200_ctx *c, const uint64_t *d_small, const uint32_t *d_idx, const uint64_t *d_luts, uint64_t *d_out, size_t batch,
            uint32_t n_iters, cudaStream_t s, const uint32_t *out_slot = nullptr);
 }  // namespace tbc
