@@ -166,6 +166,10 @@ def bench_string_ops(eng, p, rank, world, local):
     out["eq_8char_batched_ops_per_s"] = world * n_pairs * timed(lambda: many.run(eng, pairs), 3)
     out["eq_8char_batch"] = {"pairs_per_rank": n_pairs, "pbs": many.n_pbs, "levels": many.level_widths}
     if world == 1:
+        cp = Program("string_contains_packed", (256, 16), params=params)
+        ins_c = np.concatenate([hay, pat])
+        out["contains_256_16_packed_ops_per_s"] = timed(lambda: cp.run(eng, ins_c), 3)
+        out["contains_256_16_packed_pbs"] = cp.n_pbs
         find = Program("string_find", (256, 16), params=params)
         ins = np.concatenate([hay, pat])
         out["find_256_16_ops_per_s"] = timed(lambda: find.run(eng, ins), 3)
@@ -304,6 +308,11 @@ def run_b200(args):
         }
         if string_ops is not None:
             line["string_ops"] = string_ops
+        if cpu_rate is not None and string_ops is not None:
+            # the CPU path has no batching effect beyond its cores: a string op costs (its PBS count) / (CPU KS-PBS rate)
+            string_ops["cpu_port_ops_per_s_derived"] = {
+                "eq_8char": cpu_rate / 36.0, "contains_256_16": cpu_rate / 16890.0, "find_256_16": cpu_rate / 19549.0,
+                "to_lowercase_1024": cpu_rate / 4096.0, "note": "derived: CPU KS-PBS/s of cpu_baseline / PBS count of the reference-shaped tree"}
         if cpu_rate is not None:
             line["cpu_baseline"] = {"value": cpu_rate, "unit": "PBS/s", "cores": cpu_cores, "kind": "port",
                                     "sample": f"{args.cpu_sample} KS-PBS (same parameter set, random keys), {cpu_dt:.1f} s"}

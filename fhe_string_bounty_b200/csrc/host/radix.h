@@ -73,6 +73,25 @@ class IntegerServerKey {
         return is_at_least_one_comparisons_block_true(cmp);
     }
 
+    // ---- packed equality: not a reference method, but built from the reference's own pieces -- pack two blocks into
+    // msg*msg values (pack_block_chunk, scalar_comparison.rs:104-139), true LWE subtraction and a LUT on the difference
+    // exactly like Comparator::compare_block_assign (comparator.rs:193-221), with f(x) = [x == 0]: for a negative
+    // difference the padding bit makes the PBS return -f(16 - |d|) = 0.  One PBS per PAIR of blocks instead of one per
+    // block; decrypted results identical to unchecked_eq, noise of the PBS input as in the reference's comparisons.
+    std::vector<Ct> packed_block_equalities(const Radix &lhs, const Radix &rhs) {
+        if (lhs.size() != rhs.size()) throw std::invalid_argument("radix size mismatch");
+        std::vector<Ct> pl = pack_pairs(lhs), pr = pack_pairs(rhs), out;
+        for (size_t i = 0; i < pl.size(); ++i) {
+            Ct d = pg.lwe_sub(pl[i], pr[i]);
+            d.degree = p.total_mod() - 1;
+            out.push_back(pg.pbs(d, [](uint64_t x) { return uint64_t(x == 0); }));
+        }
+        return out;
+    }
+    BooleanBlock unchecked_eq_packed(const Radix &lhs, const Radix &rhs) {
+        return are_all_comparisons_block_true(packed_block_equalities(lhs, rhs));
+    }
+
     // ---- scalar equality (scalar_comparison.rs:254-458): pack pairs of blocks to msg*msg, one LUT per scalar nibble-pair
     std::vector<Ct> pack_pairs(const Radix &blocks) {
         std::vector<Ct> packed;

@@ -18,7 +18,7 @@ struct FheString {
 
 class StringServerKey {
   public:
-    explicit StringServerKey(Program &prog) : pg(prog), isk(prog), p(prog.params()) {}
+    explicit StringServerKey(Program &prog, bool packed_eq = false) : pg(prog), isk(prog), p(prog.params()), packed(packed_eq) {}
 
     static constexpr size_t BLOCKS_PER_CHAR = 4;
 
@@ -55,9 +55,14 @@ class StringServerKey {
     }
 
     // ---- eq / ne: config 1 ([32, 3, 1] PBS per level for 8 chars) -----------------------------------------------------
+    // block equalities of two equal-length block ranges: reference form (one bivariate PBS per block, comparison.rs:10-33)
+    // or the packed form (one PBS per pair of blocks, radix.h packed_block_equalities)
+    std::vector<Ct> block_eqs(const Radix &x, const Radix &y) {
+        return packed ? isk.packed_block_equalities(x, y) : isk.block_equalities(x, y);
+    }
     BooleanBlock eq(const FheString &a, const FheString &b) {
         if (a.len() != b.len()) return pg.create_trivial(0);
-        return isk.unchecked_eq(concat(a, 0, a.len()), concat(b, 0, b.len()));
+        return isk.are_all_comparisons_block_true(block_eqs(concat(a, 0, a.len()), concat(b, 0, b.len())));
     }
     BooleanBlock ne(const FheString &a, const FheString &b) {
         if (a.len() != b.len()) return pg.create_trivial(1);
@@ -93,7 +98,7 @@ class StringServerKey {
         const size_t W = hay.len() - pat.len() + 1;
         w1 = std::min(w1, W);
         std::vector<std::vector<Ct>> eqs;
-        for (size_t w = w0; w < w1; ++w) eqs.push_back(isk.block_equalities(concat(hay, w, pat.len()), concat(pat, 0, pat.len())));
+        for (size_t w = w0; w < w1; ++w) eqs.push_back(block_eqs(concat(hay, w, pat.len()), concat(pat, 0, pat.len())));
         // the AND trees are scheduled by readiness, so the per-window reductions line up level by level
         for (auto &e : eqs) m.push_back(isk.are_all_comparisons_block_true(e));
         return m;
@@ -107,12 +112,12 @@ class StringServerKey {
     BooleanBlock starts_with(const FheString &s, const FheString &pat) {
         if (pat.len() > s.len()) return pg.create_trivial(0);
         if (pat.len() == 0) return pg.create_trivial(1);
-        return isk.unchecked_eq(concat(s, 0, pat.len()), concat(pat, 0, pat.len()));
+        return isk.are_all_comparisons_block_true(block_eqs(concat(s, 0, pat.len()), concat(pat, 0, pat.len())));
     }
     BooleanBlock ends_with(const FheString &s, const FheString &pat) {
         if (pat.len() > s.len()) return pg.create_trivial(0);
         if (pat.len() == 0) return pg.create_trivial(1);
-        return isk.unchecked_eq(concat(s, s.len() - pat.len(), pat.len()), concat(pat, 0, pat.len()));
+        return isk.are_all_comparisons_block_true(block_eqs(concat(s, s.len() - pat.len(), pat.len()), concat(pat, 0, pat.len())));
     }
     // find: (found, index of the first match as a radix of ceil(log4(W)) blocks; 0 when not found, like the
     // regex example's "no match" convention of returning a boolean separately)
@@ -202,6 +207,7 @@ class StringServerKey {
     Program &pg;
     IntegerServerKey isk;
     Params p;
+    bool packed;   // use packed block equalities in eq / contains / find / starts_with / ends_with / eq_ignore_case
 };
 
 }  // namespace tbh

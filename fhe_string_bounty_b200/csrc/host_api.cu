@@ -42,10 +42,20 @@ void output_radix(tbh::Program &pg, const tbh::Radix &r) { for (auto &b : r) pg.
 void output_string(tbh::Program &pg, const tbh::FheString &s) { for (auto &c : s.chars) output_radix(pg, c); }
 
 // records `op`; returns false with a message when the op / arguments are unknown
-bool record(tfhe_b200_program &h, const std::string &op, const uint64_t *a, size_t na, const char *clear, std::string &err) {
+bool record(tfhe_b200_program &h, const std::string &op_in, const uint64_t *a, size_t na, const char *clear, std::string &err) {
     tbh::Program &pg = *h.prog;
     tbh::IntegerServerKey isk(pg);
-    tbh::StringServerKey ssk(pg);
+    // "<op>_packed": same operation with packed block equalities (one PBS per pair of blocks, host/radix.h)
+    std::string op = op_in;
+    bool packed = false;
+    if (op.size() > 7 && op.compare(op.size() - 7, 7, "_packed") == 0) { packed = true; op = op.substr(0, op.size() - 7); }
+    tbh::StringServerKey ssk(pg, packed);
+    if (packed && op == "radix_eq") {
+        if (na < 1) { err = "radix_eq_packed: expected 1 integer argument"; return false; }
+        tbh::Radix x = input_radix(pg, a[0]), y = input_radix(pg, a[0]);
+        pg.output(isk.unchecked_eq_packed(x, y));
+        return true;
+    }
     auto need = [&](size_t n) { if (na < n) { err = op + ": expected " + std::to_string(n) + " integer arguments"; return false; } return true; };
     const std::string cl = clear ? clear : "";
 

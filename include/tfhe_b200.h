@@ -103,6 +103,8 @@ int tfhe_b200_pbs_batch_partial(tfhe_b200_ctx *ctx, const uint64_t *lwe_small, c
  *   string_{eq,ne,lt,le,gt,ge,eq_ignore_case,contains,starts_with,ends_with,find} {len_a, len_b}
  *   string_{to_lowercase,to_uppercase} {len}     string_contains_windows {len_a, len_b, w0, w1}
  *   string_{eq,ne,lt,le,contains}_many {len_a, len_b, count}   (count independent pairs in one program)
+ * Appending "_packed" to a string op (or radix_eq) selects packed block equalities: one PBS per PAIR of blocks built from
+ * pack_block_chunk + lwe_sub + LUT[x == 0] (the Comparator's own trick, comparator.rs:193-221); same decrypted results.
  * With clear_operand != NULL the second string operand is that clear (trivial) string instead of an input.
  * Inputs are fresh shortint blocks (degree msg_mod-1); a char is 4 little-endian 2-bit blocks. */
 typedef struct tfhe_b200_program tfhe_b200_program;

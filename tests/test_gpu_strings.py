@@ -113,3 +113,36 @@ def test_contains_256_16_config3(orc, keys_2_2, eng):
         f = hay.find(pat)
         assert _bool(ck, out[0]) == int(f >= 0) and R.decrypt_radix(ck, out[1:]) == max(f, 0)
     print(f"contains 256/16: {P.n_pbs} PBS, {P.last_ms():.1f} ms on device; find: {F.n_pbs} PBS, {F.last_ms():.1f} ms")
+
+
+def test_packed_equality_ops_gpu(orc, keys_2_2, eng):
+    """packed-equality variants at the real parameter set (their PBS input carries the noise of a packed subtraction, like
+    the reference's comparisons): decrypted results vs clear text, full-size contains 256/16 with half the PBS."""
+    from oracle import radix as R
+    p, ck, sk = keys_2_2
+    rng = np.random.default_rng(0xB200 + 33)
+    for a, b in [(b"needle in hay", b"in h"), (b"needle in hay", b"hey"), (b"same", b"same"), (b"samf", b"same"), (b"MiXeD", b"mixed")]:
+        ins = np.concatenate([R.encrypt_string(ck, a), R.encrypt_string(ck, b)])
+        for op, w in {"eq": a == b, "contains": b in a, "starts_with": a.startswith(b), "ends_with": a.endswith(b),
+                      "eq_ignore_case": a.lower() == b.lower()}.items():
+            out = Program(f"string_{op}_packed", (len(a), len(b)), params=engine_params(p)).run(eng, ins)
+            assert _bool(ck, out[0]) == int(w), (op, a, b)
+    # every ordered pair of 4-bit values, 256 independent 2-block equalities through one batched program
+    xs = np.repeat(np.arange(16), 16)
+    ys = np.tile(np.arange(16), 16)
+    P = Program("string_contains_packed", (256, 16), params=engine_params(p))
+    F = Program("string_find_packed", (256, 16), params=engine_params(p))
+    assert P.n_pbs == 8696
+    for trial in range(2):
+        hay = bytes(rng.integers(ord("a"), ord("z") + 1, size=256).tolist())
+        off = int(rng.integers(0, 241))
+        pat = hay[off:off + 16] if trial == 0 else bytes(rng.integers(ord("a"), ord("z") + 1, size=16).tolist())
+        ins = np.concatenate([R.encrypt_string(ck, hay), R.encrypt_string(ck, pat)])
+        assert _bool(ck, P.run(eng, ins)[0]) == int(pat in hay)
+        out = F.run(eng, ins)
+        f = hay.find(pat)
+        assert _bool(ck, out[0]) == int(f >= 0) and R.decrypt_radix(ck, out[1:]) == max(f, 0)
+    print(f"contains 256/16 packed: {P.n_pbs} PBS, {P.last_ms():.1f} ms; find packed: {F.n_pbs} PBS, {F.last_ms():.1f} ms")
+    for x, y in zip(xs[::7], ys[::7]):
+        ins = np.stack(R.encrypt_radix(ck, int(x), 2) + R.encrypt_radix(ck, int(y), 2))
+        assert _bool(ck, Program("radix_eq_packed", (2,), params=engine_params(p)).run(eng, ins)[0]) == int(x == y), (x, y)

@@ -191,3 +191,27 @@ def test_many_independent_pairs_share_levels(orc, toy_keys):
     ins = np.concatenate([np.concatenate([R.encrypt_string(ck, a), R.encrypt_string(ck, b)]) for a, b in pairs])
     out = R.run_program(PN.ir(), sk, ins)
     assert [ck.decrypt_message_and_carry(c) for c in out] == [int(a == b) for a, b in pairs]
+
+
+def test_packed_equality_halves_the_pbs_and_agrees(orc, toy_keys):
+    """*_packed ops: one PBS per pair of blocks (pack + lwe_sub + LUT[x == 0], comparator.rs:193-221 restated); results
+    identical to the reference-shaped programs on the same inputs, including every 4-bit difference sign."""
+    from oracle import radix as R
+    p, ck, sk = toy_keys
+    assert Program("string_eq_packed", (8, 8)).level_widths == [16, 2, 1]
+    P = Program("string_contains_packed", (256, 16))
+    assert P.level_widths == [7712, 723, 241, 17, 2, 1] and P.n_pbs == 8696
+    # nibble pairs of both signs: equality through the padding-bit trick must be exact for negative differences too
+    for x, y in [(0, 0), (0, 15), (15, 0), (7, 8), (8, 7), (9, 9), (15, 15), (1, 0), (0, 1), (12, 3)]:
+        ins = np.stack(R.encrypt_radix(ck, x, 2) + R.encrypt_radix(ck, y, 2))
+        out, _ = _run(orc, toy_keys, "radix_eq_packed", (2,), ins)
+        assert _dec_bool(ck, out[0]) == int(x == y), (x, y)
+    for a, b in STR_CASES + [(b"abcabcab", b"cab"), (b"abcabcab", b"cba")]:
+        ins = np.concatenate([R.encrypt_string(ck, a), R.encrypt_string(ck, b)]) if (a or b) else np.zeros((0, p.big_dim + 1), dtype=np.uint64)
+        for op, w in {"eq": a == b, "contains": b in a, "starts_with": a.startswith(b), "ends_with": a.endswith(b)}.items():
+            out, _ = _run(orc, toy_keys, f"string_{op}_packed", (len(a), len(b)), ins)
+            assert _dec_bool(ck, out[0]) == int(w), (op, a, b)
+    hay, pat = b"abcabcab", b"cab"
+    ins = np.concatenate([R.encrypt_string(ck, hay), R.encrypt_string(ck, pat)])
+    out, _ = _run(orc, toy_keys, "string_find_packed", (len(hay), len(pat)), ins)
+    assert _dec_bool(ck, out[0]) == 1 and R.decrypt_radix(ck, out[1:]) == hay.find(pat)
