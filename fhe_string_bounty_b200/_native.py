@@ -98,6 +98,7 @@ EXPORTS = {
     "tfhe_b200_keyswitch_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "tfhe_b200_pbs_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "tfhe_b200_ks_pbs_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "tfhe_b200_pbs_ks_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "tfhe_b200_keyswitch_batch_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "tfhe_b200_pbs_batch_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "tfhe_b200_ks_pbs_batch_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
@@ -226,6 +227,14 @@ class Engine:
         if isinstance(lut_idx, np.ndarray):
             lut_idx = np.ascontiguousarray(lut_idx, dtype=np.uint32)
         self._check(self.lib.tfhe_b200_ks_pbs_batch(self.h, _ptr(cts), _ptr(lut_idx), _ptr(out), batch))
+        return out
+
+    def pbs_ks_batch(self, small: np.ndarray, lut_idx=None) -> np.ndarray:
+        """PBS -> KS order (ciphertexts under the small key), shortint/server_key/mod.rs:859-932"""
+        small = np.ascontiguousarray(small, dtype=np.uint64).reshape(-1, self.p.small_len)
+        out = np.empty_like(small)
+        idx = None if lut_idx is None else np.ascontiguousarray(lut_idx, dtype=np.uint32)
+        self._check(self.lib.tfhe_b200_pbs_ks_batch(self.h, _ptr(small), _ptr(idx), _ptr(out), small.shape[0]))
         return out
 
     # device-buffer hot path ---------------------------------------------------------------------------

@@ -334,6 +334,33 @@ int tfhe_b200_ks_pbs_batch(tfhe_b200_ctx *c, const uint64_t *in, const uint32_t 
     return 0;
 }
 
+/* PBS -> KS order (PBSOrder::BootstrapKeyswitch, shortint/server_key/mod.rs:859-932): ciphertexts live under the SMALL key */
+int tfhe_b200_pbs_ks_batch(tfhe_b200_ctx *c, const uint64_t *in, const uint32_t *idx, uint64_t *out, size_t batch) {
+    if (!c || (batch && (!in || !out))) return fail("null argument");
+    if (batch == 0) return 0;
+    if (c->n_luts == 0) return fail("no lookup tables uploaded");
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    cudaStream_t s = c->stream;
+    TB_CUDA(c->d_small.reserve(batch * c->small_len() * 8));
+    TB_CUDA(c->d_out.reserve(batch * c->big_len() * 8));
+    TB_CUDA(c->d_in.reserve(batch * c->small_len() * 8));
+    TB_CUDA(cudaMemcpyAsync(c->d_small.p, in, batch * c->small_len() * 8, cudaMemcpyHostToDevice, s));
+    const uint32_t *d_idx = nullptr;
+    if (idx) {
+        TB_CUDA(c->d_idx.reserve(batch * 4));
+        TB_CUDA(cudaMemcpyAsync(c->d_idx.p, idx, batch * 4, cudaMemcpyHostToDevice, s));
+        d_idx = (const uint32_t *)c->d_idx.p;
+    }
+    if (tbc::do_pbs(c, (const uint64_t *)c->d_small.p, d_idx, (const uint64_t *)c->luts.p, (uint64_t *)c->d_out.p, batch, c->p.lwe_dim, s,
+                    nullptr))
+        return 1;
+    if (tbc::do_keyswitch(c, (const uint64_t *)c->d_out.p, (uint64_t *)c->d_in.p, batch, s)) return 1;
+    TB_CUDA(cudaMemcpyAsync(out, c->d_in.p, batch * c->small_len() * 8, cudaMemcpyDeviceToHost, s));
+    TB_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
 // ---- instrumentation --------------------------------------------------------------------------------
 
 uint64_t tfhe_b200_kernel_launches(const tfhe_b200_ctx *c) { return c ? c->launches : 0; }

@@ -69,6 +69,10 @@ int tfhe_b200_pbs_batch(tfhe_b200_ctx *ctx, const uint64_t *lwe_small, const uin
                         size_t batch);
 int tfhe_b200_ks_pbs_batch(tfhe_b200_ctx *ctx, const uint64_t *lwe_big_in, const uint32_t *lut_idx,
                            uint64_t *lwe_big_out, size_t batch);
+/* PBS -> KS order (PBSOrder::BootstrapKeyswitch; programmable_bootstrap_keyswitch_assign, shortint/server_key/mod.rs:859-932):
+ * ciphertexts are batch x (n + 1) words under the SMALL key on both sides. */
+int tfhe_b200_pbs_ks_batch(tfhe_b200_ctx *ctx, const uint64_t *lwe_small_in, const uint32_t *lut_idx,
+                           uint64_t *lwe_small_out, size_t batch);
 
 /* Same operations on DEVICE buffers of the context's GPU, enqueued on `cuda_stream` (a cudaStream_t;
  * NULL = the context's own stream) without synchronising: used to chain tree levels and by the

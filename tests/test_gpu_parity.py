@@ -121,3 +121,23 @@ def test_device_entry_point_matches_host(orc, keys_2_2, eng):
     dev = d_out.cpu().numpy().view(np.uint64)
     assert np.array_equal(dev, host), "same kernels, same inputs: must be bit-identical run to run"
     assert eng.kernel_launches > 0
+
+
+def test_pbs_then_keyswitch_order(orc, keys_2_2, eng):
+    """PBSOrder::BootstrapKeyswitch (server_key/mod.rs:859-932): input and output under the SMALL key (LWE noise)."""
+    import ctypes as C
+    p, ck, sk = keys_2_2
+    L = orc.lib()
+    fs, luts = _luts(sk)
+    eng.upload_luts(luts)
+    vals = np.arange(16)
+    cts = np.zeros((16, p.lwe_dim + 1), dtype=np.uint64)
+    for i, v in enumerate(vals):
+        L.orc_lwe_encrypt(ck.small_sk, p.lwe_dim, int(v) << 59, p.lwe_std, C.byref(ck.rng), cts[i])
+    idx = (np.arange(16) % len(fs)).astype(np.uint32)
+    out = eng.pbs_ks_batch(cts, idx)
+    got = [L.orc_decode(C.byref(p), ck.decrypt_small_raw(o)) for o in out]
+    assert got == [fs[i](int(v)) for v, i in zip(vals, idx)]
+    # the same composition with the oracle: PBS then keyswitch
+    ref = np.stack([sk.keyswitch(sk.pbs(c, luts[i])) for c, i in zip(cts, idx)])
+    assert [L.orc_decode(C.byref(p), ck.decrypt_small_raw(o)) for o in ref] == got
