@@ -167,12 +167,9 @@ static cudaError_t launch_mma(const uint8_t *digits, const uint8_t *bmat, const 
                               const uint32_t *in_slot, uint64_t *lwe_out, int batch, int in_dim, int n, int K, int ldk, int half_b,
                               cudaStream_t stream) {
     const size_t smem = (size_t)STAGES * (BM + BN) * (KSTEP + PAD);
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(ks_mma_kernel<KSTEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    // function attributes are per device: set on every launch (microseconds) rather than caching a process-wide flag
+    cudaError_t e = cudaFuncSetAttribute(ks_mma_kernel<KSTEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
     dim3 grid((batch + BM - 1) / BM, (ldk * 8) / BN);
     ks_mma_kernel<KSTEP><<<grid, THREADS, smem, stream>>>(digits, bmat, colsum, lwe_in, in_slot, lwe_out, batch, in_dim, n, K, half_b);
     return cudaGetLastError();

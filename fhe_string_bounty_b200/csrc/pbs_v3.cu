@@ -378,8 +378,9 @@ cudaError_t launch_pbs_classic_v3(const uint64_t *lwe_small, const uint32_t *lut
                                   const void *tbl, uint64_t *out, const uint32_t *out_slot, int batch, int n, int base_log,
                                   int n_iters, cudaStream_t stream) {
     if (batch <= 0) return cudaSuccess;
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    int sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (batch <= sms) {   // narrow level: one ciphertext per SM, latency-oriented instance
         tb3::pbs_classic_kernel_v3<1><<<batch, 64, sizeof(tb3::Smem<1>), stream>>>(
             lwe_small, lut_idx, luts, reinterpret_cast<const tb::cplx *>(bskf3), reinterpret_cast<const tb::cplx *>(tbl), out, out_slot,
