@@ -34,17 +34,35 @@ def build_native(force: bool = False, verbose: bool = False) -> Path:
     if not force and _SO.exists() and all(_SO.stat().st_mtime >= d.stat().st_mtime for d in deps if d.exists()):
         return _SO
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, "-o", str(_SO), *map(str, srcs)]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
     env = dict(os.environ)
     env.pop("CC", None)
     env.pop("CXX", None)
-    res = subprocess.run(cmd, capture_output=True, text=True, env=env)
+    build_dir = _PKG / "build"
+    build_dir.mkdir(exist_ok=True)
+    compile_flags = [f for f in NVCC_FLAGS if f != "-shared"]
+
+    def compile_one(src: Path):
+        obj = build_dir / (src.stem + ".o")
+        cmd = [nvcc, *compile_flags, "-c", "-o", str(obj), str(src)]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        res = subprocess.run(cmd, capture_output=True, text=True, env=env)
+        return obj, res
+
+    # one nvcc per translation unit, in parallel (the kernels are independent), then one link step
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as pool:
+        results = list(pool.map(compile_one, srcs))
+    log = ""
+    for obj, res in results:
+        log += res.stderr
+        if res.returncode != 0:
+            raise NativeError("nvcc failed:\n" + res.stdout + res.stderr)
+    res = subprocess.run([nvcc, "-shared", "-o", str(_SO), *[str(o) for o, _ in results]], capture_output=True, text=True, env=env)
     if res.returncode != 0:
-        raise NativeError("nvcc failed:\n" + res.stdout + res.stderr)
+        raise NativeError("nvcc link failed:\n" + res.stdout + res.stderr)
     if verbose:
-        print(res.stderr)
+        print(log)
     return _SO
 
 
