@@ -146,3 +146,50 @@ def test_packed_equality_ops_gpu(orc, keys_2_2, eng):
     for x, y in zip(xs[::7], ys[::7]):
         ins = np.stack(R.encrypt_radix(ck, int(x), 2) + R.encrypt_radix(ck, int(y), 2))
         assert _bool(ck, Program("radix_eq_packed", (2,), params=engine_params(p)).run(eng, ins)[0]) == int(x == y), (x, y)
+
+
+def test_config2_batch_4096_real_ciphertexts(orc, keys_2_2, eng):
+    """BASELINE config 2 at its smallest named size: 4096 independent LUT evaluations, 16 LUTs round-robin, real seeded keys
+    and fresh ciphertexts; every decrypted output must equal LUT(message) (size-independent property), through both the
+    chunked host-buffer entry point and the device entry point."""
+    import torch
+    p, ck, sk = keys_2_2
+    fs = [lambda x, k=k: (x * (2 * k + 1) + k) % 16 for k in range(16)]
+    luts = np.stack([sk.generate_lookup_table(f)[0] for f in fs])
+    eng.upload_luts(luts)
+    rng = np.random.default_rng(0xB200 + 2)
+    vals = rng.integers(0, 16, size=4096)
+    idx = (np.arange(4096) % 16).astype(np.uint32)
+    cts = ck.encrypt_batch(vals)
+    want = np.array([fs[i](int(v)) for v, i in zip(vals, idx)])
+    out = eng.ks_pbs_batch(cts, idx)
+    assert np.array_equal(ck.decrypt_batch(out), want)
+    d_in = torch.from_numpy(cts.view(np.int64)).cuda()
+    d_idx = torch.from_numpy(idx.view(np.int32)).cuda()
+    d_out = torch.empty_like(d_in)
+    s = torch.cuda.Stream()
+    eng.ks_pbs_batch_device(d_in, d_idx, d_out, 4096, s.cuda_stream)
+    s.synchronize()
+    assert np.array_equal(d_out.cpu().numpy().view(np.uint64), out), "chunked host path and device path run the same kernels"
+
+
+def test_config4_case_ops_1024_chars(orc, keys_2_2, eng):
+    """BASELINE config 4: to_lowercase / to_uppercase / eq_ignore_case on 1024-char mixed-case strings."""
+    from oracle import radix as R
+    p, ck, sk = keys_2_2
+    rng = np.random.default_rng(0xB200 + 4)
+    alphabet = np.frombuffer(b"abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ0123456789 ", dtype=np.uint8)
+    a = bytes(rng.choice(alphabet, size=1024).tolist())
+    b = a.swapcase() if True else a
+    ea = R.encrypt_string(ck, a)
+    lo = Program("string_to_lowercase", (1024,), params=engine_params(p))
+    up = Program("string_to_uppercase", (1024,), params=engine_params(p))
+    assert R.decrypt_string(ck, lo.run(eng, ea)) == a.lower()
+    assert R.decrypt_string(ck, up.run(eng, ea)) == a.upper()
+    eb = R.encrypt_string(ck, b)
+    eic = Program("string_eq_ignore_case", (1024, 1024), params=engine_params(p))
+    assert _bool(ck, eic.run(eng, np.concatenate([ea, eb]))[0]) == 1
+    c = bytearray(b)
+    c[700] = ord("#")
+    assert _bool(ck, eic.run(eng, np.concatenate([ea, R.encrypt_string(ck, bytes(c))]))[0]) == 0
+    print(f"to_lowercase 1024 chars: {lo.n_pbs} PBS, {lo.last_ms():.1f} ms; eq_ignore_case: {eic.n_pbs} PBS, {eic.last_ms():.1f} ms")
