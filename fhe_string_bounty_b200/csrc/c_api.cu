@@ -222,6 +222,7 @@ int tfhe_b200_synchronize(tfhe_b200_ctx *c) {
 
 int tfhe_b200_keyswitch_batch_device(tfhe_b200_ctx *c, const uint64_t *d_in, uint64_t *d_small, size_t batch, void *stream) {
     if (!c || (batch && (!d_in || !d_small))) return fail("null argument");
+    std::lock_guard<std::mutex> lk(c->mu);   // the digit scratch buffer is per context
     DeviceGuard g(c->device);
     return do_keyswitch(c, d_in, d_small, batch, stream ? (cudaStream_t)stream : c->stream);
 }
@@ -229,6 +230,7 @@ int tfhe_b200_keyswitch_batch_device(tfhe_b200_ctx *c, const uint64_t *d_in, uin
 int tfhe_b200_pbs_batch_device(tfhe_b200_ctx *c, const uint64_t *d_small, const uint32_t *d_idx, uint64_t *d_out, size_t batch,
                                void *stream) {
     if (!c || (batch && (!d_small || !d_out))) return fail("null argument");
+    std::lock_guard<std::mutex> lk(c->mu);
     DeviceGuard g(c->device);
     return do_pbs(c, d_small, d_idx, d_out, batch, c->p.lwe_dim, stream ? (cudaStream_t)stream : c->stream);
 }
