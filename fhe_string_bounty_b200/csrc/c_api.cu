@@ -36,15 +36,18 @@ int check_params(const tfhe_b200_params &p) {
 
 namespace tbc {
 
+bool fused_supported(const tfhe_b200_ctx *c) { return c->ks_kernel == 1 && c->pbs_kernel == 3 && c->p.grouping_factor == 0; }
+
 int do_keyswitch(tfhe_b200_ctx *c, const uint64_t *d_in, uint64_t *d_small, size_t batch, cudaStream_t s, const uint32_t *in_slot,
-                 DevBuf *digits) {
+                 DevBuf *digits, bool fused) {
+    if (fused && !fused_supported(c)) return fail("internal: fused keyswitch requested on an unsupported configuration");
     if (!digits) digits = &c->ks_digits;
     if (!c->have_ksk) return fail("keyswitch key not uploaded");
     if (c->ks_kernel == 1) {
         TB_CUDA(digits->reserve(tbk::ks_mma_digits_bytes((int)batch, (int)(c->p.glwe_dim * c->p.poly_size), (int)c->p.ks_level)));
         TB_CUDA(tbk::launch_keyswitch_mma(d_in, in_slot, (uint8_t *)digits->p, (const uint8_t *)c->ksk_planes.p,
                                           (const uint64_t *)c->ksk_colsum.p, d_small, (int)batch, (int)(c->p.glwe_dim * c->p.poly_size),
-                                          (int)c->p.lwe_dim, (int)c->p.ks_base_log, (int)c->p.ks_level, s));
+                                          (int)c->p.lwe_dim, (int)c->p.ks_base_log, (int)c->p.ks_level, fused ? tb::kLogN + 1 : 0, s));
         c->launches += 2;
         return 0;
     }
@@ -56,7 +59,8 @@ int do_keyswitch(tfhe_b200_ctx *c, const uint64_t *d_in, uint64_t *d_small, size
 }
 
 int do_pbs(tfhe_b200_ctx *c, const uint64_t *d_small, const uint32_t *d_idx, const uint64_t *d_luts, uint64_t *d_out, size_t batch,
-           uint32_t n_iters, cudaStream_t s, const uint32_t *out_slot) {
+           uint32_t n_iters, cudaStream_t s, const uint32_t *out_slot, bool fused) {
+    if (fused && !fused_supported(c)) return fail("internal: fused PBS input requested on an unsupported configuration");
     if (!c->have_bsk) return fail("bootstrap key not uploaded");
     if (!d_luts) return fail("no lookup tables uploaded");
     if (c->p.grouping_factor == 3) {
@@ -68,7 +72,7 @@ int do_pbs(tfhe_b200_ctx *c, const uint64_t *d_small, const uint32_t *d_idx, con
     }
     if (c->pbs_kernel == 3) {
         TB_CUDA(tbk::launch_pbs_classic_v3(d_small, d_idx, d_luts, c->bskf.p, c->tbl.p, d_out, out_slot, (int)batch, (int)c->p.lwe_dim,
-                                           (int)c->p.pbs_base_log, (int)n_iters, s));
+                                           (int)c->p.pbs_base_log, (int)n_iters, fused ? 1 : 0, s));
         c->launches += 1;
         return 0;
     }
@@ -244,9 +248,11 @@ int tfhe_b200_ks_pbs_batch_device(tfhe_b200_ctx *c, const uint64_t *d_in, const 
     cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
     TB_CUDA(c->d_small.reserve(batch * c->small_len() * 8));
     TB_CUDA(cudaEventRecord(c->ev[0], s));
-    if (do_keyswitch(c, d_in, (uint64_t *)c->d_small.p, batch, s)) return 1;
+    const bool fused = tbc::fused_supported(c);
+    if (tbc::do_keyswitch(c, d_in, (uint64_t *)c->d_small.p, batch, s, nullptr, nullptr, fused)) return 1;
     TB_CUDA(cudaEventRecord(c->ev[1], s));
-    if (do_pbs(c, (const uint64_t *)c->d_small.p, d_idx, d_out, batch, c->p.lwe_dim, s)) return 1;
+    if (c->n_luts == 0) return fail("no lookup tables uploaded");
+    if (tbc::do_pbs(c, (const uint64_t *)c->d_small.p, d_idx, (const uint64_t *)c->luts.p, d_out, batch, c->p.lwe_dim, s, nullptr, fused)) return 1;
     TB_CUDA(cudaEventRecord(c->ev[2], s));
     c->timed = true;
     return 0;
@@ -325,9 +331,10 @@ int tfhe_b200_ks_pbs_batch(tfhe_b200_ctx *c, const uint64_t *in, const uint32_t 
         const size_t n = std::min(chunk, batch - off);
         TB_CUDA(cudaMemcpyAsync(ln.in.p, in + off * L, n * L * 8, cudaMemcpyHostToDevice, ln.s));
         if (idx) TB_CUDA(cudaMemcpyAsync(ln.idx.p, idx + off, n * 4, cudaMemcpyHostToDevice, ln.s));
-        if (tbc::do_keyswitch(c, (const uint64_t *)ln.in.p, (uint64_t *)ln.small.p, n, ln.s, nullptr, &ln.digits)) return 1;
+        const bool fused = tbc::fused_supported(c);
+        if (tbc::do_keyswitch(c, (const uint64_t *)ln.in.p, (uint64_t *)ln.small.p, n, ln.s, nullptr, &ln.digits, fused)) return 1;
         if (tbc::do_pbs(c, (const uint64_t *)ln.small.p, idx ? (const uint32_t *)ln.idx.p : nullptr, (const uint64_t *)c->luts.p,
-                        (uint64_t *)ln.out.p, n, c->p.lwe_dim, ln.s, nullptr))
+                        (uint64_t *)ln.out.p, n, c->p.lwe_dim, ln.s, nullptr, fused))
             return 1;
         TB_CUDA(cudaMemcpyAsync(out + off * L, ln.out.p, n * L * 8, cudaMemcpyDeviceToHost, ln.s));
     }

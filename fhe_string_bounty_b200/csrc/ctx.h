@@ -72,8 +72,11 @@ struct tfhe_b200_ctx {
 
 namespace tbc {
 // shared launch helpers (c_api.cu)
+// fused = the keyswitch epilogue applies the PBS modulus switch and writes u16 values; the PBS then reads u16 (classic PBS on
+// the tensor-core keyswitch + v3 kernel only; fused_supported() says whether the context can do it)
+bool fused_supported(const tfhe_b200_ctx *c);
 int do_keyswitch(tfhe_b200_ctx *c, const uint64_t *d_in, uint64_t *d_small, size_t batch, cudaStream_t s,
-                 const uint32_t *in_slot = nullptr, DevBuf *digits = nullptr);
+                 const uint32_t *in_slot = nullptr, DevBuf *digits = nullptr, bool fused = false);
 int do_pbs(tfhe_b200_ctx *c, const uint64_t *d_small, const uint32_t *d_idx, const uint64_t *d_luts, uint64_t *d_out, size_t batch,
-           uint32_t n_iters, cudaStream_t s, const uint32_t *out_slot = nullptr);
+           uint32_t n_iters, cudaStream_t s, const uint32_t *out_slot = nullptr, bool fused = false);
 }  // namespace tbc

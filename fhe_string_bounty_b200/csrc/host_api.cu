@@ -333,9 +333,10 @@ int tfhe_b200_program_run(tfhe_b200_ctx *c, tfhe_b200_program *h, const uint64_t
         }
         if (p1 > p0) {
             const size_t w = p1 - p0;
-            if (tbc::do_keyswitch(c, arena, (uint64_t *)c->d_small.p, w, s, (const uint32_t *)h->d_pbs_in.p + p0)) return 1;
+            const bool fused = tbc::fused_supported(c);
+            if (tbc::do_keyswitch(c, arena, (uint64_t *)c->d_small.p, w, s, (const uint32_t *)h->d_pbs_in.p + p0, nullptr, fused)) return 1;
             if (tbc::do_pbs(c, (const uint64_t *)c->d_small.p, (const uint32_t *)h->d_pbs_lut.p + p0, (const uint64_t *)h->d_luts.p, arena, w,
-                            c->p.lwe_dim, s, (const uint32_t *)h->d_pbs_out.p + p0))
+                            c->p.lwe_dim, s, (const uint32_t *)h->d_pbs_out.p + p0, fused))
                 return 1;
         }
     }

@@ -18,7 +18,7 @@ bool ks_mma_supported(int level);
 cudaError_t launch_ksk_planes(const uint64_t *packed, uint8_t *bmat, int rows, int ldk, cudaStream_t stream);
 cudaError_t launch_keyswitch_mma(const uint64_t *lwe_in, const uint32_t *in_slot, uint8_t *digits_scratch, const uint8_t *bmat,
                                  const uint64_t *colsum, uint64_t *lwe_out, int batch, int in_dim, int n, int base_log, int level,
-                                 cudaStream_t stream);
+                                 int ms_log2_2n, cudaStream_t stream);
 size_t ks_mma_digits_bytes(int batch, int in_dim, int level);
 
 // pbs.cu
@@ -31,7 +31,7 @@ cudaError_t launch_bsk_convert(const uint64_t *bsk_std, void *bskf, const void *
 cudaError_t pbs_v3_configure();
 cudaError_t launch_pbs_classic_v3(const uint64_t *lwe_small, const uint32_t *lut_idx, const uint64_t *luts, const void *bskf3,
                                   const void *tbl, uint64_t *out, const uint32_t *out_slot, int batch, int n, int base_log,
-                                  int n_iters, cudaStream_t stream);
+                                  int n_iters, int small_is_u16, cudaStream_t stream);
 cudaError_t launch_bsk_convert_v3(const uint64_t *bsk_std, void *bskf3, const void *tbl, int n_polys, cudaStream_t stream);
 // pbs_multibit.cu
 cudaError_t pbs_multibit_configure();

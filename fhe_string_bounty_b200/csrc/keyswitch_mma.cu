@@ -79,7 +79,7 @@ template <int KSTEP>   // bytes of K per pipeline stage = 32 mask elements x lev
 __global__ void __launch_bounds__(THREADS, 2)
 ks_mma_kernel(const uint8_t *__restrict__ digits, const uint8_t *__restrict__ bmat, const uint64_t *__restrict__ colsum,
               const uint64_t *__restrict__ lwe_in, const uint32_t *__restrict__ in_slot, uint64_t *__restrict__ lwe_out,
-              int batch, int in_dim, int n, int K, int half_b) {
+              int batch, int in_dim, int n, int K, int half_b, int ms_shift) {
     constexpr int LD = KSTEP + PAD;
     extern __shared__ __align__(16) unsigned char smem[];
     unsigned char *As = smem;                              // [STAGES][BM][LD]
@@ -156,7 +156,12 @@ ks_mma_kernel(const uint8_t *__restrict__ digits, const uint8_t *__restrict__ bm
                 if (t == 0 && b < batch && j <= n) {
                     uint64_t o = (uint64_t)half_b * __ldg(colsum + j) - v;
                     if (j == n) o += __ldg(lwe_in + (size_t)(in_slot ? in_slot[b] : b) * (in_dim + 1) + in_dim);
-                    lwe_out[(size_t)b * (n + 1) + j] = o;
+                    if (ms_shift) {
+                        // fused fast_pbs_modulus_switch (fft_impl/common.rs:26-43): the blind rotation only needs round(x / 2^(64 - log2(2N)))
+                        reinterpret_cast<uint16_t *>(lwe_out)[(size_t)b * (n + 1) + j] = (uint16_t)(((o >> ms_shift) + 1) >> 1);
+                    } else {
+                        lwe_out[(size_t)b * (n + 1) + j] = o;
+                    }
                 }
             }
         }
@@ -165,13 +170,13 @@ ks_mma_kernel(const uint8_t *__restrict__ digits, const uint8_t *__restrict__ bm
 template <int KSTEP>
 static cudaError_t launch_mma(const uint8_t *digits, const uint8_t *bmat, const uint64_t *colsum, const uint64_t *lwe_in,
                               const uint32_t *in_slot, uint64_t *lwe_out, int batch, int in_dim, int n, int K, int ldk, int half_b,
-                              cudaStream_t stream) {
+                              int ms_shift, cudaStream_t stream) {
     const size_t smem = (size_t)STAGES * (BM + BN) * (KSTEP + PAD);
     // function attributes are per device: set on every launch (microseconds) rather than caching a process-wide flag
     cudaError_t e = cudaFuncSetAttribute(ks_mma_kernel<KSTEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid((batch + BM - 1) / BM, (ldk * 8) / BN);
-    ks_mma_kernel<KSTEP><<<grid, THREADS, smem, stream>>>(digits, bmat, colsum, lwe_in, in_slot, lwe_out, batch, in_dim, n, K, half_b);
+    ks_mma_kernel<KSTEP><<<grid, THREADS, smem, stream>>>(digits, bmat, colsum, lwe_in, in_slot, lwe_out, batch, in_dim, n, K, half_b, ms_shift);
     return cudaGetLastError();
 }
 
@@ -188,7 +193,7 @@ cudaError_t launch_ksk_planes(const uint64_t *packed, uint8_t *bmat, int rows, i
 
 cudaError_t launch_keyswitch_mma(const uint64_t *lwe_in, const uint32_t *in_slot, uint8_t *digits_scratch, const uint8_t *bmat,
                                  const uint64_t *colsum, uint64_t *lwe_out, int batch, int in_dim, int n, int base_log, int level,
-                                 cudaStream_t stream) {
+                                 int ms_log2_2n, cudaStream_t stream) {
     if (batch <= 0) return cudaSuccess;
     const int ldk = ks_padded_cols(n);
     const int K = in_dim * level;
@@ -199,12 +204,13 @@ cudaError_t launch_keyswitch_mma(const uint64_t *lwe_in, const uint32_t *in_slot
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     const int half_b = 1 << (base_log - 1);
+    const int ms_shift = ms_log2_2n ? 64 - ms_log2_2n - 1 : 0;   // 0: raw u64 output; else u16 round(x / 2^(64 - log2(2N)))
     switch (level) {
-        case 1: return tbkm::launch_mma<32>(digits_scratch, bmat, colsum, lwe_in, in_slot, lwe_out, batch, in_dim, n, K, ldk, half_b, stream);
-        case 2: return tbkm::launch_mma<64>(digits_scratch, bmat, colsum, lwe_in, in_slot, lwe_out, batch, in_dim, n, K, ldk, half_b, stream);
-        case 3: return tbkm::launch_mma<96>(digits_scratch, bmat, colsum, lwe_in, in_slot, lwe_out, batch, in_dim, n, K, ldk, half_b, stream);
-        case 4: return tbkm::launch_mma<128>(digits_scratch, bmat, colsum, lwe_in, in_slot, lwe_out, batch, in_dim, n, K, ldk, half_b, stream);
-        case 5: return tbkm::launch_mma<160>(digits_scratch, bmat, colsum, lwe_in, in_slot, lwe_out, batch, in_dim, n, K, ldk, half_b, stream);
+        case 1: return tbkm::launch_mma<32>(digits_scratch, bmat, colsum, lwe_in, in_slot, lwe_out, batch, in_dim, n, K, ldk, half_b, ms_shift, stream);
+        case 2: return tbkm::launch_mma<64>(digits_scratch, bmat, colsum, lwe_in, in_slot, lwe_out, batch, in_dim, n, K, ldk, half_b, ms_shift, stream);
+        case 3: return tbkm::launch_mma<96>(digits_scratch, bmat, colsum, lwe_in, in_slot, lwe_out, batch, in_dim, n, K, ldk, half_b, ms_shift, stream);
+        case 4: return tbkm::launch_mma<128>(digits_scratch, bmat, colsum, lwe_in, in_slot, lwe_out, batch, in_dim, n, K, ldk, half_b, ms_shift, stream);
+        case 5: return tbkm::launch_mma<160>(digits_scratch, bmat, colsum, lwe_in, in_slot, lwe_out, batch, in_dim, n, K, ldk, half_b, ms_shift, stream);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -90,7 +90,7 @@ template <int CTS>
 __global__ void __launch_bounds__(64 * CTS, 1)
 pbs_classic_kernel_v3(const uint64_t *__restrict__ lwe_small, const uint32_t *__restrict__ lut_idx, const uint64_t *__restrict__ luts,
                       const cplx *__restrict__ bskf3, const cplx *__restrict__ tbl_g, uint64_t *__restrict__ out,
-                      const uint32_t *__restrict__ out_slot, int batch, int n, int base_log, int n_iters) {
+                      const uint32_t *__restrict__ out_slot, int batch, int n, int base_log, int n_iters, int small_is_u16) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int WARPS = 2 * CTS, NTHREADS = 64 * CTS, TMEM_COLS = CTS > 2 ? 256 : 128;
     Smem<CTS> &sm = *reinterpret_cast<Smem<CTS> *>(smem_raw);
@@ -106,7 +106,9 @@ pbs_classic_kernel_v3(const uint64_t *__restrict__ lwe_small, const uint32_t *__
     double *tile = reinterpret_cast<double *>(sm.mbuf[W]);
     cplx *myc = reinterpret_cast<cplx *>(sm.mbuf[W]);
     const cplx *othc = reinterpret_cast<const cplx *>(sm.mbuf[W ^ 1]);
+    // input: n+1 u64 words, or (fused keyswitch + modulus switch) n+1 u16 values already switched to [0, 2N]
     const uint64_t *lwe = lwe_small + (size_t)ct * (n + 1);
+    const uint16_t *lwe16 = reinterpret_cast<const uint16_t *>(lwe_small) + (size_t)ct * (n + 1);
     const int total_pieces = n_iters * PIECES_PER_ITER;
 
     // ---- one-time setup: twiddle table, barriers, TMEM, first ring fill ---------------------------------------------
@@ -132,7 +134,7 @@ pbs_classic_kernel_v3(const uint64_t *__restrict__ lwe_small, const uint32_t *__
     // ---- acc <- LUT * X^(-b_hat): registers (own coefficients, as u64 bit patterns in re/im), TMEM, shared -------------------
     double re[32], im[32];
     {
-        const uint32_t b_hat = modulus_switch_2n(__ldg(lwe + n)) & (2 * kN - 1);
+        const uint32_t b_hat = (small_is_u16 ? (uint32_t)__ldg(lwe16 + n) : modulus_switch_2n(__ldg(lwe + n))) & (2 * kN - 1);
         const uint32_t a0 = (2 * kN - b_hat) & (2 * kN - 1);
         const uint64_t *lut = luts + ((size_t)(lut_idx ? lut_idx[ct] : 0) * 2 + w) * kN;
 #pragma unroll
@@ -170,7 +172,7 @@ pbs_classic_kernel_v3(const uint64_t *__restrict__ lwe_small, const uint32_t *__
     if (CTS == 4 && ctl >= 1 && n_iters > 0) asm volatile("bar.sync %0, 128;" ::"r"(8 + ctl) : "memory");
 
     for (int i = 0; i < n_iters; ++i) {
-        const uint32_t a = modulus_switch_2n(__ldg(lwe + i)) & (2 * kN - 1);   // a == 0 is NOT skipped: adds exactly zero
+        const uint32_t a = (small_is_u16 ? (uint32_t)__ldg(lwe16 + i) : modulus_switch_2n(__ldg(lwe + i))) & (2 * kN - 1);   // a == 0 is NOT skipped
 
         // ct1 = acc * X^a - acc, level-1 signed digit, folded (own coefficients come from the registers)
 #pragma unroll
@@ -376,7 +378,7 @@ cudaError_t pbs_v3_configure() {
 
 cudaError_t launch_pbs_classic_v3(const uint64_t *lwe_small, const uint32_t *lut_idx, const uint64_t *luts, const void *bskf3,
                                   const void *tbl, uint64_t *out, const uint32_t *out_slot, int batch, int n, int base_log,
-                                  int n_iters, cudaStream_t stream) {
+                                  int n_iters, int small_is_u16, cudaStream_t stream) {
     if (batch <= 0) return cudaSuccess;
     int sms = 148, dev = 0;
     cudaGetDevice(&dev);
@@ -384,13 +386,13 @@ cudaError_t launch_pbs_classic_v3(const uint64_t *lwe_small, const uint32_t *lut
     if (batch <= sms) {   // narrow level: one ciphertext per SM, latency-oriented instance
         tb3::pbs_classic_kernel_v3<1><<<batch, 64, sizeof(tb3::Smem<1>), stream>>>(
             lwe_small, lut_idx, luts, reinterpret_cast<const tb::cplx *>(bskf3), reinterpret_cast<const tb::cplx *>(tbl), out, out_slot,
-            batch, n, base_log, n_iters);
+            batch, n, base_log, n_iters, small_is_u16);
         return cudaGetLastError();
     }
     const int grid = (batch + 3) / 4;
     tb3::pbs_classic_kernel_v3<4><<<grid, 256, sizeof(tb3::Smem<4>), stream>>>(
         lwe_small, lut_idx, luts, reinterpret_cast<const tb::cplx *>(bskf3), reinterpret_cast<const tb::cplx *>(tbl), out, out_slot,
-        batch, n, base_log, n_iters);
+        batch, n, base_log, n_iters, small_is_u16);
     return cudaGetLastError();
 }
 
