@@ -311,7 +311,7 @@ def run_b200(args):
         if cpu_rate is not None and string_ops is not None:
             # the CPU path has no batching effect beyond its cores: a string op costs (its PBS count) / (CPU KS-PBS rate)
             string_ops["cpu_port_ops_per_s_derived"] = {
-                "eq_8char": cpu_rate / 36.0, "contains_256_16": cpu_rate / 16890.0, "find_256_16": cpu_rate / 19549.0,
+                "eq_8char": cpu_rate / 36.0, "contains_256_16": cpu_rate / 16890.0, "find_256_16": cpu_rate / 17916.0,
                 "to_lowercase_1024": cpu_rate / 4096.0, "note": "derived: CPU KS-PBS/s of cpu_baseline / PBS count of the reference-shaped tree"}
         if cpu_rate is not None:
             line["cpu_baseline"] = {"value": cpu_rate, "unit": "PBS/s", "cores": cpu_cores, "kind": "port",

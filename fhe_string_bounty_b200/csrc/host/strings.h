@@ -130,18 +130,46 @@ class StringServerKey {
         if (W == 0) return {pg.create_trivial(0), zero_idx};
         if (pat.len() == 0) return {pg.create_trivial(1), zero_idx};
         std::vector<Ct> m = window_matches(hay, pat);
-        // inclusive prefix OR (Hillis-Steele, the structure of radix_parallel/add.rs:572-603 with an OR LUT)
-        std::vector<Ct> pre = m;
-        for (size_t d = 1; d < W; d *= 2) {
-            std::vector<Ct> next = pre;
-            for (size_t i = d; i < W; ++i) next[i] = isk.boolean_bitor(pre[i], pre[i - d]);
-            pre.swap(next);
+        // one-hot first match in THREE levels instead of a log-depth prefix OR.  Windows are cut into blocks of 14:
+        //   level 1   any_k   = [sum of the block's match flags != 0]                (leveled sum of <= 14 booleans + 1 PBS per block)
+        //   level 2   before_k = [sum_{k' < k} any_k' != 0]                         (leveled prefix sums, chunks of <= 15, 1 PBS per block)
+        //   level 3   first_w = [ (#matches before w inside its block) + before_k + (1 - m_w) == 0 ]
+        //             -- the in-block prefix count is a leveled sum (<= 13), so the argument stays <= 15 and needs one PBS per window.
+        // found = OR of the blocks' any flags (same count-tree as contains).
+        constexpr size_t BLK = 14;
+        const size_t n_blk = (W + BLK - 1) / BLK;
+        std::vector<Ct> any(n_blk);
+        for (size_t k = 0; k < n_blk; ++k) {
+            Ct sum = m[k * BLK];
+            for (size_t i = k * BLK + 1; i < std::min(W, (k + 1) * BLK); ++i) sum = pg.unchecked_add(sum, m[i]);
+            any[k] = pg.pbs(sum, [](uint64_t x) { return uint64_t(x != 0); });
         }
-        // one-hot first match: first_w = m_w AND NOT pre_{w-1}
+        // before_k: "some earlier block matched".  Prefix sums of booleans overflow after 15 terms, so carry a cleaned flag
+        // forward every 15 blocks (one extra PBS per 15 blocks, still the same level for the first 15).
+        std::vector<Ct> before(n_blk);
+        before[0] = pg.create_trivial(0);
+        {
+            Ct carry = pg.create_trivial(0);   // cleaned "matched before this group of 15 blocks"
+            for (size_t g0 = 0; g0 < n_blk; g0 += 15) {
+                Ct run = carry;
+                for (size_t k = g0; k < std::min(n_blk, g0 + 15); ++k) {
+                    if (k > 0) before[k] = pg.pbs(run, [](uint64_t x) { return uint64_t(x != 0); });
+                    run = pg.unchecked_add(run, any[k]);
+                }
+                if (g0 + 15 < n_blk) carry = pg.pbs(run, [](uint64_t x) { return uint64_t(x != 0); });
+            }
+        }
         std::vector<Ct> first(W);
-        first[0] = m[0];
-        for (size_t w = 1; w < W; ++w)
-            first[w] = pg.pbs_bivariate(m[w], pre[w - 1], [](uint64_t x, uint64_t y) { return uint64_t((x & 1) && !(y & 1)); });
+        for (size_t w = 0; w < W; ++w) {
+            const size_t k = w / BLK;
+            // y = (matches before w in the block) + before_k + 1 - m_w   in [0, 15]
+            Ct y = pg.unchecked_scalar_add(pg.unchecked_scalar_mul(m[w], uint64_t(-1)), 1);
+            y.degree = 1;
+            for (size_t i = k * BLK; i < w; ++i) y = pg.unchecked_add(y, m[i]);
+            y = pg.unchecked_add(y, before[k]);
+            first[w] = pg.pbs(y, [](uint64_t x) { return uint64_t(x == 0); });
+        }
+        Ct found = isk.is_at_least_one_comparisons_block_true(any);
         // index digit b = sum_w ((w >> 2b) & 3) * first_w: select with a LUT (clean, noise NOMINAL), then sum in
         // chunks of 15 with a cleaning PBS, exactly the chunking of scalar_comparison.rs:155-170
         const size_t max_value = p.total_mod() - 1;
@@ -167,7 +195,7 @@ class StringServerKey {
             }
             index.push_back(terms[0]);
         }
-        return {pre[W - 1], index};
+        return {found, index};
     }
 
     // ---- case conversion: config 4 --------------------------------------------------------------------------------------------

@@ -215,3 +215,26 @@ def test_packed_equality_halves_the_pbs_and_agrees(orc, toy_keys):
     ins = np.concatenate([R.encrypt_string(ck, hay), R.encrypt_string(ck, pat)])
     out, _ = _run(orc, toy_keys, "string_find_packed", (len(hay), len(pat)), ins)
     assert _dec_bool(ck, out[0]) == 1 and R.decrypt_radix(ck, out[1:]) == hay.find(pat)
+
+
+def test_find_full_size_first_match_positions(orc, toy_keys):
+    """find at BASELINE config-3 size (256/16, 241 windows = 18 blocks of 14, i.e. past the 15-block carry group) on the toy
+    set: first match in the first block, in the middle, in the last block, repeated matches, and no match."""
+    from oracle import radix as R
+    p, ck, sk = toy_keys
+    rng = np.random.default_rng(99)
+    P = Program("string_find_packed", (256, 16), params=engine_params(p))
+    ir = P.ir()
+    assert len(P.level_widths) == 10
+    base = bytes(rng.integers(ord("a"), ord("z") + 1, size=256).tolist())
+    pat = b"QRSTUVWXYZ012345"
+    for positions in ([0], [5], [13, 14], [120], [209, 230], [215], [240], [3, 100, 240], []):
+        hay = bytearray(base)
+        for pos in positions:
+            hay[pos:pos + 16] = pat
+        hay = bytes(hay)
+        ins = np.concatenate([R.encrypt_string(ck, hay), R.encrypt_string(ck, pat)])
+        out = R.run_program(ir, sk, ins)
+        want = hay.find(pat)
+        assert ck.decrypt_message_and_carry(out[0]) == int(want >= 0), positions
+        assert R.decrypt_radix(ck, out[1:]) == max(want, 0), positions
