@@ -140,20 +140,23 @@ TB_HD void dit_stage_inv(double (&re)[32], double (&im)[32]) {
             const int i0 = b + j, i1 = b + j + H;
             const int e = j * (16 / H);
             const double ur = re[i0], ui = im[i0], xr = re[i1], xi = im[i1];
-            double vr, vi;
-            if (e == 0) {
-                vr = xr; vi = xi;
-            } else if (e == 8) {          // times +i
-                vr = -xi; vi = xr;
-            } else {                      // (xr + i xi) * (c + i s)
-                const double c = w32_cos(e), s = w32_sin(e);
-                vr = DFMA(xr, c, -DMUL(xi, s));
-                vi = DFMA(xi, c, DMUL(xr, s));
+            if (e == 0 || e == 8) {
+                double vr, vi;
+                if (e == 0) { vr = xr; vi = xi; } else { vr = -xi; vi = xr; }   // times 1 / times +i
+                re[i0] = DADD(ur, vr);
+                im[i0] = DADD(ui, vi);
+                re[i1] = DSUB(ur, vr);
+                im[i1] = DSUB(ui, vi);
+            } else {
+                // u +- x * (c + i s) with the cosine factored out (t = s / c): 6 FMAs instead of 2 mul + 2 fma + 4 add
+                const double c = w32_cos(e), t = w32_sin(e) / w32_cos(e);
+                const double p = DFMA(-t, xi, xr);      // (x * (1 + i t)).re
+                const double q = DFMA(t, xr, xi);       // (x * (1 + i t)).im
+                re[i0] = DFMA(c, p, ur);
+                im[i0] = DFMA(c, q, ui);
+                re[i1] = DFMA(-c, p, ur);
+                im[i1] = DFMA(-c, q, ui);
             }
-            re[i0] = DADD(ur, vr);
-            im[i0] = DADD(ui, vi);
-            re[i1] = DSUB(ur, vr);
-            im[i1] = DSUB(ui, vi);
         }
     }
 }
