@@ -65,3 +65,43 @@ def test_both_keyswitch_kernels_and_both_pbs_kernels_agree(orc, keys_2_2, monkey
         assert list(ck.decrypt_batch(o)) == want, k
     # same FFT arithmetic (fft_core.cuh) in both kernels => identical words, not just identical plaintexts
     assert np.array_equal(outs[("mma", "2")], outs[("mma", "3")])
+
+
+def test_kernels_do_not_write_outside_their_buffers(orc, keys_2_2):
+    """compute-sanitizer is closed on this pool, so bounds are checked with canaries: device input/output/small buffers are
+    embedded in larger sentinel-filled allocations; after KS, PBS and KS-PBS on ragged batch sizes the sentinels must be intact
+    and the inputs unchanged."""
+    import torch
+    import fhe_string_bounty_b200 as F
+    p, ck, sk = keys_2_2
+    eng = F.Engine(engine_params(p))
+    eng.upload_ksk(sk.ksk)
+    eng.upload_bsk_std(sk.bsk)
+    acc, _ = sk.generate_lookup_table(lambda x: x)
+    eng.upload_luts(np.stack([acc, acc]))
+    SENT = -0x0123456789ABCDEF
+    guard = 4096
+    s = torch.cuda.Stream()
+    for batch in (1, 5, 149, 601):
+        cts = ck.encrypt_batch(np.arange(batch) % 16)
+        n_in, n_out, n_small = batch * p.big_dim + batch, batch * (p.big_dim + 1), batch * (p.lwe_dim + 1)
+        buf_in = torch.full((guard + n_in + guard,), SENT, dtype=torch.int64, device="cuda")
+        buf_out = torch.full((guard + n_out + guard,), SENT, dtype=torch.int64, device="cuda")
+        buf_small = torch.full((guard + n_small + guard,), SENT, dtype=torch.int64, device="cuda")
+        idx = torch.zeros(guard + batch + guard, dtype=torch.int32, device="cuda")
+        buf_in[guard:guard + n_in] = torch.from_numpy(cts.view(np.int64).ravel()).cuda()
+        d_in, d_out, d_small = buf_in[guard:], buf_out[guard:], buf_small[guard:]
+        eng.ks_pbs_batch_device(d_in, idx[guard:], d_out, batch, s.cuda_stream)
+        eng.keyswitch_batch_device(d_in, d_small, batch, s.cuda_stream)
+        s.synchronize()
+        for name, b, n in (("in", buf_in, n_in), ("out", buf_out, n_out), ("small", buf_small, n_small)):
+            assert bool((b[:guard] == SENT).all()) and bool((b[guard + n:] == SENT).all()), (name, batch)
+        assert np.array_equal(buf_in[guard:guard + n_in].cpu().numpy().view(np.uint64).reshape(batch, -1), cts), "inputs are read-only"
+        got = buf_out[guard:guard + n_out].cpu().numpy().view(np.uint64).reshape(batch, -1)
+        assert list(ck.decrypt_batch(got)) == list(np.arange(batch) % 16)
+        ks = buf_small[guard:guard + n_small].cpu().numpy().view(np.uint64).reshape(batch, -1)
+        assert np.array_equal(ks[0], sk.keyswitch(cts[0]))
+        eng.pbs_batch_device(d_small, idx[guard:], d_out, batch, s.cuda_stream)
+        s.synchronize()
+        assert bool((buf_out[:guard] == SENT).all()) and bool((buf_out[guard + n_out:] == SENT).all())
+    eng.close()
