@@ -373,6 +373,8 @@ namespace tbk {
 cudaError_t pbs_v3_configure() {
     cudaError_t e = cudaFuncSetAttribute(tb3::pbs_classic_kernel_v3<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tb3::Smem<4>));
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(tb3::pbs_classic_kernel_v3<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tb3::Smem<2>));
+    if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(tb3::pbs_classic_kernel_v3<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tb3::Smem<1>));
 }
 
@@ -385,6 +387,12 @@ cudaError_t launch_pbs_classic_v3(const uint64_t *lwe_small, const uint32_t *lut
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (batch <= sms) {   // narrow level: one ciphertext per SM, latency-oriented instance
         tb3::pbs_classic_kernel_v3<1><<<batch, 64, sizeof(tb3::Smem<1>), stream>>>(
+            lwe_small, lut_idx, luts, reinterpret_cast<const tb::cplx *>(bskf3), reinterpret_cast<const tb::cplx *>(tbl), out, out_slot,
+            batch, n, base_log, n_iters, small_is_u16);
+        return cudaGetLastError();
+    }
+    if (batch <= 2 * sms) {   // up to two ciphertexts per SM: still one warp per scheduler
+        tb3::pbs_classic_kernel_v3<2><<<(batch + 1) / 2, 128, sizeof(tb3::Smem<2>), stream>>>(
             lwe_small, lut_idx, luts, reinterpret_cast<const tb::cplx *>(bskf3), reinterpret_cast<const tb::cplx *>(tbl), out, out_slot,
             batch, n, base_log, n_iters, small_is_u16);
         return cudaGetLastError();

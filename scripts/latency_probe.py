@@ -23,8 +23,3 @@ for op, args in [("shortint_apply_lut", [1] + list(range(16))), ("shortint_apply
         P.run(eng, ins)
     wall = (time.perf_counter() - t0) / 5 * 1e3
     print(f"{op:22s} {str(tuple(args)[:2]):12s} pbs {P.n_pbs:6d} levels {P.level_widths}  device {P.last_ms():8.2f} ms  wall {wall:8.2f} ms")
-for b in (1, 64, 592, 4096):
-    cts = rng.integers(0, 2**64, size=(b, p.big_len), dtype=np.uint64)
-    eng.ks_pbs_batch(cts, None)
-    eng.ks_pbs_batch(cts, None)
-    print("ks_pbs batch", b, "ks/pbs ms", eng.last_kernel_ms())
