@@ -36,7 +36,7 @@ int check_params(const tfhe_b200_params &p) {
 
 namespace tbc {
 
-bool fused_supported(const tfhe_b200_ctx *c) { return c->ks_kernel == 1 && c->pbs_kernel == 3 && c->p.grouping_factor == 0; }
+bool fused_supported(const tfhe_b200_ctx *c) { return c->ks_kernel == 1 && c->pbs_kernel >= 3 && c->p.grouping_factor == 0; }
 
 int do_keyswitch(tfhe_b200_ctx *c, const uint64_t *d_in, uint64_t *d_small, size_t batch, cudaStream_t s, const uint32_t *in_slot,
                  DevBuf *digits, bool fused) {
@@ -67,6 +67,12 @@ int do_pbs(tfhe_b200_ctx *c, const uint64_t *d_small, const uint32_t *d_idx, con
         const uint32_t groups = c->p.lwe_dim / 3;
         TB_CUDA(tbk::launch_pbs_multibit(d_small, d_idx, d_luts, c->bskf.p, c->tbl.p, c->roots.p, d_out, out_slot, (int)batch,
                                          (int)c->p.lwe_dim, (int)c->p.pbs_base_log, (int)(n_iters < groups ? n_iters : groups), s));
+        c->launches += 1;
+        return 0;
+    }
+    if (c->pbs_kernel == 4) {
+        TB_CUDA(tbk::launch_pbs_classic_v4(d_small, d_idx, d_luts, c->bskf.p, c->tbl16.p, d_out, out_slot, (int)batch, (int)c->p.lwe_dim,
+                                           (int)c->p.pbs_base_log, (int)n_iters, fused ? 1 : 0, s));
         c->launches += 1;
         return 0;
     }
@@ -113,9 +119,10 @@ int tfhe_b200_ctx_create(int cuda_device, const tfhe_b200_params *params, tfhe_b
     for (auto &L : c->lane) TB_CUDA(cudaStreamCreateWithFlags(&L.s, cudaStreamNonBlocking));
     if (const char *e = std::getenv("TFHE_B200_KS_KERNEL")) c->ks_kernel = (e[0] == 'i') ? 0 : 1;
     if (!tbk::ks_mma_supported((int)params->ks_level)) c->ks_kernel = 0;
-    if (const char *e = std::getenv("TFHE_B200_PBS_KERNEL")) c->pbs_kernel = (e[0] == '2') ? 2 : 3;
+    if (const char *e = std::getenv("TFHE_B200_PBS_KERNEL")) c->pbs_kernel = (e[0] == '2') ? 2 : (e[0] == '4') ? 4 : 3;
     TB_CUDA(tbk::pbs_configure());
     TB_CUDA(tbk::pbs_v3_configure());
+    TB_CUDA(tbk::pbs_v4_configure());
     TB_CUDA(tbk::pbs_multibit_configure());
     {   // roots[e] = exp(i*pi*e/2048): monomial spectra of the multi-bit combine
         std::vector<double> r(2 * 4096);
@@ -130,6 +137,10 @@ int tfhe_b200_ctx_create(int cuda_device, const tfhe_b200_params *params, tfhe_b
     tb_make_twiddle_table(tbl.data());
     TB_CUDA(c->tbl.reserve(tbl.size() * sizeof(double)));
     TB_CUDA(cudaMemcpyAsync(c->tbl.p, tbl.data(), tbl.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    std::vector<double> tbl16(2 * (tb::kM + 64));
+    tb16_make_tables(tbl16.data(), tbl16.data() + 2 * tb::kM);
+    TB_CUDA(c->tbl16.reserve(tbl16.size() * sizeof(double)));
+    TB_CUDA(cudaMemcpyAsync(c->tbl16.p, tbl16.data(), tbl16.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     TB_CUDA(cudaStreamSynchronize(c->stream));
     *out = c;
     return 0;
@@ -139,7 +150,7 @@ int tfhe_b200_ctx_destroy(tfhe_b200_ctx *c) {
     if (!c) return 0;
     DeviceGuard g(c->device);
     cudaStreamSynchronize(c->stream);
-    for (DevBuf *b : {&c->ksk_packed, &c->ksk_colsum, &c->ksk_planes, &c->ks_digits, &c->bskf, &c->tbl, &c->roots, &c->luts, &c->d_in, &c->d_small, &c->d_out, &c->d_idx})
+    for (DevBuf *b : {&c->ksk_packed, &c->ksk_colsum, &c->ksk_planes, &c->ks_digits, &c->bskf, &c->tbl, &c->tbl16, &c->roots, &c->luts, &c->d_in, &c->d_small, &c->d_out, &c->d_idx})
         b->release();
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     for (auto &L : c->lane) {
@@ -191,6 +202,8 @@ int tfhe_b200_upload_bsk_std(tfhe_b200_ctx *c, const uint64_t *bsk, size_t len) 
     TB_CUDA(cudaMemcpyAsync(raw.p, bsk, len * 8, cudaMemcpyHostToDevice, c->stream));
     if (c->p.grouping_factor == 3)
         TB_CUDA(tbk::launch_bsk_convert_multibit((const uint64_t *)raw.p, c->bskf.p, c->tbl.p, (int)n_polys, c->stream));
+    else if (c->pbs_kernel == 4)
+        TB_CUDA(tbk::launch_bsk_convert_v4((const uint64_t *)raw.p, c->bskf.p, c->tbl16.p, (int)n_polys, c->stream));
     else if (c->pbs_kernel == 3)
         TB_CUDA(tbk::launch_bsk_convert_v3((const uint64_t *)raw.p, c->bskf.p, c->tbl.p, (int)n_polys, c->stream));
     else

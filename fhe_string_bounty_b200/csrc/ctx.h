@@ -2,6 +2,7 @@
 #pragma once
 #include "../../include/tfhe_b200.h"
 #include "fft_core.cuh"
+#include "fft16_core.cuh"
 #include "kernels.h"
 
 #include <cstdio>
@@ -51,11 +52,11 @@ struct tfhe_b200_ctx {
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     bool timed = false;
     // keys
-    tbc::DevBuf ksk_packed, ksk_colsum, ksk_planes, ks_digits, bskf, tbl, roots, luts;
+    tbc::DevBuf ksk_packed, ksk_colsum, ksk_planes, ks_digits, bskf, tbl, tbl16, roots, luts;
     int ks_kernel = 1;    // 1: tensor-core GEMM (keyswitch_mma.cu), 0: IMAD GEMM (keyswitch.cu); env TFHE_B200_KS_KERNEL=imad
     uint32_t n_luts = 0;
     bool have_ksk = false, have_bsk = false;
-    int pbs_kernel = 3;   // 3: TMEM + TMA ring (pbs_v3.cu), 2: one CTA per ciphertext (pbs.cu); env TFHE_B200_PBS_KERNEL
+    int pbs_kernel = 3;   // 3: TMEM + TMA ring (pbs_v3.cu), 4: same with 16 points per thread (pbs_v4.cu), 2: one CTA per ciphertext (pbs.cu); env TFHE_B200_PBS_KERNEL
     // staging for the host-pointer entry points
     tbc::DevBuf d_in, d_small, d_out, d_idx;
     // two copy/compute lanes for the host-buffer KS-PBS entry point: H2D of chunk k+1 and D2H of chunk k-1 overlap the

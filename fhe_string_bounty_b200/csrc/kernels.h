@@ -33,6 +33,12 @@ cudaError_t launch_pbs_classic_v3(const uint64_t *lwe_small, const uint32_t *lut
                                   const void *tbl, uint64_t *out, const uint32_t *out_slot, int batch, int n, int base_log,
                                   int n_iters, int small_is_u16, cudaStream_t stream);
 cudaError_t launch_bsk_convert_v3(const uint64_t *bsk_std, void *bskf3, const void *tbl, int n_polys, cudaStream_t stream);
+// pbs_v4.cu (tbl16 = the two twiddle tables of fft16_core.cuh, 1024 + 64 complex values)
+cudaError_t pbs_v4_configure();
+cudaError_t launch_pbs_classic_v4(const uint64_t *lwe_small, const uint32_t *lut_idx, const uint64_t *luts, const void *bskf4,
+                                  const void *tbl16, uint64_t *out, const uint32_t *out_slot, int batch, int n, int base_log,
+                                  int n_iters, int small_is_u16, cudaStream_t stream);
+cudaError_t launch_bsk_convert_v4(const uint64_t *bsk_std, void *bskf4, const void *tbl16, int n_polys, cudaStream_t stream);
 // pbs_multibit.cu
 cudaError_t pbs_multibit_configure();
 cudaError_t launch_pbs_multibit(const uint64_t *lwe_small, const uint32_t *lut_idx, const uint64_t *luts, const void *bskm,

@@ -1,0 +1,448 @@
+// pbs_v4.cu -- blind rotation, fourth generation: the v3 data path (Fourier key streamed once per SM through a TMA-fed
+// shared-memory ring, accumulator master copy in Tensor Memory) with HALF the work per thread: two warps per polynomial,
+// 16 FFT points per thread (fft16_core.cuh), so a 4-ciphertext CTA has 16 warps -- 4 per scheduler instead of 2.
+//
+// Why: ncu on v3 (profiles/r01_pbs_v3_final_b8192_summary.txt) shows FP64 pipe 45 %, LSU 52 %, issue slots 46 %: nothing is
+// saturated, the two 255-register warps per scheduler simply cannot cover each other's dependency stalls.  With 16 points
+// per thread the kernel fits 128 registers, and the schedulers get twice the warps to pick from, at the price of one more shared-memory exchange per FFT (16 x 16 x 4 instead of 32 x 32).
+//
+// Same arithmetic definition as pbs_v3.cu (bootstrap.rs:242-364, ggsw.rs:477-598, fft/mod.rs:197-326): the FFT evaluates
+// the same 1024 frequencies, only the butterfly order (hence FP64 rounding) differs.
+//
+// Shared memory per 4-ciphertext CTA: 8 x 17 KiB polynomial tiles (rotated-gather source, then exchange tile, then spectrum
+// exchange) + 9 x 8 KiB ring + 17 KiB twiddle tables = 225 KiB.  TMEM: 64 columns per ciphertext.
+// Named barriers: 1..8 one per polynomial (64 threads), 9..12 one per ciphertext (128), 13..15 start-up stagger.
+#include "kernels.h"
+#include "fft16_core.cuh"
+#include "ring_helpers.cuh"
+
+namespace tb4 {
+using namespace tb;
+using namespace tb16;
+using namespace tbr;
+
+constexpr int PIECE_CPLX = 512;        // [out poly 2][sel 2][q 2][thread 64]
+constexpr int PIECE_BYTES = PIECE_CPLX * 16;
+constexpr int PIECES_PER_ITER = 8;
+constexpr int NSLOT = 9;
+
+template <int CTS>
+struct Smem {
+    cplx tile[2 * CTS][kTileCplx];         // 17 KiB per polynomial
+    cplx ring[NSLOT][PIECE_CPLX];          // 72 KiB
+    cplx t1[kM];                           // 16 KiB
+    cplx t2[64];
+    unsigned long long full_bar[NSLOT];
+    unsigned int consumed[NSLOT];
+    uint32_t tmem_base;
+};
+static_assert(sizeof(Smem<4>) <= 227 * 1024, "shared memory budget");
+
+__device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+struct PolySync {
+    int id;
+    __device__ __forceinline__ void operator()() const { bar_sync(id, 64); }
+};
+struct BlockSync {
+    __device__ __forceinline__ void operator()() const { __syncthreads(); }
+};
+
+template <int TMEM_COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t *smem_dst) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int TMEM_COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "n"(TMEM_COLS) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+        "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
+
+// ---- the 64-thread FFT: registers <-> tile exchanges (fft16_core.cuh), `sync` = barrier over the polynomial's 64 threads -----------
+// forward: on entry the tile may still be read by the other threads (the first sync covers that); on exit thread T2 holds
+// register pv = frequency freq_of16(T2, pv) and nobody but T2 itself touches its exchange-B reader slots.
+template <class LoadT1, class LoadT2, class Sync>
+__device__ __forceinline__ void fft16_fwd(double (&re)[16], double (&im)[16], cplx *tile, LoadT1 t1, LoadT2 t2, int T, Sync sync) {
+    pretwist16_fwd(re, im);
+    radix16_dif(re, im);
+    twiddle16_fwd(re, im, [&](int p) { return t1(p * 64 + T); });
+    sync();
+    {
+        cplx *wp = tile + xa_wbase(T);
+#pragma unroll
+        for (int p = 0; p < 16; ++p) { cplx v; v.x = re[p]; v.y = im[p]; wp[xa_woff(p)] = v; }
+    }
+    sync();
+    {
+        const cplx *rp = tile + xa_rbase(T);
+#pragma unroll
+        for (int g = 0; g < 16; ++g) { const cplx v = rp[xa_roff(g)]; re[g] = v.x; im[g] = v.y; }
+    }
+    radix4x4_dif(re, im);
+    {
+        const cplx tw[3] = {t2(T & 15), t2(16 + (T & 15)), t2(32 + (T & 15))};
+        twiddle4_fwd(re, im, tw);
+    }
+    __syncwarp();     // from here on everything stays inside this half-warp's region of the tile
+    {
+        cplx *wp = tile + xb_wbase(T);
+#pragma unroll
+        for (int g = 0; g < 16; ++g) { cplx v; v.x = re[g]; v.y = im[g]; wp[xb_woff(g)] = v; }
+    }
+    __syncwarp();
+    {
+        const cplx *rp = tile + xb_rbase(T);
+#pragma unroll
+        for (int u = 0; u < 16; ++u) { const cplx v = rp[xb_roff(u)]; re[u] = v.x; im[u] = v.y; }
+    }
+    radix16_dif(re, im);
+}
+
+// inverse (scaled by 1024): on entry nobody else may be reading this thread's exchange-B reader slots; on exit the tile may
+// still be read by the other threads.
+template <class LoadT1, class LoadT2, class Sync>
+__device__ __forceinline__ void fft16_inv(double (&re)[16], double (&im)[16], cplx *tile, LoadT1 t1, LoadT2 t2, int T, Sync sync) {
+    radix16_dit_inv(re, im);
+    {
+        cplx *wp = tile + xb_rbase(T);
+#pragma unroll
+        for (int u = 0; u < 16; ++u) { cplx v; v.x = re[u]; v.y = im[u]; wp[xb_roff(u)] = v; }
+    }
+    __syncwarp();
+    {
+        const cplx *rp = tile + xb_wbase(T);
+#pragma unroll
+        for (int g = 0; g < 16; ++g) { const cplx v = rp[xb_woff(g)]; re[g] = v.x; im[g] = v.y; }
+    }
+    {
+        const cplx tw[3] = {t2(T & 15), t2(16 + (T & 15)), t2(32 + (T & 15))};
+        twiddle4_inv(re, im, tw);
+    }
+    radix4x4_dit_inv(re, im);
+    __syncwarp();
+    {
+        cplx *wp = tile + xa_rbase(T);
+#pragma unroll
+        for (int g = 0; g < 16; ++g) { cplx v; v.x = re[g]; v.y = im[g]; wp[xa_roff(g)] = v; }
+    }
+    sync();
+    {
+        const cplx *rp = tile + xa_wbase(T);
+#pragma unroll
+        for (int p = 0; p < 16; ++p) { const cplx v = rp[xa_woff(p)]; re[p] = v.x; im[p] = v.y; }
+    }
+    twiddle16_inv(re, im, [&](int p) { return t1(p * 64 + T); });
+    radix16_dit_inv(re, im);
+    posttwist16_inv(re, im);
+}
+
+// Fourier key, v4 layout: [ggsw i][chunk 8][out poly c][sel: 0 = row c, 1 = row 1-c][q 2][thread 64]; register g = 2*chunk + q
+__device__ __forceinline__ size_t bskf4_index(int i, int chunk, int c, int sel, int q) {
+    return ((((size_t)(i * PIECES_PER_ITER + chunk) * 2 + c) * 2 + sel) * 2 + q) * 64;
+}
+
+template <int CTS>
+__global__ void __launch_bounds__(128 * CTS, 1)
+pbs_classic_kernel_v4(const uint64_t *__restrict__ lwe_small, const uint32_t *__restrict__ lut_idx, const uint64_t *__restrict__ luts,
+                      const cplx *__restrict__ bskf4, const cplx *__restrict__ tbl16, uint64_t *__restrict__ out,
+                      const uint32_t *__restrict__ out_slot, int batch, int n, int base_log, int n_iters, int small_is_u16) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int WARPS = 4 * CTS, NTHREADS = 128 * CTS, TMEM_COLS = 64 * CTS;
+    Smem<CTS> &sm = *reinterpret_cast<Smem<CTS> *>(smem_raw);
+    const int W = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp -> (ciphertext, polynomial, half): the four warps of a ciphertext sit on the four schedulers (warp id % 4), so every
+    // scheduler hosts one warp of each ciphertext; the ciphertexts are started a quarter iteration apart (stagger below)
+    const int ctl = W >> 2, w = (W >> 1) & 1, T = ((W & 1) << 5) | lane, P = W >> 1;
+    const int ct_raw = blockIdx.x * CTS + ctl;
+    const bool live = ct_raw < batch;
+    const int ct = live ? ct_raw : batch - 1;        // ragged tail: recompute the last ciphertext, skip the store
+    cplx *tile = sm.tile[P];
+    const cplx *otile = sm.tile[P ^ 1];
+    uint64_t *pb = reinterpret_cast<uint64_t *>(tile);   // the polynomial (2048 words) for the rotated gather
+    const PolySync poly_sync{1 + P};
+    const int ct_bar = 9 + ctl;
+    const uint64_t *lwe = lwe_small + (size_t)ct * (n + 1);
+    const uint16_t *lwe16 = reinterpret_cast<const uint16_t *>(lwe_small) + (size_t)ct * (n + 1);
+    const int total_pieces = n_iters * PIECES_PER_ITER;
+
+    // ---- one-time setup: twiddle tables, barriers, TMEM, first ring fill ---------------------------------------------------
+    for (int i = threadIdx.x; i < kM; i += NTHREADS) sm.t1[i] = tbl16[i];
+    if (threadIdx.x < 64) sm.t2[threadIdx.x] = tbl16[kM + threadIdx.x];
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSLOT; ++s) { mbar_init(&sm.full_bar[s], 1); sm.consumed[s] = 0; }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_proxy_async();
+    }
+    if (W == 0) tmem_alloc<TMEM_COLS>(&sm.tmem_base);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_mine = sm.tmem_base + ((uint32_t)((W & 3) * 32) << 16) + (uint32_t)(ctl * 64);   // lane quarter = warp id % 4
+    if (threadIdx.x == 0) {
+        const int first = total_pieces < NSLOT ? total_pieces : NSLOT;
+        for (int g = 0; g < first; ++g) {
+            mbar_expect_tx(&sm.full_bar[g], PIECE_BYTES);
+            tma_load_1d(sm.ring[g], bskf4 + (size_t)g * PIECE_CPLX, PIECE_BYTES, &sm.full_bar[g]);
+        }
+    }
+
+    // ---- acc <- LUT * X^(-b_hat): registers (own coefficients as u64 bit patterns in re/im), TMEM, shared ------------------------
+    double re[16], im[16];
+    {
+        const uint32_t b_hat = (small_is_u16 ? (uint32_t)__ldg(lwe16 + n) : modulus_switch_2n(__ldg(lwe + n))) & (2 * kN - 1);
+        const uint32_t a0 = (2 * kN - b_hat) & (2 * kN - 1);
+        const uint64_t *lut = luts + ((size_t)(lut_idx ? lut_idx[ct] : 0) * 2 + w) * kN;
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+            const int j = T + 64 * m;
+            int s0, s1; bool n0, n1;
+            rot_src(j, a0, s0, n0);
+            rot_src(j + kM, a0, s1, n1);
+            uint64_t v0 = __ldg(lut + s0), v1 = __ldg(lut + s1);
+            v0 = n0 ? (uint64_t)0 - v0 : v0;
+            v1 = n1 ? (uint64_t)0 - v1 : v1;
+            pb[j] = v0; pb[j + kM] = v1;
+            re[m] = __longlong_as_double((long long)v0);
+            im[m] = __longlong_as_double((long long)v1);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            uint32_t v[16];
+#pragma unroll
+            for (int mm = 0; mm < 4; ++mm) {
+                const unsigned long long a = (unsigned long long)__double_as_longlong(re[4 * k + mm]);
+                const unsigned long long b = (unsigned long long)__double_as_longlong(im[4 * k + mm]);
+                v[4 * mm] = (uint32_t)a; v[4 * mm + 1] = (uint32_t)(a >> 32);
+                v[4 * mm + 2] = (uint32_t)b; v[4 * mm + 3] = (uint32_t)(b >> 32);
+            }
+            tmem_st16(tmem_mine + 16 * k, v);
+        }
+        tmem_wait_st();
+    }
+
+    // stagger: ciphertext k starts when ciphertext 0 reaches the k-th quarter of its first iteration
+    if (CTS == 4 && ctl >= 1 && n_iters > 0) bar_sync(12 + ctl, 256);
+
+    int slot = 0;            // ring position of this iteration's first piece
+    uint32_t phase = 0;
+    auto ld_t1 = [&](int idx) { return sm.t1[idx]; };
+    auto ld_t2 = [&](int idx) { return sm.t2[idx]; };
+
+    for (int i = 0; i < n_iters; ++i) {
+        const uint32_t a = (small_is_u16 ? (uint32_t)__ldg(lwe16 + i) : modulus_switch_2n(__ldg(lwe + i))) & (2 * kN - 1);   // a == 0 is NOT skipped
+        poly_sync();    // the accumulator polynomial is complete in shared memory
+
+        // ct1 = acc * X^a - acc, level-1 signed digit, folded (own coefficients come from the registers)
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+            const int j = T + 64 * m;
+            const uint32_t s0 = ((uint32_t)j - a) & (2 * kN - 1);
+            const uint32_t s1 = (s0 + kM) & (2 * kN - 1);
+            uint64_t r0 = pb[s0 & (kN - 1)], r1 = pb[s1 & (kN - 1)];
+            r0 = (s0 >= (uint32_t)kN) ? (uint64_t)0 - r0 : r0;
+            r1 = (s1 >= (uint32_t)kN) ? (uint64_t)0 - r1 : r1;
+            const uint64_t o0 = (uint64_t)__double_as_longlong(re[m]), o1 = (uint64_t)__double_as_longlong(im[m]);
+            re[m] = (double)signed_digit_l1(r0 - o0, base_log);
+            im[m] = (double)signed_digit_l1(r1 - o1, base_log);
+        }
+        if (CTS == 4 && i == 0 && ctl == 0) bar_arrive(13, 256);
+
+        fft16_fwd(re, im, tile, ld_t1, ld_t2, T, poly_sync);
+        if (CTS == 4 && i == 0 && ctl == 0) bar_arrive(14, 256);
+
+        // spectrum exchange between the two polynomials of the ciphertext: park my 16 values in my own exchange-B reader slots
+        {
+            cplx *wp = tile + xb_rbase(T);
+#pragma unroll
+            for (int g = 0; g < 16; ++g) { cplx v; v.x = re[g]; v.y = im[g]; wp[xb_roff(g)] = v; }
+        }
+        bar_sync(ct_bar, 128);
+
+        // out_fft[w] = F_w * G[w][w] + F_{1-w} * G[1-w][w], GGSW pieces from the ring (probe all barriers first, release each
+        // slot right after its chunk; the last of the WARPS warps re-arms it NSLOT pieces ahead)
+        {
+            uint32_t ready = 0;
+            {
+                int s = slot; uint32_t ph = phase;
+#pragma unroll
+                for (int c = 0; c < PIECES_PER_ITER; ++c) {
+                    ready |= (mbar_try_wait(&sm.full_bar[s], ph) ? 1u : 0u) << c;
+                    if (++s == NSLOT) { s = 0; ph ^= 1u; }
+                }
+            }
+            const cplx *fop = otile + xb_rbase(T);
+#pragma unroll
+            for (int c = 0; c < PIECES_PER_ITER; ++c) {
+                if (!((ready >> c) & 1u)) mbar_wait(&sm.full_bar[slot], phase);
+                const cplx *pc = sm.ring[slot] + (w * 2) * 2 * 64 + T;
+                cplx ga[2], gb[2], fo[2];
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    ga[q] = pc[q * 64];
+                    gb[q] = pc[(2 + q) * 64];
+                    fo[q] = fop[xb_roff(2 * c + q)];
+                }
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int g = 2 * c + q;
+                    const double fr = re[g], fi = im[g];
+                    double orr = DMUL(fr, ga[q].x);
+                    orr = DFMA(-fi, ga[q].y, orr);
+                    orr = DFMA(fo[q].x, gb[q].x, orr);
+                    orr = DFMA(-fo[q].y, gb[q].y, orr);
+                    double oi = DMUL(fr, ga[q].y);
+                    oi = DFMA(fi, ga[q].x, oi);
+                    oi = DFMA(fo[q].x, gb[q].y, oi);
+                    oi = DFMA(fo[q].y, gb[q].x, oi);
+                    re[g] = orr; im[g] = oi;
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    const unsigned int old = atomicAdd(&sm.consumed[slot], 1u);
+                    if (old == WARPS - 1) {
+                        sm.consumed[slot] = 0;
+                        const int g2 = i * PIECES_PER_ITER + c + NSLOT;
+                        if (g2 < total_pieces) {
+                            __threadfence_block();
+                            fence_proxy_async();
+                            mbar_expect_tx(&sm.full_bar[slot], PIECE_BYTES);
+                            tma_load_1d(sm.ring[slot], bskf4 + (size_t)g2 * PIECE_CPLX, PIECE_BYTES, &sm.full_bar[slot]);
+                        }
+                    }
+                }
+                if (++slot == NSLOT) { slot = 0; phase ^= 1u; }
+            }
+        }
+        bar_sync(ct_bar, 128);   // the partner polynomial has read my spectrum: the tile is mine again
+        if (CTS == 4 && i == 0 && ctl == 0) bar_arrive(15, 256);
+
+        fft16_inv(re, im, tile, ld_t1, ld_t2, T, poly_sync);
+        poly_sync();    // everyone has read the last exchange: the tile becomes the accumulator polynomial again
+
+        // acc += from_torus(.): master copy in TMEM, new values to registers (next gather's "own") and shared (next rotation)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            uint32_t v[16];
+            tmem_ld16(tmem_mine + 16 * k, v);
+            tmem_wait_ld();
+#pragma unroll
+            for (int mm = 0; mm < 4; ++mm) {
+                const int m = 4 * k + mm, j = T + 64 * m;
+                uint64_t o0 = ((uint64_t)v[4 * mm + 1] << 32) | v[4 * mm];
+                uint64_t o1 = ((uint64_t)v[4 * mm + 3] << 32) | v[4 * mm + 2];
+                o0 += from_torus_f64(re[m]);
+                o1 += from_torus_f64(im[m]);
+                v[4 * mm] = (uint32_t)o0; v[4 * mm + 1] = (uint32_t)(o0 >> 32);
+                v[4 * mm + 2] = (uint32_t)o1; v[4 * mm + 3] = (uint32_t)(o1 >> 32);
+                pb[j] = o0; pb[j + kM] = o1;
+                re[m] = __longlong_as_double((long long)o0);
+                im[m] = __longlong_as_double((long long)o1);
+            }
+            tmem_st16(tmem_mine + 16 * k, v);
+        }
+        tmem_wait_st();
+    }
+
+    // sample extraction (coefficient 0) straight from the registers: out[0] = A[0], out[N-j] = -A[j]; body = B[0]
+    if (live) {
+        uint64_t *o = out + (size_t)(out_slot ? out_slot[ct] : ct) * (kN + 1);
+        if (w == 0) {
+#pragma unroll
+            for (int m = 0; m < 16; ++m) {
+                const int j = T + 64 * m;
+                const uint64_t v0 = (uint64_t)__double_as_longlong(re[m]), v1 = (uint64_t)__double_as_longlong(im[m]);
+                if (j == 0) o[0] = v0; else o[kN - j] = (uint64_t)0 - v0;
+                o[kN - (j + kM)] = (uint64_t)0 - v1;
+            }
+        } else if (T == 0) {
+            o[kN] = (uint64_t)__double_as_longlong(re[0]);
+        }
+    }
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (W == 0) tmem_dealloc<TMEM_COLS>(sm.tmem_base);
+}
+
+// std -> Fourier key in the v4 ring layout (64 threads per polynomial; same forward transform as the kernel above)
+__global__ void __launch_bounds__(64)
+bsk_convert_kernel_v4(const uint64_t *__restrict__ bsk_std, cplx *__restrict__ bskf4, const cplx *__restrict__ tbl16, int n_polys) {
+    __shared__ cplx tile[kTileCplx];
+    const int qd = blockIdx.x, T = threadIdx.x;
+    if (qd >= n_polys) return;
+    const int i = qd >> 2, r = (qd >> 1) & 1, c = qd & 1;   // std layout [i][level 1][row r][col c][N]
+    const uint64_t *src = bsk_std + (size_t)qd * kN;
+    const double scale = 5.293955920339377e-23;              // 2^-74
+    double re[16], im[16];
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+        const int j = T + 64 * m;
+        re[m] = DMUL((double)(long long)src[j], scale);
+        im[m] = DMUL((double)(long long)src[j + kM], scale);
+    }
+    fft16_fwd(re, im, tile, [&](int idx) { return __ldg(tbl16 + idx); }, [&](int idx) { return __ldg(tbl16 + kM + idx); }, T, BlockSync{});
+    const int sel = (r == c) ? 0 : 1;
+#pragma unroll
+    for (int g = 0; g < 16; ++g) {
+        cplx v; v.x = re[g]; v.y = im[g];
+        bskf4[bskf4_index(i, g >> 1, c, sel, g & 1) + T] = v;
+    }
+}
+
+}  // namespace tb4
+
+namespace tbk {
+
+cudaError_t pbs_v4_configure() {
+    cudaError_t e = cudaFuncSetAttribute(tb4::pbs_classic_kernel_v4<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tb4::Smem<4>));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(tb4::pbs_classic_kernel_v4<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tb4::Smem<2>));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(tb4::pbs_classic_kernel_v4<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tb4::Smem<1>));
+}
+
+cudaError_t launch_pbs_classic_v4(const uint64_t *lwe_small, const uint32_t *lut_idx, const uint64_t *luts, const void *bskf4,
+                                  const void *tbl16, uint64_t *out, const uint32_t *out_slot, int batch, int n, int base_log,
+                                  int n_iters, int small_is_u16, cudaStream_t stream) {
+    if (batch <= 0) return cudaSuccess;
+    int sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const tb::cplx *bk = reinterpret_cast<const tb::cplx *>(bskf4), *tb = reinterpret_cast<const tb::cplx *>(tbl16);
+    if (batch <= sms)
+        tb4::pbs_classic_kernel_v4<1><<<batch, 128, sizeof(tb4::Smem<1>), stream>>>(lwe_small, lut_idx, luts, bk, tb, out, out_slot, batch, n,
+                                                                                  base_log, n_iters, small_is_u16);
+    else if (batch <= 2 * sms)
+        tb4::pbs_classic_kernel_v4<2><<<(batch + 1) / 2, 256, sizeof(tb4::Smem<2>), stream>>>(lwe_small, lut_idx, luts, bk, tb, out, out_slot,
+                                                                                            batch, n, base_log, n_iters, small_is_u16);
+    else
+        tb4::pbs_classic_kernel_v4<4><<<(batch + 3) / 4, 512, sizeof(tb4::Smem<4>), stream>>>(lwe_small, lut_idx, luts, bk, tb, out, out_slot,
+                                                                                            batch, n, base_log, n_iters, small_is_u16);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_bsk_convert_v4(const uint64_t *bsk_std, void *bskf4, const void *tbl16, int n_polys, cudaStream_t stream) {
+    tb4::bsk_convert_kernel_v4<<<n_polys, 64, 0, stream>>>(bsk_std, reinterpret_cast<tb::cplx *>(bskf4),
+                                                          reinterpret_cast<const tb::cplx *>(tbl16), n_polys);
+    return cudaGetLastError();
+}
+
+}  // namespace tbk

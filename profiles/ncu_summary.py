@@ -43,6 +43,8 @@ def main():
         n = int(sys.argv[sys.argv.index("--source") + 1])
         out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
         rows = list(csv.reader(io.StringIO(out)))
+        hi = next(i for i, r in enumerate(rows) if r and r[0].strip() == "Address")   # row 0 is the kernel name
+        rows = rows[hi:]
         h = rows[0]
         print("source columns:", [c for c in h][:12])
         def col(name):
@@ -62,6 +64,19 @@ def main():
         tot = sum(float(r[si]) for r in body) or 1
         for r in body[:n]:
             print(f"  {float(r[si]) / tot * 100:5.1f}%  {r[srci][:150] if srci is not None else r[:3]}")
+        # shared-memory wavefronts per opcode (where the LSU pipe's time goes)
+        wi, ei = col("L1 Wavefronts Shared"), col("Instructions Executed")
+        if wi is not None and srci is not None:
+            by = {}
+            for r in rows[1:]:
+                if len(r) > wi and r[wi].isdigit() and int(r[wi]) > 0:
+                    op = r[srci].split()[0] if not r[srci].strip().startswith("@") else r[srci].split()[1]
+                    w, e = by.get(op, (0, 0))
+                    by[op] = (w + int(r[wi]), e + int(r[ei]))
+            tw = sum(w for w, _ in by.values()) or 1
+            print("shared-memory wavefronts by opcode:")
+            for op, (w, e) in sorted(by.items(), key=lambda kv: -kv[1][0]):
+                print(f"  {op:<16s} {w:>14d} wavefronts ({w / tw * 100:5.1f}%)  {e:>12d} warp instrs  {w / max(e, 1):.2f}/instr")
 
 
 if __name__ == "__main__":
