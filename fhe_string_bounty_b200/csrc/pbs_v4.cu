@@ -10,7 +10,8 @@
 // the same 1024 frequencies, only the butterfly order (hence FP64 rounding) differs.
 //
 // Shared memory per 4-ciphertext CTA: 8 x 17 KiB polynomial tiles (rotated-gather source, then exchange tile, then spectrum
-// exchange) + 9 x 8 KiB ring + 17 KiB twiddle tables = 225 KiB.  TMEM: 64 columns per ciphertext.
+// exchange) + 10 x 8 KiB ring = 216 KiB.  TMEM: 64 columns per ciphertext (accumulator master copy) + 80 columns of
+// per-thread FFT twiddles (ncu: the kernel is bound by the LSU pipe, tcgen05.ld is not on it).
 // Named barriers: 1..8 one per polynomial (64 threads), 9..12 one per ciphertext (128), 13..15 start-up stagger.
 #include "kernels.h"
 #include "fft16_core.cuh"
@@ -24,14 +25,12 @@ using namespace tbr;
 constexpr int PIECE_CPLX = 512;        // [out poly 2][sel 2][q 2][thread 64]
 constexpr int PIECE_BYTES = PIECE_CPLX * 16;
 constexpr int PIECES_PER_ITER = 8;
-constexpr int NSLOT = 9;
+constexpr int NSLOT = 10;
 
 template <int CTS>
 struct Smem {
     cplx tile[2 * CTS][kTileCplx];         // 17 KiB per polynomial
-    cplx ring[NSLOT][PIECE_CPLX];          // 72 KiB
-    cplx t1[kM];                           // 16 KiB
-    cplx t2[64];
+    cplx ring[NSLOT][PIECE_CPLX];          // 80 KiB
     unsigned long long full_bar[NSLOT];
     unsigned int consumed[NSLOT];
     uint32_t tmem_base;
@@ -76,14 +75,69 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
         : "memory");
 }
 
+// ---- twiddles from Tensor Memory: each thread keeps its own 16 inter-pass twiddles T1[p][T] (64 columns) and its three pass-2
+// twiddles (12 columns) in its TMEM lane, so the blind-rotation loop reads them with tcgen05.ld instead of through the LSU pipe.
+__device__ __forceinline__ cplx cplx_from_words(const uint32_t (&v)[16], int q) {
+    cplx w;
+    w.x = __hiloint2double((int)v[4 * q + 1], (int)v[4 * q]);
+    w.y = __hiloint2double((int)v[4 * q + 3], (int)v[4 * q + 2]);
+    return w;
+}
+struct TmemTwiddles {
+    uint32_t col;     // TMEM address of this thread's first twiddle column
+    template <bool INV>
+    __device__ __forceinline__ void apply16(double (&re)[16], double (&im)[16]) const {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            uint32_t v[16];
+            tmem_ld16(col + 16 * k, v);
+            tmem_wait_ld();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const cplx w = cplx_from_words(v, q);
+                const int p = 4 * k + q;
+                const double a = re[p], b = im[p];
+                if (!INV) {
+                    re[p] = DFMA(a, w.x, -DMUL(b, w.y));
+                    im[p] = DFMA(b, w.x, DMUL(a, w.y));
+                } else {
+                    re[p] = DFMA(a, w.x, DMUL(b, w.y));
+                    im[p] = DFMA(b, w.x, -DMUL(a, w.y));
+                }
+            }
+        }
+    }
+    __device__ __forceinline__ void load3(cplx (&tw)[3]) const {
+        uint32_t v[16];
+        tmem_ld16(col + 64, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int q = 0; q < 3; ++q) tw[q] = cplx_from_words(v, q);
+    }
+};
+// the same twiddles straight from the global tables (key conversion kernel): identical values, identical arithmetic
+struct GlobalTwiddles {
+    const cplx *tbl16;
+    int T;
+    template <bool INV>
+    __device__ __forceinline__ void apply16(double (&re)[16], double (&im)[16]) const {
+        if (!INV) twiddle16_fwd(re, im, [&](int p) { return __ldg(tbl16 + p * 64 + T); });
+        else twiddle16_inv(re, im, [&](int p) { return __ldg(tbl16 + p * 64 + T); });
+    }
+    __device__ __forceinline__ void load3(cplx (&tw)[3]) const {
+#pragma unroll
+        for (int q = 0; q < 3; ++q) tw[q] = __ldg(tbl16 + kM + 16 * q + (T & 15));
+    }
+};
+
 // ---- the 64-thread FFT: registers <-> tile exchanges (fft16_core.cuh), `sync` = barrier over the polynomial's 64 threads -----------
 // forward: on entry the tile may still be read by the other threads (the first sync covers that); on exit thread T2 holds
 // register pv = frequency freq_of16(T2, pv) and nobody but T2 itself touches its exchange-B reader slots.
-template <class LoadT1, class LoadT2, class Sync>
-__device__ __forceinline__ void fft16_fwd(double (&re)[16], double (&im)[16], cplx *tile, LoadT1 t1, LoadT2 t2, int T, Sync sync) {
+template <class Tw, class Sync>
+__device__ __forceinline__ void fft16_fwd(double (&re)[16], double (&im)[16], cplx *tile, const Tw &twd, int T, Sync sync) {
     pretwist16_fwd(re, im);
     radix16_dif(re, im);
-    twiddle16_fwd(re, im, [&](int p) { return t1(p * 64 + T); });
+    twd.template apply16<false>(re, im);
     sync();
     {
         cplx *wp = tile + xa_wbase(T);
@@ -98,7 +152,8 @@ __device__ __forceinline__ void fft16_fwd(double (&re)[16], double (&im)[16], cp
     }
     radix4x4_dif(re, im);
     {
-        const cplx tw[3] = {t2(T & 15), t2(16 + (T & 15)), t2(32 + (T & 15))};
+        cplx tw[3];
+        twd.load3(tw);
         twiddle4_fwd(re, im, tw);
     }
     __syncwarp();     // from here on everything stays inside this half-warp's region of the tile
@@ -118,8 +173,8 @@ __device__ __forceinline__ void fft16_fwd(double (&re)[16], double (&im)[16], cp
 
 // inverse (scaled by 1024): on entry nobody else may be reading this thread's exchange-B reader slots; on exit the tile may
 // still be read by the other threads.
-template <class LoadT1, class LoadT2, class Sync>
-__device__ __forceinline__ void fft16_inv(double (&re)[16], double (&im)[16], cplx *tile, LoadT1 t1, LoadT2 t2, int T, Sync sync) {
+template <class Tw, class Sync>
+__device__ __forceinline__ void fft16_inv(double (&re)[16], double (&im)[16], cplx *tile, const Tw &twd, int T, Sync sync) {
     radix16_dit_inv(re, im);
     {
         cplx *wp = tile + xb_rbase(T);
@@ -133,7 +188,8 @@ __device__ __forceinline__ void fft16_inv(double (&re)[16], double (&im)[16], cp
         for (int g = 0; g < 16; ++g) { const cplx v = rp[xb_woff(g)]; re[g] = v.x; im[g] = v.y; }
     }
     {
-        const cplx tw[3] = {t2(T & 15), t2(16 + (T & 15)), t2(32 + (T & 15))};
+        cplx tw[3];
+        twd.load3(tw);
         twiddle4_inv(re, im, tw);
     }
     radix4x4_dit_inv(re, im);
@@ -149,7 +205,7 @@ __device__ __forceinline__ void fft16_inv(double (&re)[16], double (&im)[16], cp
 #pragma unroll
         for (int p = 0; p < 16; ++p) { const cplx v = rp[xa_woff(p)]; re[p] = v.x; im[p] = v.y; }
     }
-    twiddle16_inv(re, im, [&](int p) { return t1(p * 64 + T); });
+    twd.template apply16<true>(re, im);
     radix16_dit_inv(re, im);
     posttwist16_inv(re, im);
 }
@@ -165,7 +221,7 @@ pbs_classic_kernel_v4(const uint64_t *__restrict__ lwe_small, const uint32_t *__
                       const cplx *__restrict__ bskf4, const cplx *__restrict__ tbl16, uint64_t *__restrict__ out,
                       const uint32_t *__restrict__ out_slot, int batch, int n, int base_log, int n_iters, int small_is_u16) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    constexpr int WARPS = 4 * CTS, NTHREADS = 128 * CTS, TMEM_COLS = 64 * CTS;
+    constexpr int WARPS = 4 * CTS, TMEM_COLS = CTS == 4 ? 512 : 256, TW_COL = 64 * CTS;
     Smem<CTS> &sm = *reinterpret_cast<Smem<CTS> *>(smem_raw);
     const int W = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // warp -> (ciphertext, polynomial, half): the four warps of a ciphertext sit on the four schedulers (warp id % 4), so every
@@ -184,8 +240,6 @@ pbs_classic_kernel_v4(const uint64_t *__restrict__ lwe_small, const uint32_t *__
     const int total_pieces = n_iters * PIECES_PER_ITER;
 
     // ---- one-time setup: twiddle tables, barriers, TMEM, first ring fill ---------------------------------------------------
-    for (int i = threadIdx.x; i < kM; i += NTHREADS) sm.t1[i] = tbl16[i];
-    if (threadIdx.x < 64) sm.t2[threadIdx.x] = tbl16[kM + threadIdx.x];
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSLOT; ++s) { mbar_init(&sm.full_bar[s], 1); sm.consumed[s] = 0; }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -196,6 +250,20 @@ pbs_classic_kernel_v4(const uint64_t *__restrict__ lwe_small, const uint32_t *__
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_mine = sm.tmem_base + ((uint32_t)((W & 3) * 32) << 16) + (uint32_t)(ctl * 64);   // lane quarter = warp id % 4
+    const TmemTwiddles twd{sm.tmem_base + ((uint32_t)((W & 3) * 32) << 16) + (uint32_t)TW_COL};
+    {   // this thread's twiddles -> TMEM (5 x 16 columns: T1[p][T], p = 0..15, then the three pass-2 twiddles)
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            uint32_t v[16];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const cplx t = k < 4 ? __ldg(tbl16 + (4 * k + q) * 64 + T) : __ldg(tbl16 + kM + 16 * (q < 3 ? q : 0) + (T & 15));
+                v[4 * q] = (uint32_t)__double2loint(t.x); v[4 * q + 1] = (uint32_t)__double2hiint(t.x);
+                v[4 * q + 2] = (uint32_t)__double2loint(t.y); v[4 * q + 3] = (uint32_t)__double2hiint(t.y);
+            }
+            tmem_st16(twd.col + 16 * k, v);
+        }
+    }
     if (threadIdx.x == 0) {
         const int first = total_pieces < NSLOT ? total_pieces : NSLOT;
         for (int g = 0; g < first; ++g) {
@@ -243,8 +311,6 @@ pbs_classic_kernel_v4(const uint64_t *__restrict__ lwe_small, const uint32_t *__
 
     int slot = 0;            // ring position of this iteration's first piece
     uint32_t phase = 0;
-    auto ld_t1 = [&](int idx) { return sm.t1[idx]; };
-    auto ld_t2 = [&](int idx) { return sm.t2[idx]; };
 
     for (int i = 0; i < n_iters; ++i) {
         const uint32_t a = (small_is_u16 ? (uint32_t)__ldg(lwe16 + i) : modulus_switch_2n(__ldg(lwe + i))) & (2 * kN - 1);   // a == 0 is NOT skipped
@@ -265,7 +331,7 @@ pbs_classic_kernel_v4(const uint64_t *__restrict__ lwe_small, const uint32_t *__
         }
         if (CTS == 4 && i == 0 && ctl == 0) bar_arrive(13, 256);
 
-        fft16_fwd(re, im, tile, ld_t1, ld_t2, T, poly_sync);
+        fft16_fwd(re, im, tile, twd, T, poly_sync);
         if (CTS == 4 && i == 0 && ctl == 0) bar_arrive(14, 256);
 
         // spectrum exchange between the two polynomials of the ciphertext: park my 16 values in my own exchange-B reader slots
@@ -334,7 +400,7 @@ pbs_classic_kernel_v4(const uint64_t *__restrict__ lwe_small, const uint32_t *__
         bar_sync(ct_bar, 128);   // the partner polynomial has read my spectrum: the tile is mine again
         if (CTS == 4 && i == 0 && ctl == 0) bar_arrive(15, 256);
 
-        fft16_inv(re, im, tile, ld_t1, ld_t2, T, poly_sync);
+        fft16_inv(re, im, tile, twd, T, poly_sync);
         poly_sync();    // everyone has read the last exchange: the tile becomes the accumulator polynomial again
 
         // acc += from_torus(.): master copy in TMEM, new values to registers (next gather's "own") and shared (next rotation)
@@ -398,7 +464,7 @@ bsk_convert_kernel_v4(const uint64_t *__restrict__ bsk_std, cplx *__restrict__ b
         re[m] = DMUL((double)(long long)src[j], scale);
         im[m] = DMUL((double)(long long)src[j + kM], scale);
     }
-    fft16_fwd(re, im, tile, [&](int idx) { return __ldg(tbl16 + idx); }, [&](int idx) { return __ldg(tbl16 + kM + idx); }, T, BlockSync{});
+    fft16_fwd(re, im, tile, GlobalTwiddles{tbl16, T}, T, BlockSync{});
     const int sel = (r == c) ? 0 : 1;
 #pragma unroll
     for (int g = 0; g < 16; ++g) {
