@@ -297,7 +297,7 @@ def run_b200(args):
             "e2e": {"value": e2e, "unit": "PBS/s", "h2d_bytes_per_step": B * (CT_BYTES + 4), "d2h_bytes_per_step": B * CT_BYTES},
             "gpu_launches": launches,
             "kernels": {"keyswitch_ms": ks_ms, "pbs_ms": pbs_ms},
-            "roofline": {"bound": "fp64", "kernel": "pbs_classic_kernel_v3" if args.params == "2_2" else "pbs_multibit_kernel", "achieved": pbs_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
+            "roofline": {"bound": "fp64", "kernel": "pbs_classic_kernel_v4" if args.params == "2_2" else "pbs_multibit_kernel", "achieved": pbs_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": pbs_tflops / fp64_peak if fp64_peak else None, "traffic": traffic,
                          "algorithmic_bytes_per_launch": BSK_BYTES + B * (743 * 8 + CT_BYTES) + 16 * 4096 * 8,
                          "peak_source": "FP64 FMA microbenchmark run in this process (MEASURED_PEAKS.json has no FP64 figure)",

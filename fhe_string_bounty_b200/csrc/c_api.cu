@@ -119,7 +119,7 @@ int tfhe_b200_ctx_create(int cuda_device, const tfhe_b200_params *params, tfhe_b
     for (auto &L : c->lane) TB_CUDA(cudaStreamCreateWithFlags(&L.s, cudaStreamNonBlocking));
     if (const char *e = std::getenv("TFHE_B200_KS_KERNEL")) c->ks_kernel = (e[0] == 'i') ? 0 : 1;
     if (!tbk::ks_mma_supported((int)params->ks_level)) c->ks_kernel = 0;
-    if (const char *e = std::getenv("TFHE_B200_PBS_KERNEL")) c->pbs_kernel = (e[0] == '2') ? 2 : (e[0] == '4') ? 4 : 3;
+    if (const char *e = std::getenv("TFHE_B200_PBS_KERNEL")) c->pbs_kernel = (e[0] == '2') ? 2 : (e[0] == '3') ? 3 : 4;
     TB_CUDA(tbk::pbs_configure());
     TB_CUDA(tbk::pbs_v3_configure());
     TB_CUDA(tbk::pbs_v4_configure());

@@ -56,7 +56,7 @@ struct tfhe_b200_ctx {
     int ks_kernel = 1;    // 1: tensor-core GEMM (keyswitch_mma.cu), 0: IMAD GEMM (keyswitch.cu); env TFHE_B200_KS_KERNEL=imad
     uint32_t n_luts = 0;
     bool have_ksk = false, have_bsk = false;
-    int pbs_kernel = 3;   // 3: TMEM + TMA ring (pbs_v3.cu), 4: same with 16 points per thread (pbs_v4.cu), 2: one CTA per ciphertext (pbs.cu); env TFHE_B200_PBS_KERNEL
+    int pbs_kernel = 4;   // 4: TMEM + TMA ring, 16 FFT points per thread (pbs_v4.cu); 3: same data path, 32 points per thread (pbs_v3.cu); 2: one CTA per ciphertext (pbs.cu); env TFHE_B200_PBS_KERNEL
     // staging for the host-pointer entry points
     tbc::DevBuf d_in, d_small, d_out, d_idx;
     // two copy/compute lanes for the host-buffer KS-PBS entry point: H2D of chunk k+1 and D2H of chunk k-1 overlap the

@@ -57,3 +57,16 @@ def test_cpu_mirror_of_warp_fft(tmp_path):
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout
     assert "OK" in out.stdout
+
+
+def test_cpu_mirror_of_two_warp_fft(tmp_path):
+    """tests/cpu_mirror/fft16_mirror.cpp emulates the 64 threads of the 16 x 4 x 16 FFT of the v4 blind-rotation kernel from the
+    SAME header the kernel compiles (fft16_core.cuh): DFT definition, frequency map, round trip, bank-conflict-free and
+    region-confined exchange addressing."""
+    import subprocess
+    exe = tmp_path / "fft16_mirror"
+    subprocess.run(["g++", "-O1", "-std=c++17", "-ffp-contract=off", str(ROOT / "tests/cpu_mirror/fft16_mirror.cpp"), "-o", str(exe)],
+                   check=True, env={"PATH": "/usr/bin:/bin"})
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout
+    assert "OK" in out.stdout
