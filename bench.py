@@ -65,31 +65,42 @@ def _peaks():
     return {"hbm_gbs": 6650.0}, "fallback"
 
 
-def cpu_reference_rate(n_cts: int, threads: int = 0):
-    """Times the CPU oracle (restatement of the reference's KS-PBS, one ciphertext per OpenMP thread, the
-    structure of tfhe/benches/core_crypto/pbs_bench.rs:512-536).  Only this leg may touch oracle/."""
-    from oracle import oracle as O
-    p = O.params("2_2")
-    rng = np.random.default_rng(0xB200)
-    ksk = rng.integers(0, 2**64, size=O.lib().orc_ksk_len(p), dtype=np.uint64)
-    bsk = rng.integers(0, 2**64, size=O.lib().orc_bsk_len(p), dtype=np.uint64)
+class CpuReference:
+    """The CPU oracle (restatement of the reference's KS-PBS, one ciphertext per OpenMP thread, the structure of
+    tfhe/benches/core_crypto/pbs_bench.rs:512-536) set up once and timed per call.  Only this leg may touch oracle/."""
 
-    class _SK:  # ServerKey without key generation: random words give the same work
-        pass
-    import ctypes as C
-    f = O.lib().orc_fourier_bsk_new(C.byref(p), bsk)
-    luts = rng.integers(0, 2**64, size=(16, p.lut_len), dtype=np.uint64)
-    cts = rng.integers(0, 2**64, size=(n_cts, p.big_dim + 1), dtype=np.uint64)
-    idx = (np.arange(n_cts) % 16).astype(np.uint32)
-    out = np.zeros_like(cts)
-    L = O.lib()
-    cores = threads or L.orc_max_threads()
-    warm = min(n_cts, cores)
-    L.orc_ks_pbs_batch(C.byref(p), ksk, f, luts, idx.ctypes.data_as(C.c_void_p), cts[:warm], out[:warm], None, warm, cores)
-    t0 = time.perf_counter()
-    used = L.orc_ks_pbs_batch(C.byref(p), ksk, f, luts, idx.ctypes.data_as(C.c_void_p), cts, out, None, n_cts, cores)
-    dt = time.perf_counter() - t0
-    L.orc_fourier_bsk_free(f)
+    def __init__(self, max_cts: int, threads: int = 0):
+        from oracle import oracle as O
+        import ctypes as C
+        self.C, self.L = C, O.lib()
+        self.p = O.params("2_2")
+        rng = np.random.default_rng(0xB200)
+        # random words instead of generated keys: the arithmetic does not depend on the key values
+        self.ksk = rng.integers(0, 2**64, size=self.L.orc_ksk_len(self.p), dtype=np.uint64)
+        bsk = rng.integers(0, 2**64, size=self.L.orc_bsk_len(self.p), dtype=np.uint64)
+        self.f = self.L.orc_fourier_bsk_new(C.byref(self.p), bsk)
+        self.luts = rng.integers(0, 2**64, size=(16, self.p.lut_len), dtype=np.uint64)
+        self.cts = rng.integers(0, 2**64, size=(max_cts, self.p.big_dim + 1), dtype=np.uint64)
+        self.idx = (np.arange(max_cts) % 16).astype(np.uint32)
+        self.out = np.zeros_like(self.cts)
+        self.cores = threads or self.L.orc_max_threads()
+
+    def run(self, n_cts: int):
+        C = self.C
+        t0 = time.perf_counter()
+        used = self.L.orc_ks_pbs_batch(C.byref(self.p), self.ksk, self.f, self.luts, self.idx.ctypes.data_as(C.c_void_p),
+                                       self.cts[:n_cts], self.out[:n_cts], None, n_cts, self.cores)
+        return time.perf_counter() - t0, used
+
+    def close(self):
+        self.L.orc_fourier_bsk_free(self.f)
+
+
+def cpu_reference_rate(n_cts: int, threads: int = 0):
+    ref = CpuReference(n_cts, threads)
+    ref.run(min(n_cts, ref.cores))          # warm-up: page in the Fourier key, spin up the OpenMP team
+    dt, used = ref.run(n_cts)
+    ref.close()
     return n_cts / dt, used, dt
 
 
@@ -97,24 +108,24 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import oracle as O
-    cores = O.lib().orc_max_threads()
-    per_step = max(cores * 2, 16)
-    rates = []
-    t_all = time.perf_counter()
+    ref = CpuReference(1)
+    per_step = ref.cores * 32               # about 0.8 s of work per step on the box's 16 cores
+    ref.close()
+    ref = CpuReference(per_step)
+    total_t, used = 0.0, ref.cores
     for s in range(args.warmup + args.steps):
-        r, used, dt = cpu_reference_rate(per_step)
+        dt, used = ref.run(per_step)
         if s >= args.warmup:
-            rates.append((r, dt))
-    total_t = sum(dt for _, dt in rates)
-    value = per_step * len(rates) / total_t
+            total_t += dt
+    ref.close()
+    value = per_step * args.steps / total_t
     line = {
         "impl": "reference", "metric": "batched KS-PBS throughput", "value": value, "unit": "PBS/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_t / max(len(rates), 1), "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_t / max(args.steps, 1), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "PARAM_MESSAGE_2_CARRY_2_KS_PBS batched KS-PBS (configs[1])", "batch_per_step": per_step,
                    "note": "reference Rust crate cannot be built here (no cargo); CPU oracle port of its algorithm, all host cores"},
-        "cpu_baseline": {"value": value, "unit": "PBS/s", "cores": cores, "kind": "port",
+        "cpu_baseline": {"value": value, "unit": "PBS/s", "cores": used, "kind": "port",
                          "sample": f"{per_step} KS-PBS per step x {args.steps} steps, one ciphertext per OpenMP thread"},
         "e2e": {"value": value, "unit": "PBS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -331,7 +342,7 @@ def main():
     ap.add_argument("--batch", type=int, default=8192, help="ciphertexts per GPU per step")
     ap.add_argument("--params", default="2_2", choices=["2_2", "multibit"], help="2_2 = PARAM_MESSAGE_2_CARRY_2_KS_PBS (headline); multibit = ..._GROUP_3_KS_PBS")
     ap.add_argument("--string-ops", type=int, default=1, help="also time FheString eq/contains/find through the host layer (0 = skip)")
-    ap.add_argument("--cpu-sample", type=int, default=256, help="KS-PBS evaluated by the CPU baseline leg (0 = skip)")
+    ap.add_argument("--cpu-sample", type=int, default=8192, help="KS-PBS evaluated by the CPU baseline leg (0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
