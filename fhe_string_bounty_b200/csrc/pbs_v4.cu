@@ -342,8 +342,8 @@ pbs_classic_kernel_v4(const uint64_t *__restrict__ lwe_small, const uint32_t *__
         }
         bar_sync(ct_bar, 128);
 
-        // out_fft[w] = F_w * G[w][w] + F_{1-w} * G[1-w][w], GGSW pieces from the ring (probe all barriers first, release each
-        // slot right after its chunk; the last of the WARPS warps re-arms it NSLOT pieces ahead)
+        // out_fft[w] = F_w * G[w][w] + F_{1-w} * G[1-w][w], GGSW pieces from the ring (probe all barriers first, count
+        // this warp out of each slot right after its chunk)
         {
             uint32_t ready = 0;
             {
@@ -355,6 +355,8 @@ pbs_classic_kernel_v4(const uint64_t *__restrict__ lwe_small, const uint32_t *__
                 }
             }
             const cplx *fop = otile + xb_rbase(T);
+            unsigned int my_old = 0;
+            int my_slot = 0;
 #pragma unroll
             for (int c = 0; c < PIECES_PER_ITER; ++c) {
                 if (!((ready >> c) & 1u)) mbar_wait(&sm.full_bar[slot], phase);
@@ -380,21 +382,22 @@ pbs_classic_kernel_v4(const uint64_t *__restrict__ lwe_small, const uint32_t *__
                     oi = DFMA(fo[q].y, gb[q].x, oi);
                     re[g] = orr; im[g] = oi;
                 }
+                // release: lane c counts this warp out of chunk c's slot; nobody looks at the result inside the loop
                 __syncwarp();
-                if (lane == 0) {
-                    const unsigned int old = atomicAdd(&sm.consumed[slot], 1u);
-                    if (old == WARPS - 1) {
-                        sm.consumed[slot] = 0;
-                        const int g2 = i * PIECES_PER_ITER + c + NSLOT;
-                        if (g2 < total_pieces) {
-                            __threadfence_block();
-                            fence_proxy_async();
-                            mbar_expect_tx(&sm.full_bar[slot], PIECE_BYTES);
-                            tma_load_1d(sm.ring[slot], bskf4 + (size_t)g2 * PIECE_CPLX, PIECE_BYTES, &sm.full_bar[slot]);
-                        }
-                    }
-                }
+                if (lane == c) { my_old = atomicAdd(&sm.consumed[slot], 1u); my_slot = slot; }
                 if (++slot == NSLOT) { slot = 0; phase ^= 1u; }
+            }
+            // the last of the WARPS warps to leave a slot re-arms it with the piece NSLOT ahead (a few hundred cycles after the
+            // fact, against 1.25 iterations of lookahead)
+            if (lane < PIECES_PER_ITER && my_old == WARPS - 1) {
+                sm.consumed[my_slot] = 0;
+                const int g2 = i * PIECES_PER_ITER + lane + NSLOT;
+                if (g2 < total_pieces) {
+                    __threadfence_block();
+                    fence_proxy_async();
+                    mbar_expect_tx(&sm.full_bar[my_slot], PIECE_BYTES);
+                    tma_load_1d(sm.ring[my_slot], bskf4 + (size_t)g2 * PIECE_CPLX, PIECE_BYTES, &sm.full_bar[my_slot]);
+                }
             }
         }
         bar_sync(ct_bar, 128);   // the partner polynomial has read my spectrum: the tile is mine again
