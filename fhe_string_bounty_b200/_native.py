@@ -14,7 +14,7 @@ import numpy as np
 
 _PKG = Path(__file__).resolve().parent
 _SO = _PKG / "libtfhe_b200.so"
-_SOURCES = ["csrc/pbs.cu", "csrc/pbs_v3.cu", "csrc/pbs_v4.cu", "csrc/pbs_multibit.cu", "csrc/keyswitch.cu", "csrc/keyswitch_mma.cu", "csrc/leveled.cu", "csrc/c_api.cu", "csrc/host_api.cu"]
+_SOURCES = ["csrc/pbs.cu", "csrc/pbs_v3.cu", "csrc/pbs_v4.cu", "csrc/pbs_multibit.cu", "csrc/keyswitch.cu", "csrc/keyswitch_mma.cu", "csrc/leveled.cu", "csrc/seeded.cu", "csrc/c_api.cu", "csrc/host_api.cu"]
 _HEADERS = ["csrc/fft_core.cuh", "csrc/fft16_core.cuh", "csrc/ring_helpers.cuh", "csrc/kernels.h", "csrc/ctx.h", "csrc/host/program.h", "csrc/host/radix.h", "csrc/host/strings.h", "../include/tfhe_b200.h"]
 
 NVCC_FLAGS = [
@@ -112,6 +112,8 @@ EXPORTS = {
     "tfhe_b200_last_error": (C.c_char_p, []),
     "tfhe_b200_upload_ksk": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "tfhe_b200_upload_bsk_std": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "tfhe_b200_upload_seeded_ksk": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "tfhe_b200_upload_seeded_bsk": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "tfhe_b200_upload_luts": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32]),
     "tfhe_b200_keyswitch_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "tfhe_b200_pbs_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
@@ -208,6 +210,20 @@ class Engine:
     def upload_bsk_std(self, bsk: np.ndarray):
         bsk = np.ascontiguousarray(bsk, dtype=np.uint64)
         self._check(self.lib.tfhe_b200_upload_bsk_std(self.h, _ptr(bsk), bsk.size))
+
+    def upload_seeded_ksk(self, seed16: np.ndarray, bodies: np.ndarray):
+        """seeded LweKeyswitchKey: 16 seed bytes (u128 little endian) + one body word per (input key bit, level)"""
+        seed16 = np.ascontiguousarray(seed16, dtype=np.uint8)
+        bodies = np.ascontiguousarray(bodies, dtype=np.uint64)
+        assert seed16.size == 16
+        self._check(self.lib.tfhe_b200_upload_seeded_ksk(self.h, _ptr(seed16), _ptr(bodies), bodies.size))
+
+    def upload_seeded_bsk(self, seed16: np.ndarray, bodies: np.ndarray):
+        """seeded Lwe(MultiBit)BootstrapKey: 16 seed bytes + one body polynomial per GLWE row"""
+        seed16 = np.ascontiguousarray(seed16, dtype=np.uint8)
+        bodies = np.ascontiguousarray(bodies, dtype=np.uint64)
+        assert seed16.size == 16
+        self._check(self.lib.tfhe_b200_upload_seeded_bsk(self.h, _ptr(seed16), _ptr(bodies), bodies.size))
 
     def upload_luts(self, luts: np.ndarray):
         luts = np.ascontiguousarray(luts, dtype=np.uint64).reshape(-1, self.p.lut_len)

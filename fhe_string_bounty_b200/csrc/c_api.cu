@@ -1,6 +1,7 @@
 // c_api.cu -- extern "C" boundary of libtfhe_b200.so (see include/tfhe_b200.h for the reference
 // interfaces each entry point replaces).  Plain pointers and sizes only; no torch types.
 #include "ctx.h"
+#include <chrono>
 
 namespace {
 thread_local std::string g_last_error;
@@ -162,18 +163,12 @@ int tfhe_b200_ctx_destroy(tfhe_b200_ctx *c) {
     return 0;
 }
 
-int tfhe_b200_upload_ksk(tfhe_b200_ctx *c, const uint64_t *ksk, size_t len) {
-    if (!c || !ksk) return fail("null argument");
-    std::lock_guard<std::mutex> lk(c->mu);
-    DeviceGuard g(c->device);
+// raw (standard-layout) keys already in device memory -> the engine's own layouts
+static int finish_ksk(tfhe_b200_ctx *c, const tbc::DevBuf &raw) {
     const size_t rows = (size_t)c->p.glwe_dim * c->p.poly_size * c->p.ks_level;
-    if (len != rows * (c->p.lwe_dim + 1)) return fail("keyswitch key length does not match the parameters");
     const int ldk = tbk::ks_padded_cols((int)c->p.lwe_dim);
-    DevBuf raw;
-    TB_CUDA(raw.reserve(len * 8));
     TB_CUDA(c->ksk_packed.reserve(rows * ldk * 8));
     TB_CUDA(c->ksk_colsum.reserve((size_t)ldk * 8));
-    TB_CUDA(cudaMemcpyAsync(raw.p, ksk, len * 8, cudaMemcpyHostToDevice, c->stream));
     TB_CUDA(tbk::launch_ksk_pack((const uint64_t *)raw.p, (uint64_t *)c->ksk_packed.p, (uint64_t *)c->ksk_colsum.p, (int)rows,
                                  (int)c->p.lwe_dim, c->stream));
     c->launches += 2;
@@ -183,23 +178,19 @@ int tfhe_b200_upload_ksk(tfhe_b200_ctx *c, const uint64_t *ksk, size_t len) {
         c->launches += 1;
     }
     TB_CUDA(cudaStreamSynchronize(c->stream));
-    raw.release();
     c->have_ksk = true;
     return 0;
 }
 
-int tfhe_b200_upload_bsk_std(tfhe_b200_ctx *c, const uint64_t *bsk, size_t len) {
-    if (!c || !bsk) return fail("null argument");
-    std::lock_guard<std::mutex> lk(c->mu);
-    DeviceGuard g(c->device);
+static size_t bsk_poly_count(const tfhe_b200_ctx *c) {
     const size_t k1 = c->p.glwe_dim + 1;
     const size_t n_ggsw = c->p.grouping_factor ? (size_t)(c->p.lwe_dim / c->p.grouping_factor) << c->p.grouping_factor : c->p.lwe_dim;
-    const size_t n_polys = n_ggsw * c->p.pbs_level * k1 * k1;
-    if (len != n_polys * c->p.poly_size) return fail("bootstrap key length does not match the parameters");
-    DevBuf raw;
-    TB_CUDA(raw.reserve(len * 8));
+    return n_ggsw * c->p.pbs_level * k1 * k1;
+}
+
+static int finish_bsk(tfhe_b200_ctx *c, const tbc::DevBuf &raw) {
+    const size_t n_polys = bsk_poly_count(c);
     TB_CUDA(c->bskf.reserve(n_polys * tb::kM * sizeof(double) * 2));
-    TB_CUDA(cudaMemcpyAsync(raw.p, bsk, len * 8, cudaMemcpyHostToDevice, c->stream));
     if (c->p.grouping_factor == 3)
         TB_CUDA(tbk::launch_bsk_convert_multibit((const uint64_t *)raw.p, c->bskf.p, c->tbl.p, (int)n_polys, c->stream));
     else if (c->pbs_kernel == 4)
@@ -210,9 +201,84 @@ int tfhe_b200_upload_bsk_std(tfhe_b200_ctx *c, const uint64_t *bsk, size_t len) 
         TB_CUDA(tbk::launch_bsk_convert((const uint64_t *)raw.p, c->bskf.p, c->tbl.p, (int)n_polys, c->stream));
     c->launches += 1;
     TB_CUDA(cudaStreamSynchronize(c->stream));
-    raw.release();
     c->have_bsk = true;
     return 0;
+}
+
+int tfhe_b200_upload_ksk(tfhe_b200_ctx *c, const uint64_t *ksk, size_t len) {
+    if (!c || !ksk) return fail("null argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    const size_t rows = (size_t)c->p.glwe_dim * c->p.poly_size * c->p.ks_level;
+    if (len != rows * (c->p.lwe_dim + 1)) return fail("keyswitch key length does not match the parameters");
+    DevBuf raw;
+    TB_CUDA(raw.reserve(len * 8));
+    TB_CUDA(cudaMemcpyAsync(raw.p, ksk, len * 8, cudaMemcpyHostToDevice, c->stream));
+    const int rc = finish_ksk(c, raw);
+    raw.release();
+    return rc;
+}
+
+int tfhe_b200_upload_bsk_std(tfhe_b200_ctx *c, const uint64_t *bsk, size_t len) {
+    if (!c || !bsk) return fail("null argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    if (len != bsk_poly_count(c) * c->p.poly_size) return fail("bootstrap key length does not match the parameters");
+    DevBuf raw;
+    TB_CUDA(raw.reserve(len * 8));
+    TB_CUDA(cudaMemcpyAsync(raw.p, bsk, len * 8, cudaMemcpyHostToDevice, c->stream));
+    const int rc = finish_bsk(c, raw);
+    raw.release();
+    return rc;
+}
+
+// seeded keys: bodies from the host, masks re-drawn on the device from the compression seed (seeded.cu)
+static int upload_seeded(tfhe_b200_ctx *c, const uint8_t *seed, const uint64_t *bodies, size_t len, bool is_bsk) {
+    if (!c || !seed || !bodies) return fail("null argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    size_t n_rows, mask_len, body_len;
+    if (is_bsk) {
+        n_rows = bsk_poly_count(c) / (c->p.glwe_dim + 1);          // GLWE rows
+        mask_len = (size_t)c->p.glwe_dim * c->p.poly_size;
+        body_len = c->p.poly_size;
+    } else {
+        n_rows = (size_t)c->p.glwe_dim * c->p.poly_size * c->p.ks_level;   // LWE rows
+        mask_len = c->p.lwe_dim;
+        body_len = 1;
+    }
+    if (len != n_rows * body_len) return fail(is_bsk ? "seeded bootstrap key length does not match the parameters"
+                                                     : "seeded keyswitch key length does not match the parameters");
+    const bool trace = std::getenv("TFHE_B200_TRACE") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    const auto t0 = now();
+    DevBuf d_bodies, raw;
+    TB_CUDA(d_bodies.reserve(len * 8));
+    TB_CUDA(raw.reserve(n_rows * (mask_len + body_len) * 8));
+    const auto t1 = now();
+    TB_CUDA(cudaMemcpyAsync(d_bodies.p, bodies, len * 8, cudaMemcpyHostToDevice, c->stream));
+    const auto t2 = now();
+    TB_CUDA(tbk::launch_seeded_expand(seed, (uint64_t *)raw.p, (const uint64_t *)d_bodies.p, n_rows, (uint32_t)mask_len, (uint32_t)body_len,
+                                      c->stream));
+    c->launches += 1;
+    if (trace) cudaStreamSynchronize(c->stream);
+    const auto t3 = now();
+    const int rc = is_bsk ? finish_bsk(c, raw) : finish_ksk(c, raw);
+    const auto t4 = now();
+    d_bodies.release();
+    raw.release();
+    const auto t5 = now();
+    if (trace) fprintf(stderr, "[tfhe_b200] upload_seeded(%s): alloc %.2f ms, h2d %.2f, expand %.2f, finish %.2f, free %.2f\n", is_bsk ? "bsk" : "ksk",
+                       ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, t4), ms(t4, t5));
+    return rc;
+}
+
+int tfhe_b200_upload_seeded_ksk(tfhe_b200_ctx *c, const uint8_t seed[16], const uint64_t *bodies, size_t len) {
+    return upload_seeded(c, seed, bodies, len, false);
+}
+int tfhe_b200_upload_seeded_bsk(tfhe_b200_ctx *c, const uint8_t seed[16], const uint64_t *bodies, size_t len) {
+    return upload_seeded(c, seed, bodies, len, true);
 }
 
 int tfhe_b200_upload_luts(tfhe_b200_ctx *c, const uint64_t *luts, uint32_t n_luts) {

@@ -59,4 +59,7 @@ struct LinTerm {
 cudaError_t launch_linear(uint64_t *arena, const LinInstr *instrs, const LinTerm *terms, int n_instrs, int lwe_len,
                           cudaStream_t stream);
 
+// seeded.cu: dst row g = [mask_len words of the AES-128 CTR stream of `seed` | body_len words copied from bodies]
+cudaError_t launch_seeded_expand(const uint8_t seed[16], uint64_t *dst, const uint64_t *bodies, size_t n_rows, uint32_t mask_len,
+                                 uint32_t body_len, cudaStream_t stream);
 }  // namespace tbk

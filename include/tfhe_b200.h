@@ -56,6 +56,18 @@ int tfhe_b200_upload_ksk(tfhe_b200_ctx *ctx, const uint64_t *ksk, size_t len);
 int tfhe_b200_upload_bsk_std(tfhe_b200_ctx *ctx, const uint64_t *bsk, size_t len);
 int tfhe_b200_upload_luts(tfhe_b200_ctx *ctx, const uint64_t *luts, uint32_t n_luts);
 
+/* Seeded (compressed) keys: what shortint::CompressedServerKey holds (shortint/server_key/mod.rs:935-1023) -- per key a 128-bit
+ * compression seed and the ciphertext BODIES only.  Replaces SeededLweKeyswitchKey::par_decompress_into_lwe_keyswitch_key
+ * (core_crypto/algorithms/seeded_lwe_keyswitch_key_decompression.rs, seeded_lwe_ciphertext_list_decompression.rs:9-60) and
+ * SeededLweBootstrapKey / SeededLweMultiBitBootstrapKey::par_decompress_into_* followed by the Fourier conversion
+ * (seeded_lwe_bootstrap_key_decompression.rs, seeded_ggsw_ciphertext_list_decompression.rs, seeded_glwe_ciphertext_decompression.rs):
+ * the masks are re-drawn ON THE DEVICE from concrete-csprng's AES-128 CTR stream (bit-exact with the reference's generator).
+ * seed:   the 16 bytes of Seed(u128).0.to_ne_bytes() (little endian), i.e. the AES key of soft/block_cipher.rs:16.
+ * bodies: ksk: [k*N][ks_level] one word per LWE ciphertext (entities/seeded_lwe_keyswitch_key.rs);
+ *         bsk: [n or groups*2^g][pbs_level][k+1 rows][N] one body polynomial per GLWE row (entities/seeded_ggsw_ciphertext_list.rs). */
+int tfhe_b200_upload_seeded_ksk(tfhe_b200_ctx *ctx, const uint8_t seed[16], const uint64_t *bodies, size_t len);
+int tfhe_b200_upload_seeded_bsk(tfhe_b200_ctx *ctx, const uint8_t seed[16], const uint64_t *bodies, size_t len);
+
 /* Batched hot path, HOST buffers (H2D + kernels + D2H inside the call, synchronous).
  * lwe_big:   batch x (k*N + 1) words under the big key;  lwe_small: batch x (n + 1) words.
  * lut_idx:   batch indices into the uploaded LUT table (NULL = LUT 0 for all).

@@ -53,6 +53,7 @@ _u64p = np.ctypeslib.ndpointer(dtype=np.uint64, flags="C_CONTIGUOUS")
 _i64p = np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")
 _u32p = np.ctypeslib.ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS")
 _f64p = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+_u8p = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
 _PP = C.POINTER(Params)
 _RP = C.POINTER(Rng)
 
@@ -101,6 +102,18 @@ def lib():
         "orc_pbs_exact": (None, [_PP, _u64p, _u64p, _u64p, _u64p]),
         "orc_ks_pbs_batch": (C.c_int, [_PP, _u64p, C.c_void_p, _u64p, C.c_void_p, _u64p, _u64p, C.c_void_p, C.c_size_t, C.c_int]),
         "orc_max_threads": (C.c_int, []),
+        "orc_aes_sbox": (C.POINTER(C.c_uint8), []),
+        "orc_aes128_expand_key": (None, [_u8p, _u8p]),
+        "orc_aes128_encrypt_block": (None, [_u8p, _u8p, _u8p]),
+        "orc_csprng_table_bytes": (None, [_u8p, C.c_uint64, _u8p, C.c_size_t]),
+        "orc_csprng_generate_bytes": (None, [_u8p, C.c_uint64, _u8p, C.c_size_t]),
+        "orc_csprng_mask_words": (None, [_u8p, C.c_uint64, _u64p, C.c_size_t]),
+        "orc_seeded_bsk_len": (C.c_size_t, [_PP]),
+        "orc_seeded_ksk_len": (C.c_size_t, [_PP]),
+        "orc_decompress_seeded_bsk": (None, [_PP, _u8p, _u64p, _u64p]),
+        "orc_decompress_seeded_ksk": (None, [_PP, _u8p, _u64p, _u64p]),
+        "orc_compress_bsk": (None, [_PP, _u64p, _u8p, _u64p, _u64p]),
+        "orc_compress_ksk": (None, [_PP, _u64p, _u8p, _u64p, _u64p]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -252,3 +265,34 @@ def decompose(x: int, base_log: int, level: int) -> list[int]:
     d = np.zeros(level, dtype=np.int64)
     lib().orc_decompose(x, base_log, level, d)
     return [int(v) for v in d]
+
+
+def seed_bytes(seed: int) -> np.ndarray:
+    """concrete-csprng Seed(u128) -> the 16 key bytes the block cipher sees (soft/block_cipher.rs:16: to_ne_bytes, little endian)."""
+    return np.frombuffer(int(seed).to_bytes(16, "little"), dtype=np.uint8).copy()
+
+
+class CompressedServerKey:
+    """shortint::CompressedServerKey (shortint/server_key/mod.rs:935-1023): seeded KSK + seeded (multi-bit) BSK, i.e. one compression
+    seed per key plus the ciphertext bodies.  Built here from a ServerKey by re-drawing every mask from the seeded stream (test-side
+    key generation); decompress() restates seeded_lwe_keyswitch_key_decompression.rs / seeded_lwe_bootstrap_key_decompression.rs."""
+
+    def __init__(self, ck: ClientKey, sk: ServerKey, ksk_seed: int, bsk_seed: int):
+        L = lib()
+        p = sk.p
+        self.p = p
+        self.ksk_seed, self.bsk_seed = seed_bytes(ksk_seed), seed_bytes(bsk_seed)
+        self.ksk_bodies = np.zeros(L.orc_seeded_ksk_len(C.byref(p)), dtype=np.uint64)
+        self.bsk_bodies = np.zeros(L.orc_seeded_bsk_len(C.byref(p)), dtype=np.uint64)
+        L.orc_compress_ksk(C.byref(p), ck.small_sk, self.ksk_seed, sk.ksk, self.ksk_bodies)
+        L.orc_compress_bsk(C.byref(p), ck.glwe_sk, self.bsk_seed, sk.bsk, self.bsk_bodies)
+
+    def decompress(self):
+        """-> (ksk, bsk) in the standard layouts of ServerKey"""
+        L = lib()
+        p = self.p
+        ksk = np.zeros(L.orc_ksk_len(C.byref(p)), dtype=np.uint64)
+        bsk = np.zeros(L.orc_bsk_len(C.byref(p)), dtype=np.uint64)
+        L.orc_decompress_seeded_ksk(C.byref(p), self.ksk_seed, self.ksk_bodies, ksk)
+        L.orc_decompress_seeded_bsk(C.byref(p), self.bsk_seed, self.bsk_bodies, bsk)
+        return ksk, bsk

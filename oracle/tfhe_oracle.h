@@ -15,7 +15,9 @@
  *   - FFT roundtrip |d| < 2^14 and product-vs-schoolbook tolerance (fft64/math/fft/tests.rs:44,157-172),
  *   - decrypt-and-compare over all messages (algorithms/test/lwe_keyswitch.rs, lwe_programmable_bootstrapping.rs),
  *   - trivial-PBS == real PBS after decryption (shortint/server_key/tests/shortint.rs:3233-3296),
- *   - the ASCII tutorial KAT (docs/tutorials/ascii_fhe_string.md:140-153).
+ *   - the ASCII tutorial KAT (docs/tutorials/ascii_fhe_string.md:140-153),
+ *   - seeded keys (csprng_oracle.c): the FIPS-197 AES-128 key schedule and ciphertext held by concrete-csprng's tests
+ *     (implem/aesni/block_cipher.rs:188-229, implem/soft/block_cipher.rs:84-113).
  * Integer arithmetic (decomposition, keyswitch, monomial ops, sample extraction, LUT layout) is pinned
  * bit-exactly by those KATs; the f64 FFT result bits are "parity unpinned" (tolerance pins only), so
  * an EXACT integer external product (no FFT) is provided as independent ground truth.
@@ -115,6 +117,21 @@ int orc_ks_pbs_batch(const orc_params *p, const uint64_t *ksk, const orc_fourier
                      const uint64_t *luts, const uint32_t *lut_idx,
                      const uint64_t *in, uint64_t *out, uint64_t *ks_out, size_t batch, int threads);
 int orc_max_threads(void);
+
+/* ---- seeded keys (csprng_oracle.c): concrete-csprng's AES-128 CTR table + tfhe's seeded_*_decompression.rs ---- */
+const uint8_t *orc_aes_sbox(void);
+void orc_aes128_expand_key(const uint8_t key[16], uint8_t rk[176]);
+void orc_aes128_encrypt_block(const uint8_t rk[176], const uint8_t in[16], uint8_t out[16]);
+void orc_csprng_table_bytes(const uint8_t seed[16], uint64_t first, uint8_t *out, size_t n);   /* table byte 16*A + b */
+void orc_csprng_generate_bytes(const uint8_t seed[16], uint64_t skip, uint8_t *out, size_t n); /* a fresh generator's output */
+void orc_csprng_mask_words(const uint8_t seed[16], uint64_t first_word, uint64_t *out, size_t n);
+size_t orc_seeded_bsk_len(const orc_params *p);   /* body polynomials only: rows * N */
+size_t orc_seeded_ksk_len(const orc_params *p);   /* one body per (input key bit, level) */
+void orc_decompress_seeded_bsk(const orc_params *p, const uint8_t seed[16], const uint64_t *bodies, uint64_t *bsk_std);
+void orc_decompress_seeded_ksk(const orc_params *p, const uint8_t seed[16], const uint64_t *bodies, uint64_t *ksk);
+/* test-side key generation: the seeded key a client would have produced (same plaintexts and noise, masks from the stream) */
+void orc_compress_bsk(const orc_params *p, const uint64_t *glwe_sk, const uint8_t seed[16], const uint64_t *bsk_std, uint64_t *bodies);
+void orc_compress_ksk(const orc_params *p, const uint64_t *small_sk, const uint8_t seed[16], const uint64_t *ksk, uint64_t *bodies);
 
 #ifdef __cplusplus
 }
