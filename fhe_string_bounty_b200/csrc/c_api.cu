@@ -66,8 +66,12 @@ int do_pbs(tfhe_b200_ctx *c, const uint64_t *d_small, const uint32_t *d_idx, con
     if (!d_luts) return fail("no lookup tables uploaded");
     if (c->p.grouping_factor == 3) {
         const uint32_t groups = c->p.lwe_dim / 3;
-        TB_CUDA(tbk::launch_pbs_multibit(d_small, d_idx, d_luts, c->bskf.p, c->tbl.p, c->roots.p, d_out, out_slot, (int)batch,
-                                         (int)c->p.lwe_dim, (int)c->p.pbs_base_log, (int)(n_iters < groups ? n_iters : groups), s));
+        if (c->mb_kernel == 4)
+            TB_CUDA(tbk::launch_pbs_multibit_v4(d_small, d_idx, d_luts, c->bskf.p, c->tbl16.p, c->roots.p, d_out, out_slot, (int)batch,
+                                                (int)c->p.lwe_dim, (int)c->p.pbs_base_log, (int)(n_iters < groups ? n_iters : groups), s));
+        else
+            TB_CUDA(tbk::launch_pbs_multibit(d_small, d_idx, d_luts, c->bskf.p, c->tbl.p, c->roots.p, d_out, out_slot, (int)batch,
+                                             (int)c->p.lwe_dim, (int)c->p.pbs_base_log, (int)(n_iters < groups ? n_iters : groups), s));
         c->launches += 1;
         return 0;
     }
@@ -124,7 +128,9 @@ int tfhe_b200_ctx_create(int cuda_device, const tfhe_b200_params *params, tfhe_b
     TB_CUDA(tbk::pbs_configure());
     TB_CUDA(tbk::pbs_v3_configure());
     TB_CUDA(tbk::pbs_v4_configure());
+    if (const char *e = std::getenv("TFHE_B200_MB_KERNEL")) c->mb_kernel = (e[0] == '3') ? 3 : 4;
     TB_CUDA(tbk::pbs_multibit_configure());
+    TB_CUDA(tbk::pbs_multibit_v4_configure());
     {   // roots[e] = exp(i*pi*e/2048): monomial spectra of the multi-bit combine
         std::vector<double> r(2 * 4096);
         const long double pi = 3.14159265358979323846264338327950288L;
@@ -191,7 +197,9 @@ static size_t bsk_poly_count(const tfhe_b200_ctx *c) {
 static int finish_bsk(tfhe_b200_ctx *c, const tbc::DevBuf &raw) {
     const size_t n_polys = bsk_poly_count(c);
     TB_CUDA(c->bskf.reserve(n_polys * tb::kM * sizeof(double) * 2));
-    if (c->p.grouping_factor == 3)
+    if (c->p.grouping_factor == 3 && c->mb_kernel == 4)
+        TB_CUDA(tbk::launch_bsk_convert_multibit_v4((const uint64_t *)raw.p, c->bskf.p, c->tbl16.p, (int)n_polys, c->stream));
+    else if (c->p.grouping_factor == 3)
         TB_CUDA(tbk::launch_bsk_convert_multibit((const uint64_t *)raw.p, c->bskf.p, c->tbl.p, (int)n_polys, c->stream));
     else if (c->pbs_kernel == 4)
         TB_CUDA(tbk::launch_bsk_convert_v4((const uint64_t *)raw.p, c->bskf.p, c->tbl16.p, (int)n_polys, c->stream));

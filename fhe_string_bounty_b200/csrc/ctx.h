@@ -56,6 +56,7 @@ struct tfhe_b200_ctx {
     int ks_kernel = 1;    // 1: tensor-core GEMM (keyswitch_mma.cu), 0: IMAD GEMM (keyswitch.cu); env TFHE_B200_KS_KERNEL=imad
     uint32_t n_luts = 0;
     bool have_ksk = false, have_bsk = false;
+    int mb_kernel = 4;    // multi-bit: 4 = pbs_multibit_v4.cu (16 points per thread), 3 = pbs_multibit.cu; env TFHE_B200_MB_KERNEL
     int pbs_kernel = 4;   // 4: TMEM + TMA ring, 16 FFT points per thread (pbs_v4.cu); 3: same data path, 32 points per thread (pbs_v3.cu); 2: one CTA per ciphertext (pbs.cu); env TFHE_B200_PBS_KERNEL
     // staging for the host-pointer entry points
     tbc::DevBuf d_in, d_small, d_out, d_idx;

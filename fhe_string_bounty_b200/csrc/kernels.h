@@ -59,6 +59,13 @@ struct LinTerm {
 cudaError_t launch_linear(uint64_t *arena, const LinInstr *instrs, const LinTerm *terms, int n_instrs, int lwe_len,
                           cudaStream_t stream);
 
+// pbs_multibit_v4.cu (16 FFT points per thread, 1/2/4 ciphertexts per CTA; tbl16 = fft16_core.cuh tables)
+cudaError_t pbs_multibit_v4_configure();
+cudaError_t launch_pbs_multibit_v4(const uint64_t *lwe_small, const uint32_t *lut_idx, const uint64_t *luts, const void *bskm,
+                                   const void *tbl16, const void *roots, uint64_t *out, const uint32_t *out_slot, int batch, int n,
+                                   int base_log, int n_groups, cudaStream_t stream);
+cudaError_t launch_bsk_convert_multibit_v4(const uint64_t *bsk_std, void *bskm, const void *tbl16, int n_polys, cudaStream_t stream);
+
 // seeded.cu: dst row g = [mask_len words of the AES-128 CTR stream of `seed` | body_len words copied from bodies]
 cudaError_t launch_seeded_expand(const uint8_t seed[16], uint64_t *dst, const uint64_t *bodies, size_t n_rows, uint32_t mask_len,
                                  uint32_t body_len, cudaStream_t stream);
