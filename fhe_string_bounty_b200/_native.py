@@ -115,6 +115,12 @@ EXPORTS = {
     "tfhe_b200_upload_seeded_ksk": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "tfhe_b200_upload_seeded_bsk": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "tfhe_b200_upload_luts": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32]),
+    "tfhe_b200_wire_parse_compressed_server_key": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p]),
+    "tfhe_b200_load_compressed_server_key": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "tfhe_b200_wire_read_ciphertexts": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p,
+                                                  C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "tfhe_b200_wire_write_ciphertexts": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t,
+                                                   C.POINTER(C.c_size_t)]),
     "tfhe_b200_keyswitch_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "tfhe_b200_pbs_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "tfhe_b200_ks_pbs_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
@@ -224,6 +230,11 @@ class Engine:
         bodies = np.ascontiguousarray(bodies, dtype=np.uint64)
         assert seed16.size == 16
         self._check(self.lib.tfhe_b200_upload_seeded_bsk(self.h, _ptr(seed16), _ptr(bodies), bodies.size))
+
+    def load_compressed_server_key(self, blob: bytes):
+        """bincode-serialized shortint::CompressedServerKey (tfhe-rs 0.5): parsed on the host, masks re-drawn on the device"""
+        buf = np.frombuffer(blob, dtype=np.uint8)
+        self._check(self.lib.tfhe_b200_load_compressed_server_key(self.h, _ptr(buf), buf.size))
 
     def upload_luts(self, luts: np.ndarray):
         luts = np.ascontiguousarray(luts, dtype=np.uint64).reshape(-1, self.p.lut_len)

@@ -1,6 +1,7 @@
 // c_api.cu -- extern "C" boundary of libtfhe_b200.so (see include/tfhe_b200.h for the reference
 // interfaces each entry point replaces).  Plain pointers and sizes only; no torch types.
 #include "ctx.h"
+#include "host/wire.h"
 #include <chrono>
 
 namespace {
@@ -287,6 +288,90 @@ int tfhe_b200_upload_seeded_ksk(tfhe_b200_ctx *c, const uint8_t seed[16], const 
 }
 int tfhe_b200_upload_seeded_bsk(tfhe_b200_ctx *c, const uint8_t seed[16], const uint64_t *bodies, size_t len) {
     return upload_seeded(c, seed, bodies, len, true);
+}
+
+// ---- tfhe-rs wire format (host/wire.h) ----------------------------------------------------------------------------------
+static void fill_wire_view(const tbw::ServerKeyView &v, tfhe_b200_wire_server_key *out) {
+    std::memset(out, 0, sizeof(*out));
+    out->params.lwe_dim = v.lwe_dim; out->params.glwe_dim = v.glwe_dim; out->params.poly_size = v.poly_size;
+    out->params.pbs_base_log = v.pbs_base_log; out->params.pbs_level = v.pbs_level;
+    out->params.ks_base_log = v.ks_base_log; out->params.ks_level = v.ks_level;
+    out->params.grouping_factor = v.grouping_factor; out->params.msg_mod = v.msg_mod; out->params.carry_mod = v.carry_mod;
+    out->pbs_order = v.pbs_order; out->deterministic_execution = v.deterministic; out->max_degree = v.max_degree;
+    std::memcpy(out->ksk_seed, v.ksk_seed, 16); std::memcpy(out->bsk_seed, v.bsk_seed, 16);
+    out->ksk_byte_offset = v.ksk_off; out->ksk_words = v.ksk_len; out->bsk_byte_offset = v.bsk_off; out->bsk_words = v.bsk_len;
+}
+
+int tfhe_b200_wire_parse_compressed_server_key(const uint8_t *bytes, size_t len, tfhe_b200_wire_server_key *out) {
+    if (!bytes || !out) return fail("null argument");
+    try {
+        fill_wire_view(tbw::parse_compressed_server_key(bytes, len), out);
+    } catch (const std::exception &e) {
+        return fail(e.what());
+    }
+    return 0;
+}
+
+int tfhe_b200_load_compressed_server_key(tfhe_b200_ctx *c, const uint8_t *bytes, size_t len) {
+    if (!c || !bytes) return fail("null argument");
+    tbw::ServerKeyView v;
+    try {
+        v = tbw::parse_compressed_server_key(bytes, len);
+    } catch (const std::exception &e) {
+        return fail(e.what());
+    }
+    const tfhe_b200_params &p = c->p;
+    if (v.lwe_dim != p.lwe_dim || v.glwe_dim != p.glwe_dim || v.poly_size != p.poly_size || v.pbs_base_log != p.pbs_base_log ||
+        v.pbs_level != p.pbs_level || v.ks_base_log != p.ks_base_log || v.ks_level != p.ks_level ||
+        v.grouping_factor != p.grouping_factor || v.msg_mod != p.msg_mod || v.carry_mod != p.carry_mod)
+        return fail("serialized server key does not match the context's parameter set");
+    // the u64 arrays sit at arbitrary byte offsets inside the blob: copy them out to aligned storage first
+    std::vector<uint64_t> ksk(v.ksk_len), bsk(v.bsk_len);
+    std::memcpy(ksk.data(), bytes + v.ksk_off, v.ksk_len * 8);
+    std::memcpy(bsk.data(), bytes + v.bsk_off, v.bsk_len * 8);
+    if (int rc = tfhe_b200_upload_seeded_ksk(c, v.ksk_seed, ksk.data(), ksk.size())) return rc;
+    return tfhe_b200_upload_seeded_bsk(c, v.bsk_seed, bsk.data(), bsk.size());
+}
+
+int tfhe_b200_wire_read_ciphertexts(const uint8_t *bytes, size_t len, int is_radix, uint64_t *lwe_out, size_t lwe_cap_words,
+                                    uint64_t *meta_out, size_t *n_cts, size_t *lwe_len) {
+    if (!bytes || !n_cts || !lwe_len) return fail("null argument");
+    std::vector<uint64_t> lwe;
+    std::vector<tbw::CiphertextMeta> meta;
+    size_t ll = 0;
+    try {
+        tbw::parse_ciphertexts(bytes, len, is_radix != 0, lwe, ll, meta);
+    } catch (const std::exception &e) {
+        return fail(e.what());
+    }
+    *n_cts = meta.size();
+    *lwe_len = ll;
+    if (!lwe_out) return 0;                       // size query
+    if (lwe_cap_words < lwe.size()) return fail("output buffer too small for the serialized ciphertexts");
+    std::memcpy(lwe_out, lwe.data(), lwe.size() * 8);
+    if (meta_out)
+        for (size_t i = 0; i < meta.size(); ++i) {
+            meta_out[5 * i] = meta[i].degree; meta_out[5 * i + 1] = meta[i].noise_level; meta_out[5 * i + 2] = meta[i].msg_mod;
+            meta_out[5 * i + 3] = meta[i].carry_mod; meta_out[5 * i + 4] = meta[i].pbs_order;
+        }
+    return 0;
+}
+
+int tfhe_b200_wire_write_ciphertexts(const uint64_t *lwe, size_t lwe_len, const uint64_t *meta, size_t n_cts, int is_radix,
+                                     uint8_t *out, size_t out_cap, size_t *out_len) {
+    if (!lwe || !meta || !out_len || lwe_len == 0) return fail("null argument");
+    if (!is_radix && n_cts != 1) return fail("a single shortint::Ciphertext holds exactly one LWE ciphertext");
+    std::vector<tbw::CiphertextMeta> m(n_cts);
+    for (size_t i = 0; i < n_cts; ++i) {
+        m[i].degree = meta[5 * i]; m[i].noise_level = meta[5 * i + 1]; m[i].msg_mod = meta[5 * i + 2];
+        m[i].carry_mod = meta[5 * i + 3]; m[i].pbs_order = (uint32_t)meta[5 * i + 4];
+    }
+    const std::vector<uint8_t> b = tbw::write_ciphertexts(lwe, lwe_len, m.data(), n_cts, is_radix != 0);
+    *out_len = b.size();
+    if (!out) return 0;                           // size query
+    if (out_cap < b.size()) return fail("output buffer too small for the serialized ciphertexts");
+    std::memcpy(out, b.data(), b.size());
+    return 0;
 }
 
 int tfhe_b200_upload_luts(tfhe_b200_ctx *c, const uint64_t *luts, uint32_t n_luts) {

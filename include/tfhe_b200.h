@@ -68,6 +68,30 @@ int tfhe_b200_upload_luts(tfhe_b200_ctx *ctx, const uint64_t *luts, uint32_t n_l
 int tfhe_b200_upload_seeded_ksk(tfhe_b200_ctx *ctx, const uint8_t seed[16], const uint64_t *bodies, size_t len);
 int tfhe_b200_upload_seeded_bsk(tfhe_b200_ctx *ctx, const uint8_t seed[16], const uint64_t *bodies, size_t len);
 
+/* tfhe-rs wire format: bincode 1.3.3 with fixed-width little-endian integers, i.e. what `bincode::serialize` and
+ * safe_serialize (tfhe/src/safe_deserialization.rs:13-34) emit, for shortint::CompressedServerKey (shortint/server_key/compressed.rs:
+ * 10-17,43-55), shortint::Ciphertext (shortint/ciphertext/mod.rs:261-270) and BaseRadixCiphertext { blocks: Vec<Ciphertext> }
+ * (integer/ciphertext/mod.rs:18-30).  Layout restated from the serde derives (fhe_string_bounty_b200/csrc/host/wire.h); no real
+ * tfhe-rs blob is available in this environment to pin it ("parity unpinned").
+ * parse_compressed_server_key: no GPU needed; tells the caller which parameter set to create the context with.
+ * load_compressed_server_key:  parse + tfhe_b200_upload_seeded_ksk + tfhe_b200_upload_seeded_bsk.
+ * read/write_ciphertexts:      lwe = n_cts x lwe_len words; meta = 5 words per ciphertext {degree, noise_level, message_modulus,
+ *                              carry_modulus, pbs_order}.  Pass lwe_out / out = NULL to query the sizes. */
+typedef struct {
+    tfhe_b200_params params;
+    uint32_t pbs_order;                 /* core_crypto/commons/parameters.rs:233-245: 0 = KeyswitchBootstrap, 1 = BootstrapKeyswitch */
+    uint32_t deterministic_execution;   /* multi-bit only */
+    uint64_t max_degree;
+    uint8_t ksk_seed[16], bsk_seed[16];
+    uint64_t ksk_byte_offset, ksk_words, bsk_byte_offset, bsk_words;   /* where the two body arrays sit inside the blob */
+} tfhe_b200_wire_server_key;
+int tfhe_b200_wire_parse_compressed_server_key(const uint8_t *bytes, size_t len, tfhe_b200_wire_server_key *out);
+int tfhe_b200_load_compressed_server_key(tfhe_b200_ctx *ctx, const uint8_t *bytes, size_t len);
+int tfhe_b200_wire_read_ciphertexts(const uint8_t *bytes, size_t len, int is_radix, uint64_t *lwe_out, size_t lwe_cap_words,
+                                    uint64_t *meta_out, size_t *n_cts, size_t *lwe_len);
+int tfhe_b200_wire_write_ciphertexts(const uint64_t *lwe, size_t lwe_len, const uint64_t *meta, size_t n_cts, int is_radix,
+                                     uint8_t *out, size_t out_cap, size_t *out_len);
+
 /* Batched hot path, HOST buffers (H2D + kernels + D2H inside the call, synchronous).
  * lwe_big:   batch x (k*N + 1) words under the big key;  lwe_small: batch x (n + 1) words.
  * lut_idx:   batch indices into the uploaded LUT table (NULL = LUT 0 for all).

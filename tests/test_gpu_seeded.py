@@ -71,3 +71,34 @@ def test_seeded_upload_errors(orc, keys_2_2):
         e.upload_seeded_bsk(seed, np.zeros(2048, dtype=np.uint64))
     assert e.lib.tfhe_b200_upload_seeded_ksk(e.h, None, None, 0) != 0
     e.close()
+
+
+def test_load_serialized_compressed_server_key(orc, keys_2_2):
+    """bincode blob -> tfhe_b200_load_compressed_server_key == upload_seeded_* with the same seeds and bodies (identical ciphertexts);
+    a blob of another parameter set is refused."""
+    import fhe_string_bounty_b200 as F
+    from fhe_string_bounty_b200 import wire
+    from oracle import wire as W
+    p, ck, sk = keys_2_2
+    csk = orc.CompressedServerKey(ck, sk, ksk_seed=11, bsk_seed=22)
+    blob = W.serialize_compressed_server_key(csk)
+    v = wire.parse_compressed_server_key(blob)
+    a = F.Engine(F.Params(**{k: getattr(v.params, k) for k, _ in F.Params._fields_}))   # parameter set discovered from the blob
+    a.load_compressed_server_key(blob)
+    b = F.Engine(engine_params(p))
+    b.upload_seeded_ksk(csk.ksk_seed, csk.ksk_bodies)
+    b.upload_seeded_bsk(csk.bsk_seed, csk.bsk_bodies)
+    acc, _ = sk.generate_lookup_table(lambda x: (x + 7) % 16)
+    for e in (a, b):
+        e.upload_luts(acc[None, :])
+    vals = np.arange(16)
+    cts = ck.encrypt_batch(vals)
+    out_a, out_b = a.ks_pbs_batch(cts, None), b.ks_pbs_batch(cts, None)
+    assert np.array_equal(out_a, out_b)
+    assert list(ck.decrypt_batch(out_a)) == [(int(x) + 7) % 16 for x in vals]
+    toy = orc.params("toy")
+    tck = orc.ClientKey(toy, 1)
+    tsk = orc.ServerKey(tck, 2, fourier=False)
+    with pytest.raises(RuntimeError, match="parameter set"):
+        a.load_compressed_server_key(W.serialize_compressed_server_key(orc.CompressedServerKey(tck, tsk, 1, 2)))
+    a.close(); b.close()
