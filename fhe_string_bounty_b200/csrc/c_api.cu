@@ -76,6 +76,12 @@ int do_pbs(tfhe_b200_ctx *c, const uint64_t *d_small, const uint32_t *d_idx, con
         c->launches += 1;
         return 0;
     }
+    if (c->pbs_kernel == 4 && c->narrow_kernel == 8 && batch <= (size_t)2 * c->sms) {
+        TB_CUDA(tbk::launch_pbs_classic_v8(d_small, d_idx, d_luts, c->bskf8.p, c->tbl8.p, d_out, out_slot, (int)batch, (int)c->p.lwe_dim,
+                                           (int)c->p.pbs_base_log, (int)n_iters, fused ? 1 : 0, s));
+        c->launches += 1;
+        return 0;
+    }
     if (c->pbs_kernel == 4) {
         TB_CUDA(tbk::launch_pbs_classic_v4(d_small, d_idx, d_luts, c->bskf.p, c->tbl16.p, d_out, out_slot, (int)batch, (int)c->p.lwe_dim,
                                            (int)c->p.pbs_base_log, (int)n_iters, fused ? 1 : 0, s));
@@ -129,6 +135,9 @@ int tfhe_b200_ctx_create(int cuda_device, const tfhe_b200_params *params, tfhe_b
     TB_CUDA(tbk::pbs_configure());
     TB_CUDA(tbk::pbs_v3_configure());
     TB_CUDA(tbk::pbs_v4_configure());
+    TB_CUDA(tbk::pbs_v8_configure());
+    if (const char *e = std::getenv("TFHE_B200_NARROW_KERNEL")) c->narrow_kernel = (e[0] == '8') ? 8 : 0;
+    TB_CUDA(cudaDeviceGetAttribute(&c->sms, cudaDevAttrMultiProcessorCount, cuda_device));
     if (const char *e = std::getenv("TFHE_B200_MB_KERNEL")) c->mb_kernel = (e[0] == '3') ? 3 : 4;
     TB_CUDA(tbk::pbs_multibit_configure());
     TB_CUDA(tbk::pbs_multibit_v4_configure());
@@ -149,6 +158,10 @@ int tfhe_b200_ctx_create(int cuda_device, const tfhe_b200_params *params, tfhe_b
     tb16_make_tables(tbl16.data(), tbl16.data() + 2 * tb::kM);
     TB_CUDA(c->tbl16.reserve(tbl16.size() * sizeof(double)));
     TB_CUDA(cudaMemcpyAsync(c->tbl16.p, tbl16.data(), tbl16.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    std::vector<double> tbl8(2 * 24 * 128);
+    tb8_make_tables(tbl8.data());
+    TB_CUDA(c->tbl8.reserve(tbl8.size() * sizeof(double)));
+    TB_CUDA(cudaMemcpyAsync(c->tbl8.p, tbl8.data(), tbl8.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     TB_CUDA(cudaStreamSynchronize(c->stream));
     *out = c;
     return 0;
@@ -158,7 +171,7 @@ int tfhe_b200_ctx_destroy(tfhe_b200_ctx *c) {
     if (!c) return 0;
     DeviceGuard g(c->device);
     cudaStreamSynchronize(c->stream);
-    for (DevBuf *b : {&c->ksk_packed, &c->ksk_colsum, &c->ksk_planes, &c->ks_digits, &c->bskf, &c->tbl, &c->tbl16, &c->roots, &c->luts, &c->d_in, &c->d_small, &c->d_out, &c->d_idx})
+    for (DevBuf *b : {&c->ksk_packed, &c->ksk_colsum, &c->ksk_planes, &c->ks_digits, &c->bskf, &c->bskf8, &c->tbl, &c->tbl16, &c->tbl8, &c->roots, &c->luts, &c->d_in, &c->d_small, &c->d_out, &c->d_idx})
         b->release();
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     for (auto &L : c->lane) {
@@ -202,8 +215,14 @@ static int finish_bsk(tfhe_b200_ctx *c, const tbc::DevBuf &raw) {
         TB_CUDA(tbk::launch_bsk_convert_multibit_v4((const uint64_t *)raw.p, c->bskf.p, c->tbl16.p, (int)n_polys, c->stream));
     else if (c->p.grouping_factor == 3)
         TB_CUDA(tbk::launch_bsk_convert_multibit((const uint64_t *)raw.p, c->bskf.p, c->tbl.p, (int)n_polys, c->stream));
-    else if (c->pbs_kernel == 4)
+    else if (c->pbs_kernel == 4) {
         TB_CUDA(tbk::launch_bsk_convert_v4((const uint64_t *)raw.p, c->bskf.p, c->tbl16.p, (int)n_polys, c->stream));
+        if (c->narrow_kernel == 8) {   // second copy of the key, in the narrow-level kernel's (thread, register) order
+            TB_CUDA(c->bskf8.reserve(n_polys * tb::kM * sizeof(double) * 2));
+            TB_CUDA(tbk::launch_bsk_convert_v8((const uint64_t *)raw.p, c->bskf8.p, c->tbl8.p, (int)n_polys, c->stream));
+            c->launches += 1;
+        }
+    }
     else if (c->pbs_kernel == 3)
         TB_CUDA(tbk::launch_bsk_convert_v3((const uint64_t *)raw.p, c->bskf.p, c->tbl.p, (int)n_polys, c->stream));
     else

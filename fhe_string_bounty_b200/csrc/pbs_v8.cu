@@ -1,0 +1,448 @@
+// pbs_v8.cu -- blind rotation for NARROW tree levels (at most two ciphertexts per SM): the data path of pbs_v4.cu (TMA-fed key
+// ring, accumulator master copy and FFT twiddles in Tensor Memory) with FOUR warps per polynomial and 8 FFT points per thread
+// (fft8_core.cuh), i.e. eight warps per ciphertext.
+//
+// Why: a level of <= 148 blocks puts one ciphertext on an SM.  With pbs_v4's four warps per ciphertext that is one warp per
+// scheduler: ncu (scripts/narrow_level_case.py) shows issue slots 26 % busy and the warp stalled on its own instruction fetch
+// (no_instruction 0.55 per instruction), fixed-latency waits (0.68) and shared-memory round trips (0.60) -- nothing to overlap
+// them with.  Eight warps do half the instructions each and give every scheduler two warps.  The price (a third exchange per
+// FFT, 50 % more shared-memory traffic) does not matter when the SM is otherwise idle; wide levels keep using pbs_v4.cu.
+//
+// STATUS: experimental, off by default (TFHE_B200_NARROW_KERNEL=8).  Measured: a 148-block level takes 4.02 ms against pbs_v4's 4.13-4.19 ms.
+// ncu (one ciphertext per SM): this kernel moves 7.1 k shared-memory wavefronts per iteration (pbs_v4: 3.6 k; the third exchange is
+// 2-way bank conflicted), so its LSU pipe is 69 % busy while pbs_v4's narrow instance is purely latency bound (LSU 36 %, issue 26 %):
+// the iteration is a ~10.5 k-cycle dependency chain either way.  Kept as the starting point for a shuffle-based third exchange.
+//
+// Same arithmetic definition as the other generations (bootstrap.rs:242-364, ggsw.rs:477-598, fft/mod.rs:197-326).
+// Named barriers: 1..4 one per polynomial (128 threads), 5..6 one per ciphertext (256 threads).
+#include "kernels.h"
+#include "fft8_core.cuh"
+#include "pbs16_common.cuh"
+
+namespace tb8k {
+using namespace tb;          // cplx, kN, kM, integer helpers of the blind rotation
+using namespace tbr;         // mbarrier / bulk-copy helpers
+using namespace tb8;         // the 128-thread FFT
+using tb16k::bar_sync;
+using tb16k::BlockSync;
+using tb16k::cplx_from_words;
+using tb16k::tmem_alloc;
+using tb16k::tmem_dealloc;
+using tb16k::tmem_ld16;
+using tb16k::tmem_st16;
+using tb16k::tmem_wait_ld;
+using tb16k::tmem_wait_st;
+
+constexpr int PIECE_CPLX = 512;        // [out poly 2][sel 2][thread 128]: one frequency (register) per thread
+constexpr int PIECE_BYTES = PIECE_CPLX * 16;
+constexpr int PIECES_PER_ITER = 8;
+constexpr int NSLOT = 10;
+
+template <int CTS>
+struct Smem {
+    cplx tile[2 * CTS][tb8::kTileCplx];    // 17 KiB per polynomial
+    cplx ring[NSLOT][PIECE_CPLX];          // 80 KiB
+    unsigned long long full_bar[NSLOT];
+    unsigned int consumed[NSLOT];
+    uint32_t tmem_base;
+};
+static_assert(sizeof(Smem<2>) <= 227 * 1024, "shared memory budget");
+
+struct PolySync128 {
+    int id;
+    __device__ __forceinline__ void operator()() const { bar_sync(id, 128); }
+};
+
+// Fourier key, v8 layout: [ggsw i][register g 8][out poly c][sel: 0 = row c, 1 = row 1-c][thread 128]
+__device__ __forceinline__ size_t bskf8_index(int i, int g, int c, int sel) {
+    return (((size_t)(i * PIECES_PER_ITER + g) * 2 + c) * 2 + sel) * 128;
+}
+
+// the 24 per-thread twiddles (fft8_core.cuh: T1, T2, T3) from this thread's TMEM lane (96 columns) or from the global table
+struct TmemTw8 {
+    uint32_t col;
+    __device__ __forceinline__ void load(int block, cplx (&tw)[8]) const {
+        uint32_t v[16];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            tmem_ld16(col + 32 * block + 16 * h, v);
+            tmem_wait_ld();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) tw[4 * h + q] = cplx_from_words(v, q);
+        }
+    }
+};
+// one ciphertext per CTA leaves 255 registers per thread: all 24 twiddles simply stay in registers
+struct RegTw8 {
+    const cplx (&t)[24];
+    __device__ __forceinline__ void load(int block, cplx (&tw)[8]) const {
+#pragma unroll
+        for (int p = 0; p < 8; ++p) tw[p] = t[8 * block + p];
+    }
+};
+struct GlobalTw8 {
+    const cplx *row;     // table + 24 * T
+    __device__ __forceinline__ void load(int block, cplx (&tw)[8]) const {
+#pragma unroll
+        for (int p = 0; p < 8; ++p) tw[p] = __ldg(row + 8 * block + p);
+    }
+};
+
+template <class F>
+__device__ __forceinline__ void st8(cplx *base, const double (&re)[8], const double (&im)[8], F off) {
+#pragma unroll
+    for (int p = 0; p < 8; ++p) { cplx v; v.x = re[p]; v.y = im[p]; base[off(p)] = v; }
+}
+template <class F>
+__device__ __forceinline__ void ld8(const cplx *base, double (&re)[8], double (&im)[8], F off) {
+#pragma unroll
+    for (int p = 0; p < 8; ++p) { const cplx v = base[off(p)]; re[p] = v.x; im[p] = v.y; }
+}
+
+// forward: on entry the tile may still be read by other threads (the first sync covers that); on exit thread t holds register r =
+// frequency freq_of8(t, r) and nobody but t touches t's exchange-C reader slots.
+template <class Tw, class Sync>
+__device__ __forceinline__ void fft8_fwd(double (&re)[8], double (&im)[8], cplx *tile, const Tw &twd, int T, Sync sync) {
+    cplx tw[8];
+    pretwist8_fwd(re, im);
+    radix8_dif(re, im);
+    twd.load(0, tw);
+    twiddle8<false>(re, im, tw, 0);
+    sync();
+    st8(tile + xa_wbase(T), re, im, [](int p) { return xa_woff(p); });
+    sync();
+    ld8(tile + xa_rbase(T), re, im, [](int p) { return xa_roff(p); });
+    radix8_dif(re, im);
+    twd.load(1, tw);
+    twiddle8<false>(re, im, tw, 1);
+    __syncwarp();     // from here on everything stays inside this half-warp's region of the tile
+    st8(tile + xb_wbase(T), re, im, [](int p) { return xb_woff(p); });
+    __syncwarp();
+    ld8(tile + xb_rbase(T), re, im, [](int p) { return xb_roff(p); });
+    radix4x2_dif(re, im);
+    twd.load(2, tw);
+    twiddle8<false>(re, im, tw, 0);
+    __syncwarp();
+    st8(tile + xc_wbase(T), re, im, [](int p) { return xc_woff(p); });
+    __syncwarp();
+    ld8(tile + xc_rbase(T), re, im, [](int p) { return xc_roff(p); });
+    radix4x2_dif(re, im);
+}
+
+// inverse (scaled by 1024): on entry nobody else may be reading this thread's exchange-C reader slots; on exit the tile may still be
+// read by other threads.
+template <class Tw, class Sync>
+__device__ __forceinline__ void fft8_inv(double (&re)[8], double (&im)[8], cplx *tile, const Tw &twd, int T, Sync sync) {
+    cplx tw[8];
+    radix4x2_dit_inv(re, im);
+    st8(tile + xc_rbase(T), re, im, [](int p) { return xc_roff(p); });
+    __syncwarp();
+    ld8(tile + xc_wbase(T), re, im, [](int p) { return xc_woff(p); });
+    twd.load(2, tw);
+    twiddle8<true>(re, im, tw, 0);
+    radix4x2_dit_inv(re, im);
+    __syncwarp();
+    st8(tile + xb_rbase(T), re, im, [](int p) { return xb_roff(p); });
+    __syncwarp();
+    ld8(tile + xb_wbase(T), re, im, [](int p) { return xb_woff(p); });
+    twd.load(1, tw);
+    twiddle8<true>(re, im, tw, 1);
+    radix8_dit_inv(re, im);
+    __syncwarp();
+    st8(tile + xa_rbase(T), re, im, [](int p) { return xa_roff(p); });
+    sync();
+    ld8(tile + xa_wbase(T), re, im, [](int p) { return xa_woff(p); });
+    twd.load(0, tw);
+    twiddle8<true>(re, im, tw, 0);
+    radix8_dit_inv(re, im);
+    posttwist8_inv(re, im);
+}
+
+template <int CTS>
+__global__ void __launch_bounds__(256 * CTS, 1)
+pbs_classic_kernel_v8(const uint64_t *__restrict__ lwe_small, const uint32_t *__restrict__ lut_idx, const uint64_t *__restrict__ luts,
+                      const cplx *__restrict__ bskf8, const cplx *__restrict__ tbl8, uint64_t *__restrict__ out,
+                      const uint32_t *__restrict__ out_slot, int batch, int n, int base_log, int n_iters, int small_is_u16) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int WARPS = 8 * CTS, TMEM_COLS = 256, TW_COL = 128;   // accumulators: 32 columns per (ciphertext, polynomial); twiddles: 96
+    constexpr bool REGS = CTS == 1;     // one ciphertext per CTA: twiddles and the accumulator master copy live in registers, no TMEM
+    Smem<CTS> &sm = *reinterpret_cast<Smem<CTS> *>(smem_raw);
+    const int W = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp -> (ciphertext, polynomial, quarter of the polynomial); TMEM lane quarter = warp id % 4 = quarter of the polynomial, so
+    // all warps that share a TMEM lane have the same thread index T and can share the twiddle columns
+    const int ctl = W >> 3, w = (W >> 2) & 1, T = ((W & 3) << 5) | lane, P = W >> 2;
+    const int ct_raw = blockIdx.x * CTS + ctl;
+    const bool live = ct_raw < batch;
+    const int ct = live ? ct_raw : batch - 1;        // ragged tail: recompute the last ciphertext, skip the store
+    cplx *tile = sm.tile[P];
+    const cplx *otile = sm.tile[P ^ 1];
+    uint64_t *pb = reinterpret_cast<uint64_t *>(tile);   // the polynomial (2048 words) for the rotated gather
+    const PolySync128 poly_sync{1 + P};
+    const int ct_bar = 5 + ctl;
+    const uint64_t *lwe = lwe_small + (size_t)ct * (n + 1);
+    const uint16_t *lwe16 = reinterpret_cast<const uint16_t *>(lwe_small) + (size_t)ct * (n + 1);
+    const int total_pieces = n_iters * PIECES_PER_ITER;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSLOT; ++s) { mbar_init(&sm.full_bar[s], 1); sm.consumed[s] = 0; }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_proxy_async();
+    }
+    if (!REGS && W == 0) tmem_alloc<TMEM_COLS>(&sm.tmem_base);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_lane = REGS ? 0u : sm.tmem_base + ((uint32_t)((W & 3) * 32) << 16);
+    const uint32_t tmem_mine = tmem_lane + (uint32_t)(32 * P);
+    const TmemTw8 twd_t{tmem_lane + (uint32_t)TW_COL};
+    cplx twr[24];
+    uint64_t accr[16];
+    const RegTw8 twd_r{twr};
+    if (REGS) {
+#pragma unroll
+        for (int k = 0; k < 24; ++k) twr[k] = __ldg(tbl8 + 24 * T + k);
+    } else {   // this thread's 24 twiddles -> TMEM (6 x 16 columns)
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            uint32_t v[16];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const cplx t = __ldg(tbl8 + 24 * T + 4 * k + q);
+                v[4 * q] = (uint32_t)__double2loint(t.x); v[4 * q + 1] = (uint32_t)__double2hiint(t.x);
+                v[4 * q + 2] = (uint32_t)__double2loint(t.y); v[4 * q + 3] = (uint32_t)__double2hiint(t.y);
+            }
+            tmem_st16(twd_t.col + 16 * k, v);
+        }
+    }
+    if (threadIdx.x == 0) {
+        const int first = total_pieces < NSLOT ? total_pieces : NSLOT;
+        for (int g = 0; g < first; ++g) {
+            mbar_expect_tx(&sm.full_bar[g], PIECE_BYTES);
+            tma_load_1d(sm.ring[g], bskf8 + (size_t)g * PIECE_CPLX, PIECE_BYTES, &sm.full_bar[g]);
+        }
+    }
+
+    // ---- acc <- LUT * X^(-b_hat): registers (own coefficients as u64 bit patterns in re/im), TMEM, shared ------------------------
+    double re[8], im[8];
+    {
+        const uint32_t b_hat = (small_is_u16 ? (uint32_t)__ldg(lwe16 + n) : modulus_switch_2n(__ldg(lwe + n))) & (2 * kN - 1);
+        const uint32_t a0 = (2 * kN - b_hat) & (2 * kN - 1);
+        const uint64_t *lut = luts + ((size_t)(lut_idx ? lut_idx[ct] : 0) * 2 + w) * kN;
+        uint32_t v[2][16];
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            const int j = T + 128 * m;
+            int s0, s1; bool n0, n1;
+            rot_src(j, a0, s0, n0);
+            rot_src(j + kM, a0, s1, n1);
+            uint64_t v0 = __ldg(lut + s0), v1 = __ldg(lut + s1);
+            v0 = n0 ? (uint64_t)0 - v0 : v0;
+            v1 = n1 ? (uint64_t)0 - v1 : v1;
+            pb[j] = v0; pb[j + kM] = v1;
+            re[m] = __longlong_as_double((long long)v0);
+            im[m] = __longlong_as_double((long long)v1);
+            uint32_t *d = &v[m >> 2][4 * (m & 3)];
+            d[0] = (uint32_t)v0; d[1] = (uint32_t)(v0 >> 32); d[2] = (uint32_t)v1; d[3] = (uint32_t)(v1 >> 32);
+            accr[2 * m] = v0; accr[2 * m + 1] = v1;
+        }
+        if (!REGS) {
+            tmem_st16(tmem_mine, v[0]);
+            tmem_st16(tmem_mine + 16, v[1]);
+            tmem_wait_st();
+        }
+    }
+
+    int slot = 0;            // ring position of this iteration's first piece
+    uint32_t phase = 0;
+
+    for (int i = 0; i < n_iters; ++i) {
+        const uint32_t a = (small_is_u16 ? (uint32_t)__ldg(lwe16 + i) : modulus_switch_2n(__ldg(lwe + i))) & (2 * kN - 1);   // a == 0 is NOT skipped
+        poly_sync();    // the accumulator polynomial is complete in shared memory
+
+        // ct1 = acc * X^a - acc, level-1 signed digit, folded (own coefficients come from the registers)
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            const int j = T + 128 * m;
+            const uint32_t s0 = ((uint32_t)j - a) & (2 * kN - 1);
+            const uint32_t s1 = (s0 + kM) & (2 * kN - 1);
+            uint64_t r0 = pb[s0 & (kN - 1)], r1 = pb[s1 & (kN - 1)];
+            r0 = (s0 >= (uint32_t)kN) ? (uint64_t)0 - r0 : r0;
+            r1 = (s1 >= (uint32_t)kN) ? (uint64_t)0 - r1 : r1;
+            const uint64_t o0 = (uint64_t)__double_as_longlong(re[m]), o1 = (uint64_t)__double_as_longlong(im[m]);
+            re[m] = (double)signed_digit_l1(r0 - o0, base_log);
+            im[m] = (double)signed_digit_l1(r1 - o1, base_log);
+        }
+
+        if (REGS) fft8_fwd(re, im, tile, twd_r, T, poly_sync); else fft8_fwd(re, im, tile, twd_t, T, poly_sync);
+
+        // spectrum exchange between the two polynomials of the ciphertext: park my 8 values in my own exchange-C reader slots
+        st8(tile + xc_rbase(T), re, im, [](int p) { return xc_roff(p); });
+        bar_sync(ct_bar, 256);
+
+        // out_fft[w] = F_w * G[w][w] + F_{1-w} * G[1-w][w]: one ring piece per register
+        {
+            uint32_t ready = 0;
+            {
+                int s = slot; uint32_t ph = phase;
+#pragma unroll
+                for (int c = 0; c < PIECES_PER_ITER; ++c) {
+                    ready |= (mbar_try_wait(&sm.full_bar[s], ph) ? 1u : 0u) << c;
+                    if (++s == NSLOT) { s = 0; ph ^= 1u; }
+                }
+            }
+            const cplx *fop = otile + xc_rbase(T);
+            unsigned int my_old = 0;
+            int my_slot = 0;
+#pragma unroll
+            for (int c = 0; c < PIECES_PER_ITER; ++c) {
+                if (!((ready >> c) & 1u)) mbar_wait(&sm.full_bar[slot], phase);
+                const cplx *pc = sm.ring[slot] + (w * 2) * 128 + T;
+                const cplx A = pc[0], B = pc[128], F = fop[xc_roff(c)];
+                const double fr = re[c], fi = im[c];
+                double orr = DMUL(fr, A.x);
+                orr = DFMA(-fi, A.y, orr);
+                orr = DFMA(F.x, B.x, orr);
+                orr = DFMA(-F.y, B.y, orr);
+                double oi = DMUL(fr, A.y);
+                oi = DFMA(fi, A.x, oi);
+                oi = DFMA(F.x, B.y, oi);
+                oi = DFMA(F.y, B.x, oi);
+                re[c] = orr; im[c] = oi;
+                // release: lane c counts this warp out of piece c's slot; nobody looks at the result inside the loop
+                __syncwarp();
+                if (lane == c) { my_old = atomicAdd(&sm.consumed[slot], 1u); my_slot = slot; }
+                if (++slot == NSLOT) { slot = 0; phase ^= 1u; }
+            }
+            if (lane < PIECES_PER_ITER && my_old == WARPS - 1) {
+                sm.consumed[my_slot] = 0;
+                const int g2 = i * PIECES_PER_ITER + lane + NSLOT;
+                if (g2 < total_pieces) {
+                    __threadfence_block();
+                    fence_proxy_async();
+                    mbar_expect_tx(&sm.full_bar[my_slot], PIECE_BYTES);
+                    tma_load_1d(sm.ring[my_slot], bskf8 + (size_t)g2 * PIECE_CPLX, PIECE_BYTES, &sm.full_bar[my_slot]);
+                }
+            }
+        }
+        bar_sync(ct_bar, 256);   // the partner polynomial has read my spectrum: the tile is mine again
+
+        if (REGS) fft8_inv(re, im, tile, twd_r, T, poly_sync); else fft8_inv(re, im, tile, twd_t, T, poly_sync);
+        poly_sync();    // everyone has read the last exchange: the tile becomes the accumulator polynomial again
+
+        // acc += from_torus(.): master copy in TMEM (registers when REGS), new values to registers (next gather's "own") and shared
+        if (REGS) {
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                const int j = T + 128 * m;
+                const uint64_t o0 = accr[2 * m] + from_torus_f64(re[m]), o1 = accr[2 * m + 1] + from_torus_f64(im[m]);
+                accr[2 * m] = o0; accr[2 * m + 1] = o1;
+                pb[j] = o0; pb[j + kM] = o1;
+                re[m] = __longlong_as_double((long long)o0);
+                im[m] = __longlong_as_double((long long)o1);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                uint32_t v[16];
+                tmem_ld16(tmem_mine + 16 * k, v);
+                tmem_wait_ld();
+#pragma unroll
+                for (int mm = 0; mm < 4; ++mm) {
+                    const int m = 4 * k + mm, j = T + 128 * m;
+                    uint64_t o0 = ((uint64_t)v[4 * mm + 1] << 32) | v[4 * mm];
+                    uint64_t o1 = ((uint64_t)v[4 * mm + 3] << 32) | v[4 * mm + 2];
+                    o0 += from_torus_f64(re[m]);
+                    o1 += from_torus_f64(im[m]);
+                    v[4 * mm] = (uint32_t)o0; v[4 * mm + 1] = (uint32_t)(o0 >> 32);
+                    v[4 * mm + 2] = (uint32_t)o1; v[4 * mm + 3] = (uint32_t)(o1 >> 32);
+                    pb[j] = o0; pb[j + kM] = o1;
+                    re[m] = __longlong_as_double((long long)o0);
+                    im[m] = __longlong_as_double((long long)o1);
+                }
+                tmem_st16(tmem_mine + 16 * k, v);
+            }
+            tmem_wait_st();
+        }
+    }
+
+    // sample extraction (coefficient 0) straight from the registers: out[0] = A[0], out[N-j] = -A[j]; body = B[0]
+    if (live) {
+        uint64_t *o = out + (size_t)(out_slot ? out_slot[ct] : ct) * (kN + 1);
+        if (w == 0) {
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                const int j = T + 128 * m;
+                const uint64_t v0 = (uint64_t)__double_as_longlong(re[m]), v1 = (uint64_t)__double_as_longlong(im[m]);
+                if (j == 0) o[0] = v0; else o[kN - j] = (uint64_t)0 - v0;
+                o[kN - (j + kM)] = (uint64_t)0 - v1;
+            }
+        } else if (T == 0) {
+            o[kN] = (uint64_t)__double_as_longlong(re[0]);
+        }
+    }
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (!REGS && W == 0) tmem_dealloc<TMEM_COLS>(sm.tmem_base);
+}
+
+// std -> Fourier key in the v8 ring layout (128 threads per polynomial; same forward transform as the kernel above)
+__global__ void __launch_bounds__(128)
+bsk_convert_kernel_v8(const uint64_t *__restrict__ bsk_std, cplx *__restrict__ bskf8, const cplx *__restrict__ tbl8, int n_polys) {
+    __shared__ cplx tile[tb8::kTileCplx];
+    const int qd = blockIdx.x, T = threadIdx.x;
+    if (qd >= n_polys) return;
+    const int i = qd >> 2, r = (qd >> 1) & 1, c = qd & 1;   // std layout [i][level 1][row r][col c][N]
+    const uint64_t *src = bsk_std + (size_t)qd * kN;
+    const double scale = 5.293955920339377e-23;              // 2^-74
+    double re[8], im[8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+        const int j = T + 128 * m;
+        re[m] = DMUL((double)(long long)src[j], scale);
+        im[m] = DMUL((double)(long long)src[j + kM], scale);
+    }
+    fft8_fwd(re, im, tile, GlobalTw8{tbl8 + 24 * T}, T, BlockSync{});
+    const int sel = (r == c) ? 0 : 1;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+        cplx v; v.x = re[g]; v.y = im[g];
+        bskf8[bskf8_index(i, g, c, sel) + T] = v;
+    }
+}
+
+}  // namespace tb8k
+
+namespace tbk {
+
+cudaError_t pbs_v8_configure() {
+    cudaError_t e = cudaFuncSetAttribute(tb8k::pbs_classic_kernel_v8<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tb8k::Smem<2>));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(tb8k::pbs_classic_kernel_v8<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tb8k::Smem<1>));
+}
+
+// batch <= 2 * SM count only (the caller dispatches wider levels to launch_pbs_classic_v4)
+cudaError_t launch_pbs_classic_v8(const uint64_t *lwe_small, const uint32_t *lut_idx, const uint64_t *luts, const void *bskf8,
+                                  const void *tbl8, uint64_t *out, const uint32_t *out_slot, int batch, int n, int base_log,
+                                  int n_iters, int small_is_u16, cudaStream_t stream) {
+    if (batch <= 0) return cudaSuccess;
+    int sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const tb::cplx *bk = reinterpret_cast<const tb::cplx *>(bskf8), *tb = reinterpret_cast<const tb::cplx *>(tbl8);
+    if (batch <= sms)
+        tb8k::pbs_classic_kernel_v8<1><<<batch, 256, sizeof(tb8k::Smem<1>), stream>>>(lwe_small, lut_idx, luts, bk, tb, out, out_slot, batch, n,
+                                                                                   base_log, n_iters, small_is_u16);
+    else
+        tb8k::pbs_classic_kernel_v8<2><<<(batch + 1) / 2, 512, sizeof(tb8k::Smem<2>), stream>>>(lwe_small, lut_idx, luts, bk, tb, out, out_slot,
+                                                                                             batch, n, base_log, n_iters, small_is_u16);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_bsk_convert_v8(const uint64_t *bsk_std, void *bskf8, const void *tbl8, int n_polys, cudaStream_t stream) {
+    tb8k::bsk_convert_kernel_v8<<<n_polys, 128, 0, stream>>>(bsk_std, reinterpret_cast<tb::cplx *>(bskf8),
+                                                           reinterpret_cast<const tb::cplx *>(tbl8), n_polys);
+    return cudaGetLastError();
+}
+
+}  // namespace tbk

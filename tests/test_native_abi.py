@@ -70,3 +70,14 @@ def test_cpu_mirror_of_two_warp_fft(tmp_path):
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout
     assert "OK" in out.stdout
+
+
+def test_cpu_mirror_of_four_warp_fft(tmp_path):
+    """tests/cpu_mirror/fft8_mirror.cpp: the 128-thread x 8-point FFT of the experimental narrow-level kernel (fft8_core.cuh)."""
+    import subprocess
+    exe = tmp_path / "fft8_mirror"
+    subprocess.run(["g++", "-O1", "-std=c++17", "-ffp-contract=off", str(ROOT / "tests/cpu_mirror/fft8_mirror.cpp"), "-o", str(exe)],
+                   check=True, env={"PATH": "/usr/bin:/bin"})
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout
+    assert "OK" in out.stdout
