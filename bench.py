@@ -192,6 +192,42 @@ def bench_string_ops(eng, p, rank, world, local):
     return out
 
 
+def bench_string_ops_multibit(eng, p, rank, world):
+    """BASELINE.json configs[4]: lexicographic lt / le on 128-char strings with the multi-bit parameter set.  A comparison is one
+    10-level tree ([256, 128, ..., 1, 1] blocks) that does not shard, so every rank runs whole comparisons (replicas): ops/s = ranks x
+    one rank's rate, latency = one rank's time."""
+    import torch
+    import torch.distributed as dist
+    import fhe_string_bounty_b200 as F
+    from fhe_string_bounty_b200.host import Program
+    params = dict(F.PARAM_MULTI_BIT_MESSAGE_2_CARRY_2_GROUP_3_KS_PBS)
+    rng = np.random.default_rng(78 + rank)
+    out = {}
+    for op in ("string_lt", "string_le"):
+        prog = Program(op, (128, 128), params=params)
+        ins = rng.integers(0, 2**64, size=(prog.n_inputs, p.big_len), dtype=np.uint64)
+        prog.run(eng, ins)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        reps = 5
+        for _ in range(reps):
+            prog.run(eng, ins)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t[0])
+        out[op[7:] + "_128char_ms"] = 1e3 * dt / reps
+        out[op[7:] + "_128char_ops_per_s"] = world * reps / dt
+        out[op[7:] + "_128char_pbs"] = prog.n_pbs
+        out[op[7:] + "_128char_levels"] = prog.level_widths
+    out["note"] = "host buffers in/out; a comparison tree does not shard: replicas only (each rank compares its own pair of strings)"
+    return out
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -279,6 +315,8 @@ def run_b200(args):
     string_ops = None
     if args.string_ops and args.params == "2_2":
         string_ops = bench_string_ops(eng, p, rank, world, local)
+    elif args.string_ops:
+        string_ops = bench_string_ops_multibit(eng, p, rank, world)
 
     if world > 1:
         t = torch.tensor([ms, e2e_s], device="cuda", dtype=torch.float64)
