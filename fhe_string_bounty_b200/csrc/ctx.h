@@ -57,7 +57,7 @@ struct tfhe_b200_ctx {
     int ks_kernel = 1;    // 1: tensor-core GEMM (keyswitch_mma.cu), 0: IMAD GEMM (keyswitch.cu); env TFHE_B200_KS_KERNEL=imad
     uint32_t n_luts = 0;
     bool have_ksk = false, have_bsk = false;
-    int narrow_kernel = 0;   // classic PBS, levels of <= 2 * SM count ciphertexts: 0 = the narrow instances of pbs_kernel (default); 8 = pbs_v8.cu, experimental (measured 3 % faster only; keeps a second copy of the Fourier key); env TFHE_B200_NARROW_KERNEL=8
+    int narrow_kernel = 8;   // classic PBS, levels of <= 2 * SM count ciphertexts: 8 = pbs_v8.cu (8 FFT points per thread, 8 warps per ciphertext; keeps a second copy of the Fourier key in its own layout), 0 = the narrow instances of pbs_kernel; env TFHE_B200_NARROW_KERNEL
     int sms = 148;
     int mb_kernel = 4;    // multi-bit: 4 = pbs_multibit_v4.cu (16 points per thread), 3 = pbs_multibit.cu; env TFHE_B200_MB_KERNEL
     int pbs_kernel = 4;   // 4: TMEM + TMA ring, 16 FFT points per thread (pbs_v4.cu); 3: same data path, 32 points per thread (pbs_v3.cu); 2: one CTA per ciphertext (pbs.cu); env TFHE_B200_PBS_KERNEL

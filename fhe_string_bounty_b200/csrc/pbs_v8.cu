@@ -8,10 +8,9 @@
 // them with.  Eight warps do half the instructions each and give every scheduler two warps.  The price (a third exchange per
 // FFT, 50 % more shared-memory traffic) does not matter when the SM is otherwise idle; wide levels keep using pbs_v4.cu.
 //
-// STATUS: experimental, off by default (TFHE_B200_NARROW_KERNEL=8).  Measured: a 148-block level takes 4.02 ms against pbs_v4's 4.13-4.19 ms.
-// ncu (one ciphertext per SM): this kernel moves 7.1 k shared-memory wavefronts per iteration (pbs_v4: 3.6 k; the third exchange is
-// 2-way bank conflicted), so its LSU pipe is 69 % busy while pbs_v4's narrow instance is purely latency bound (LSU 36 %, issue 26 %):
-// the iteration is a ~10.5 k-cycle dependency chain either way.  Kept as the starting point for a shuffle-based third exchange.
+// Measured on a 148-block level: pbs_v4's narrow instance 4.13 ms; this kernel with all three exchanges through shared memory 4.02 ms
+// (it moves 7.1 k shared-memory wavefronts per iteration against 3.6 k and becomes LSU bound, the pair exchange being 2-way bank
+// conflicted); with the pair exchange done by register shuffles (exchange_c_* below) 3.52 ms.  TFHE_B200_NARROW_KERNEL=0 disables it.
 //
 // Same arithmetic definition as the other generations (bootstrap.rs:242-364, ggsw.rs:477-598, fft/mod.rs:197-326).
 // Named barriers: 1..4 one per polynomial (128 threads), 5..6 one per ciphertext (256 threads).
@@ -99,6 +98,50 @@ __device__ __forceinline__ void ld8(const cplx *base, double (&re)[8], double (&
     for (int p = 0; p < 8; ++p) { const cplx v = base[off(p)]; re[p] = v.x; im[p] = v.y; }
 }
 
+// Exchange C between the two lanes of a pair through ONE shuffle per word instead of the tile (xc_* in fft8_core.cuh, which the CPU
+// mirror checks and which costs as many shared-memory wavefronts as exchanges A and B together because it is 2-way bank conflicted).
+// Lane bit b = c' (before) = e' (after).  Forward: register pe + 4*cl -> c + 4*pe0; a lane keeps its pe1 = b values and receives the
+// partner's.  The kept value goes to position c = cl, the received one to c = cl + 2 on BOTH lanes; on the b = 1 lane that is the wrong
+// way round (c and c + 2 swapped), which a radix-4 turns into a factor (-1)^f on its outputs -- fixed by negating the odd-f outputs.
+__device__ __forceinline__ void flip_odd_f(double (&re)[8], double (&im)[8], int b) {
+    if (b) {
+#pragma unroll
+        for (int g = 0; g < 8; g += 4) { re[g + 2] = -re[g + 2]; im[g + 2] = -im[g + 2]; re[g + 3] = -re[g + 3]; im[g + 3] = -im[g + 3]; }
+    }
+}
+__device__ __forceinline__ void exchange_c_fwd(double (&re)[8], double (&im)[8], int b) {
+    double ore[8], oim[8];
+#pragma unroll
+    for (int cl = 0; cl < 2; ++cl)
+#pragma unroll
+        for (int pe0 = 0; pe0 < 2; ++pe0) {
+            const int i0 = pe0 + 4 * cl, i1 = i0 + 2;                   // pe1 = 0, 1
+            const double kr = b ? re[i1] : re[i0], ki = b ? im[i1] : im[i0];
+            const double sr = b ? re[i0] : re[i1], si = b ? im[i0] : im[i1];
+            ore[cl + 4 * pe0] = kr; oim[cl + 4 * pe0] = ki;
+            ore[cl + 2 + 4 * pe0] = __shfl_xor_sync(0xffffffffu, sr, 1);
+            oim[cl + 2 + 4 * pe0] = __shfl_xor_sync(0xffffffffu, si, 1);
+        }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) { re[r] = ore[r]; im[r] = oim[r]; }
+}
+// inverse: register c + 4*pe0 (already swapped on the b = 1 lane by negating the odd-f INPUTS of the inverse radix-4) -> pe + 4*cl
+__device__ __forceinline__ void exchange_c_inv(double (&re)[8], double (&im)[8], int b) {
+    double ore[8], oim[8];
+#pragma unroll
+    for (int cl = 0; cl < 2; ++cl)
+#pragma unroll
+        for (int pe0 = 0; pe0 < 2; ++pe0) {
+            const double kr = re[cl + 4 * pe0], ki = im[cl + 4 * pe0];
+            const double rr = __shfl_xor_sync(0xffffffffu, re[cl + 2 + 4 * pe0], 1), ri = __shfl_xor_sync(0xffffffffu, im[cl + 2 + 4 * pe0], 1);
+            const int i0 = pe0 + 4 * cl, i1 = i0 + 2;
+            ore[i0] = b ? rr : kr; oim[i0] = b ? ri : ki;
+            ore[i1] = b ? kr : rr; oim[i1] = b ? ki : ri;
+        }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) { re[r] = ore[r]; im[r] = oim[r]; }
+}
+
 // forward: on entry the tile may still be read by other threads (the first sync covers that); on exit thread t holds register r =
 // frequency freq_of8(t, r) and nobody but t touches t's exchange-C reader slots.
 template <class Tw, class Sync>
@@ -122,11 +165,10 @@ __device__ __forceinline__ void fft8_fwd(double (&re)[8], double (&im)[8], cplx 
     radix4x2_dif(re, im);
     twd.load(2, tw);
     twiddle8<false>(re, im, tw, 0);
-    __syncwarp();
-    st8(tile + xc_wbase(T), re, im, [](int p) { return xc_woff(p); });
-    __syncwarp();
-    ld8(tile + xc_rbase(T), re, im, [](int p) { return xc_roff(p); });
+    exchange_c_fwd(re, im, T & 1);
     radix4x2_dif(re, im);
+    flip_odd_f(re, im, T & 1);
+    __syncwarp();     // the other lanes of the half-warp are done reading exchange B: the C-reader slots may be reused for the spectrum
 }
 
 // inverse (scaled by 1024): on entry nobody else may be reading this thread's exchange-C reader slots; on exit the tile may still be
@@ -134,10 +176,9 @@ __device__ __forceinline__ void fft8_fwd(double (&re)[8], double (&im)[8], cplx 
 template <class Tw, class Sync>
 __device__ __forceinline__ void fft8_inv(double (&re)[8], double (&im)[8], cplx *tile, const Tw &twd, int T, Sync sync) {
     cplx tw[8];
+    flip_odd_f(re, im, T & 1);
     radix4x2_dit_inv(re, im);
-    st8(tile + xc_rbase(T), re, im, [](int p) { return xc_roff(p); });
-    __syncwarp();
-    ld8(tile + xc_wbase(T), re, im, [](int p) { return xc_woff(p); });
+    exchange_c_inv(re, im, T & 1);
     twd.load(2, tw);
     twiddle8<true>(re, im, tw, 0);
     radix4x2_dit_inv(re, im);

@@ -108,24 +108,25 @@ def test_kernels_do_not_write_outside_their_buffers(orc, keys_2_2):
     eng.close()
 
 
-def test_experimental_narrow_level_kernel(orc, keys_2_2, monkeypatch):
-    """pbs_v8.cu (TFHE_B200_NARROW_KERNEL=8: 8 FFT points per thread, 8 warps per ciphertext) decrypts like the default kernels for both of
-    its instances (<= SM count: 1 ciphertext per CTA, registers only; <= 2 * SM count: 2 per CTA, TMEM)."""
+def test_narrow_level_kernel_on_and_off(orc, keys_2_2, monkeypatch):
+    """pbs_v8.cu (8 FFT points per thread, 8 warps per ciphertext; TFHE_B200_NARROW_KERNEL=0 falls back to pbs_v4's narrow instances) decrypts
+    correctly for both of its instances (<= SM count: 1 ciphertext per CTA, registers only; <= 2 * SM count: 2 per CTA, TMEM)."""
     import torch
     import fhe_string_bounty_b200 as F
     p, ck, sk = keys_2_2
-    monkeypatch.setenv("TFHE_B200_NARROW_KERNEL", "8")
-    eng = F.Engine(engine_params(p))
-    eng.upload_ksk(sk.ksk)
-    eng.upload_bsk_std(sk.bsk)
     acc, _ = sk.generate_lookup_table(lambda x: (11 * x + 5) % 16)
-    eng.upload_luts(acc[None, :])
     sms = torch.cuda.get_device_properties(0).multi_processor_count
     base = ck.encrypt_batch(np.arange(32) % 16)
-    for batch in (1, 7, sms, sms + 5, 2 * sms):
-        reps = -(-batch // 32)
-        cts = np.tile(base, (reps, 1))[:batch]
-        vals = np.tile(np.arange(32) % 16, reps)[:batch]
-        out = eng.ks_pbs_batch(cts, None)
-        assert list(ck.decrypt_batch(out)) == [(11 * int(v) + 5) % 16 for v in vals], batch
-    eng.close()
+    for mode in ("8", "0"):
+        monkeypatch.setenv("TFHE_B200_NARROW_KERNEL", mode)
+        eng = F.Engine(engine_params(p))
+        eng.upload_ksk(sk.ksk)
+        eng.upload_bsk_std(sk.bsk)
+        eng.upload_luts(acc[None, :])
+        for batch in (1, 7, sms, sms + 5, 2 * sms):
+            reps = -(-batch // 32)
+            cts = np.tile(base, (reps, 1))[:batch]
+            vals = np.tile(np.arange(32) % 16, reps)[:batch]
+            out = eng.ks_pbs_batch(cts, None)
+            assert list(ck.decrypt_batch(out)) == [(11 * int(v) + 5) % 16 for v in vals], (mode, batch)
+        eng.close()

@@ -146,14 +146,14 @@ def test_pbs_then_keyswitch_order(orc, keys_2_2, eng):
 def test_every_kernel_instance_boundary(orc, keys_2_2, eng):
     """Batch sizes around the switches between the 1-, 2- and 4-ciphertext-per-CTA instances of the blind-rotation kernel (and ragged
     tails inside a CTA): every ciphertext must decrypt to its LUT value, and a ciphertext's result must not depend on which instance or
-    which batch it was computed in (same kernel arithmetic per ciphertext => identical words)."""
+    which batch it was computed in: identical words within a kernel family (narrow levels run pbs_v8.cu, wide ones pbs_v4.cu)."""
     import torch
     p, ck, sk = keys_2_2
     fs, luts = _luts(sk)
     eng.upload_luts(luts)
     sms = torch.cuda.get_device_properties(0).multi_processor_count
     base = ck.encrypt_batch(np.arange(64) % 16)                      # 64 real ciphertexts, tiled to the batch size
-    first = None
+    first = {}
     for batch in (1, 3, sms, sms + 1, 2 * sms, 2 * sms + 1, 4 * sms + 3):
         reps = -(-batch // 64)
         cts = np.tile(base, (reps, 1))[:batch]
@@ -162,6 +162,6 @@ def test_every_kernel_instance_boundary(orc, keys_2_2, eng):
         out = eng.ks_pbs_batch(cts, idx)
         want = np.array([fs[i](int(v)) for v, i in zip(vals, idx)])
         assert np.array_equal(ck.decrypt_batch(out), want), batch
-        if first is None:
-            first = out[0].copy()
-        assert np.array_equal(out[0], first), f"ciphertext 0 differs between batch sizes (batch {batch})"
+        family = "narrow" if batch <= 2 * sms else "wide"     # pbs_v8.cu / pbs_v4.cu: different FFT factorisations, different rounding
+        first.setdefault(family, out[0].copy())
+        assert np.array_equal(out[0], first[family]), f"ciphertext 0 differs between batch sizes (batch {batch})"
