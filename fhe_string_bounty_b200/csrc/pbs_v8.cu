@@ -316,45 +316,52 @@ pbs_classic_kernel_v8(const uint64_t *__restrict__ lwe_small, const uint32_t *__
 
         if (REGS) fft8_fwd(re, im, tile, twd_r, T, poly_sync); else fft8_fwd(re, im, tile, twd_t, T, poly_sync);
 
-        // spectrum exchange between the two polynomials of the ciphertext: park my 8 values in my own exchange-C reader slots
-        st8(tile + xc_rbase(T), re, im, [](int p) { return xc_roff(p); });
+        // spectrum exchange between the two polynomials of the ciphertext: park my 8 values in my own exchange-A reader slots (conflict
+        // free, private to this thread, and nobody in the half-warp still reads the tile: fft8_fwd ends with a __syncwarp)
+        st8(tile + xa_rbase(T), re, im, [](int p) { return xa_roff(p); });
         bar_sync(ct_bar, 256);
 
-        // out_fft[w] = F_w * G[w][w] + F_{1-w} * G[1-w][w]: one ring piece per register
+        // out_fft[w] = F_w * G[w][w] + F_{1-w} * G[1-w][w]: one ring piece per register.  The ring (10 slots) holds a whole iteration
+        // (8 pieces), so nothing is released inside the loop: 24 independent 16-byte loads and 64 FP64 instructions the compiler can
+        // interleave freely, then one release per piece by lanes 0..7.
         {
-            uint32_t ready = 0;
+            int s0 = slot;
+            uint32_t ph0 = phase;
             {
-                int s = slot; uint32_t ph = phase;
+                int s = s0; uint32_t ph = ph0;
 #pragma unroll
                 for (int c = 0; c < PIECES_PER_ITER; ++c) {
-                    ready |= (mbar_try_wait(&sm.full_bar[s], ph) ? 1u : 0u) << c;
+                    if (!mbar_try_wait(&sm.full_bar[s], ph)) mbar_wait(&sm.full_bar[s], ph);
                     if (++s == NSLOT) { s = 0; ph ^= 1u; }
                 }
             }
-            const cplx *fop = otile + xc_rbase(T);
-            unsigned int my_old = 0;
+            const cplx *fop = otile + xa_rbase(T);
             int my_slot = 0;
+            {
+                int s = s0;
 #pragma unroll
-            for (int c = 0; c < PIECES_PER_ITER; ++c) {
-                if (!((ready >> c) & 1u)) mbar_wait(&sm.full_bar[slot], phase);
-                const cplx *pc = sm.ring[slot] + (w * 2) * 128 + T;
-                const cplx A = pc[0], B = pc[128], F = fop[xc_roff(c)];
-                const double fr = re[c], fi = im[c];
-                double orr = DMUL(fr, A.x);
-                orr = DFMA(-fi, A.y, orr);
-                orr = DFMA(F.x, B.x, orr);
-                orr = DFMA(-F.y, B.y, orr);
-                double oi = DMUL(fr, A.y);
-                oi = DFMA(fi, A.x, oi);
-                oi = DFMA(F.x, B.y, oi);
-                oi = DFMA(F.y, B.x, oi);
-                re[c] = orr; im[c] = oi;
-                // release: lane c counts this warp out of piece c's slot; nobody looks at the result inside the loop
-                __syncwarp();
-                if (lane == c) { my_old = atomicAdd(&sm.consumed[slot], 1u); my_slot = slot; }
-                if (++slot == NSLOT) { slot = 0; phase ^= 1u; }
+                for (int c = 0; c < PIECES_PER_ITER; ++c) {
+                    const cplx *pc = sm.ring[s] + (w * 2) * 128 + T;
+                    const cplx A = pc[0], B = pc[128], F = fop[xa_roff(c)];
+                    const double fr = re[c], fi = im[c];
+                    double orr = DMUL(fr, A.x);
+                    orr = DFMA(-fi, A.y, orr);
+                    orr = DFMA(F.x, B.x, orr);
+                    orr = DFMA(-F.y, B.y, orr);
+                    double oi = DMUL(fr, A.y);
+                    oi = DFMA(fi, A.x, oi);
+                    oi = DFMA(F.x, B.y, oi);
+                    oi = DFMA(F.y, B.x, oi);
+                    re[c] = orr; im[c] = oi;
+                    if (lane == c) my_slot = s;
+                    if (++s == NSLOT) s = 0;
+                }
             }
-            if (lane < PIECES_PER_ITER && my_old == WARPS - 1) {
+#pragma unroll
+            for (int c = 0; c < PIECES_PER_ITER; ++c)
+                if (++slot == NSLOT) { slot = 0; phase ^= 1u; }
+            __syncwarp();     // every lane's loads from the ring have returned (their values fed the arithmetic above)
+            if (lane < PIECES_PER_ITER && atomicAdd(&sm.consumed[my_slot], 1u) == WARPS - 1) {
                 sm.consumed[my_slot] = 0;
                 const int g2 = i * PIECES_PER_ITER + lane + NSLOT;
                 if (g2 < total_pieces) {
