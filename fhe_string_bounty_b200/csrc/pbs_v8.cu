@@ -13,6 +13,7 @@
 // conflicted); with the pair exchange done by register shuffles (exchange_c_* below) 3.52 ms.  TFHE_B200_NARROW_KERNEL=0 disables it.
 //
 // Same arithmetic definition as the other generations (bootstrap.rs:242-364, ggsw.rs:477-598, fft/mod.rs:197-326).
+// Shared memory: 17 KiB tile per polynomial + the key ring, double buffered by whole iterations (2 x 64 KiB).
 // Named barriers: 1..4 one per polynomial (128 threads), 5..6 one per ciphertext (256 threads).
 #include "kernels.h"
 #include "fft8_core.cuh"
@@ -33,16 +34,17 @@ using tb16k::tmem_wait_ld;
 using tb16k::tmem_wait_st;
 
 constexpr int PIECE_CPLX = 512;        // [out poly 2][sel 2][thread 128]: one frequency (register) per thread
-constexpr int PIECE_BYTES = PIECE_CPLX * 16;
 constexpr int PIECES_PER_ITER = 8;
-constexpr int NSLOT = 10;
+constexpr int ITER_CPLX = PIECES_PER_ITER * PIECE_CPLX;   // one GGSW = one blind-rotation iteration = 64 KiB
+constexpr int ITER_BYTES = ITER_CPLX * 16;
+constexpr int NBUF = 2;                // the key ring is double buffered by whole iterations: one barrier, one release per iteration
 
 template <int CTS>
 struct Smem {
     cplx tile[2 * CTS][tb8::kTileCplx];    // 17 KiB per polynomial
-    cplx ring[NSLOT][PIECE_CPLX];          // 80 KiB
-    unsigned long long full_bar[NSLOT];
-    unsigned int consumed[NSLOT];
+    cplx ring[NBUF][ITER_CPLX];            // 128 KiB
+    unsigned long long full_bar[NBUF];
+    unsigned int consumed[NBUF];
     uint32_t tmem_base;
 };
 static_assert(sizeof(Smem<2>) <= 227 * 1024, "shared memory budget");
@@ -222,10 +224,9 @@ pbs_classic_kernel_v8(const uint64_t *__restrict__ lwe_small, const uint32_t *__
     const int ct_bar = 5 + ctl;
     const uint64_t *lwe = lwe_small + (size_t)ct * (n + 1);
     const uint16_t *lwe16 = reinterpret_cast<const uint16_t *>(lwe_small) + (size_t)ct * (n + 1);
-    const int total_pieces = n_iters * PIECES_PER_ITER;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NSLOT; ++s) { mbar_init(&sm.full_bar[s], 1); sm.consumed[s] = 0; }
+        for (int s = 0; s < NBUF; ++s) { mbar_init(&sm.full_bar[s], 1); sm.consumed[s] = 0; }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_proxy_async();
     }
@@ -256,10 +257,9 @@ pbs_classic_kernel_v8(const uint64_t *__restrict__ lwe_small, const uint32_t *__
         }
     }
     if (threadIdx.x == 0) {
-        const int first = total_pieces < NSLOT ? total_pieces : NSLOT;
-        for (int g = 0; g < first; ++g) {
-            mbar_expect_tx(&sm.full_bar[g], PIECE_BYTES);
-            tma_load_1d(sm.ring[g], bskf8 + (size_t)g * PIECE_CPLX, PIECE_BYTES, &sm.full_bar[g]);
+        for (int g = 0; g < NBUF && g < n_iters; ++g) {
+            mbar_expect_tx(&sm.full_bar[g], ITER_BYTES);
+            tma_load_1d(sm.ring[g], bskf8 + (size_t)g * ITER_CPLX, ITER_BYTES, &sm.full_bar[g]);
         }
     }
 
@@ -293,9 +293,6 @@ pbs_classic_kernel_v8(const uint64_t *__restrict__ lwe_small, const uint32_t *__
         }
     }
 
-    int slot = 0;            // ring position of this iteration's first piece
-    uint32_t phase = 0;
-
     for (int i = 0; i < n_iters; ++i) {
         const uint32_t a = (small_is_u16 ? (uint32_t)__ldg(lwe16 + i) : modulus_switch_2n(__ldg(lwe + i))) & (2 * kN - 1);   // a == 0 is NOT skipped
         poly_sync();    // the accumulator polynomial is complete in shared memory
@@ -321,54 +318,37 @@ pbs_classic_kernel_v8(const uint64_t *__restrict__ lwe_small, const uint32_t *__
         st8(tile + xa_rbase(T), re, im, [](int p) { return xa_roff(p); });
         bar_sync(ct_bar, 256);
 
-        // out_fft[w] = F_w * G[w][w] + F_{1-w} * G[1-w][w]: one ring piece per register.  The ring (10 slots) holds a whole iteration
-        // (8 pieces), so nothing is released inside the loop: 24 independent 16-byte loads and 64 FP64 instructions the compiler can
-        // interleave freely, then one release per piece by lanes 0..7.
+        // out_fft[w] = F_w * G[w][w] + F_{1-w} * G[1-w][w].  The whole GGSW of this iteration sits in ring buffer i & 1 behind ONE
+        // barrier: 24 independent 16-byte loads and 64 FP64 instructions the compiler can interleave freely, then one release; the last
+        // of the WARPS warps refills the buffer with the GGSW of iteration i + 2 (a single 64 KiB bulk copy).
         {
-            int s0 = slot;
-            uint32_t ph0 = phase;
-            {
-                int s = s0; uint32_t ph = ph0;
-#pragma unroll
-                for (int c = 0; c < PIECES_PER_ITER; ++c) {
-                    if (!mbar_try_wait(&sm.full_bar[s], ph)) mbar_wait(&sm.full_bar[s], ph);
-                    if (++s == NSLOT) { s = 0; ph ^= 1u; }
-                }
-            }
+            const int buf = i & (NBUF - 1);
+            const uint32_t ph = (uint32_t)(i / NBUF) & 1u;
+            if (!mbar_try_wait(&sm.full_bar[buf], ph)) mbar_wait(&sm.full_bar[buf], ph);
             const cplx *fop = otile + xa_rbase(T);
-            int my_slot = 0;
-            {
-                int s = s0;
+            const cplx *pc = sm.ring[buf] + (w * 2) * 128 + T;
 #pragma unroll
-                for (int c = 0; c < PIECES_PER_ITER; ++c) {
-                    const cplx *pc = sm.ring[s] + (w * 2) * 128 + T;
-                    const cplx A = pc[0], B = pc[128], F = fop[xa_roff(c)];
-                    const double fr = re[c], fi = im[c];
-                    double orr = DMUL(fr, A.x);
-                    orr = DFMA(-fi, A.y, orr);
-                    orr = DFMA(F.x, B.x, orr);
-                    orr = DFMA(-F.y, B.y, orr);
-                    double oi = DMUL(fr, A.y);
-                    oi = DFMA(fi, A.x, oi);
-                    oi = DFMA(F.x, B.y, oi);
-                    oi = DFMA(F.y, B.x, oi);
-                    re[c] = orr; im[c] = oi;
-                    if (lane == c) my_slot = s;
-                    if (++s == NSLOT) s = 0;
-                }
+            for (int c = 0; c < PIECES_PER_ITER; ++c) {
+                const cplx A = pc[c * PIECE_CPLX], B = pc[c * PIECE_CPLX + 128], F = fop[xa_roff(c)];
+                const double fr = re[c], fi = im[c];
+                double orr = DMUL(fr, A.x);
+                orr = DFMA(-fi, A.y, orr);
+                orr = DFMA(F.x, B.x, orr);
+                orr = DFMA(-F.y, B.y, orr);
+                double oi = DMUL(fr, A.y);
+                oi = DFMA(fi, A.x, oi);
+                oi = DFMA(F.x, B.y, oi);
+                oi = DFMA(F.y, B.x, oi);
+                re[c] = orr; im[c] = oi;
             }
-#pragma unroll
-            for (int c = 0; c < PIECES_PER_ITER; ++c)
-                if (++slot == NSLOT) { slot = 0; phase ^= 1u; }
             __syncwarp();     // every lane's loads from the ring have returned (their values fed the arithmetic above)
-            if (lane < PIECES_PER_ITER && atomicAdd(&sm.consumed[my_slot], 1u) == WARPS - 1) {
-                sm.consumed[my_slot] = 0;
-                const int g2 = i * PIECES_PER_ITER + lane + NSLOT;
-                if (g2 < total_pieces) {
+            if (lane == 0 && atomicAdd(&sm.consumed[buf], 1u) == WARPS - 1) {
+                sm.consumed[buf] = 0;
+                if (i + NBUF < n_iters) {
                     __threadfence_block();
                     fence_proxy_async();
-                    mbar_expect_tx(&sm.full_bar[my_slot], PIECE_BYTES);
-                    tma_load_1d(sm.ring[my_slot], bskf8 + (size_t)g2 * PIECE_CPLX, PIECE_BYTES, &sm.full_bar[my_slot]);
+                    mbar_expect_tx(&sm.full_bar[buf], ITER_BYTES);
+                    tma_load_1d(sm.ring[buf], bskf8 + (size_t)(i + NBUF) * ITER_CPLX, ITER_BYTES, &sm.full_bar[buf]);
                 }
             }
         }
