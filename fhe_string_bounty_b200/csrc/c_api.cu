@@ -67,25 +67,49 @@ int do_pbs(tfhe_b200_ctx *c, const uint64_t *d_small, const uint32_t *d_idx, con
     if (!d_luts) return fail("no lookup tables uploaded");
     if (c->p.grouping_factor == 3) {
         const uint32_t groups = c->p.lwe_dim / 3;
-        if (c->mb_kernel == 4)
-            TB_CUDA(tbk::launch_pbs_multibit_v4(d_small, d_idx, d_luts, c->bskf.p, c->tbl16.p, c->roots.p, d_out, out_slot, (int)batch,
-                                                (int)c->p.lwe_dim, (int)c->p.pbs_base_log, (int)(n_iters < groups ? n_iters : groups), s));
-        else
+        if (c->mb_kernel == 4) {
+            // whole waves of 4 ciphertexts per SM, then the remainder on the 1- / 2-ciphertext instances if it fits them (the launcher
+            // picks the instance from the batch size)
+            const size_t wave = (size_t)4 * c->sms, rem = batch % wave;
+            const size_t tail = (batch > wave && rem != 0 && rem <= (size_t)2 * c->sms) ? rem : 0, wide = batch - tail;
+            const int steps = (int)(n_iters < groups ? n_iters : groups);
+            TB_CUDA(tbk::launch_pbs_multibit_v4(d_small, d_idx, d_luts, c->bskf.p, c->tbl16.p, c->roots.p, d_out, out_slot, (int)wide,
+                                                (int)c->p.lwe_dim, (int)c->p.pbs_base_log, steps, s));
+            if (tail) {
+                const uint64_t *t_small = d_small + wide * (size_t)(c->p.lwe_dim + 1);
+                uint64_t *t_out = out_slot ? d_out : d_out + wide * ((size_t)c->p.glwe_dim * c->p.poly_size + 1);
+                TB_CUDA(tbk::launch_pbs_multibit_v4(t_small, d_idx ? d_idx + wide : nullptr, d_luts, c->bskf.p, c->tbl16.p, c->roots.p, t_out,
+                                                    out_slot ? out_slot + wide : nullptr, (int)tail, (int)c->p.lwe_dim, (int)c->p.pbs_base_log,
+                                                    steps, s));
+                c->launches += 1;
+            }
+        } else
             TB_CUDA(tbk::launch_pbs_multibit(d_small, d_idx, d_luts, c->bskf.p, c->tbl.p, c->roots.p, d_out, out_slot, (int)batch,
                                              (int)c->p.lwe_dim, (int)c->p.pbs_base_log, (int)(n_iters < groups ? n_iters : groups), s));
         c->launches += 1;
         return 0;
     }
-    if (c->pbs_kernel == 4 && c->narrow_kernel == 8 && batch <= (size_t)2 * c->sms) {
-        TB_CUDA(tbk::launch_pbs_classic_v8(d_small, d_idx, d_luts, c->bskf8.p, c->tbl8.p, d_out, out_slot, (int)batch, (int)c->p.lwe_dim,
-                                           (int)c->p.pbs_base_log, (int)n_iters, fused ? 1 : 0, s));
-        c->launches += 1;
-        return 0;
-    }
     if (c->pbs_kernel == 4) {
-        TB_CUDA(tbk::launch_pbs_classic_v4(d_small, d_idx, d_luts, c->bskf.p, c->tbl16.p, d_out, out_slot, (int)batch, (int)c->p.lwe_dim,
-                                           (int)c->p.pbs_base_log, (int)n_iters, fused ? 1 : 0, s));
-        c->launches += 1;
+        // Wide part: whole waves of 4 ciphertexts per SM on pbs_v4.cu.  What is left over, if it fits two ciphertexts per SM, runs on
+        // the narrow-level kernel pbs_v8.cu (2.9 ms for <= SM count, 4.4 ms for <= 2 x SM count) instead of a mostly empty 7.8 ms wave.
+        const size_t wave = (size_t)4 * c->sms, narrow = c->narrow_kernel == 8 ? (size_t)(c->narrow_max ? c->narrow_max : 2 * c->sms) : 0;
+        const size_t rem = batch % wave;
+        const size_t tail = batch <= narrow ? batch : (rem != 0 && rem <= narrow) ? rem : 0;
+        const size_t wide = batch - tail;
+        if (wide) {
+            TB_CUDA(tbk::launch_pbs_classic_v4(d_small, d_idx, d_luts, c->bskf.p, c->tbl16.p, d_out, out_slot, (int)wide, (int)c->p.lwe_dim,
+                                               (int)c->p.pbs_base_log, (int)n_iters, fused ? 1 : 0, s));
+            c->launches += 1;
+        }
+        if (tail) {
+            const size_t in_stride = (size_t)(c->p.lwe_dim + 1) * (fused ? 2 : 8);
+            const uint64_t *t_small = reinterpret_cast<const uint64_t *>(reinterpret_cast<const char *>(d_small) + wide * in_stride);
+            uint64_t *t_out = out_slot ? d_out : d_out + wide * ((size_t)c->p.glwe_dim * c->p.poly_size + 1);
+            TB_CUDA(tbk::launch_pbs_classic_v8(t_small, d_idx ? d_idx + wide : nullptr, d_luts, c->bskf8.p, c->tbl8.p, t_out,
+                                               out_slot ? out_slot + wide : nullptr, (int)tail, (int)c->p.lwe_dim, (int)c->p.pbs_base_log,
+                                               (int)n_iters, fused ? 1 : 0, s));
+            c->launches += 1;
+        }
         return 0;
     }
     if (c->pbs_kernel == 3) {
@@ -137,6 +161,7 @@ int tfhe_b200_ctx_create(int cuda_device, const tfhe_b200_params *params, tfhe_b
     TB_CUDA(tbk::pbs_v4_configure());
     TB_CUDA(tbk::pbs_v8_configure());
     if (const char *e = std::getenv("TFHE_B200_NARROW_KERNEL")) c->narrow_kernel = (e[0] == '8') ? 8 : 0;
+    if (const char *e = std::getenv("TFHE_B200_NARROW_MAX")) c->narrow_max = atoi(e);
     TB_CUDA(cudaDeviceGetAttribute(&c->sms, cudaDevAttrMultiProcessorCount, cuda_device));
     if (const char *e = std::getenv("TFHE_B200_MB_KERNEL")) c->mb_kernel = (e[0] == '3') ? 3 : 4;
     TB_CUDA(tbk::pbs_multibit_configure());

@@ -59,6 +59,7 @@ struct tfhe_b200_ctx {
     bool have_ksk = false, have_bsk = false;
     int narrow_kernel = 8;   // classic PBS, levels of <= 2 * SM count ciphertexts: 8 = pbs_v8.cu (8 FFT points per thread, 8 warps per ciphertext; keeps a second copy of the Fourier key in its own layout), 0 = the narrow instances of pbs_kernel; env TFHE_B200_NARROW_KERNEL
     int sms = 148;
+    int narrow_max = 0;      // widest level the narrow kernel takes (0 = 2 * SM count); env TFHE_B200_NARROW_MAX
     int mb_kernel = 4;    // multi-bit: 4 = pbs_multibit_v4.cu (16 points per thread), 3 = pbs_multibit.cu; env TFHE_B200_MB_KERNEL
     int pbs_kernel = 4;   // 4: TMEM + TMA ring, 16 FFT points per thread (pbs_v4.cu); 3: same data path, 32 points per thread (pbs_v3.cu); 2: one CTA per ciphertext (pbs.cu); env TFHE_B200_PBS_KERNEL
     // staging for the host-pointer entry points

@@ -86,3 +86,28 @@ def test_multibit_string_lt_le_config5(orc, keys_multibit, eng):
         for op, P in progs.items():
             assert ck.decrypt_message_and_carry(P.run(eng, ins)[0]) == int(clear[op]), (op, k)
     print(f"lt 128 chars (multi-bit): {progs['lt'].n_pbs} PBS, {progs['lt'].last_ms():.1f} ms on device")
+
+
+def test_multibit_wide_level_with_tail(orc, keys_multibit):
+    """A level a little wider than one 4-ciphertext-per-SM wave: the whole wave runs on the 4-ciphertext instance, the remainder on the
+    narrow instances (c_api.cu do_pbs); every ciphertext must land in its own output row and decrypt to its LUT value."""
+    import torch
+    import fhe_string_bounty_b200 as F
+    p, ck, sk = keys_multibit
+    eng = F.Engine(engine_params(p))
+    eng.upload_ksk(sk.ksk)
+    eng.upload_bsk_std(sk.bsk)
+    acc0, _ = sk.generate_lookup_table(lambda x: (x + 1) % 16)
+    acc1, _ = sk.generate_lookup_table(lambda x: (3 * x) % 16)
+    eng.upload_luts(np.stack([acc0, acc1]))
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    base = ck.encrypt_batch(np.arange(48) % 16)
+    for batch in (4 * sms + 7, 4 * sms + sms + 9):
+        reps = -(-batch // 48)
+        cts = np.tile(base, (reps, 1))[:batch]
+        vals = np.tile(np.arange(48) % 16, reps)[:batch]
+        idx = (np.arange(batch) % 2).astype(np.uint32)
+        out = eng.ks_pbs_batch(cts, idx)
+        want = [(int(v) + 1) % 16 if i == 0 else (3 * int(v)) % 16 for v, i in zip(vals, idx)]
+        assert list(ck.decrypt_batch(out)) == want, batch
+    eng.close()
