@@ -166,50 +166,21 @@ pbs_classic_kernel_v4(const uint64_t *__restrict__ lwe_small, const uint32_t *__
         }
         bar_sync(ct_bar, 128);
 
-        // out_fft[w] = F_w * G[w][w] + F_{1-w} * G[1-w][w], GGSW pieces from the ring (probe all barriers first, count
-        // this warp out of each slot right after its chunk)
+        // out_fft[w] = F_w * G[w][w] + F_{1-w} * G[1-w][w], GGSW pieces from the ring.  Nothing is synchronised inside the loop (the
+        // compiler is free to run chunk c+1's loads under chunk c's arithmetic); after it lane c counts this warp out of piece c's slot,
+        // and the last of the WARPS warps to leave a slot re-arms it with the piece NSLOT ahead (measured against releasing each slot
+        // right after its chunk: 104.7 vs 106.0 ms per 8192).
         {
-            uint32_t ready = 0;
-            {
-                int s = slot; uint32_t ph = phase;
-#pragma unroll
-                for (int c = 0; c < PIECES_PER_ITER; ++c) {
-                    ready |= (mbar_try_wait(&sm.full_bar[s], ph) ? 1u : 0u) << c;
-                    if (++s == NSLOT) { s = 0; ph ^= 1u; }
-                }
-            }
             const cplx *fop = otile + xb_rbase(T);
-            unsigned int my_old = 0;
             int my_slot = 0;
-            // narrow-level instances (one warp per scheduler: latency matters) issue chunk c+1's six 16-byte loads before chunk
-            // c's arithmetic; the 16-warp instance loads each chunk just in time (measured: pipelining costs it 8 %)
-            constexpr bool PIPE = CTS < 4;
-            cplx ga[2][2], gb[2][2], fo[2][2];
-            auto load_chunk = [&](int c, int sl, uint32_t ph, cplx (&a)[2], cplx (&b)[2], cplx (&f)[2]) {
-                if (!((ready >> c) & 1u)) mbar_wait(&sm.full_bar[sl], ph);
-                const cplx *pc = sm.ring[sl] + (w * 2) * 2 * 64 + T;
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    a[q] = pc[q * 64];
-                    b[q] = pc[(2 + q) * 64];
-                    f[q] = fop[xb_roff(2 * c + q)];
-                }
-            };
-            int nslot = slot;
-            uint32_t nphase = phase;
-            if (PIPE) load_chunk(0, nslot, nphase, ga[0], gb[0], fo[0]);
 #pragma unroll
             for (int c = 0; c < PIECES_PER_ITER; ++c) {
-                if (!PIPE) {
-                    load_chunk(c, slot, phase, ga[c & 1], gb[c & 1], fo[c & 1]);
-                } else if (c + 1 < PIECES_PER_ITER) {
-                    if (++nslot == NSLOT) { nslot = 0; nphase ^= 1u; }
-                    load_chunk(c + 1, nslot, nphase, ga[(c + 1) & 1], gb[(c + 1) & 1], fo[(c + 1) & 1]);
-                }
+                if (!mbar_try_wait(&sm.full_bar[slot], phase)) mbar_wait(&sm.full_bar[slot], phase);
+                const cplx *pc = sm.ring[slot] + (w * 2) * 2 * 64 + T;
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
                     const int g = 2 * c + q;
-                    const cplx A = ga[c & 1][q], B = gb[c & 1][q], F = fo[c & 1][q];
+                    const cplx A = pc[q * 64], B = pc[(2 + q) * 64], F = fop[xb_roff(g)];
                     const double fr = re[g], fi = im[g];
                     double orr = DMUL(fr, A.x);
                     orr = DFMA(-fi, A.y, orr);
@@ -221,14 +192,11 @@ pbs_classic_kernel_v4(const uint64_t *__restrict__ lwe_small, const uint32_t *__
                     oi = DFMA(F.y, B.x, oi);
                     re[g] = orr; im[g] = oi;
                 }
-                // release: lane c counts this warp out of chunk c's slot; nobody looks at the result inside the loop
-                __syncwarp();
-                if (lane == c) { my_old = atomicAdd(&sm.consumed[slot], 1u); my_slot = slot; }
+                if (lane == c) my_slot = slot;
                 if (++slot == NSLOT) { slot = 0; phase ^= 1u; }
             }
-            // the last of the WARPS warps to leave a slot re-arms it with the piece NSLOT ahead (a few hundred cycles after the
-            // fact, against 1.25 iterations of lookahead)
-            if (lane < PIECES_PER_ITER && my_old == WARPS - 1) {
+            __syncwarp();     // every lane's loads from the ring have returned (their values fed the arithmetic above)
+            if (lane < PIECES_PER_ITER && atomicAdd(&sm.consumed[my_slot], 1u) == WARPS - 1) {
                 sm.consumed[my_slot] = 0;
                 const int g2 = i * PIECES_PER_ITER + lane + NSLOT;
                 if (g2 < total_pieces) {
