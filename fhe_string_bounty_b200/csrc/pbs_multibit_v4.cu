@@ -174,7 +174,6 @@ pbs_multibit_kernel_v4(const uint64_t *__restrict__ lwe_small, const uint32_t *_
 
         {
             const cplx *fop = otile + xb_rbase(T);
-            unsigned int my_old = 0;
             int my_slot = 0, my_piece = 0;
             // (measured: software-pipelining the loads of piece p+1 under piece p's arithmetic does not help -- 37.9 vs 36.3 ms for the
             // 128-char comparison -- the narrow-level instances are bound by key delivery, hence their deeper rings)
@@ -226,22 +225,20 @@ pbs_multibit_kernel_v4(const uint64_t *__restrict__ lwe_small, const uint32_t *_
                             }
                         }
                     }
-                    // count this warp out of the slot; the results are looked at once per chunk (lane = piece index within the step)
-                    __syncwarp();
-                    if (lane == p) { my_old = atomicAdd(&sm.consumed[slot], 1u); my_slot = slot; my_piece = grp * PIECES_PER_ITER + p; }
+                    if (lane == p) { my_slot = slot; my_piece = grp * PIECES_PER_ITER + p; }
                     if (++slot == NSLOT) { slot = 0; phase ^= 1u; }
-                    // with only NSLOT pieces of lookahead the re-arm cannot wait for the end of the step: check after every chunk
-                    if (pc == PIECES_PER_CHUNK - 1) {
-                        if (lane >= c * PIECES_PER_CHUNK && lane < (c + 1) * PIECES_PER_CHUNK && my_old == WARPS - 1) {
-                            sm.consumed[my_slot] = 0;
-                            const int g2 = my_piece + NSLOT;
-                            if (g2 < total_pieces) {
-                                __threadfence_block();
-                                fence_proxy_async();
-                                mbar_expect_tx(&sm.full_bar[my_slot], PIECE_BYTES);
-                                tma_load_1d(sm.ring[my_slot], bskm + (size_t)g2 * PIECE_CPLX, PIECE_BYTES, &sm.full_bar[my_slot]);
-                            }
-                        }
+                }
+                // release the chunk's four slots (lane = piece index within the step); with only NSLOT pieces of lookahead the re-arm
+                // cannot wait for the end of the step.  Nothing is synchronised inside a chunk.
+                __syncwarp();
+                if (lane >= c * PIECES_PER_CHUNK && lane < (c + 1) * PIECES_PER_CHUNK && atomicAdd(&sm.consumed[my_slot], 1u) == WARPS - 1) {
+                    sm.consumed[my_slot] = 0;
+                    const int g2 = my_piece + NSLOT;
+                    if (g2 < total_pieces) {
+                        __threadfence_block();
+                        fence_proxy_async();
+                        mbar_expect_tx(&sm.full_bar[my_slot], PIECE_BYTES);
+                        tma_load_1d(sm.ring[my_slot], bskm + (size_t)g2 * PIECE_CPLX, PIECE_BYTES, &sm.full_bar[my_slot]);
                     }
                 }
                 // out_fft[w] = F_w * Gc[w][w] + F_{1-w} * Gc[1-w][w]
