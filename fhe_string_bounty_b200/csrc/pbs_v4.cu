@@ -10,7 +10,7 @@
 // the same 1024 frequencies, only the butterfly order (hence FP64 rounding) differs.
 //
 // Shared memory per 4-ciphertext CTA: 8 x 17 KiB polynomial tiles (rotated-gather source, then exchange tile, then spectrum
-// exchange) + 10 x 8 KiB ring = 216 KiB.  TMEM: 64 columns per ciphertext (accumulator master copy) + 80 columns of
+// exchange) + 5 x 16 KiB ring = 216 KiB.  TMEM: 64 columns per ciphertext (accumulator master copy) + 80 columns of
 // per-thread FFT twiddles (ncu: the kernel is bound by the LSU pipe, tcgen05.ld is not on it).
 // Named barriers: 1..8 one per polynomial (64 threads), 9..12 one per ciphertext (128), 13..15 start-up stagger.
 #include "kernels.h"
@@ -19,10 +19,11 @@
 namespace tb4 {
 using namespace tb16k;
 
-constexpr int PIECE_CPLX = 512;        // [out poly 2][sel 2][q 2][thread 64]
+constexpr int QPP = 4;                 // frequencies (registers) per ring piece
+constexpr int PIECE_CPLX = 2 * 2 * QPP * 64;   // [out poly 2][sel 2][q QPP][thread 64]
 constexpr int PIECE_BYTES = PIECE_CPLX * 16;
-constexpr int PIECES_PER_ITER = 8;
-constexpr int NSLOT = 10;
+constexpr int PIECES_PER_ITER = 16 / QPP;
+constexpr int NSLOT = 81920 / (PIECE_CPLX * 16);   // 80 KiB of ring
 
 template <int CTS>
 struct Smem {
@@ -34,9 +35,11 @@ struct Smem {
 };
 static_assert(sizeof(Smem<4>) <= 227 * 1024, "shared memory budget");
 
-// Fourier key, v4 layout: [ggsw i][chunk 8][out poly c][sel: 0 = row c, 1 = row 1-c][q 2][thread 64]; register g = 2*chunk + q
+// Fourier key, v4 layout: [ggsw i][chunk 16/QPP][out poly c][sel: 0 = row c, 1 = row 1-c][q QPP][thread 64]; register g = QPP*chunk + q
+// (QPP = 4: 16 KiB pieces, 5 ring slots, measured 101.9 ms per 8192 against 104.1 ms for QPP = 2; QPP = 8 leaves two slots, which cannot
+// hold the ciphertexts' quarter-iteration stagger: the kernel deadlocks into its spin-limit trap)
 __device__ __forceinline__ size_t bskf4_index(int i, int chunk, int c, int sel, int q) {
-    return ((((size_t)(i * PIECES_PER_ITER + chunk) * 2 + c) * 2 + sel) * 2 + q) * 64;
+    return ((((size_t)(i * PIECES_PER_ITER + chunk) * 2 + c) * 2 + sel) * QPP + q) * 64;
 }
 
 template <int CTS>
@@ -176,11 +179,11 @@ pbs_classic_kernel_v4(const uint64_t *__restrict__ lwe_small, const uint32_t *__
 #pragma unroll
             for (int c = 0; c < PIECES_PER_ITER; ++c) {
                 if (!mbar_try_wait(&sm.full_bar[slot], phase)) mbar_wait(&sm.full_bar[slot], phase);
-                const cplx *pc = sm.ring[slot] + (w * 2) * 2 * 64 + T;
+                const cplx *pc = sm.ring[slot] + (w * 2) * QPP * 64 + T;
 #pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    const int g = 2 * c + q;
-                    const cplx A = pc[q * 64], B = pc[(2 + q) * 64], F = fop[xb_roff(g)];
+                for (int q = 0; q < QPP; ++q) {
+                    const int g = QPP * c + q;
+                    const cplx A = pc[q * 64], B = pc[(QPP + q) * 64], F = fop[xb_roff(g)];
                     const double fr = re[g], fi = im[g];
                     double orr = DMUL(fr, A.x);
                     orr = DFMA(-fi, A.y, orr);
@@ -279,7 +282,7 @@ bsk_convert_kernel_v4(const uint64_t *__restrict__ bsk_std, cplx *__restrict__ b
 #pragma unroll
     for (int g = 0; g < 16; ++g) {
         cplx v; v.x = re[g]; v.y = im[g];
-        bskf4[bskf4_index(i, g >> 1, c, sel, g & 1) + T] = v;
+        bskf4[bskf4_index(i, g / QPP, c, sel, g % QPP) + T] = v;
     }
 }
 
