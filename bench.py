@@ -188,6 +188,13 @@ def bench_string_ops(eng, p, rank, world, local):
         low = Program("string_to_lowercase", (1024,), params=params)
         s1024 = rng.integers(0, 2**64, size=(4096, p.big_len), dtype=np.uint64)
         out["to_lowercase_1024_ops_per_s"] = timed(lambda: low.run(eng, s1024), 3)
+        out["to_lowercase_1024_pbs"] = low.n_pbs
+        up = Program("string_to_uppercase", (1024,), params=params)
+        out["to_uppercase_1024_ops_per_s"] = timed(lambda: up.run(eng, s1024), 3)
+        eic = Program("string_eq_ignore_case", (1024, 1024), params=params)
+        two = rng.integers(0, 2**64, size=(eic.n_inputs, p.big_len), dtype=np.uint64)
+        out["eq_ignore_case_1024_ops_per_s"] = timed(lambda: eic.run(eng, two), 2)
+        out["eq_ignore_case_1024_pbs"] = eic.n_pbs
     out["note"] = "host buffers in/out; eq shards chars, contains shards windows across ranks + one all-reduce of a 2049-word LWE"
     return out
 
