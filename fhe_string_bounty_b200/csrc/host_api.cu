@@ -19,7 +19,7 @@ struct tfhe_b200_program {
     std::string op;
     // device copies (valid for `owner`)
     tfhe_b200_ctx *owner = nullptr;
-    DevBuf d_luts, d_lin, d_terms, d_pbs_in, d_pbs_out, d_pbs_lut, d_arena;
+    DevBuf d_luts, d_lin, d_terms, d_pbs_in, d_pbs_out, d_pbs_lut, d_arena, d_out_slots, d_out_rows;
     std::vector<uint32_t> lin_off, pbs_off;   // per level offsets
     float last_ms = 0.f;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -215,7 +215,7 @@ int tfhe_b200_program_destroy(tfhe_b200_program *h) {
     if (!h) return 0;
     if (h->owner) {
         DeviceGuard g(h->owner->device);
-        for (DevBuf *b : {&h->d_luts, &h->d_lin, &h->d_terms, &h->d_pbs_in, &h->d_pbs_out, &h->d_pbs_lut, &h->d_arena}) b->release();
+        for (DevBuf *b : {&h->d_luts, &h->d_lin, &h->d_terms, &h->d_pbs_in, &h->d_pbs_out, &h->d_pbs_lut, &h->d_arena, &h->d_out_slots, &h->d_out_rows}) b->release();
         if (h->ev0) cudaEventDestroy(h->ev0);
         if (h->ev1) cudaEventDestroy(h->ev1);
     }
@@ -316,6 +316,8 @@ int tfhe_b200_program_run(tfhe_b200_ctx *c, tfhe_b200_program *h, const uint64_t
         TB_CUDA(up(h->d_pbs_in, pin.data(), pin.size() * 4));
         TB_CUDA(up(h->d_pbs_out, pout.data(), pout.size() * 4));
         TB_CUDA(up(h->d_pbs_lut, plut.data(), plut.size() * 4));
+        TB_CUDA(up(h->d_out_slots, pg.outputs().data(), pg.outputs().size() * 4));
+        TB_CUDA(h->d_out_rows.reserve(std::max<size_t>(pg.outputs().size(), 1) * L * 8));
         TB_CUDA(h->d_arena.reserve(std::max<size_t>(pg.n_slots(), 1) * L * 8));
         TB_CUDA(cudaStreamSynchronize(s));   // the staging vectors above go out of scope
     }
@@ -341,8 +343,11 @@ int tfhe_b200_program_run(tfhe_b200_ctx *c, tfhe_b200_program *h, const uint64_t
         }
     }
     TB_CUDA(cudaEventRecord(h->ev1, s));
-    for (size_t o = 0; o < pg.outputs().size(); ++o)
-        TB_CUDA(cudaMemcpyAsync(outputs + o * L, arena + (size_t)pg.outputs()[o] * L, L * 8, cudaMemcpyDeviceToHost, s));
+    if (!pg.outputs().empty()) {   // gather the output rows on the device, one copy back
+        TB_CUDA(tbk::launch_gather_rows(arena, (const uint32_t *)h->d_out_slots.p, (uint64_t *)h->d_out_rows.p, (int)pg.outputs().size(), (int)L, s));
+        c->launches += 1;
+        TB_CUDA(cudaMemcpyAsync(outputs, h->d_out_rows.p, pg.outputs().size() * L * 8, cudaMemcpyDeviceToHost, s));
+    }
     TB_CUDA(cudaStreamSynchronize(s));
     TB_CUDA(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
     return 0;

@@ -72,6 +72,8 @@ cudaError_t launch_pbs_multibit_v4(const uint64_t *lwe_small, const uint32_t *lu
                                    int base_log, int n_groups, cudaStream_t stream);
 cudaError_t launch_bsk_convert_multibit_v4(const uint64_t *bsk_std, void *bskm, const void *tbl16, int n_polys, cudaStream_t stream);
 
+cudaError_t launch_gather_rows(const uint64_t *arena, const uint32_t *slots, uint64_t *dst, int n_rows, int lwe_len, cudaStream_t stream);
+
 // seeded.cu: dst row g = [mask_len words of the AES-128 CTR stream of `seed` | body_len words copied from bodies]
 cudaError_t launch_seeded_expand(const uint8_t seed[16], uint64_t *dst, const uint64_t *bodies, size_t n_rows, uint32_t mask_len,
                                  uint32_t body_len, cudaStream_t stream);

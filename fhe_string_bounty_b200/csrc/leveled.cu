@@ -33,7 +33,23 @@ linear_kernel(uint64_t *__restrict__ arena, const tbk::LinInstr *__restrict__ in
 
 }  // namespace tblin
 
+namespace tblin {
+// dst row o = arena row slots[o] (the outputs of a program, gathered so that they leave the device in ONE copy)
+__global__ void __launch_bounds__(256) gather_rows_kernel(const uint64_t *__restrict__ arena, const uint32_t *__restrict__ slots,
+                                                          uint64_t *__restrict__ dst, int lwe_len) {
+    const uint64_t *src = arena + (size_t)slots[blockIdx.x] * lwe_len;
+    uint64_t *d = dst + (size_t)blockIdx.x * lwe_len;
+    for (int j = threadIdx.x; j < lwe_len; j += blockDim.x) d[j] = src[j];
+}
+}  // namespace tblin
+
 namespace tbk {
+
+cudaError_t launch_gather_rows(const uint64_t *arena, const uint32_t *slots, uint64_t *dst, int n_rows, int lwe_len, cudaStream_t stream) {
+    if (n_rows <= 0) return cudaSuccess;
+    tblin::gather_rows_kernel<<<n_rows, 256, 0, stream>>>(arena, slots, dst, lwe_len);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_linear(uint64_t *arena, const LinInstr *instrs, const LinTerm *terms, int n_instrs, int lwe_len,
                           cudaStream_t stream) {
