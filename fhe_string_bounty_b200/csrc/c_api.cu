@@ -68,9 +68,9 @@ int do_pbs(tfhe_b200_ctx *c, const uint64_t *d_small, const uint32_t *d_idx, con
     if (c->p.grouping_factor == 3) {
         const uint32_t groups = c->p.lwe_dim / 3;
         if (c->mb_kernel == 4) {
-            // whole waves of 4 ciphertexts per SM, then the remainder on the 1- / 2-ciphertext instances if it fits them (the launcher
+            // whole waves of 3 ciphertexts per SM, then the remainder on the 1- / 2-ciphertext instances if it fits them (the launcher
             // picks the instance from the batch size)
-            const size_t wave = (size_t)4 * c->sms, rem = batch % wave;
+            const size_t wave = (size_t)3 * c->sms, rem = batch % wave;
             const size_t tail = (batch > wave && rem != 0 && rem <= (size_t)2 * c->sms) ? rem : 0, wide = batch - tail;
             const int steps = (int)(n_iters < groups ? n_iters : groups);
             TB_CUDA(tbk::launch_pbs_multibit_v4(d_small, d_idx, d_luts, c->bskf.p, c->tbl16.p, c->roots.p, d_out, out_slot, (int)wide,
@@ -529,10 +529,11 @@ int tfhe_b200_ks_pbs_batch(tfhe_b200_ctx *c, const uint64_t *in, const uint32_t 
     if (c->n_luts == 0) return fail("no lookup tables uploaded");
     std::lock_guard<std::mutex> lk(c->mu);
     DeviceGuard g(c->device);
-    // chunks of four full waves (148 SMs x 4 ciphertexts), alternating between two lanes (stream + staging buffers)
+    // chunks of whole waves (classic: 4 ciphertexts per SM x 4 waves; multi-bit: 3 per SM x 5 waves), alternating between two lanes
+    // (stream + staging buffers)
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
-    const size_t chunk = std::min<size_t>(batch, (size_t)sms * 4 * 4);
+    const size_t chunk = std::min<size_t>(batch, c->p.grouping_factor && c->mb_kernel == 4 ? (size_t)sms * 3 * 5 : (size_t)sms * 4 * 4);
     const size_t L = c->big_len();
     for (auto &ln : c->lane) {
         TB_CUDA(ln.in.reserve(chunk * L * 8));

@@ -15,6 +15,7 @@
 // 2-frequency chunk each), fed by bulk asynchronous copies; shared memory = 8 x 17 KiB tiles + 80 KiB ring.
 #include "kernels.h"
 #include "pbs16_common.cuh"
+#include <cstdlib>
 
 namespace tbm4 {
 using namespace tb16k;
@@ -32,7 +33,7 @@ __constant__ double c_w16[16][2];              // exp(-2*pi*i*e/16)
 
 template <int CTS>
 struct Smem {
-    static constexpr int NSLOT = CTS == 4 ? 5 : CTS == 2 ? 9 : 11;
+    static constexpr int NSLOT = CTS == 4 ? 5 : CTS == 3 ? 7 : CTS == 2 ? 9 : 11;
     cplx tile[2 * CTS][kTileCplx];
     cplx ring[NSLOT][PIECE_CPLX];
     cplx root_hi[64], root_lo[64];         // w^(64 x), w^y: w^e = root_hi[e >> 6] * root_lo[e & 63] (no L2 round trips per step)
@@ -40,7 +41,7 @@ struct Smem {
     unsigned int consumed[NSLOT];
     uint32_t tmem_base;
 };
-static_assert(sizeof(Smem<4>) <= 227 * 1024 && sizeof(Smem<2>) <= 227 * 1024 && sizeof(Smem<1>) <= 227 * 1024, "shared memory budget");
+static_assert(sizeof(Smem<4>) <= 227 * 1024 && sizeof(Smem<3>) <= 227 * 1024 && sizeof(Smem<2>) <= 227 * 1024 && sizeof(Smem<1>) <= 227 * 1024, "shared memory budget");
 
 // Fourier key layout: piece = (group*8 + chunk)*4 + (j >> 1); inside [j & 1][out poly c][sel][q][thread]; register g = 2*chunk + q
 __device__ __forceinline__ size_t bskm4_index(int grp, int j, int chunk, int c, int sel, int q) {
@@ -331,6 +332,8 @@ cudaError_t pbs_multibit_v4_configure() {
     if (err != cudaSuccess) return err;
     err = cudaFuncSetAttribute(tbm4::pbs_multibit_kernel_v4<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tbm4::Smem<4>));
     if (err != cudaSuccess) return err;
+    err = cudaFuncSetAttribute(tbm4::pbs_multibit_kernel_v4<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tbm4::Smem<3>));
+    if (err != cudaSuccess) return err;
     err = cudaFuncSetAttribute(tbm4::pbs_multibit_kernel_v4<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tbm4::Smem<2>));
     if (err != cudaSuccess) return err;
     return cudaFuncSetAttribute(tbm4::pbs_multibit_kernel_v4<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tbm4::Smem<1>));
@@ -345,11 +348,19 @@ cudaError_t launch_pbs_multibit_v4(const uint64_t *lwe_small, const uint32_t *lu
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const tb::cplx *bk = reinterpret_cast<const tb::cplx *>(bskm), *tb = reinterpret_cast<const tb::cplx *>(tbl16),
                    *rt = reinterpret_cast<const tb::cplx *>(roots);
-    if (batch <= sms)
+    // ciphertexts per CTA: 1 / 2 for narrow levels; wide levels run THREE per SM (12 warps, ring of 7 pieces): measured 92.6 ms per 8192
+    // against 99.7 ms with four per SM and a ring of 5 -- the key stream (512 KiB per step) wants the shared memory more than a fourth
+    // ciphertext does.  TFHE_B200_MB_CTS = 1..4 forces an instance.
+    static const int force = [] { const char *e = std::getenv("TFHE_B200_MB_CTS"); return e ? atoi(e) : 0; }();
+    const int cts = force ? force : batch <= sms ? 1 : batch <= 2 * sms ? 2 : 3;
+    if (cts == 1)
         tbm4::pbs_multibit_kernel_v4<1><<<batch, 128, sizeof(tbm4::Smem<1>), stream>>>(lwe_small, lut_idx, luts, bk, tb, rt, out, out_slot, batch,
                                                                                     n, base_log, n_groups);
-    else if (batch <= 2 * sms)
+    else if (cts == 2)
         tbm4::pbs_multibit_kernel_v4<2><<<(batch + 1) / 2, 256, sizeof(tbm4::Smem<2>), stream>>>(lwe_small, lut_idx, luts, bk, tb, rt, out,
+                                                                                              out_slot, batch, n, base_log, n_groups);
+    else if (cts == 3)
+        tbm4::pbs_multibit_kernel_v4<3><<<(batch + 2) / 3, 384, sizeof(tbm4::Smem<3>), stream>>>(lwe_small, lut_idx, luts, bk, tb, rt, out,
                                                                                               out_slot, batch, n, base_log, n_groups);
     else
         tbm4::pbs_multibit_kernel_v4<4><<<(batch + 3) / 4, 512, sizeof(tbm4::Smem<4>), stream>>>(lwe_small, lut_idx, luts, bk, tb, rt, out,
