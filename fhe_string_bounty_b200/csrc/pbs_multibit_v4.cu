@@ -351,7 +351,8 @@ cudaError_t launch_pbs_multibit_v4(const uint64_t *lwe_small, const uint32_t *lu
     // ciphertexts per CTA: 1 / 2 for narrow levels; wide levels run THREE per SM (12 warps, ring of 7 pieces): measured 92.6 ms per 8192
     // against 99.7 ms with four per SM and a ring of 5 -- the key stream (512 KiB per step) wants the shared memory more than a fourth
     // ciphertext does.  TFHE_B200_MB_CTS = 1..4 forces an instance.
-    static const int force = [] { const char *e = std::getenv("TFHE_B200_MB_CTS"); return e ? atoi(e) : 0; }();
+    const char *fe = std::getenv("TFHE_B200_MB_CTS");
+    const int force = fe ? atoi(fe) : 0;
     const int cts = force ? force : batch <= sms ? 1 : batch <= 2 * sms ? 2 : 3;
     if (cts == 1)
         tbm4::pbs_multibit_kernel_v4<1><<<batch, 128, sizeof(tbm4::Smem<1>), stream>>>(lwe_small, lut_idx, luts, bk, tb, rt, out, out_slot, batch,

@@ -111,3 +111,25 @@ def test_multibit_wide_level_with_tail(orc, keys_multibit):
         want = [(int(v) + 1) % 16 if i == 0 else (3 * int(v)) % 16 for v, i in zip(vals, idx)]
         assert list(ck.decrypt_batch(out)) == want, batch
     eng.close()
+
+
+def test_every_multibit_instance(orc, keys_multibit, monkeypatch):
+    """The 1-, 2-, 3- and 4-ciphertext-per-CTA instances of the multi-bit kernel (TFHE_B200_MB_CTS forces one; by default the batch size
+    picks 1, 2 or 3) on a ragged batch: same decrypted values."""
+    import fhe_string_bounty_b200 as F
+    p, ck, sk = keys_multibit
+    acc, _ = sk.generate_lookup_table(lambda x: (9 * x + 4) % 16)
+    vals = np.arange(13) % 16
+    cts = ck.encrypt_batch(vals)
+    want = [(9 * int(v) + 4) % 16 for v in vals]
+    eng = F.Engine(engine_params(p))
+    eng.upload_ksk(sk.ksk)
+    eng.upload_bsk_std(sk.bsk)
+    eng.upload_luts(acc[None, :])
+    outs = []
+    for cts_per_cta in ("1", "2", "3", "4"):
+        monkeypatch.setenv("TFHE_B200_MB_CTS", cts_per_cta)      # read by the launcher at every launch
+        out = eng.ks_pbs_batch(cts, None)
+        assert list(ck.decrypt_batch(out)) == want, cts_per_cta
+        outs.append(out)
+    eng.close()
