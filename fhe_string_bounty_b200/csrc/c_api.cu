@@ -69,20 +69,30 @@ int do_pbs(tfhe_b200_ctx *c, const uint64_t *d_small, const uint32_t *d_idx, con
         const uint32_t groups = c->p.lwe_dim / 3;
         if (c->mb_kernel == 4) {
             // whole waves of 3 ciphertexts per SM, then the remainder on the 1- / 2-ciphertext instances if it fits them (the launcher
-            // picks the instance from the batch size)
+            // picks the instance from the batch size); a remainder or a whole level of at most one ciphertext per SM runs on the
+            // 8-points-per-thread kernel pbs_multibit_v8.cu
             const size_t wave = (size_t)3 * c->sms, rem = batch % wave;
-            const size_t tail = (batch > wave && rem != 0 && rem <= (size_t)2 * c->sms) ? rem : 0, wide = batch - tail;
+            const size_t tail = batch <= (size_t)2 * c->sms ? batch : (rem != 0 && rem <= (size_t)2 * c->sms) ? rem : 0, wide = batch - tail;
             const int steps = (int)(n_iters < groups ? n_iters : groups);
-            TB_CUDA(tbk::launch_pbs_multibit_v4(d_small, d_idx, d_luts, c->bskf.p, c->tbl16.p, c->roots.p, d_out, out_slot, (int)wide,
-                                                (int)c->p.lwe_dim, (int)c->p.pbs_base_log, steps, s));
+            if (wide) {
+                TB_CUDA(tbk::launch_pbs_multibit_v4(d_small, d_idx, d_luts, c->bskf.p, c->tbl16.p, c->roots.p, d_out, out_slot, (int)wide,
+                                                    (int)c->p.lwe_dim, (int)c->p.pbs_base_log, steps, s));
+                c->launches += 1;
+            }
             if (tail) {
                 const uint64_t *t_small = d_small + wide * (size_t)(c->p.lwe_dim + 1);
                 uint64_t *t_out = out_slot ? d_out : d_out + wide * ((size_t)c->p.glwe_dim * c->p.poly_size + 1);
-                TB_CUDA(tbk::launch_pbs_multibit_v4(t_small, d_idx ? d_idx + wide : nullptr, d_luts, c->bskf.p, c->tbl16.p, c->roots.p, t_out,
-                                                    out_slot ? out_slot + wide : nullptr, (int)tail, (int)c->p.lwe_dim, (int)c->p.pbs_base_log,
-                                                    steps, s));
+                if (c->narrow_kernel == 8 && tail <= (size_t)(c->narrow_max ? c->narrow_max : c->sms))
+                    TB_CUDA(tbk::launch_pbs_multibit_v8(t_small, d_idx ? d_idx + wide : nullptr, d_luts, c->bskf8.p, c->tbl8.p, c->roots.p, t_out,
+                                                        out_slot ? out_slot + wide : nullptr, (int)tail, (int)c->p.lwe_dim,
+                                                        (int)c->p.pbs_base_log, steps, s));
+                else
+                    TB_CUDA(tbk::launch_pbs_multibit_v4(t_small, d_idx ? d_idx + wide : nullptr, d_luts, c->bskf.p, c->tbl16.p, c->roots.p, t_out,
+                                                        out_slot ? out_slot + wide : nullptr, (int)tail, (int)c->p.lwe_dim,
+                                                        (int)c->p.pbs_base_log, steps, s));
                 c->launches += 1;
             }
+            return 0;
         } else
             TB_CUDA(tbk::launch_pbs_multibit(d_small, d_idx, d_luts, c->bskf.p, c->tbl.p, c->roots.p, d_out, out_slot, (int)batch,
                                              (int)c->p.lwe_dim, (int)c->p.pbs_base_log, (int)(n_iters < groups ? n_iters : groups), s));
@@ -166,6 +176,7 @@ int tfhe_b200_ctx_create(int cuda_device, const tfhe_b200_params *params, tfhe_b
     if (const char *e = std::getenv("TFHE_B200_MB_KERNEL")) c->mb_kernel = (e[0] == '3') ? 3 : 4;
     TB_CUDA(tbk::pbs_multibit_configure());
     TB_CUDA(tbk::pbs_multibit_v4_configure());
+    TB_CUDA(tbk::pbs_multibit_v8_configure());
     {   // roots[e] = exp(i*pi*e/2048): monomial spectra of the multi-bit combine
         std::vector<double> r(2 * 4096);
         const long double pi = 3.14159265358979323846264338327950288L;
@@ -237,7 +248,13 @@ static int finish_bsk(tfhe_b200_ctx *c, const tbc::DevBuf &raw) {
     const size_t n_polys = bsk_poly_count(c);
     TB_CUDA(c->bskf.reserve(n_polys * tb::kM * sizeof(double) * 2));
     if (c->p.grouping_factor == 3 && c->mb_kernel == 4)
+    {
         TB_CUDA(tbk::launch_bsk_convert_multibit_v4((const uint64_t *)raw.p, c->bskf.p, c->tbl16.p, (int)n_polys, c->stream));
+        if (c->narrow_kernel == 8) {   // second copy of the key for the narrow-level kernel
+            TB_CUDA(c->bskf8.reserve(n_polys * tb::kM * sizeof(double) * 2));
+            TB_CUDA(tbk::launch_bsk_convert_multibit_v8((const uint64_t *)raw.p, c->bskf8.p, c->tbl8.p, (int)n_polys, c->stream));
+        }
+    }
     else if (c->p.grouping_factor == 3)
         TB_CUDA(tbk::launch_bsk_convert_multibit((const uint64_t *)raw.p, c->bskf.p, c->tbl.p, (int)n_polys, c->stream));
     else if (c->pbs_kernel == 4) {

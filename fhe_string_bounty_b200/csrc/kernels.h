@@ -72,6 +72,13 @@ cudaError_t launch_pbs_multibit_v4(const uint64_t *lwe_small, const uint32_t *lu
                                    int base_log, int n_groups, cudaStream_t stream);
 cudaError_t launch_bsk_convert_multibit_v4(const uint64_t *bsk_std, void *bskm, const void *tbl16, int n_polys, cudaStream_t stream);
 
+// pbs_multibit_v8.cu: multi-bit narrow levels (batch <= SM count), 8 FFT points per thread, one ciphertext per CTA
+cudaError_t pbs_multibit_v8_configure();
+cudaError_t launch_pbs_multibit_v8(const uint64_t *lwe_small, const uint32_t *lut_idx, const uint64_t *luts, const void *bskm8,
+                                   const void *tbl8, const void *roots, uint64_t *out, const uint32_t *out_slot, int batch, int n,
+                                   int base_log, int n_groups, cudaStream_t stream);
+cudaError_t launch_bsk_convert_multibit_v8(const uint64_t *bsk_std, void *bskm8, const void *tbl8, int n_polys, cudaStream_t stream);
+
 cudaError_t launch_gather_rows(const uint64_t *arena, const uint32_t *slots, uint64_t *dst, int n_rows, int lwe_len, cudaStream_t stream);
 
 // seeded.cu: dst row g = [mask_len words of the AES-128 CTR stream of `seed` | body_len words copied from bodies]

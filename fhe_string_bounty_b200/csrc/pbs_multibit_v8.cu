@@ -1,0 +1,279 @@
+// pbs_multibit_v8.cu -- multi-bit programmable bootstrap (grouping factor 3) for NARROW tree levels (at most one ciphertext per SM):
+// the arithmetic of pbs_multibit_v4.cu (lwe_multi_bit_programmable_bootstrapping.rs:18-84,295-546; fft/mod.rs:408-445;
+// ggsw.rs:699-754) on the thread layout of pbs_v8.cu -- four warps per polynomial, 8 FFT points per thread (pbs8_common.cuh), eight
+// warps per ciphertext -- because a narrow multi-bit level is bound by the per-thread key-combine loop (7 complex products per key
+// entry and frequency): halving the frequencies per thread halves that chain.
+//
+// With one ciphertext per CTA everything per-thread lives in registers: the accumulator (as u64 bit patterns in the FFT registers --
+// the monomials are applied in the Fourier domain, nothing is gathered), the 24 FFT twiddles and the step's seven A_j; no TMEM.
+// M_j[k] = zeta_k^(deg_j), zeta_k = w^(1 - 4k), k = kT + 128*x(register), x = (r >> 2) + 2*brev2(r & 3):
+//     M_j = A_j * W8^(deg_j * x),  A_j = w^(deg_j * (1 - 4*kT)) from two 64-entry root tables in shared memory.
+// Key stream: 512 KiB per step through a ring of eleven 16 KiB pieces ([j & 1][out poly][sel][thread 128]: two GGSWs of ONE frequency);
+// the four pieces of a frequency are released together.
+#include "kernels.h"
+#include "pbs8_common.cuh"
+
+namespace tbm8 {
+using namespace tb8c;
+
+constexpr int GF = 3, NGGSW = 1 << GF;
+constexpr int PIECE_CPLX = 1024;               // [jl 2][out poly 2][sel 2][thread 128]
+constexpr int PIECE_BYTES = PIECE_CPLX * 16;   // 16 KiB
+constexpr int PIECES_PER_REG = NGGSW / 2;      // 4
+constexpr int PIECES_PER_ITER = 8 * PIECES_PER_REG;   // 32 = 512 KiB per group
+constexpr int NSLOT = 11;
+constexpr int WARPS = 8;
+
+__constant__ double c_w8[8][2];                // exp(-2*pi*i*e/8)
+
+struct Smem {
+    cplx tile[2][tb8::kTileCplx];
+    cplx ring[NSLOT][PIECE_CPLX];
+    cplx root_hi[64], root_lo[64];             // w^(64 x), w^y: w^e = root_hi[e >> 6] * root_lo[e & 63]
+    unsigned long long full_bar[NSLOT];
+    unsigned int consumed[NSLOT];
+};
+static_assert(sizeof(Smem) <= 227 * 1024, "shared memory budget");
+
+// Fourier key layout: piece = (group*8 + register g)*4 + (j >> 1); inside [j & 1][out poly c][sel][thread 128]
+__device__ __forceinline__ size_t bskm8_index(int grp, int j, int g, int c, int sel) {
+    return (((((size_t)(grp * 8 + g) * PIECES_PER_REG + (j >> 1)) * 2 + (j & 1)) * 2 + c) * 2 + sel) * 128;
+}
+
+__global__ void __launch_bounds__(256, 1)
+pbs_multibit_kernel_v8(const uint64_t *__restrict__ lwe_small, const uint32_t *__restrict__ lut_idx, const uint64_t *__restrict__ luts,
+                       const cplx *__restrict__ bskm, const cplx *__restrict__ tbl8, const cplx *__restrict__ roots,   // roots[e] = exp(i*pi*e/2048)
+                       uint64_t *__restrict__ out, const uint32_t *__restrict__ out_slot, int batch, int n, int base_log, int n_groups) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
+    const int W = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int w = W >> 2, T = ((W & 3) << 5) | lane;
+    const int ct = blockIdx.x < batch ? blockIdx.x : batch - 1;
+    cplx *tile = sm.tile[w];
+    const cplx *otile = sm.tile[w ^ 1];
+    const PolySync128 poly_sync{1 + w};
+    const uint64_t *lwe = lwe_small + (size_t)ct * (n + 1);
+    const int total_pieces = n_groups * PIECES_PER_ITER;
+
+    if (threadIdx.x < 64) {
+        sm.root_hi[threadIdx.x] = __ldg(roots + 64 * threadIdx.x);
+        sm.root_lo[threadIdx.x] = __ldg(roots + threadIdx.x);
+    }
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSLOT; ++s) { mbar_init(&sm.full_bar[s], 1); sm.consumed[s] = 0; }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_proxy_async();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int first = total_pieces < NSLOT ? total_pieces : NSLOT;
+        for (int g = 0; g < first; ++g) {
+            mbar_expect_tx(&sm.full_bar[g], PIECE_BYTES);
+            tma_load_1d(sm.ring[g], bskm + (size_t)g * PIECE_CPLX, PIECE_BYTES, &sm.full_bar[g]);
+        }
+    }
+    cplx twr[24];
+#pragma unroll
+    for (int k = 0; k < 24; ++k) twr[k] = __ldg(tbl8 + 24 * T + k);
+    const RegTw8 twd{twr};
+
+    // acc <- LUT * X^(-b_hat) (lwe_multi_bit_programmable_bootstrapping.rs:373-391), own coefficients only
+    double re[8], im[8];
+    {
+        const uint32_t b_hat = modulus_switch_2n(__ldg(lwe + n)) & (2 * kN - 1);
+        const uint32_t a0 = (2 * kN - b_hat) & (2 * kN - 1);
+        const uint64_t *lut = luts + ((size_t)(lut_idx ? lut_idx[ct] : 0) * 2 + w) * kN;
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            const int j = T + 128 * m;
+            int s0, s1; bool n0, n1;
+            rot_src(j, a0, s0, n0);
+            rot_src(j + kM, a0, s1, n1);
+            uint64_t v0 = __ldg(lut + s0), v1 = __ldg(lut + s1);
+            v0 = n0 ? (uint64_t)0 - v0 : v0;
+            v1 = n1 ? (uint64_t)0 - v1 : v1;
+            re[m] = __longlong_as_double((long long)v0);
+            im[m] = __longlong_as_double((long long)v1);
+        }
+    }
+    // exponent of the thread-dependent part of zeta_k = w^(1 - 4k): kT = frequency of register 0
+    const int rot_t = (1 - 4 * freq_of8(T, 0)) & (2 * kN - 1);
+
+    int slot = 0;
+    uint32_t phase = 0;
+    for (int grp = 0; grp < n_groups; ++grp) {
+        // monomial degrees of the 7 non-constant GGSWs (:44-62): bit (g-1-t) of j selects mask element t; modulus switch of the SUM
+        cplx A[NGGSW];
+        uint32_t deg3 = 0;       // deg_j mod 8 (all the register-dependent factor needs), 3 bits per j
+        {
+            const uint64_t a0v = __ldg(lwe + GF * grp), a1v = __ldg(lwe + GF * grp + 1), a2v = __ldg(lwe + GF * grp + 2);
+#pragma unroll
+            for (int j = 1; j < NGGSW; ++j) {
+                const uint64_t s = ((j & 4) ? a0v : 0) + ((j & 2) ? a1v : 0) + ((j & 1) ? a2v : 0);
+                const uint32_t deg = modulus_switch_2n(s) & (2 * kN - 1);
+                deg3 |= (deg & 7u) << (3 * j);
+                const uint32_t e = (deg * (uint32_t)rot_t) & (2 * kN - 1);       // A_j = w^(deg * (1 - 4*kT))
+                const cplx hi = sm.root_hi[e >> 6], lo = sm.root_lo[e & 63];
+                A[j].x = DFMA(hi.x, lo.x, -DMUL(hi.y, lo.y));
+                A[j].y = DFMA(hi.x, lo.y, DMUL(hi.y, lo.x));
+            }
+        }
+
+        // decomposition of the accumulator itself (ggsw.rs:515-533 on src = acc_old), folded
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            re[m] = (double)signed_digit_l1((uint64_t)__double_as_longlong(re[m]), base_log);
+            im[m] = (double)signed_digit_l1((uint64_t)__double_as_longlong(im[m]), base_log);
+        }
+
+        fft8_fwd(re, im, tile, twd, T, poly_sync);
+        // park my 8 spectrum values for the partner polynomial (own exchange-A reader slots: conflict free, private)
+        st8(tile + xa_rbase(T), re, im, [](int p) { return xa_roff(p); });
+        __syncthreads();
+
+        {
+            const cplx *fop = otile + xa_rbase(T);
+            int my_slot = 0, my_piece = 0;
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+                cplx Ga, Gb;
+                const uint32_t x = (uint32_t)((g >> 2) + 2 * brev2(g & 3));
+#pragma unroll
+                for (int pc = 0; pc < PIECES_PER_REG; ++pc) {
+                    const int p = g * PIECES_PER_REG + pc;
+                    if (!mbar_try_wait(&sm.full_bar[slot], phase)) mbar_wait(&sm.full_bar[slot], phase);
+#pragma unroll
+                    for (int jl = 0; jl < 2; ++jl) {
+                        const int j = pc * 2 + jl;
+                        const cplx *base = sm.ring[slot] + ((jl * 2 + w) * 2) * 128 + T;
+                        const cplx ga = base[0], gb = base[128];
+                        if (j == 0) {
+                            Ga = ga; Gb = gb;
+                        } else {
+                            // M = A_j * W8^(deg_j * x): monomial spectrum at this thread's frequency (fft/mod.rs:413-444)
+                            const uint32_t e = (((deg3 >> (3 * j)) & 7u) * x) & 7u;
+                            const double br = c_w8[e][0], bi = c_w8[e][1];
+                            const double mr = DFMA(A[j].x, br, -DMUL(A[j].y, bi));
+                            const double mi = DFMA(A[j].x, bi, DMUL(A[j].y, br));
+                            Ga.x = DFMA(ga.x, mr, DFMA(-ga.y, mi, Ga.x));
+                            Ga.y = DFMA(ga.x, mi, DFMA(ga.y, mr, Ga.y));
+                            Gb.x = DFMA(gb.x, mr, DFMA(-gb.y, mi, Gb.x));
+                            Gb.y = DFMA(gb.x, mi, DFMA(gb.y, mr, Gb.y));
+                        }
+                    }
+                    if (lane == p) { my_slot = slot; my_piece = grp * PIECES_PER_ITER + p; }
+                    if (++slot == NSLOT) { slot = 0; phase ^= 1u; }
+                }
+                // release the register's four slots (lane = piece index within the step); nothing is synchronised in between
+                __syncwarp();
+                if (lane >= g * PIECES_PER_REG && lane < (g + 1) * PIECES_PER_REG && atomicAdd(&sm.consumed[my_slot], 1u) == WARPS - 1) {
+                    sm.consumed[my_slot] = 0;
+                    const int g2 = my_piece + NSLOT;
+                    if (g2 < total_pieces) {
+                        __threadfence_block();
+                        fence_proxy_async();
+                        mbar_expect_tx(&sm.full_bar[my_slot], PIECE_BYTES);
+                        tma_load_1d(sm.ring[my_slot], bskm + (size_t)g2 * PIECE_CPLX, PIECE_BYTES, &sm.full_bar[my_slot]);
+                    }
+                }
+                // out_fft[w] = F_w * Gc[w][w] + F_{1-w} * Gc[1-w][w]
+                const cplx F = fop[xa_roff(g)];
+                const double fr = re[g], fi = im[g];
+                double orr = DMUL(fr, Ga.x);
+                orr = DFMA(-fi, Ga.y, orr);
+                orr = DFMA(F.x, Gb.x, orr);
+                orr = DFMA(-F.y, Gb.y, orr);
+                double oi = DMUL(fr, Ga.y);
+                oi = DFMA(fi, Ga.x, oi);
+                oi = DFMA(F.x, Gb.y, oi);
+                oi = DFMA(F.y, Gb.x, oi);
+                re[g] = orr; im[g] = oi;
+            }
+        }
+        __syncthreads();   // the partner polynomial has read my spectrum: the tile is mine again
+
+        fft8_inv(re, im, tile, twd, T, poly_sync);
+
+        // dst = 0; dst += G (x) src  (:503): the accumulator is REPLACED by the rounded product
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            re[m] = __longlong_as_double((long long)from_torus_f64(re[m]));
+            im[m] = __longlong_as_double((long long)from_torus_f64(im[m]));
+        }
+    }
+
+    if (blockIdx.x < batch) {
+        uint64_t *o = out + (size_t)(out_slot ? out_slot[ct] : ct) * (kN + 1);
+        if (w == 0) {
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                const int j = T + 128 * m;
+                const uint64_t v0 = (uint64_t)__double_as_longlong(re[m]), v1 = (uint64_t)__double_as_longlong(im[m]);
+                if (j == 0) o[0] = v0; else o[kN - j] = (uint64_t)0 - v0;
+                o[kN - (j + kM)] = (uint64_t)0 - v1;
+            }
+        } else if (T == 0) {
+            o[kN] = (uint64_t)__double_as_longlong(re[0]);
+        }
+    }
+}
+
+// std multi-bit key [group][j 8][level 1][row r][col c][N] (entities/lwe_multi_bit_bootstrap_key.rs:11-62) -> ring layout
+__global__ void __launch_bounds__(128)
+bsk_convert_multibit_kernel_v8(const uint64_t *__restrict__ bsk_std, cplx *__restrict__ bskm, const cplx *__restrict__ tbl8, int n_polys) {
+    __shared__ cplx tile[tb8::kTileCplx];
+    const int qd = blockIdx.x, T = threadIdx.x;
+    if (qd >= n_polys) return;
+    const int c = qd & 1, r = (qd >> 1) & 1, j = (qd >> 2) & 7, grp = qd >> 5;
+    const uint64_t *src = bsk_std + (size_t)qd * kN;
+    const double scale = 5.293955920339377e-23;   // 2^-74
+    double re[8], im[8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+        const int jj = T + 128 * m;
+        re[m] = DMUL((double)(long long)src[jj], scale);
+        im[m] = DMUL((double)(long long)src[jj + kM], scale);
+    }
+    fft8_fwd(re, im, tile, GlobalTw8{tbl8 + 24 * T}, T, BlockSync{});
+    const int sel = (r == c) ? 0 : 1;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+        cplx v; v.x = re[g]; v.y = im[g];
+        bskm[bskm8_index(grp, j, g, c, sel) + T] = v;
+    }
+}
+
+}  // namespace tbm8
+
+namespace tbk {
+
+cudaError_t pbs_multibit_v8_configure() {
+    double h[8][2];
+    const long double pi = 3.14159265358979323846264338327950288L;
+    for (int e = 0; e < 8; ++e) {
+        h[e][0] = (double)cosl(-2.0L * pi * e / 8.0L);
+        h[e][1] = (double)sinl(-2.0L * pi * e / 8.0L);
+    }
+    cudaError_t err = cudaMemcpyToSymbol(tbm8::c_w8, h, sizeof(h));
+    if (err != cudaSuccess) return err;
+    return cudaFuncSetAttribute(tbm8::pbs_multibit_kernel_v8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tbm8::Smem));
+}
+
+// one ciphertext per CTA: for batch <= SM count (the caller dispatches wider levels to launch_pbs_multibit_v4)
+cudaError_t launch_pbs_multibit_v8(const uint64_t *lwe_small, const uint32_t *lut_idx, const uint64_t *luts, const void *bskm8,
+                                   const void *tbl8, const void *roots, uint64_t *out, const uint32_t *out_slot, int batch, int n,
+                                   int base_log, int n_groups, cudaStream_t stream) {
+    if (batch <= 0) return cudaSuccess;
+    tbm8::pbs_multibit_kernel_v8<<<batch, 256, sizeof(tbm8::Smem), stream>>>(
+        lwe_small, lut_idx, luts, reinterpret_cast<const tb::cplx *>(bskm8), reinterpret_cast<const tb::cplx *>(tbl8),
+        reinterpret_cast<const tb::cplx *>(roots), out, out_slot, batch, n, base_log, n_groups);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_bsk_convert_multibit_v8(const uint64_t *bsk_std, void *bskm8, const void *tbl8, int n_polys, cudaStream_t stream) {
+    tbm8::bsk_convert_multibit_kernel_v8<<<n_polys, 128, 0, stream>>>(bsk_std, reinterpret_cast<tb::cplx *>(bskm8),
+                                                                    reinterpret_cast<const tb::cplx *>(tbl8), n_polys);
+    return cudaGetLastError();
+}
+
+}  // namespace tbk

@@ -122,6 +122,7 @@ def test_every_multibit_instance(orc, keys_multibit, monkeypatch):
     vals = np.arange(13) % 16
     cts = ck.encrypt_batch(vals)
     want = [(9 * int(v) + 4) % 16 for v in vals]
+    monkeypatch.setenv("TFHE_B200_NARROW_KERNEL", "0")           # read at context creation: keep the narrow batch on pbs_multibit_v4.cu
     eng = F.Engine(engine_params(p))
     eng.upload_ksk(sk.ksk)
     eng.upload_bsk_std(sk.bsk)
@@ -133,3 +134,54 @@ def test_every_multibit_instance(orc, keys_multibit, monkeypatch):
         assert list(ck.decrypt_batch(out)) == want, cts_per_cta
         outs.append(out)
     eng.close()
+
+
+def test_multibit_narrow_level_kernel(orc, keys_multibit, monkeypatch):
+    """Levels of at most one ciphertext per SM run on pbs_multibit_v8.cu (8 FFT points per thread, accumulator in registers). Against the
+    16-points-per-thread kernel on the same inputs: LUT rotation + sample extraction identical words, one multi-bit step within the FFT
+    tolerance (2^44), full PBS decrypting identically over all messages, for 1 ciphertext, a ragged batch and a full
+    wave; a wide level's remainder lands in the right output rows."""
+    import torch
+    import fhe_string_bounty_b200 as F
+    p, ck, sk = keys_multibit
+    fs = [lambda x: (7 * x + 2) % 16, lambda x: int(x >= 5)]
+    luts = np.stack([sk.generate_lookup_table(f)[0] for f in fs])
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+
+    def make():
+        e = F.Engine(engine_params(p))
+        e.upload_ksk(sk.ksk)
+        e.upload_bsk_std(sk.bsk)
+        e.upload_luts(luts)
+        return e
+
+    e8 = make()
+    monkeypatch.setenv("TFHE_B200_NARROW_KERNEL", "0")
+    e4 = make()
+    monkeypatch.delenv("TFHE_B200_NARROW_KERNEL")
+    base = ck.encrypt_batch(np.arange(32) % 16)
+    for batch in (1, 37, sms):
+        reps = -(-batch // 32)
+        cts = np.tile(base, (reps, 1))[:batch]
+        vals = np.tile(np.arange(32) % 16, reps)[:batch]
+        idx = (np.arange(batch) % 2).astype(np.uint32)
+        want = [fs[i](int(v)) for v, i in zip(vals, idx)]
+        out8 = e8.ks_pbs_batch(cts, idx)
+        assert list(ck.decrypt_batch(out8)) == want, batch
+        assert list(ck.decrypt_batch(e4.ks_pbs_batch(cts, idx))) == want, batch
+        assert np.array_equal(out8, e8.ks_pbs_batch(cts, idx))          # deterministic
+        err = phase_error(ck, out8, np.array(want))
+        assert err.max() < 2**55
+        small = e8.keyswitch_batch(cts)
+        assert np.array_equal(e8.pbs_batch(small, idx, n_iters=0), e4.pbs_batch(small, idx, n_iters=0))
+        d = (e8.pbs_batch(small, idx, n_iters=1) - e4.pbs_batch(small, idx, n_iters=1)).view(np.int64)
+        assert np.abs(d).max() <= 2**44, (batch, int(np.abs(d).max()))
+    # three ciphertexts per SM + a remainder of 11: the remainder runs on the narrow kernel
+    batch = 3 * sms + 11
+    reps = -(-batch // 32)
+    cts = np.tile(base, (reps, 1))[:batch]
+    vals = np.tile(np.arange(32) % 16, reps)[:batch]
+    idx = (np.arange(batch) % 2).astype(np.uint32)
+    assert list(ck.decrypt_batch(e8.ks_pbs_batch(cts, idx))) == [fs[i](int(v)) for v, i in zip(vals, idx)]
+    e8.close()
+    e4.close()
