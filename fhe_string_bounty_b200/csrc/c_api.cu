@@ -22,9 +22,15 @@ using tbc::fail;
 namespace {
 
 int check_params(const tfhe_b200_params &p) {
-    if (p.poly_size != (uint32_t)tb::kN) return fail("unsupported poly_size (engine is built for N = 2048)");
-    if (p.glwe_dim != 1) return fail("unsupported glwe_dim (engine is built for k = 1)");
-    if (p.pbs_level != 1) return fail("unsupported pbs_level (engine is built for l = 1)");
+    // N = 2048, k = 1, one PBS level: the specialised kernels; every other (N, k) of shortint/parameters/mod.rs with N <= 8192 and any
+    // level count: pbs_generic.cu (classic PBS only)
+    const bool tuned = p.poly_size == (uint32_t)tb::kN && p.glwe_dim == 1 && p.pbs_level == 1;
+    if (!tuned) {
+        if (!tbk::pbs_generic_supported((int)p.poly_size, (int)p.glwe_dim))
+            return fail("unsupported (poly_size, glwe_dim): supported pairs are (256,5) (512,3) (512,2) (1024,2) (2048,1) (4096,1) (8192,1)");
+        if (p.pbs_level < 1 || p.pbs_level > 8 || p.pbs_base_log * p.pbs_level > 52) return fail("unsupported pbs_level / pbs_base_log");
+        if (p.grouping_factor != 0) return fail("multi-bit PBS needs poly_size 2048, glwe_dim 1, pbs_level 1");
+    }
     if (p.pbs_base_log < 2 || p.pbs_base_log > 30) return fail("unsupported pbs_base_log");
     if (p.ks_level < 1 || p.ks_base_log < 2 || p.ks_base_log > 7 || p.ks_base_log * p.ks_level > 31)
         return fail("unsupported keyswitch decomposition");
@@ -38,7 +44,7 @@ int check_params(const tfhe_b200_params &p) {
 
 namespace tbc {
 
-bool fused_supported(const tfhe_b200_ctx *c) { return c->ks_kernel == 1 && c->pbs_kernel >= 3 && c->p.grouping_factor == 0; }
+bool fused_supported(const tfhe_b200_ctx *c) { return c->ks_kernel == 1 && c->pbs_kernel >= 3 && c->p.grouping_factor == 0 && !c->generic; }
 
 int do_keyswitch(tfhe_b200_ctx *c, const uint64_t *d_in, uint64_t *d_small, size_t batch, cudaStream_t s, const uint32_t *in_slot,
                  DevBuf *digits, bool fused) {
@@ -65,6 +71,13 @@ int do_pbs(tfhe_b200_ctx *c, const uint64_t *d_small, const uint32_t *d_idx, con
     if (fused && !fused_supported(c)) return fail("internal: fused PBS input requested on an unsupported configuration");
     if (!c->have_bsk) return fail("bootstrap key not uploaded");
     if (!d_luts) return fail("no lookup tables uploaded");
+    if (c->generic) {
+        TB_CUDA(tbk::launch_pbs_generic(d_small, d_idx, d_luts, c->bskf.p, c->tw_generic.p, d_out, out_slot, (int)batch, (int)c->p.lwe_dim,
+                                        (int)c->p.poly_size, (int)c->p.glwe_dim, (int)c->p.pbs_base_log, (int)c->p.pbs_level,
+                                        (int)(n_iters < c->p.lwe_dim ? n_iters : c->p.lwe_dim), s));
+        c->launches += 1;
+        return 0;
+    }
     if (c->p.grouping_factor == 3) {
         const uint32_t groups = c->p.lwe_dim / 3;
         if (c->mb_kernel == 4) {
@@ -146,7 +159,7 @@ static int do_pbs(tfhe_b200_ctx *c, const uint64_t *d_small, const uint32_t *d_i
 extern "C" {
 
 const char *tfhe_b200_last_error(void) { return g_last_error.c_str(); }
-const char *tfhe_b200_version(void) { return "tfhe_b200 0.2 (sm_100a; classic + multi-bit(g=3) KS-PBS, N=2048, k=1, l=1)"; }
+const char *tfhe_b200_version(void) { return "tfhe_b200 0.3 (sm_100a; classic + multi-bit(g=3) KS-PBS tuned for N=2048, k=1, l=1; classic KS-PBS for every (N <= 8192, k, l) parameter set)"; }
 
 int tfhe_b200_ctx_create(int cuda_device, const tfhe_b200_params *params, tfhe_b200_ctx **out) {
     if (!out) return fail("null out pointer");
@@ -166,6 +179,16 @@ int tfhe_b200_ctx_create(int cuda_device, const tfhe_b200_params *params, tfhe_b
     if (const char *e = std::getenv("TFHE_B200_KS_KERNEL")) c->ks_kernel = (e[0] == 'i') ? 0 : 1;
     if (!tbk::ks_mma_supported((int)params->ks_level)) c->ks_kernel = 0;
     if (const char *e = std::getenv("TFHE_B200_PBS_KERNEL")) c->pbs_kernel = (e[0] == '2') ? 2 : (e[0] == '3') ? 3 : 4;
+    c->generic = !(params->poly_size == (uint32_t)tb::kN && params->glwe_dim == 1 && params->pbs_level == 1);
+    if (const char *e = std::getenv("TFHE_B200_PBS_KERNEL")) if (e[0] == 'g' && params->grouping_factor == 0) c->generic = true;
+    if (c->generic) {   // twist table of pbs_generic.cu: exp(i*pi*j/N), j < N/2 (fft/mod.rs:58-69)
+        const size_t M = params->poly_size / 2;
+        std::vector<double> tw(2 * M);
+        const long double pi = 3.14159265358979323846264338327950288L;
+        for (size_t j = 0; j < M; ++j) { tw[2 * j] = (double)cosl(pi * j / (long double)params->poly_size); tw[2 * j + 1] = (double)sinl(pi * j / (long double)params->poly_size); }
+        TB_CUDA(c->tw_generic.reserve(tw.size() * 8));
+        TB_CUDA(cudaMemcpy(c->tw_generic.p, tw.data(), tw.size() * 8, cudaMemcpyHostToDevice));
+    }
     TB_CUDA(tbk::pbs_configure());
     TB_CUDA(tbk::pbs_v3_configure());
     TB_CUDA(tbk::pbs_v4_configure());
@@ -207,7 +230,7 @@ int tfhe_b200_ctx_destroy(tfhe_b200_ctx *c) {
     if (!c) return 0;
     DeviceGuard g(c->device);
     cudaStreamSynchronize(c->stream);
-    for (DevBuf *b : {&c->ksk_packed, &c->ksk_colsum, &c->ksk_planes, &c->ks_digits, &c->bskf, &c->bskf8, &c->tbl, &c->tbl16, &c->tbl8, &c->roots, &c->luts, &c->d_in, &c->d_small, &c->d_out, &c->d_idx})
+    for (DevBuf *b : {&c->ksk_packed, &c->ksk_colsum, &c->ksk_planes, &c->ks_digits, &c->bskf, &c->bskf8, &c->tbl, &c->tbl16, &c->tbl8, &c->tw_generic, &c->roots, &c->luts, &c->d_in, &c->d_small, &c->d_out, &c->d_idx})
         b->release();
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     for (auto &L : c->lane) {
@@ -246,8 +269,10 @@ static size_t bsk_poly_count(const tfhe_b200_ctx *c) {
 
 static int finish_bsk(tfhe_b200_ctx *c, const tbc::DevBuf &raw) {
     const size_t n_polys = bsk_poly_count(c);
-    TB_CUDA(c->bskf.reserve(n_polys * tb::kM * sizeof(double) * 2));
-    if (c->p.grouping_factor == 3 && c->mb_kernel == 4)
+    TB_CUDA(c->bskf.reserve(n_polys * (c->p.poly_size / 2) * sizeof(double) * 2));
+    if (c->generic)
+        TB_CUDA(tbk::launch_bsk_convert_generic((const uint64_t *)raw.p, c->bskf.p, c->tw_generic.p, n_polys, (int)c->p.poly_size, c->stream));
+    else if (c->p.grouping_factor == 3 && c->mb_kernel == 4)
     {
         TB_CUDA(tbk::launch_bsk_convert_multibit_v4((const uint64_t *)raw.p, c->bskf.p, c->tbl16.p, (int)n_polys, c->stream));
         if (c->narrow_kernel == 8) {   // second copy of the key for the narrow-level kernel

@@ -53,11 +53,12 @@ struct tfhe_b200_ctx {
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     bool timed = false;
     // keys
-    tbc::DevBuf ksk_packed, ksk_colsum, ksk_planes, ks_digits, bskf, bskf8, tbl, tbl16, tbl8, roots, luts;
+    tbc::DevBuf ksk_packed, ksk_colsum, ksk_planes, ks_digits, bskf, bskf8, tbl, tbl16, tbl8, tw_generic, roots, luts;
     int ks_kernel = 1;    // 1: tensor-core GEMM (keyswitch_mma.cu), 0: IMAD GEMM (keyswitch.cu); env TFHE_B200_KS_KERNEL=imad
     uint32_t n_luts = 0;
     bool have_ksk = false, have_bsk = false;
     int narrow_kernel = 8;   // classic PBS, levels of <= 2 * SM count ciphertexts: 8 = pbs_v8.cu (8 FFT points per thread, 8 warps per ciphertext; keeps a second copy of the Fourier key in its own layout), 0 = the narrow instances of pbs_kernel; env TFHE_B200_NARROW_KERNEL
+    bool generic = false;    // parameter sets outside N = 2048, k = 1, l = 1 (or TFHE_B200_PBS_KERNEL=generic): pbs_generic.cu, no fused modulus switch
     int sms = 148;
     int narrow_max = 0;      // widest level the narrow kernel takes (0 = 2 * SM count); env TFHE_B200_NARROW_MAX
     int mb_kernel = 4;    // multi-bit: 4 = pbs_multibit_v4.cu (16 points per thread), 3 = pbs_multibit.cu; env TFHE_B200_MB_KERNEL

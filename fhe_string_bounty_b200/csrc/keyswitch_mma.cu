@@ -184,7 +184,7 @@ static cudaError_t launch_mma(const uint8_t *digits, const uint8_t *bmat, const 
 
 namespace tbk {
 
-bool ks_mma_supported(int level) { return level == 5 || level == 2 || level == 1 || level == 3 || level == 4; }
+bool ks_mma_supported(int level) { return level >= 1 && level <= 7; }
 
 cudaError_t launch_ksk_planes(const uint64_t *packed, uint8_t *bmat, int rows, int ldk, cudaStream_t stream) {
     tbkm::ksk_planes_kernel<<<2048, 256, 0, stream>>>(packed, bmat, rows, ldk);
@@ -211,6 +211,8 @@ cudaError_t launch_keyswitch_mma(const uint64_t *lwe_in, const uint32_t *in_slot
         case 3: return tbkm::launch_mma<96>(digits_scratch, bmat, colsum, lwe_in, in_slot, lwe_out, batch, in_dim, n, K, ldk, half_b, ms_shift, stream);
         case 4: return tbkm::launch_mma<128>(digits_scratch, bmat, colsum, lwe_in, in_slot, lwe_out, batch, in_dim, n, K, ldk, half_b, ms_shift, stream);
         case 5: return tbkm::launch_mma<160>(digits_scratch, bmat, colsum, lwe_in, in_slot, lwe_out, batch, in_dim, n, K, ldk, half_b, ms_shift, stream);
+        case 6: return tbkm::launch_mma<192>(digits_scratch, bmat, colsum, lwe_in, in_slot, lwe_out, batch, in_dim, n, K, ldk, half_b, ms_shift, stream);
+        case 7: return tbkm::launch_mma<224>(digits_scratch, bmat, colsum, lwe_in, in_slot, lwe_out, batch, in_dim, n, K, ldk, half_b, ms_shift, stream);
         default: return cudaErrorInvalidValue;
     }
 }

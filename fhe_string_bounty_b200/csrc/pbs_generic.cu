@@ -1,0 +1,290 @@
+// pbs_generic.cu -- programmable bootstrap for every classic shortint parameter set the specialised kernels do not cover
+// (SURVEY section 8(f) N4): polynomial sizes 256 ... 8192, GLWE dimension 1 ... 5, any number of PBS decomposition levels --
+// PARAM_MESSAGE_1_CARRY_0 ... PARAM_MESSAGE_6_CARRY_0 (shortint/parameters/mod.rs:598-911).  Same arithmetic as pbs_v4.cu, restated
+// from bootstrap.rs:242-364 (blind rotation), ggsw.rs:477-598 (external product: levels l..1, rows, columns),
+// math/decomposition.rs:25-86 + iter.rs:120-127 (multi-level signed decomposition with carry), fft/mod.rs:220-326 (fold/twist) and
+// glwe_sample_extraction.rs:91-147, but with none of that kernel's shape assumptions:
+//
+//   * one CTA per ciphertext, T = min(512, N/4) threads; the accumulator ((k+1) * N u64, <= 128 KiB) and ONE transform buffer
+//     (N/2 complex, <= 64 KiB) live in shared memory;
+//   * the size-N/2 complex FFT is a shared-memory radix-2 pass structure (forward DIF: natural -> bit-reversed, inverse DIT: back),
+//     so nothing is ever reordered -- the Fourier key is produced by the same device function and multiplied position by position;
+//   * every thread keeps the Fourier-domain output of "its" PER = (N/2)/T positions for all k+1 output polynomials in registers
+//     (<= 16 complex values), so the (k+1)(level) forward transforms of an iteration share the one buffer;
+//   * the Fourier key [ggsw][level][row][col][N/2] is read with coalesced 16-byte loads, once per ciphertext and iteration.
+//
+// This is the coverage kernel, not the tuned one: N = 2048, k = 1, one level stays on pbs_v4.cu / pbs_v8.cu (TFHE_B200_PBS_KERNEL=generic
+// forces this one for cross-checks).
+#include "kernels.h"
+#include "fft_core.cuh"
+
+namespace tbg {
+using tb::cplx;
+
+template <int LOGN>
+struct Shape {
+    static constexpr int N = 1 << LOGN, M = N / 2;
+    static constexpr int PER = M > 1024 ? M / 512 : 2;
+    static constexpr int T = M / PER;
+};
+
+__device__ __forceinline__ cplx cmul(cplx a, cplx b) {
+    cplx r;
+    r.x = DFMA(a.x, b.x, -DMUL(a.y, b.y));
+    r.y = DFMA(a.x, b.y, DMUL(a.y, b.x));
+    return r;
+}
+__device__ __forceinline__ cplx cmul_conj(cplx a, cplx b) {   // a * conj(b)
+    cplx r;
+    r.x = DFMA(a.x, b.x, DMUL(a.y, b.y));
+    r.y = DFMA(a.y, b.x, -DMUL(a.x, b.y));
+    return r;
+}
+
+// W_M^e = exp(-2*pi*i*e/M), e < M/2, from the twist table tw[j] = exp(i*pi*j/N), j < M (N = 2M): W_M^e = conj(tw[4e]) for e < M/4,
+// and -i * conj(tw[4e - M]) above
+template <int M>
+__device__ __forceinline__ cplx root(const cplx *__restrict__ tw, int e) {
+    if (M < 4) { cplx r; r.x = e ? 0.0 : 1.0; r.y = e ? -1.0 : 0.0; return r; }
+    const bool hi = e >= M / 4;
+    const cplx t = __ldg(tw + (hi ? 4 * e - M : 4 * e));
+    cplx r;
+    r.x = hi ? -t.y : t.x;
+    r.y = hi ? -t.x : -t.y;
+    return r;
+}
+
+// forward: natural order in, bit-reversed positions out.  Ends with a barrier.
+template <int M, int T>
+__device__ __forceinline__ void fft_fwd(cplx *buf, const cplx *__restrict__ tw) {
+    for (int half = M / 2; half >= 1; half >>= 1) {
+        __syncthreads();
+        const int stride = M / 2 / half;
+        for (int b = threadIdx.x; b < M / 2; b += T) {
+            const int j = b & (half - 1), i0 = ((b - j) << 1) + j, i1 = i0 + half;
+            const cplx u = buf[i0], v = buf[i1];
+            cplx s, d;
+            s.x = DADD(u.x, v.x); s.y = DADD(u.y, v.y);
+            d.x = DSUB(u.x, v.x); d.y = DSUB(u.y, v.y);
+            buf[i0] = s;
+            buf[i1] = half == 1 ? d : cmul(d, root<M>(tw, j * stride));
+        }
+    }
+    __syncthreads();
+}
+
+// inverse (unscaled): bit-reversed positions in, natural order out.  Ends with a barrier.
+template <int M, int T>
+__device__ __forceinline__ void fft_inv(cplx *buf, const cplx *__restrict__ tw) {
+    for (int half = 1; half <= M / 2; half <<= 1) {
+        __syncthreads();
+        const int stride = M / 2 / half;
+        for (int b = threadIdx.x; b < M / 2; b += T) {
+            const int j = b & (half - 1), i0 = ((b - j) << 1) + j, i1 = i0 + half;
+            const cplx u = buf[i0];
+            const cplx v = half == 1 ? buf[i1] : cmul_conj(buf[i1], root<M>(tw, j * stride));
+            cplx s, d;
+            s.x = DADD(u.x, v.x); s.y = DADD(u.y, v.y);
+            d.x = DSUB(u.x, v.x); d.y = DSUB(u.y, v.y);
+            buf[i0] = s;
+            buf[i1] = d;
+        }
+    }
+    __syncthreads();
+}
+
+// digit of level `lv` (1 = most significant) of the `levels`-level signed decomposition of x: closest representable
+// (decomposer.rs:98-118), then the carry chain from the least significant level up (iter.rs:120-127)
+__device__ __forceinline__ int64_t signed_digit(uint64_t x, int base_log, int levels, int lv) {
+    const int shift = 64 - base_log * levels - 1;
+    uint64_t state = (((x >> shift) + 1) & ~(uint64_t)1) >> 1;      // closest_representable(x) >> (64 - base_log * levels)
+    const uint64_t mask = ((uint64_t)1 << base_log) - 1;
+    uint64_t digit = 0;
+    for (int l = levels; l >= lv; --l) {
+        digit = state & mask;
+        state >>= base_log;
+        const uint64_t carry = (((digit - 1) | state) & digit) >> (base_log - 1);
+        state += carry;
+        digit -= carry << base_log;
+    }
+    return (int64_t)digit;
+}
+
+template <int LOGN, int K1>
+__global__ void __launch_bounds__(Shape<LOGN>::T)
+pbs_generic_kernel(const uint64_t *__restrict__ lwe_small, const uint32_t *__restrict__ lut_idx, const uint64_t *__restrict__ luts,
+                   const cplx *__restrict__ bskf, const cplx *__restrict__ tw, uint64_t *__restrict__ out,
+                   const uint32_t *__restrict__ out_slot, int n, int base_log, int levels, int n_iters) {
+    using S = Shape<LOGN>;
+    constexpr int N = S::N, M = S::M, PER = S::PER, T = S::T;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t *acc = reinterpret_cast<uint64_t *>(smem_raw);                 // [K1][N]
+    cplx *buf = reinterpret_cast<cplx *>(smem_raw + (size_t)K1 * N * 8);      // [M]
+    const int ct = blockIdx.x, t = threadIdx.x;
+    const uint64_t *lwe = lwe_small + (size_t)ct * (n + 1);
+    const auto mod_switch = [](uint64_t x) { return (uint32_t)(((x >> (64 - LOGN - 2)) + 1) >> 1) & (2 * N - 1); };
+
+    // acc <- LUT * X^(-b_hat)   (bootstrap.rs:262-270; polynomial_algorithms.rs:315-366)
+    {
+        const uint32_t a0 = (2 * N - mod_switch(__ldg(lwe + n))) & (2 * N - 1);
+        const uint64_t *lut = luts + (size_t)(lut_idx ? lut_idx[ct] : 0) * K1 * N;
+        for (int c = 0; c < K1; ++c)
+            for (int j = t; j < N; j += T) {
+                const uint32_t s = ((uint32_t)j - a0) & (2 * N - 1);
+                const uint64_t v = __ldg(lut + c * N + (s & (N - 1)));
+                acc[c * N + j] = s >= (uint32_t)N ? (uint64_t)0 - v : v;
+            }
+    }
+    __syncthreads();
+
+    for (int i = 0; i < n_iters; ++i) {
+        const uint32_t a_hat = mod_switch(__ldg(lwe + i));
+        if (a_hat == 0) continue;                                            // bootstrap.rs:281 (result-neutral)
+        cplx o[K1][PER];
+#pragma unroll
+        for (int c = 0; c < K1; ++c)
+#pragma unroll
+            for (int q = 0; q < PER; ++q) { o[c][q].x = 0.0; o[c][q].y = 0.0; }
+        const cplx *ggsw = bskf + (size_t)i * levels * K1 * K1 * M;
+
+        for (int lv = levels; lv >= 1; --lv) {                               // ggsw.rs:524: level l first
+            for (int r = 0; r < K1; ++r) {
+                // digits of (acc * X^a_hat - acc)[r] (bootstrap.rs:286-300), folded (coefficient j + i * coefficient j+M) and twisted
+                const uint64_t *src = acc + r * N;
+#pragma unroll
+                for (int q = 0; q < PER; ++q) {
+                    const int j = t + T * q;
+                    const uint32_t s0 = ((uint32_t)j - a_hat) & (2 * N - 1), s1 = ((uint32_t)(j + M) - a_hat) & (2 * N - 1);
+                    uint64_t v0 = src[s0 & (N - 1)], v1 = src[s1 & (N - 1)];
+                    v0 = (s0 >= (uint32_t)N ? (uint64_t)0 - v0 : v0) - src[j];
+                    v1 = (s1 >= (uint32_t)N ? (uint64_t)0 - v1 : v1) - src[j + M];
+                    cplx z;
+                    z.x = (double)signed_digit(v0, base_log, levels, lv);
+                    z.y = (double)signed_digit(v1, base_log, levels, lv);
+                    buf[j] = cmul(z, __ldg(tw + j));
+                }
+                fft_fwd<M, T>(buf, tw);
+                const cplx *g = ggsw + ((size_t)(lv - 1) * K1 + r) * K1 * M;
+#pragma unroll
+                for (int q = 0; q < PER; ++q) {
+                    const cplx f = buf[t + T * q];
+#pragma unroll
+                    for (int c = 0; c < K1; ++c) {
+                        const cplx gv = __ldg(g + (size_t)c * M + t + T * q);
+                        o[c][q].x = DFMA(f.x, gv.x, DFMA(-f.y, gv.y, o[c][q].x));
+                        o[c][q].y = DFMA(f.x, gv.y, DFMA(f.y, gv.x, o[c][q].y));
+                    }
+                }
+                __syncthreads();                                             // the buffer is rewritten next
+            }
+        }
+        // ct0[c] += round(inverse transform)   (fft/mod.rs:285-326; the 1/(N/2) and the 2^-64 of the key are folded into the key)
+#pragma unroll
+        for (int c = 0; c < K1; ++c) {
+#pragma unroll
+            for (int q = 0; q < PER; ++q) buf[t + T * q] = o[c][q];
+            fft_inv<M, T>(buf, tw);
+#pragma unroll
+            for (int q = 0; q < PER; ++q) {
+                const int j = t + T * q;
+                const cplx z = cmul_conj(buf[j], __ldg(tw + j));
+                acc[c * N + j] += tb::from_torus_f64(z.x);
+                acc[c * N + j + M] += tb::from_torus_f64(z.y);
+            }
+            __syncthreads();
+        }
+    }
+
+    // sample extraction of coefficient 0 (glwe_sample_extraction.rs:91-147)
+    uint64_t *dst = out + (size_t)(out_slot ? out_slot[ct] : ct) * ((size_t)(K1 - 1) * N + 1);
+    for (int r = 0; r < K1 - 1; ++r)
+        for (int j = t; j < N; j += T) dst[r * N + j] = j == 0 ? acc[r * N] : (uint64_t)0 - acc[r * N + N - j];
+    if (t == 0) dst[(K1 - 1) * N] = acc[(K1 - 1) * N];
+}
+
+// std key polynomial (u64 torus, fft/mod.rs:197-218) -> the kernel's Fourier layout, scale 2^-64 / (N/2) folded in
+template <int LOGN>
+__global__ void __launch_bounds__(Shape<LOGN>::T)
+bsk_convert_generic_kernel(const uint64_t *__restrict__ bsk_std, cplx *__restrict__ bskf, const cplx *__restrict__ tw) {
+    using S = Shape<LOGN>;
+    constexpr int N = S::N, M = S::M, PER = S::PER, T = S::T;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx *buf = reinterpret_cast<cplx *>(smem_raw);
+    const uint64_t *src = bsk_std + (size_t)blockIdx.x * N;
+    const double scale = 1.0 / (18446744073709551616.0 * (double)M);
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+        const int j = threadIdx.x + T * q;
+        cplx z;
+        z.x = DMUL((double)(long long)src[j], scale);
+        z.y = DMUL((double)(long long)src[j + M], scale);
+        buf[j] = cmul(z, __ldg(tw + j));
+    }
+    fft_fwd<M, T>(buf, tw);
+#pragma unroll
+    for (int q = 0; q < PER; ++q) bskf[(size_t)blockIdx.x * M + threadIdx.x + T * q] = buf[threadIdx.x + T * q];
+}
+
+template <int LOGN, int K1>
+cudaError_t launch(const uint64_t *lwe_small, const uint32_t *lut_idx, const uint64_t *luts, const void *bskf, const void *tw,
+                   uint64_t *out, const uint32_t *out_slot, int batch, int n, int base_log, int levels, int n_iters, cudaStream_t stream) {
+    using S = Shape<LOGN>;
+    const size_t smem = (size_t)K1 * S::N * 8 + (size_t)S::M * 16;
+    // function attributes are per device: set on every launch (microseconds) rather than caching a process-wide flag
+    cudaError_t e = cudaFuncSetAttribute(pbs_generic_kernel<LOGN, K1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    pbs_generic_kernel<LOGN, K1><<<batch, S::T, smem, stream>>>(lwe_small, lut_idx, luts, reinterpret_cast<const cplx *>(bskf),
+                                                                 reinterpret_cast<const cplx *>(tw), out, out_slot, n, base_log, levels, n_iters);
+    return cudaGetLastError();
+}
+
+template <int LOGN>
+cudaError_t convert(const uint64_t *bsk_std, void *bskf, const void *tw, size_t n_polys, cudaStream_t stream) {
+    using S = Shape<LOGN>;
+    const size_t smem = (size_t)S::M * 16;
+    cudaError_t e = cudaFuncSetAttribute(bsk_convert_generic_kernel<LOGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    bsk_convert_generic_kernel<LOGN><<<(unsigned)n_polys, S::T, smem, stream>>>(bsk_std, reinterpret_cast<cplx *>(bskf),
+                                                                                 reinterpret_cast<const cplx *>(tw));
+    return cudaGetLastError();
+}
+
+}  // namespace tbg
+
+namespace tbk {
+
+// (polynomial size, GLWE dimension) pairs of shortint/parameters/mod.rs with N <= 8192
+#define TBG_SHAPES(X) X(8, 5) X(9, 3) X(9, 2) X(10, 2) X(11, 1) X(12, 1) X(13, 1)
+
+bool pbs_generic_supported(int poly_size, int glwe_dim) {
+#define X(LOGN, K) if (poly_size == (1 << LOGN) && glwe_dim == K) return true;
+    TBG_SHAPES(X)
+#undef X
+    return false;
+}
+
+cudaError_t launch_pbs_generic(const uint64_t *lwe_small, const uint32_t *lut_idx, const uint64_t *luts, const void *bskf, const void *tw,
+                               uint64_t *out, const uint32_t *out_slot, int batch, int n, int poly_size, int glwe_dim, int base_log,
+                               int levels, int n_iters, cudaStream_t stream) {
+    if (batch <= 0) return cudaSuccess;
+#define X(LOGN, K)                                                                                                                   \
+    if (poly_size == (1 << LOGN) && glwe_dim == K)                                                                                   \
+        return tbg::launch<LOGN, K + 1>(lwe_small, lut_idx, luts, bskf, tw, out, out_slot, batch, n, base_log, levels, n_iters, stream);
+    TBG_SHAPES(X)
+#undef X
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_bsk_convert_generic(const uint64_t *bsk_std, void *bskf, const void *tw, size_t n_polys, int poly_size, cudaStream_t stream) {
+    switch (poly_size) {
+    case 256: return tbg::convert<8>(bsk_std, bskf, tw, n_polys, stream);
+    case 512: return tbg::convert<9>(bsk_std, bskf, tw, n_polys, stream);
+    case 1024: return tbg::convert<10>(bsk_std, bskf, tw, n_polys, stream);
+    case 2048: return tbg::convert<11>(bsk_std, bskf, tw, n_polys, stream);
+    case 4096: return tbg::convert<12>(bsk_std, bskf, tw, n_polys, stream);
+    case 8192: return tbg::convert<13>(bsk_std, bskf, tw, n_polys, stream);
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace tbk

@@ -132,9 +132,28 @@ def params(name: str = "2_2") -> Params:
         L.orc_params_multi_bit_message_2_carry_2_group_3_ks_pbs(C.byref(p))
     elif name == "toy":
         L.orc_params_toy(C.byref(p))
+    elif name in OTHER_CLASSIC_SETS:
+        (p.lwe_dim, p.glwe_dim, p.poly_size, p.lwe_std, p.glwe_std, p.pbs_base_log, p.pbs_level, p.ks_level, p.ks_base_log,
+         p.msg_mod, p.carry_mod) = OTHER_CLASSIC_SETS[name]
+        p.grouping_factor = 0
     else:
         raise KeyError(name)
     return p
+
+
+# PARAM_MESSAGE_<m>_CARRY_<c>_KS_PBS, name "<m>_<c>" (shortint/parameters/mod.rs:598-911), fields in the order of the struct literal:
+# lwe_dimension, glwe_dimension, polynomial_size, lwe_modular_std_dev, glwe_modular_std_dev, pbs_base_log, pbs_level, ks_level,
+# ks_base_log, message_modulus, carry_modulus
+OTHER_CLASSIC_SETS = {
+    "1_0": (678, 5, 256, 0.000022810107419132102, 0.00000000037411618952047216, 15, 1, 2, 5, 2, 1),  # :598-612
+    "1_1": (684, 3, 512, 0.00002043784477291318, 0.0000000000034525330484572114, 18, 1, 3, 4, 2, 2),  # :613-627
+    "2_0": (656, 2, 512, 0.000034119201269311964, 0.00000004053919869756513, 8, 2, 4, 3, 4, 1),  # :628-642
+    "1_2": (742, 2, 1024, 0.000007069849454709433, 0.00000000000000029403601535432533, 23, 1, 3, 4, 2, 4),  # :643-657
+    "1_3": (745, 1, 2048, 0.000006692125069956277, 0.00000000000000029403601535432533, 23, 1, 5, 3, 2, 8),  # :688-702
+    "1_4": (807, 1, 4096, 0.0000021515145918907506, 0.0000000000000000002168404344971009, 15, 2, 5, 3, 2, 16),  # :748-762
+    "2_3": (856, 1, 4096, 0.0000008775214009854235, 0.0000000000000000002168404344971009, 22, 1, 6, 3, 4, 8),  # :763-777
+    "3_3": (864, 1, 8192, 0.000000757998020150446, 0.0000000000000000002168404344971009, 15, 2, 6, 3, 8, 8),  # :853-867
+}
 
 
 class ClientKey:

@@ -10,7 +10,8 @@ def oracle_partial_pbs(orc, sk, lwe_small, lut, n_iters):
     L = orc.lib()
     p = sk.p
     N, k1 = p.poly_size, p.glwe_dim + 1
-    b_hat = L.orc_modulus_switch(int(lwe_small[p.lwe_dim]), 11)
+    lg = int(N).bit_length() - 1
+    b_hat = L.orc_modulus_switch(int(lwe_small[p.lwe_dim]), lg)
     acc = np.zeros(k1 * N, dtype=np.uint64)
     for q in range(k1):
         tmp = np.zeros(N, dtype=np.uint64)
@@ -19,7 +20,7 @@ def oracle_partial_pbs(orc, sk, lwe_small, lut, n_iters):
     for i in range(n_iters):
         if int(lwe_small[i]) == 0:
             continue
-        a_hat = L.orc_modulus_switch(int(lwe_small[i]), 11)
+        a_hat = L.orc_modulus_switch(int(lwe_small[i]), lg)
         ct1 = np.zeros_like(acc)
         for q in range(k1):
             tmp = np.zeros(N, dtype=np.uint64)

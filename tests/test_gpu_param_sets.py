@@ -1,0 +1,107 @@
+"""GPU parity for the classic parameter sets outside N = 2048 / k = 1 / one PBS level: pbs_generic.cu and the
+keyswitch with 2 ... 6 levels, against the oracle on identical seeded keys and ciphertexts.  Per set: keyswitch bit-exact; LUT rotation +
+sample extraction bit-exact; one CMUX within the FFT tolerance of DESIGN section 4 (2^44 u64 torus units; the multi-level, k > 1 external
+product exercises ggsw.rs:477-598 in full); KS-PBS decrypts to the LUT value for every message, with the phase error stated next to the
+oracle's.  PARAM_MESSAGE_2_CARRY_2 itself runs through the generic kernel too (TFHE_B200_PBS_KERNEL=generic) and must agree with the tuned
+kernels."""
+import numpy as np
+import pytest
+
+from helpers import engine_params, oracle_partial_pbs
+
+pytestmark = pytest.mark.gpu
+
+SETS = ["1_0", "1_1", "2_0", "1_2", "1_3", "2_3", "1_4", "3_3"]
+
+
+def _phase_error(ck, p, cts, want):
+    delta = 2**63 // (p.msg_mod * p.carry_mod)
+    errs = []
+    for ct, v in zip(cts, want):
+        d = (ck.decrypt_raw(ct) - int(v) * delta) % 2**64
+        errs.append(min(d, 2**64 - d))
+    return np.array(errs, dtype=np.float64)
+
+
+@pytest.mark.parametrize("name", SETS)
+def test_parameter_set(orc, name):
+    import fhe_string_bounty_b200 as F
+    p = orc.params(name)
+    ck = orc.ClientKey(p, 0xB200 + 40)
+    sk = orc.ServerKey(ck, 0xB300 + 40)
+    space = p.msg_mod * p.carry_mod
+    fs = [lambda x: x, lambda x: (3 * x + 1) % space, lambda x: int(x >= space // 2)]
+    luts = np.stack([sk.generate_lookup_table(f)[0] for f in fs])
+    eng = F.Engine(engine_params(p))
+    eng.upload_ksk(sk.ksk)
+    eng.upload_bsk_std(sk.bsk)
+    eng.upload_luts(luts)
+
+    vals = np.array([v for v in range(space) for _ in fs][:96])
+    idx = np.array([i for _ in range(space) for i in range(len(fs))][:96], dtype=np.uint32)
+    cts = ck.encrypt_batch(vals)
+    # keyswitch: exact integer arithmetic, including decomposer edge words
+    edge = cts[:3].copy()
+    edge[0, :] = np.uint64(2**64 - 1)
+    edge[1, :] = np.random.default_rng(7).integers(0, 2**64, size=edge.shape[1], dtype=np.uint64)
+    ks_in = np.concatenate([edge, cts[:6]])
+    assert np.array_equal(eng.keyswitch_batch(ks_in), np.stack([sk.keyswitch(c) for c in ks_in])), name
+    # blind rotation, step by step
+    small = np.stack([sk.keyswitch(c) for c in cts[:3]])
+    worst = 0
+    for n_iters in (0, 1, 2):
+        got = eng.pbs_batch(small, idx[:3], n_iters=n_iters)
+        for b in range(3):
+            want = oracle_partial_pbs(orc, sk, small[b], luts[idx[b]], n_iters)
+            d = int(np.abs((got[b] - want).view(np.int64)).max())
+            if n_iters == 0:
+                assert d == 0, (name, "LUT rotation / sample extraction must be bit-exact")
+            elif n_iters == 1:
+                worst = max(worst, d)
+                assert d <= 2**44, (name, b, np.log2(max(d, 1)))
+    # full KS-PBS
+    out = eng.ks_pbs_batch(cts, idx)
+    want = np.array([fs[i](int(v)) for v, i in zip(vals, idx)])
+    assert np.array_equal(ck.decrypt_batch(out), want), name
+    assert np.array_equal(out, eng.ks_pbs_batch(cts, idx)), "deterministic"
+    ref = sk.ks_pbs_batch(cts[:12], luts, idx[:12])
+    assert np.array_equal(ck.decrypt_batch(ref), want[:12])
+    e_gpu, e_cpu = _phase_error(ck, p, out, want), _phase_error(ck, p, ref, want[:12])
+    margin = 2**63 // space // 2
+    print(f"{name}: N={p.poly_size} k={p.glwe_dim} l={p.pbs_level}: one CMUX max|delta| 2^{np.log2(max(worst, 1)):.1f}; phase error gpu max "
+          f"2^{np.log2(e_gpu.max()):.1f} rms 2^{np.log2(np.sqrt((e_gpu**2).mean())):.1f}, oracle max 2^{np.log2(e_cpu.max()):.1f} "
+          f"(decoding margin 2^{np.log2(margin):.0f})")
+    assert e_gpu.max() < margin / 4
+    eng.close()
+
+
+def test_generic_kernel_agrees_with_tuned_kernel(orc, keys_2_2, monkeypatch):
+    """PARAM_MESSAGE_2_CARRY_2 through pbs_generic.cu: same words as pbs_v8.cu after LUT rotation, within 2^44 after one CMUX, same decrypted
+    values after the full blind rotation."""
+    import fhe_string_bounty_b200 as F
+    p, ck, sk = keys_2_2
+    acc, _ = sk.generate_lookup_table(lambda x: (5 * x + 2) % 16)
+
+    def make():
+        e = F.Engine(engine_params(p))
+        e.upload_ksk(sk.ksk)
+        e.upload_bsk_std(sk.bsk)
+        e.upload_luts(acc[None, :])
+        return e
+
+    tuned = make()
+    monkeypatch.setenv("TFHE_B200_PBS_KERNEL", "generic")
+    gen = make()
+    monkeypatch.delenv("TFHE_B200_PBS_KERNEL")
+    vals = np.arange(32) % 16
+    cts = ck.encrypt_batch(vals)
+    small = tuned.keyswitch_batch(cts)
+    assert np.array_equal(small, gen.keyswitch_batch(cts))
+    assert np.array_equal(tuned.pbs_batch(small, None, n_iters=0), gen.pbs_batch(small, None, n_iters=0))
+    d = np.abs((tuned.pbs_batch(small, None, n_iters=1) - gen.pbs_batch(small, None, n_iters=1)).view(np.int64)).max()
+    assert d <= 2**44, np.log2(float(d))
+    want = [(5 * int(v) + 2) % 16 for v in vals]
+    assert list(ck.decrypt_batch(gen.ks_pbs_batch(cts, None))) == want
+    assert list(ck.decrypt_batch(tuned.ks_pbs_batch(cts, None))) == want
+    tuned.close()
+    gen.close()
