@@ -22,12 +22,12 @@ using tbc::fail;
 namespace {
 
 int check_params(const tfhe_b200_params &p) {
-    // N = 2048, k = 1, one PBS level: the specialised kernels; every other (N, k) of shortint/parameters/mod.rs with N <= 8192 and any
+    // N = 2048, k = 1, one PBS level: the specialised kernels; every other (N, k) of shortint/parameters/mod.rs and any
     // level count: pbs_generic.cu (classic PBS only)
     const bool tuned = p.poly_size == (uint32_t)tb::kN && p.glwe_dim == 1 && p.pbs_level == 1;
     if (!tuned) {
         if (!tbk::pbs_generic_supported((int)p.poly_size, (int)p.glwe_dim))
-            return fail("unsupported (poly_size, glwe_dim): supported pairs are (256,5) (512,3) (512,2) (1024,2) (2048,1) (4096,1) (8192,1)");
+            return fail("unsupported (poly_size, glwe_dim): supported pairs are (256,5) (512,3) (512,2) (1024,2) (2048,1) (4096,1) (8192,1) (16384,1) (32768,1)");
         if (p.pbs_level < 1 || p.pbs_level > 8 || p.pbs_base_log * p.pbs_level > 52) return fail("unsupported pbs_level / pbs_base_log");
         if (p.grouping_factor != 0) return fail("multi-bit PBS needs poly_size 2048, glwe_dim 1, pbs_level 1");
     }
@@ -159,7 +159,7 @@ static int do_pbs(tfhe_b200_ctx *c, const uint64_t *d_small, const uint32_t *d_i
 extern "C" {
 
 const char *tfhe_b200_last_error(void) { return g_last_error.c_str(); }
-const char *tfhe_b200_version(void) { return "tfhe_b200 0.3 (sm_100a; classic + multi-bit(g=3) KS-PBS tuned for N=2048, k=1, l=1; classic KS-PBS for every (N <= 8192, k, l) parameter set)"; }
+const char *tfhe_b200_version(void) { return "tfhe_b200 0.3 (sm_100a; classic + multi-bit(g=3) KS-PBS tuned for N=2048, k=1, l=1; classic KS-PBS for every (N, k, l) of shortint/parameters/mod.rs)"; }
 
 int tfhe_b200_ctx_create(int cuda_device, const tfhe_b200_params *params, tfhe_b200_ctx **out) {
     if (!out) return fail("null out pointer");

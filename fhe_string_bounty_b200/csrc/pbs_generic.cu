@@ -1,11 +1,11 @@
 // pbs_generic.cu -- programmable bootstrap for every classic shortint parameter set the specialised kernels do not cover
-// (SURVEY section 8(f) N4): polynomial sizes 256 ... 8192, GLWE dimension 1 ... 5, any number of PBS decomposition levels --
-// PARAM_MESSAGE_1_CARRY_0 ... PARAM_MESSAGE_6_CARRY_0 (shortint/parameters/mod.rs:598-911).  Same arithmetic as pbs_v4.cu, restated
+// (SURVEY section 8(f) N4): polynomial sizes 256 ... 32768, GLWE dimension 1 ... 5, any number of PBS decomposition levels --
+// PARAM_MESSAGE_1_CARRY_0 ... PARAM_MESSAGE_8_CARRY_0 (shortint/parameters/mod.rs:598-1136).  Same arithmetic as pbs_v4.cu, restated
 // from bootstrap.rs:242-364 (blind rotation), ggsw.rs:477-598 (external product: levels l..1, rows, columns),
 // math/decomposition.rs:25-86 + iter.rs:120-127 (multi-level signed decomposition with carry), fft/mod.rs:220-326 (fold/twist) and
 // glwe_sample_extraction.rs:91-147, but with none of that kernel's shape assumptions:
 //
-//   * one CTA per ciphertext, T = min(512, N/4) threads; the accumulator ((k+1) * N u64, <= 128 KiB) and ONE transform buffer
+//   * N <= 8192: one CTA per ciphertext, T = min(512, N/4) threads; the accumulator ((k+1) * N u64, <= 128 KiB) and ONE transform buffer
 //     (N/2 complex, <= 64 KiB) live in shared memory;
 //   * the size-N/2 complex FFT is a shared-memory radix-2 pass structure (forward DIF: natural -> bit-reversed, inverse DIT: back),
 //     so nothing is ever reordered -- the Fourier key is produced by the same device function and multiplied position by position;
@@ -249,6 +249,223 @@ cudaError_t convert(const uint64_t *bsk_std, void *bskf, const void *tw, size_t 
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------------
+// N = 16384 and 32768 (PARAM_MESSAGE_1_CARRY_6 ... PARAM_MESSAGE_8_CARRY_0, mod.rs:913-1136): accumulator (up to 512 KiB), transform
+// buffer and Fourier-domain outputs do not fit one SM's shared memory, so they live in a per-CTA global scratch area (L2 resident:
+// 1.25 MiB per CTA) and only the FFT's inner stages run in shared memory: forward = log2(M / 4096) radix-2 stages through L2, then each
+// contiguous 4096-point block is finished in a 64 KiB shared buffer; the inverse mirrors it.  Two 512-thread CTAs per SM, each walking
+// over ciphertexts blockIdx.x, blockIdx.x + gridDim.x, ...
+// ---------------------------------------------------------------------------------------------------------------------------------
+constexpr int BIG_T = 512, BIG_CH = 4096;
+
+template <int M>
+__device__ __forceinline__ void fft_fwd_big(cplx *g, cplx *sm, const cplx *__restrict__ tw) {
+    for (int half = M / 2; half >= BIG_CH; half >>= 1) {
+        __syncthreads();
+        const int stride = M / 2 / half;
+        for (int b = threadIdx.x; b < M / 2; b += BIG_T) {
+            const int j = b & (half - 1), i0 = ((b - j) << 1) + j, i1 = i0 + half;
+            const cplx u = g[i0], v = g[i1];
+            cplx s, d;
+            s.x = DADD(u.x, v.x); s.y = DADD(u.y, v.y);
+            d.x = DSUB(u.x, v.x); d.y = DSUB(u.y, v.y);
+            g[i0] = s;
+            g[i1] = cmul(d, root<M>(tw, j * stride));
+        }
+    }
+    for (int c0 = 0; c0 < M; c0 += BIG_CH) {
+        __syncthreads();
+        for (int j = threadIdx.x; j < BIG_CH; j += BIG_T) sm[j] = g[c0 + j];
+        for (int half = BIG_CH / 2; half >= 1; half >>= 1) {
+            __syncthreads();
+            const int stride = M / 2 / half;
+            for (int b = threadIdx.x; b < BIG_CH / 2; b += BIG_T) {
+                const int j = b & (half - 1), i0 = ((b - j) << 1) + j, i1 = i0 + half;
+                const cplx u = sm[i0], v = sm[i1];
+                cplx s, d;
+                s.x = DADD(u.x, v.x); s.y = DADD(u.y, v.y);
+                d.x = DSUB(u.x, v.x); d.y = DSUB(u.y, v.y);
+                sm[i0] = s;
+                sm[i1] = half == 1 ? d : cmul(d, root<M>(tw, j * stride));
+            }
+        }
+        __syncthreads();
+        for (int j = threadIdx.x; j < BIG_CH; j += BIG_T) g[c0 + j] = sm[j];
+    }
+    __syncthreads();
+}
+
+template <int M>
+__device__ __forceinline__ void fft_inv_big(cplx *g, cplx *sm, const cplx *__restrict__ tw) {
+    for (int c0 = 0; c0 < M; c0 += BIG_CH) {
+        __syncthreads();
+        for (int j = threadIdx.x; j < BIG_CH; j += BIG_T) sm[j] = g[c0 + j];
+        for (int half = 1; half <= BIG_CH / 2; half <<= 1) {
+            __syncthreads();
+            const int stride = M / 2 / half;
+            for (int b = threadIdx.x; b < BIG_CH / 2; b += BIG_T) {
+                const int j = b & (half - 1), i0 = ((b - j) << 1) + j, i1 = i0 + half;
+                const cplx u = sm[i0];
+                const cplx v = half == 1 ? sm[i1] : cmul_conj(sm[i1], root<M>(tw, j * stride));
+                cplx s, d;
+                s.x = DADD(u.x, v.x); s.y = DADD(u.y, v.y);
+                d.x = DSUB(u.x, v.x); d.y = DSUB(u.y, v.y);
+                sm[i0] = s;
+                sm[i1] = d;
+            }
+        }
+        __syncthreads();
+        for (int j = threadIdx.x; j < BIG_CH; j += BIG_T) g[c0 + j] = sm[j];
+    }
+    for (int half = BIG_CH; half <= M / 2; half <<= 1) {
+        __syncthreads();
+        const int stride = M / 2 / half;
+        for (int b = threadIdx.x; b < M / 2; b += BIG_T) {
+            const int j = b & (half - 1), i0 = ((b - j) << 1) + j, i1 = i0 + half;
+            const cplx u = g[i0];
+            const cplx v = cmul_conj(g[i1], root<M>(tw, j * stride));
+            cplx s, d;
+            s.x = DADD(u.x, v.x); s.y = DADD(u.y, v.y);
+            d.x = DSUB(u.x, v.x); d.y = DSUB(u.y, v.y);
+            g[i0] = s;
+            g[i1] = d;
+        }
+    }
+    __syncthreads();
+}
+
+template <int LOGN, int K1>
+__host__ __device__ constexpr size_t big_scratch_bytes() { return (size_t)K1 * (1 << LOGN) * 8 + (size_t)(1 << (LOGN - 1)) * 16 * (1 + K1); }
+
+template <int LOGN, int K1>
+__global__ void __launch_bounds__(BIG_T, 2)
+pbs_generic_big_kernel(const uint64_t *__restrict__ lwe_small, const uint32_t *__restrict__ lut_idx, const uint64_t *__restrict__ luts,
+                       const cplx *__restrict__ bskf, const cplx *__restrict__ tw, uint64_t *__restrict__ out,
+                       const uint32_t *__restrict__ out_slot, unsigned char *scratch, int batch, int n, int base_log, int levels,
+                       int n_iters) {
+    constexpr int N = 1 << LOGN, M = N / 2, T = BIG_T;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx *sm = reinterpret_cast<cplx *>(smem_raw);                                              // [BIG_CH]
+    unsigned char *mine = scratch + (size_t)blockIdx.x * big_scratch_bytes<LOGN, K1>();
+    uint64_t *acc = reinterpret_cast<uint64_t *>(mine);                                         // [K1][N]
+    cplx *buf = reinterpret_cast<cplx *>(mine + (size_t)K1 * N * 8);                            // [M]
+    cplx *o = buf + M;                                                                          // [K1][M]
+    const int t = threadIdx.x;
+    const auto mod_switch = [](uint64_t x) { return (uint32_t)(((x >> (64 - LOGN - 2)) + 1) >> 1) & (2 * N - 1); };
+
+    for (int ct = blockIdx.x; ct < batch; ct += gridDim.x) {
+        const uint64_t *lwe = lwe_small + (size_t)ct * (n + 1);
+        {
+            const uint32_t a0 = (2 * N - mod_switch(__ldg(lwe + n))) & (2 * N - 1);
+            const uint64_t *lut = luts + (size_t)(lut_idx ? lut_idx[ct] : 0) * K1 * N;
+            for (int c = 0; c < K1; ++c)
+                for (int j = t; j < N; j += T) {
+                    const uint32_t s = ((uint32_t)j - a0) & (2 * N - 1);
+                    const uint64_t v = __ldg(lut + c * N + (s & (N - 1)));
+                    acc[c * N + j] = s >= (uint32_t)N ? (uint64_t)0 - v : v;
+                }
+        }
+        __syncthreads();
+        for (int i = 0; i < n_iters; ++i) {
+            const uint32_t a_hat = mod_switch(__ldg(lwe + i));
+            if (a_hat == 0) continue;
+            for (int e = t; e < K1 * M; e += T) { o[e].x = 0.0; o[e].y = 0.0; }
+            const cplx *ggsw = bskf + (size_t)i * levels * K1 * K1 * M;
+            for (int lv = levels; lv >= 1; --lv) {
+                for (int r = 0; r < K1; ++r) {
+                    const uint64_t *src = acc + r * N;
+                    for (int j = t; j < M; j += T) {
+                        const uint32_t s0 = ((uint32_t)j - a_hat) & (2 * N - 1), s1 = ((uint32_t)(j + M) - a_hat) & (2 * N - 1);
+                        uint64_t v0 = src[s0 & (N - 1)], v1 = src[s1 & (N - 1)];
+                        v0 = (s0 >= (uint32_t)N ? (uint64_t)0 - v0 : v0) - src[j];
+                        v1 = (s1 >= (uint32_t)N ? (uint64_t)0 - v1 : v1) - src[j + M];
+                        cplx z;
+                        z.x = (double)signed_digit(v0, base_log, levels, lv);
+                        z.y = (double)signed_digit(v1, base_log, levels, lv);
+                        buf[j] = cmul(z, __ldg(tw + j));
+                    }
+                    fft_fwd_big<M>(buf, sm, tw);
+                    const cplx *g = ggsw + ((size_t)(lv - 1) * K1 + r) * K1 * M;
+                    for (int pos = t; pos < M; pos += T) {
+                        const cplx f = buf[pos];
+#pragma unroll
+                        for (int c = 0; c < K1; ++c) {
+                            const cplx gv = __ldg(g + (size_t)c * M + pos);
+                            cplx a = o[c * M + pos];
+                            a.x = DFMA(f.x, gv.x, DFMA(-f.y, gv.y, a.x));
+                            a.y = DFMA(f.x, gv.y, DFMA(f.y, gv.x, a.y));
+                            o[c * M + pos] = a;
+                        }
+                    }
+                    __syncthreads();
+                }
+            }
+            for (int c = 0; c < K1; ++c) {
+                fft_inv_big<M>(o + c * M, sm, tw);
+                for (int j = t; j < M; j += T) {
+                    const cplx z = cmul_conj(o[c * M + j], __ldg(tw + j));
+                    acc[c * N + j] += tb::from_torus_f64(z.x);
+                    acc[c * N + j + M] += tb::from_torus_f64(z.y);
+                }
+            }
+            __syncthreads();
+        }
+        uint64_t *dst = out + (size_t)(out_slot ? out_slot[ct] : ct) * ((size_t)(K1 - 1) * N + 1);
+        for (int r = 0; r < K1 - 1; ++r)
+            for (int j = t; j < N; j += T) dst[r * N + j] = j == 0 ? acc[r * N] : (uint64_t)0 - acc[r * N + N - j];
+        if (t == 0) dst[(K1 - 1) * N] = acc[(K1 - 1) * N];
+        __syncthreads();      // the next ciphertext overwrites the accumulator
+    }
+}
+
+template <int LOGN>
+__global__ void __launch_bounds__(BIG_T)
+bsk_convert_generic_big_kernel(const uint64_t *__restrict__ bsk_std, cplx *bskf, const cplx *__restrict__ tw) {
+    constexpr int N = 1 << LOGN, M = N / 2;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx *sm = reinterpret_cast<cplx *>(smem_raw);
+    const uint64_t *src = bsk_std + (size_t)blockIdx.x * N;
+    cplx *dst = bskf + (size_t)blockIdx.x * M;            // transformed in place
+    const double scale = 1.0 / (18446744073709551616.0 * (double)M);
+    for (int j = threadIdx.x; j < M; j += BIG_T) {
+        cplx z;
+        z.x = DMUL((double)(long long)src[j], scale);
+        z.y = DMUL((double)(long long)src[j + M], scale);
+        dst[j] = cmul(z, __ldg(tw + j));
+    }
+    fft_fwd_big<M>(dst, sm, tw);
+}
+
+template <int LOGN, int K1>
+cudaError_t launch_big(const uint64_t *lwe_small, const uint32_t *lut_idx, const uint64_t *luts, const void *bskf, const void *tw,
+                       uint64_t *out, const uint32_t *out_slot, int batch, int n, int base_log, int levels, int n_iters, cudaStream_t stream) {
+    const size_t smem = (size_t)BIG_CH * 16;
+    cudaError_t e = cudaFuncSetAttribute(pbs_generic_big_kernel<LOGN, K1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int dev = 0, sms = 0;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+    const int grid = batch < 2 * sms ? batch : 2 * sms;
+    unsigned char *scratch = nullptr;     // stream-ordered: concurrent launches on other streams get their own area
+    if ((e = cudaMallocAsync((void **)&scratch, (size_t)grid * big_scratch_bytes<LOGN, K1>(), stream)) != cudaSuccess) return e;
+    pbs_generic_big_kernel<LOGN, K1><<<grid, BIG_T, smem, stream>>>(lwe_small, lut_idx, luts, reinterpret_cast<const cplx *>(bskf),
+                                                                    reinterpret_cast<const cplx *>(tw), out, out_slot, scratch, batch, n,
+                                                                    base_log, levels, n_iters);
+    e = cudaGetLastError();
+    const cudaError_t e2 = cudaFreeAsync(scratch, stream);
+    return e != cudaSuccess ? e : e2;
+}
+
+template <int LOGN>
+cudaError_t convert_big(const uint64_t *bsk_std, void *bskf, const void *tw, size_t n_polys, cudaStream_t stream) {
+    const size_t smem = (size_t)BIG_CH * 16;
+    cudaError_t e = cudaFuncSetAttribute(bsk_convert_generic_big_kernel<LOGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    bsk_convert_generic_big_kernel<LOGN><<<(unsigned)n_polys, BIG_T, smem, stream>>>(bsk_std, reinterpret_cast<cplx *>(bskf),
+                                                                                     reinterpret_cast<const cplx *>(tw));
+    return cudaGetLastError();
+}
+
 }  // namespace tbg
 
 namespace tbk {
@@ -260,7 +477,7 @@ bool pbs_generic_supported(int poly_size, int glwe_dim) {
 #define X(LOGN, K) if (poly_size == (1 << LOGN) && glwe_dim == K) return true;
     TBG_SHAPES(X)
 #undef X
-    return false;
+    return glwe_dim == 1 && (poly_size == 16384 || poly_size == 32768);
 }
 
 cudaError_t launch_pbs_generic(const uint64_t *lwe_small, const uint32_t *lut_idx, const uint64_t *luts, const void *bskf, const void *tw,
@@ -272,6 +489,10 @@ cudaError_t launch_pbs_generic(const uint64_t *lwe_small, const uint32_t *lut_id
         return tbg::launch<LOGN, K + 1>(lwe_small, lut_idx, luts, bskf, tw, out, out_slot, batch, n, base_log, levels, n_iters, stream);
     TBG_SHAPES(X)
 #undef X
+    if (glwe_dim == 1 && poly_size == 16384)
+        return tbg::launch_big<14, 2>(lwe_small, lut_idx, luts, bskf, tw, out, out_slot, batch, n, base_log, levels, n_iters, stream);
+    if (glwe_dim == 1 && poly_size == 32768)
+        return tbg::launch_big<15, 2>(lwe_small, lut_idx, luts, bskf, tw, out, out_slot, batch, n, base_log, levels, n_iters, stream);
     return cudaErrorInvalidValue;
 }
 
@@ -283,6 +504,8 @@ cudaError_t launch_bsk_convert_generic(const uint64_t *bsk_std, void *bskf, cons
     case 2048: return tbg::convert<11>(bsk_std, bskf, tw, n_polys, stream);
     case 4096: return tbg::convert<12>(bsk_std, bskf, tw, n_polys, stream);
     case 8192: return tbg::convert<13>(bsk_std, bskf, tw, n_polys, stream);
+    case 16384: return tbg::convert_big<14>(bsk_std, bskf, tw, n_polys, stream);
+    case 32768: return tbg::convert_big<15>(bsk_std, bskf, tw, n_polys, stream);
     }
     return cudaErrorInvalidValue;
 }

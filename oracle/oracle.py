@@ -153,6 +153,8 @@ OTHER_CLASSIC_SETS = {
     "1_4": (807, 1, 4096, 0.0000021515145918907506, 0.0000000000000000002168404344971009, 15, 2, 5, 3, 2, 16),  # :748-762
     "2_3": (856, 1, 4096, 0.0000008775214009854235, 0.0000000000000000002168404344971009, 22, 1, 6, 3, 4, 8),  # :763-777
     "3_3": (864, 1, 8192, 0.000000757998020150446, 0.0000000000000000002168404344971009, 15, 2, 6, 3, 8, 8),  # :853-867
+    "4_3": (930, 1, 16384, 0.00000022649232786295453, 0.0000000000000000002168404344971009, 15, 2, 6, 3, 16, 8),  # :958-972
+    "4_4": (996, 1, 32768, 0.00000006767666038309478, 0.0000000000000000002168404344971009, 15, 2, 7, 3, 16, 16),  # :1063-1077
 }
 
 

@@ -11,7 +11,8 @@ from helpers import engine_params, oracle_partial_pbs
 
 pytestmark = pytest.mark.gpu
 
-SETS = ["1_0", "1_1", "2_0", "1_2", "1_3", "2_3", "1_4", "3_3"]
+SETS = ["1_0", "1_1", "2_0", "1_2", "1_3", "2_3", "1_4", "3_3", "4_3", "4_4"]   # N = 256 ... 32768 (4_4: the oracle's key generation alone
+                                                                                # takes about a minute on 16 cores)
 
 
 def _phase_error(ck, p, cts, want):
@@ -37,8 +38,9 @@ def test_parameter_set(orc, name):
     eng.upload_bsk_std(sk.bsk)
     eng.upload_luts(luts)
 
-    vals = np.array([v for v in range(space) for _ in fs][:96])
-    idx = np.array([i for _ in range(space) for i in range(len(fs))][:96], dtype=np.uint32)
+    n_cts = 96 if p.poly_size <= 8192 else 24
+    vals = np.array([(v * 7) % space for v in range(space) for _ in fs][:n_cts])
+    idx = np.array([i for _ in range(space) for i in range(len(fs))][:n_cts], dtype=np.uint32)
     cts = ck.encrypt_batch(vals)
     # keyswitch: exact integer arithmetic, including decomposer edge words
     edge = cts[:3].copy()
