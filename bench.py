@@ -69,11 +69,11 @@ class CpuReference:
     """The CPU oracle (restatement of the reference's KS-PBS, one ciphertext per OpenMP thread, the structure of
     tfhe/benches/core_crypto/pbs_bench.rs:512-536) set up once and timed per call.  Only this leg may touch oracle/."""
 
-    def __init__(self, max_cts: int, threads: int = 0):
+    def __init__(self, max_cts: int, threads: int = 0, params_name: str = "2_2"):
         from oracle import oracle as O
         import ctypes as C
         self.C, self.L = C, O.lib()
-        self.p = O.params("2_2")
+        self.p = O.params(params_name)
         rng = np.random.default_rng(0xB200)
         # random words instead of generated keys: the arithmetic does not depend on the key values
         self.ksk = rng.integers(0, 2**64, size=self.L.orc_ksk_len(self.p), dtype=np.uint64)
@@ -131,6 +131,64 @@ def run_reference(args):
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+def run_param_sweep(args):
+    """--param-sweep: KS-PBS/s of other classic parameter sets (pbs_generic.cu) on one GPU next to the CPU oracle on the
+    same box.  Device-resident inputs, CUDA events on the launching stream, random key words (the arithmetic does not depend on the key
+    values).  One JSON line; not the headline metric."""
+    import math
+    import torch
+    import fhe_string_bounty_b200 as F
+    torch.cuda.set_device(0)
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    rows = []
+    for name in args.param_sweep.split(","):
+        p = F.Params(**F.classic_params(name))
+        eng = F.Engine(p, device=0)
+        rng = np.random.default_rng(0xB200)
+        eng.upload_ksk(rng.integers(0, 2**64, size=p.ksk_len, dtype=np.uint64))
+        eng.upload_bsk_std(rng.integers(0, 2**64, size=p.bsk_len, dtype=np.uint64))
+        eng.upload_luts(rng.integers(0, 2**64, size=(4, p.lut_len), dtype=np.uint64))
+        small_n = p.poly_size <= 8192
+        B = (8 if small_n else 2) * sms
+        d_in = torch.randint(-2**63, 2**63 - 1, (B, p.big_len), dtype=torch.int64, device="cuda")
+        d_idx = (torch.arange(B, device="cuda", dtype=torch.int32) % 4).contiguous()
+        d_out = torch.empty_like(d_in)
+        ts = torch.cuda.Stream()
+        torch.cuda.set_stream(ts)
+        eng.ks_pbs_batch_device(d_in, d_idx, d_out, B, ts.cuda_stream)
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 3 if small_n else 1
+        ev0.record()
+        for _ in range(reps):
+            eng.ks_pbs_batch_device(d_in, d_idx, d_out, B, ts.cuda_stream)
+        ev1.record()
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1) / reps
+        ks_ms, pbs_ms = eng.last_kernel_ms()
+        eng.close()
+        del d_in, d_out
+        torch.cuda.empty_cache()
+        M, k1, l = p.poly_size // 2, p.glwe_dim + 1, p.pbs_level
+        flop = p.lwe_dim * (k1 * (l + 1) * (5 * M * math.log2(M) + 6 * M) + k1 * k1 * l * M * 8)
+        row = {"params": f"PARAM_MESSAGE_{name.replace('_', '_CARRY_')}_KS_PBS", "N": p.poly_size, "k": p.glwe_dim, "pbs_level": l,
+               "batch": B, "ms": ms, "keyswitch_ms": ks_ms, "pbs_ms": pbs_ms, "ks_pbs_per_s": B / (ms * 1e-3), "flop_per_pbs": flop,
+               "pbs_tflops": B * flop / (pbs_ms * 1e-3) / 1e12}
+        if args.cpu_sample > 0:
+            ref = CpuReference(1, params_name=name)
+            n_cpu = ref.cores * (2 if small_n else 1)
+            ref.close()
+            ref = CpuReference(n_cpu, params_name=name)
+            ref.run(min(n_cpu, ref.cores))
+            dt, used = ref.run(n_cpu)
+            ref.close()
+            row["cpu_port_ks_pbs_per_s"] = n_cpu / dt
+            row["cpu_cores"] = used
+            row["gpu_over_cpu"] = row["ks_pbs_per_s"] / row["cpu_port_ks_pbs_per_s"]
+        rows.append(row)
+    print(json.dumps({"metric": "KS-PBS throughput per classic parameter set (1 GPU, device-resident)", "unit": "PBS/s", "sets": rows}))
 
 
 def bench_string_ops(eng, p, rank, world, local):
@@ -387,9 +445,12 @@ def main():
     ap.add_argument("--batch", type=int, default=8192, help="ciphertexts per GPU per step")
     ap.add_argument("--params", default="2_2", choices=["2_2", "multibit"], help="2_2 = PARAM_MESSAGE_2_CARRY_2_KS_PBS (headline); multibit = ..._GROUP_3_KS_PBS")
     ap.add_argument("--string-ops", type=int, default=1, help="also time FheString eq/contains/find through the host layer (0 = skip)")
+    ap.add_argument("--param-sweep", default="", help="comma-separated classic sets (e.g. 1_1,3_3,4_4): per-set KS-PBS/s on one GPU + CPU oracle, then exit")
     ap.add_argument("--cpu-sample", type=int, default=8192, help="KS-PBS evaluated by the CPU baseline leg (0 = skip)")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.param_sweep:
+        run_param_sweep(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_b200(args)

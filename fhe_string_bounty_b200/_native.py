@@ -106,6 +106,55 @@ PARAM_MESSAGE_2_CARRY_2_KS_PBS = dict(lwe_dim=742, glwe_dim=1, poly_size=2048, p
 PARAM_MULTI_BIT_MESSAGE_2_CARRY_2_GROUP_3_KS_PBS = dict(lwe_dim=888, glwe_dim=1, poly_size=2048, pbs_base_log=21, pbs_level=1,
                                                         ks_base_log=7, ks_level=2, grouping_factor=3, msg_mod=4, carry_mod=4)
 
+# every PARAM_MESSAGE_<m>_CARRY_<c>_KS_PBS of shortint/parameters/mod.rs:598-1136, keyed "<m>_<c>":
+# (lwe_dim, glwe_dim, poly_size, pbs_base_log, pbs_level, ks_base_log, ks_level, msg_mod, carry_mod)
+_CLASSIC_SETS = {
+    "1_0": (678, 5, 256, 15, 1, 5, 2, 2, 1),  # :598
+    "1_1": (684, 3, 512, 18, 1, 4, 3, 2, 2),  # :613
+    "2_0": (656, 2, 512, 8, 2, 3, 4, 4, 1),  # :628
+    "1_2": (742, 2, 1024, 23, 1, 4, 3, 2, 4),  # :643
+    "2_1": (742, 2, 1024, 23, 1, 4, 3, 4, 2),  # :658
+    "3_0": (742, 2, 1024, 23, 1, 4, 3, 8, 1),  # :673
+    "1_3": (745, 1, 2048, 23, 1, 3, 5, 2, 8),  # :688
+    "2_2": (742, 1, 2048, 23, 1, 3, 5, 4, 4),  # :703
+    "3_1": (742, 1, 2048, 23, 1, 3, 5, 8, 2),  # :718
+    "4_0": (742, 1, 2048, 23, 1, 3, 5, 16, 1),  # :733
+    "1_4": (807, 1, 4096, 15, 2, 3, 5, 2, 16),  # :748
+    "2_3": (856, 1, 4096, 22, 1, 3, 6, 4, 8),  # :763
+    "3_2": (812, 1, 4096, 22, 1, 3, 5, 8, 4),  # :778
+    "4_1": (808, 1, 4096, 22, 1, 3, 5, 16, 2),  # :793
+    "5_0": (807, 1, 4096, 22, 1, 3, 5, 32, 1),  # :808
+    "1_5": (864, 1, 8192, 15, 2, 3, 6, 2, 32),  # :823
+    "2_4": (864, 1, 8192, 15, 2, 3, 6, 4, 16),  # :838
+    "3_3": (864, 1, 8192, 15, 2, 3, 6, 8, 8),  # :853
+    "4_2": (864, 1, 8192, 15, 2, 3, 6, 16, 4),  # :868
+    "5_1": (875, 1, 8192, 22, 1, 3, 6, 32, 2),  # :883
+    "6_0": (915, 1, 8192, 22, 1, 4, 4, 64, 1),  # :898
+    "1_6": (930, 1, 16384, 11, 3, 3, 6, 2, 64),  # :913
+    "2_5": (934, 1, 16384, 15, 2, 3, 6, 4, 32),  # :928
+    "3_4": (930, 1, 16384, 15, 2, 3, 6, 8, 16),  # :943
+    "4_3": (930, 1, 16384, 15, 2, 3, 6, 16, 8),  # :958
+    "5_2": (930, 1, 16384, 15, 2, 3, 6, 32, 4),  # :973
+    "6_1": (930, 1, 16384, 15, 2, 3, 6, 64, 2),  # :988
+    "7_0": (930, 1, 16384, 15, 2, 3, 6, 128, 1),  # :1003
+    "1_7": (1004, 1, 32768, 11, 3, 3, 7, 2, 128),  # :1018
+    "2_6": (987, 1, 32768, 11, 3, 3, 7, 4, 64),  # :1033
+    "3_5": (985, 1, 32768, 11, 3, 3, 7, 8, 32),  # :1048
+    "4_4": (996, 1, 32768, 15, 2, 3, 7, 16, 16),  # :1063
+    "5_3": (1020, 1, 32768, 15, 2, 4, 5, 32, 8),  # :1078
+    "6_2": (1018, 1, 32768, 15, 2, 4, 5, 64, 4),  # :1093
+    "7_1": (1017, 1, 32768, 15, 2, 4, 5, 128, 2),  # :1108
+    "8_0": (1017, 1, 32768, 15, 2, 4, 5, 256, 1),  # :1123
+}
+
+
+def classic_params(name: str) -> dict:
+    """PARAM_MESSAGE_<m>_CARRY_<c>_KS_PBS as the keyword arguments of Params; name = "<m>_<c>" (e.g. "2_2", "3_3", "4_4")."""
+    t = _CLASSIC_SETS[name]
+    return dict(lwe_dim=t[0], glwe_dim=t[1], poly_size=t[2], pbs_base_log=t[3], pbs_level=t[4], ks_base_log=t[5], ks_level=t[6],
+                grouping_factor=0, msg_mod=t[7], carry_mod=t[8])
+
+
 EXPORTS = {
     "tfhe_b200_ctx_create": (C.c_int, [C.c_int, C.POINTER(Params), C.POINTER(C.c_void_p)]),
     "tfhe_b200_ctx_destroy": (C.c_int, [C.c_void_p]),
