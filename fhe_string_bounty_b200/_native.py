@@ -154,6 +154,24 @@ def classic_params(name: str) -> dict:
     return dict(lwe_dim=t[0], glwe_dim=t[1], poly_size=t[2], pbs_base_log=t[3], pbs_level=t[4], ks_base_log=t[5], ks_level=t[6],
                 grouping_factor=0, msg_mod=t[7], carry_mod=t[8])
 
+# every PARAM_MULTI_BIT_MESSAGE_<m>_CARRY_<c>_GROUP_<g>_KS_PBS of shortint/parameters/multi_bit.rs:96-209, keyed "<m>_<c>_g<g>":
+# (lwe_dim, glwe_dim, poly_size, pbs_base_log, pbs_level, ks_base_log, ks_level, msg_mod, carry_mod, grouping_factor)
+_MULTI_BIT_SETS = {
+    "1_1_g2": (764, 3, 512, 18, 1, 6, 2, 2, 2, 2),   # :96
+    "2_2_g2": (818, 1, 2048, 22, 1, 5, 3, 4, 4, 2),  # :115
+    "3_3_g2": (922, 1, 8192, 14, 2, 4, 4, 8, 8, 2),  # :134
+    "1_1_g3": (765, 3, 512, 18, 1, 6, 2, 2, 2, 3),   # :154
+    "2_2_g3": (888, 1, 2048, 21, 1, 7, 2, 4, 4, 3),  # :173
+    "3_3_g3": (972, 1, 8192, 14, 2, 6, 3, 8, 8, 3),  # :192
+}
+
+
+def multi_bit_params(name: str) -> dict:
+    """PARAM_MULTI_BIT_MESSAGE_<m>_CARRY_<c>_GROUP_<g>_KS_PBS as the keyword arguments of Params; name = "<m>_<c>_g<g>"."""
+    t = _MULTI_BIT_SETS[name]
+    return dict(lwe_dim=t[0], glwe_dim=t[1], poly_size=t[2], pbs_base_log=t[3], pbs_level=t[4], ks_base_log=t[5], ks_level=t[6],
+                msg_mod=t[7], carry_mod=t[8], grouping_factor=t[9])
+
 
 EXPORTS = {
     "tfhe_b200_ctx_create": (C.c_int, [C.c_int, C.POINTER(Params), C.POINTER(C.c_void_p)]),

@@ -29,14 +29,15 @@ int check_params(const tfhe_b200_params &p) {
         if (!tbk::pbs_generic_supported((int)p.poly_size, (int)p.glwe_dim))
             return fail("unsupported (poly_size, glwe_dim): supported pairs are (256,5) (512,3) (512,2) (1024,2) (2048,1) (4096,1) (8192,1) (16384,1) (32768,1)");
         if (p.pbs_level < 1 || p.pbs_level > 8 || p.pbs_base_log * p.pbs_level > 52) return fail("unsupported pbs_level / pbs_base_log");
-        if (p.grouping_factor != 0) return fail("multi-bit PBS needs poly_size 2048, glwe_dim 1, pbs_level 1");
+        if (p.grouping_factor != 0 && p.poly_size > 8192) return fail("multi-bit PBS needs poly_size <= 8192");
     }
     if (p.pbs_base_log < 2 || p.pbs_base_log > 30) return fail("unsupported pbs_base_log");
     if (p.ks_level < 1 || p.ks_base_log < 2 || p.ks_base_log > 7 || p.ks_base_log * p.ks_level > 31)
         return fail("unsupported keyswitch decomposition");
     if (p.lwe_dim < 1 || p.lwe_dim > 4096) return fail("unsupported lwe_dim");
-    if (p.grouping_factor != 0 && p.grouping_factor != 3) return fail("unsupported grouping_factor (0 = classic, 3 = multi-bit)");
-    if (p.grouping_factor == 3 && p.lwe_dim % 3 != 0) return fail("multi-bit: lwe_dim must be a multiple of the grouping factor");
+    if (p.grouping_factor != 0 && p.grouping_factor != 2 && p.grouping_factor != 3)
+        return fail("unsupported grouping_factor (0 = classic, 2 or 3 = multi-bit)");
+    if (p.grouping_factor != 0 && p.lwe_dim % p.grouping_factor != 0) return fail("multi-bit: lwe_dim must be a multiple of the grouping factor");
     return 0;
 }
 
@@ -72,9 +73,10 @@ int do_pbs(tfhe_b200_ctx *c, const uint64_t *d_small, const uint32_t *d_idx, con
     if (!c->have_bsk) return fail("bootstrap key not uploaded");
     if (!d_luts) return fail("no lookup tables uploaded");
     if (c->generic) {
+        const uint32_t steps = c->p.grouping_factor ? c->p.lwe_dim / c->p.grouping_factor : c->p.lwe_dim;
         TB_CUDA(tbk::launch_pbs_generic(d_small, d_idx, d_luts, c->bskf.p, c->tw_generic.p, d_out, out_slot, (int)batch, (int)c->p.lwe_dim,
                                         (int)c->p.poly_size, (int)c->p.glwe_dim, (int)c->p.pbs_base_log, (int)c->p.pbs_level,
-                                        (int)(n_iters < c->p.lwe_dim ? n_iters : c->p.lwe_dim), s));
+                                        (int)c->p.grouping_factor, (int)(n_iters < steps ? n_iters : steps), s));
         c->launches += 1;
         return 0;
     }
@@ -179,8 +181,8 @@ int tfhe_b200_ctx_create(int cuda_device, const tfhe_b200_params *params, tfhe_b
     if (const char *e = std::getenv("TFHE_B200_KS_KERNEL")) c->ks_kernel = (e[0] == 'i') ? 0 : 1;
     if (!tbk::ks_mma_supported((int)params->ks_level)) c->ks_kernel = 0;
     if (const char *e = std::getenv("TFHE_B200_PBS_KERNEL")) c->pbs_kernel = (e[0] == '2') ? 2 : (e[0] == '3') ? 3 : 4;
-    c->generic = !(params->poly_size == (uint32_t)tb::kN && params->glwe_dim == 1 && params->pbs_level == 1);
-    if (const char *e = std::getenv("TFHE_B200_PBS_KERNEL")) if (e[0] == 'g' && params->grouping_factor == 0) c->generic = true;
+    c->generic = !(params->poly_size == (uint32_t)tb::kN && params->glwe_dim == 1 && params->pbs_level == 1) || params->grouping_factor == 2;
+    if (const char *e = std::getenv("TFHE_B200_PBS_KERNEL")) if (e[0] == 'g') c->generic = true;
     if (c->generic) {   // twist table of pbs_generic.cu: exp(i*pi*j/N), j < N/2 (fft/mod.rs:58-69)
         const size_t M = params->poly_size / 2;
         std::vector<double> tw(2 * M);

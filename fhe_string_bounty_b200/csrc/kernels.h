@@ -83,7 +83,8 @@ cudaError_t launch_bsk_convert_multibit_v8(const uint64_t *bsk_std, void *bskm8,
 bool pbs_generic_supported(int poly_size, int glwe_dim);
 cudaError_t launch_pbs_generic(const uint64_t *lwe_small, const uint32_t *lut_idx, const uint64_t *luts, const void *bskf, const void *tw,
                                uint64_t *out, const uint32_t *out_slot, int batch, int n, int poly_size, int glwe_dim, int base_log,
-                               int levels, int n_iters, cudaStream_t stream);
+                               int levels, int grouping_factor /* 0 = classic, 2 / 3 = multi-bit (poly_size <= 8192) */, int n_iters,
+                               cudaStream_t stream);
 cudaError_t launch_bsk_convert_generic(const uint64_t *bsk_std, void *bskf, const void *tw, size_t n_polys, int poly_size, cudaStream_t stream);
 
 cudaError_t launch_gather_rows(const uint64_t *arena, const uint32_t *slots, uint64_t *dst, int n_rows, int lwe_len, cudaStream_t stream);

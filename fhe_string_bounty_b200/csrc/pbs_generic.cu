@@ -110,7 +110,22 @@ __device__ __forceinline__ int64_t signed_digit(uint64_t x, int base_log, int le
     return (int64_t)digit;
 }
 
-template <int LOGN, int K1>
+// w^e = exp(i*pi*e/N) for e in [0, 2N) from the twist table (e < N/2) and the quadrant
+template <int N>
+__device__ __forceinline__ cplx root2n(const cplx *__restrict__ tw, uint32_t e) {
+    const cplx t = __ldg(tw + (e & (N / 2 - 1)));
+    const uint32_t quad = (e / (N / 2)) & 3u;
+    cplx r;
+    r.x = quad == 0 ? t.x : quad == 1 ? -t.y : quad == 2 ? -t.x : t.y;
+    r.y = quad == 0 ? t.y : quad == 1 ? t.x : quad == 2 ? -t.y : -t.x;
+    return r;
+}
+
+// GF = 0: classic blind rotation.  GF = 2, 3: multi-bit (lwe_multi_bit_programmable_bootstrapping.rs:18-84,295-546, deterministic order):
+// per group of GF mask elements acc <- G (x) acc with G = G_0 + sum_j G_j * X^(deg_j) combined on the fly in the Fourier domain -- position
+// `pos` of the transform holds the evaluation at zeta = w^(1 - 4*brev(pos)), so the monomial's spectrum there is w^(deg_j * (1 - 4*brev(pos)))
+// (fft/mod.rs:408-445).  n_iters counts groups.
+template <int LOGN, int K1, int GF>
 __global__ void __launch_bounds__(Shape<LOGN>::T)
 pbs_generic_kernel(const uint64_t *__restrict__ lwe_small, const uint32_t *__restrict__ lut_idx, const uint64_t *__restrict__ luts,
                    const cplx *__restrict__ bskf, const cplx *__restrict__ tw, uint64_t *__restrict__ out,
@@ -138,26 +153,46 @@ pbs_generic_kernel(const uint64_t *__restrict__ lwe_small, const uint32_t *__res
     __syncthreads();
 
     for (int i = 0; i < n_iters; ++i) {
-        const uint32_t a_hat = mod_switch(__ldg(lwe + i));
-        if (a_hat == 0) continue;                                            // bootstrap.rs:281 (result-neutral)
+        uint32_t a_hat = 0;
+        uint32_t deg[GF ? (1 << GF) : 1];                                    // multi-bit: monomial degree of GGSW j (:44-62)
+        if (GF == 0) {
+            a_hat = mod_switch(__ldg(lwe + i));
+            if (a_hat == 0) continue;                                        // bootstrap.rs:281 (result-neutral)
+        } else {
+#pragma unroll
+            for (int j = 1; j < (1 << GF); ++j) {
+                uint64_t sum = 0;
+#pragma unroll
+                for (int mi = 0; mi < GF; ++mi)
+                    if ((j >> (GF - 1 - mi)) & 1) sum += __ldg(lwe + GF * i + mi);
+                deg[j] = mod_switch(sum);
+            }
+        }
         cplx o[K1][PER];
 #pragma unroll
         for (int c = 0; c < K1; ++c)
 #pragma unroll
             for (int q = 0; q < PER; ++q) { o[c][q].x = 0.0; o[c][q].y = 0.0; }
-        const cplx *ggsw = bskf + (size_t)i * levels * K1 * K1 * M;
+        const size_t ggsw_len = (size_t)levels * K1 * K1 * M;
+        const cplx *ggsw = bskf + (size_t)i * (GF ? (1 << GF) : 1) * ggsw_len;
 
         for (int lv = levels; lv >= 1; --lv) {                               // ggsw.rs:524: level l first
             for (int r = 0; r < K1; ++r) {
-                // digits of (acc * X^a_hat - acc)[r] (bootstrap.rs:286-300), folded (coefficient j + i * coefficient j+M) and twisted
+                // digits of (acc * X^a_hat - acc)[r] (bootstrap.rs:286-300; multi-bit: of acc[r] itself), folded (coefficient j +
+                // i * coefficient j+M) and twisted
                 const uint64_t *src = acc + r * N;
 #pragma unroll
                 for (int q = 0; q < PER; ++q) {
                     const int j = t + T * q;
-                    const uint32_t s0 = ((uint32_t)j - a_hat) & (2 * N - 1), s1 = ((uint32_t)(j + M) - a_hat) & (2 * N - 1);
-                    uint64_t v0 = src[s0 & (N - 1)], v1 = src[s1 & (N - 1)];
-                    v0 = (s0 >= (uint32_t)N ? (uint64_t)0 - v0 : v0) - src[j];
-                    v1 = (s1 >= (uint32_t)N ? (uint64_t)0 - v1 : v1) - src[j + M];
+                    uint64_t v0, v1;
+                    if (GF == 0) {
+                        const uint32_t s0 = ((uint32_t)j - a_hat) & (2 * N - 1), s1 = ((uint32_t)(j + M) - a_hat) & (2 * N - 1);
+                        v0 = src[s0 & (N - 1)]; v1 = src[s1 & (N - 1)];
+                        v0 = (s0 >= (uint32_t)N ? (uint64_t)0 - v0 : v0) - src[j];
+                        v1 = (s1 >= (uint32_t)N ? (uint64_t)0 - v1 : v1) - src[j + M];
+                    } else {
+                        v0 = src[j]; v1 = src[j + M];
+                    }
                     cplx z;
                     z.x = (double)signed_digit(v0, base_log, levels, lv);
                     z.y = (double)signed_digit(v1, base_log, levels, lv);
@@ -167,12 +202,28 @@ pbs_generic_kernel(const uint64_t *__restrict__ lwe_small, const uint32_t *__res
                 const cplx *g = ggsw + ((size_t)(lv - 1) * K1 + r) * K1 * M;
 #pragma unroll
                 for (int q = 0; q < PER; ++q) {
-                    const cplx f = buf[t + T * q];
+                    const int pos = t + T * q;
+                    const cplx f = buf[pos];
+                    if (GF == 0) {
 #pragma unroll
-                    for (int c = 0; c < K1; ++c) {
-                        const cplx gv = __ldg(g + (size_t)c * M + t + T * q);
-                        o[c][q].x = DFMA(f.x, gv.x, DFMA(-f.y, gv.y, o[c][q].x));
-                        o[c][q].y = DFMA(f.x, gv.y, DFMA(f.y, gv.x, o[c][q].y));
+                        for (int c = 0; c < K1; ++c) {
+                            const cplx gv = __ldg(g + (size_t)c * M + pos);
+                            o[c][q].x = DFMA(f.x, gv.x, DFMA(-f.y, gv.y, o[c][q].x));
+                            o[c][q].y = DFMA(f.x, gv.y, DFMA(f.y, gv.x, o[c][q].y));
+                        }
+                    } else {
+                        // F * (G_0 + sum_j G_j * M_j) = F * G_0 + sum_j (F * M_j) * G_j
+                        const uint32_t rot = (1u - 4u * (__brev((uint32_t)pos) >> (33 - LOGN))) & (2 * N - 1);
+#pragma unroll
+                        for (int j = 0; j < (1 << GF); ++j) {
+                            const cplx fm = j == 0 ? f : cmul(f, root2n<N>(tw, (deg[j] * rot) & (2 * N - 1)));
+#pragma unroll
+                            for (int c = 0; c < K1; ++c) {
+                                const cplx gv = __ldg(g + (size_t)j * ggsw_len + (size_t)c * M + pos);
+                                o[c][q].x = DFMA(fm.x, gv.x, DFMA(-fm.y, gv.y, o[c][q].x));
+                                o[c][q].y = DFMA(fm.x, gv.y, DFMA(fm.y, gv.x, o[c][q].y));
+                            }
+                        }
                     }
                 }
                 __syncthreads();                                             // the buffer is rewritten next
@@ -188,8 +239,13 @@ pbs_generic_kernel(const uint64_t *__restrict__ lwe_small, const uint32_t *__res
             for (int q = 0; q < PER; ++q) {
                 const int j = t + T * q;
                 const cplx z = cmul_conj(buf[j], __ldg(tw + j));
-                acc[c * N + j] += tb::from_torus_f64(z.x);
-                acc[c * N + j + M] += tb::from_torus_f64(z.y);
+                if (GF == 0) {
+                    acc[c * N + j] += tb::from_torus_f64(z.x);
+                    acc[c * N + j + M] += tb::from_torus_f64(z.y);
+                } else {                                                     // dst = 0; dst += G (x) src (:503)
+                    acc[c * N + j] = tb::from_torus_f64(z.x);
+                    acc[c * N + j + M] = tb::from_torus_f64(z.y);
+                }
             }
             __syncthreads();
         }
@@ -225,15 +281,15 @@ bsk_convert_generic_kernel(const uint64_t *__restrict__ bsk_std, cplx *__restric
     for (int q = 0; q < PER; ++q) bskf[(size_t)blockIdx.x * M + threadIdx.x + T * q] = buf[threadIdx.x + T * q];
 }
 
-template <int LOGN, int K1>
+template <int LOGN, int K1, int GF>
 cudaError_t launch(const uint64_t *lwe_small, const uint32_t *lut_idx, const uint64_t *luts, const void *bskf, const void *tw,
                    uint64_t *out, const uint32_t *out_slot, int batch, int n, int base_log, int levels, int n_iters, cudaStream_t stream) {
     using S = Shape<LOGN>;
     const size_t smem = (size_t)K1 * S::N * 8 + (size_t)S::M * 16;
     // function attributes are per device: set on every launch (microseconds) rather than caching a process-wide flag
-    cudaError_t e = cudaFuncSetAttribute(pbs_generic_kernel<LOGN, K1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(pbs_generic_kernel<LOGN, K1, GF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    pbs_generic_kernel<LOGN, K1><<<batch, S::T, smem, stream>>>(lwe_small, lut_idx, luts, reinterpret_cast<const cplx *>(bskf),
+    pbs_generic_kernel<LOGN, K1, GF><<<batch, S::T, smem, stream>>>(lwe_small, lut_idx, luts, reinterpret_cast<const cplx *>(bskf),
                                                                  reinterpret_cast<const cplx *>(tw), out, out_slot, n, base_log, levels, n_iters);
     return cudaGetLastError();
 }
@@ -482,13 +538,21 @@ bool pbs_generic_supported(int poly_size, int glwe_dim) {
 
 cudaError_t launch_pbs_generic(const uint64_t *lwe_small, const uint32_t *lut_idx, const uint64_t *luts, const void *bskf, const void *tw,
                                uint64_t *out, const uint32_t *out_slot, int batch, int n, int poly_size, int glwe_dim, int base_log,
-                               int levels, int n_iters, cudaStream_t stream) {
+                               int levels, int grouping_factor, int n_iters, cudaStream_t stream) {
     if (batch <= 0) return cudaSuccess;
 #define X(LOGN, K)                                                                                                                   \
-    if (poly_size == (1 << LOGN) && glwe_dim == K)                                                                                   \
-        return tbg::launch<LOGN, K + 1>(lwe_small, lut_idx, luts, bskf, tw, out, out_slot, batch, n, base_log, levels, n_iters, stream);
+    if (poly_size == (1 << LOGN) && glwe_dim == K) {                                                                                 \
+        if (grouping_factor == 0)                                                                                                    \
+            return tbg::launch<LOGN, K + 1, 0>(lwe_small, lut_idx, luts, bskf, tw, out, out_slot, batch, n, base_log, levels, n_iters, stream); \
+        if (grouping_factor == 2)                                                                                                    \
+            return tbg::launch<LOGN, K + 1, 2>(lwe_small, lut_idx, luts, bskf, tw, out, out_slot, batch, n, base_log, levels, n_iters, stream); \
+        if (grouping_factor == 3)                                                                                                    \
+            return tbg::launch<LOGN, K + 1, 3>(lwe_small, lut_idx, luts, bskf, tw, out, out_slot, batch, n, base_log, levels, n_iters, stream); \
+        return cudaErrorInvalidValue;                                                                                                \
+    }
     TBG_SHAPES(X)
 #undef X
+    if (grouping_factor != 0) return cudaErrorInvalidValue;
     if (glwe_dim == 1 && poly_size == 16384)
         return tbg::launch_big<14, 2>(lwe_small, lut_idx, luts, bskf, tw, out, out_slot, batch, n, base_log, levels, n_iters, stream);
     if (glwe_dim == 1 && poly_size == 32768)

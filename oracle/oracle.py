@@ -136,9 +136,24 @@ def params(name: str = "2_2") -> Params:
         (p.lwe_dim, p.glwe_dim, p.poly_size, p.lwe_std, p.glwe_std, p.pbs_base_log, p.pbs_level, p.ks_level, p.ks_base_log,
          p.msg_mod, p.carry_mod) = OTHER_CLASSIC_SETS[name]
         p.grouping_factor = 0
+    elif name in OTHER_MULTI_BIT_SETS:
+        (p.lwe_dim, p.glwe_dim, p.poly_size, p.lwe_std, p.glwe_std, p.pbs_base_log, p.pbs_level, p.ks_base_log, p.ks_level,
+         p.msg_mod, p.carry_mod, p.grouping_factor) = OTHER_MULTI_BIT_SETS[name]
     else:
         raise KeyError(name)
     return p
+
+
+# PARAM_MULTI_BIT_MESSAGE_<m>_CARRY_<c>_GROUP_<g>_KS_PBS, name "multibit_<m>_<c>_g<g>" (shortint/parameters/multi_bit.rs), fields:
+# lwe_dimension, glwe_dimension, polynomial_size, lwe_modular_std_dev, glwe_modular_std_dev, pbs_base_log, pbs_level, ks_base_log,
+# ks_level, message_modulus, carry_modulus, grouping_factor
+OTHER_MULTI_BIT_SETS = {
+    "multibit_1_1_g2": (764, 3, 512, 0.000006025673585415336, 0.0000000000039666089171633006, 18, 1, 6, 2, 2, 2, 2),          # :96
+    "multibit_2_2_g2": (818, 1, 2048, 0.000002226459789930014, 0.0000000000000003152931493498455, 22, 1, 5, 3, 4, 4, 2),        # :115
+    "multibit_3_3_g2": (922, 1, 8192, 0.0000003272369292345697, 0.0000000000000000002168404344971009, 14, 2, 4, 4, 8, 8, 2),    # :134
+    "multibit_1_1_g3": (765, 3, 512, 0.000005915594083804978, 0.0000000000039666089171633006, 18, 1, 6, 2, 2, 2, 3),           # :154
+    "multibit_3_3_g3": (972, 1, 8192, 0.00000013016688349592805, 0.0000000000000000002168404344971009, 14, 2, 6, 3, 8, 8, 3),   # :192
+}
 
 
 # PARAM_MESSAGE_<m>_CARRY_<c>_KS_PBS, name "<m>_<c>" (shortint/parameters/mod.rs:598-911), fields in the order of the struct literal:

@@ -107,3 +107,74 @@ def test_generic_kernel_agrees_with_tuned_kernel(orc, keys_2_2, monkeypatch):
     assert list(ck.decrypt_batch(tuned.ks_pbs_batch(cts, None))) == want
     tuned.close()
     gen.close()
+
+
+MULTI_BIT_SETS = ["multibit_1_1_g2", "multibit_2_2_g2", "multibit_3_3_g2", "multibit_1_1_g3", "multibit_3_3_g3"]
+
+
+@pytest.mark.parametrize("name", MULTI_BIT_SETS)
+def test_multi_bit_parameter_set(orc, name):
+    """The other multi-bit sets of shortint/parameters/multi_bit.rs (grouping factor 2 and 3, N = 512 ... 8192, k up to 3, two PBS levels)
+    on the generic kernel: keyswitch bit-exact, LUT rotation bit-exact, decrypted LUT values for every message, deterministic, phase error
+    next to the oracle's deterministic multi-bit restatement."""
+    import fhe_string_bounty_b200 as F
+    p = orc.params(name)
+    ck = orc.ClientKey(p, 0xB200 + 41)
+    sk = orc.ServerKey(ck, 0xB300 + 41)
+    space = p.msg_mod * p.carry_mod
+    fs = [lambda x: x, lambda x: (3 * x + 1) % space, lambda x: int(x >= space // 2)]
+    luts = np.stack([sk.generate_lookup_table(f)[0] for f in fs])
+    eng = F.Engine(engine_params(p))
+    eng.upload_ksk(sk.ksk)
+    eng.upload_bsk_std(sk.bsk)
+    eng.upload_luts(luts)
+    vals = np.array([(v * 7) % space for v in range(space) for _ in fs][:96])
+    idx = np.array([i for _ in range(space) for i in range(len(fs))][:96], dtype=np.uint32)
+    cts = ck.encrypt_batch(vals)
+    assert np.array_equal(eng.keyswitch_batch(cts[:6]), np.stack([sk.keyswitch(c) for c in cts[:6]])), name
+    small = np.stack([sk.keyswitch(c) for c in cts[:3]])
+    got0 = eng.pbs_batch(small, idx[:3], n_iters=0)
+    for b in range(3):
+        assert np.array_equal(got0[b], oracle_partial_pbs(orc, sk, small[b], luts[idx[b]], 0)), name
+    out = eng.ks_pbs_batch(cts, idx)
+    want = np.array([fs[i](int(v)) for v, i in zip(vals, idx)])
+    assert np.array_equal(ck.decrypt_batch(out), want), name
+    assert np.array_equal(out, eng.ks_pbs_batch(cts, idx)), "deterministic"
+    ref = sk.ks_pbs_batch(cts[:12], luts, idx[:12])
+    assert np.array_equal(ck.decrypt_batch(ref), want[:12])
+    e_gpu, e_cpu = _phase_error(ck, p, out, want), _phase_error(ck, p, ref, want[:12])
+    margin = 2**63 // space // 2
+    print(f"{name}: N={p.poly_size} k={p.glwe_dim} l={p.pbs_level} g={p.grouping_factor}: phase error gpu max 2^{np.log2(e_gpu.max()):.1f} rms "
+          f"2^{np.log2(np.sqrt((e_gpu**2).mean())):.1f}, oracle max 2^{np.log2(e_cpu.max()):.1f} (decoding margin 2^{np.log2(margin):.0f})")
+    assert e_gpu.max() < margin / 4
+    eng.close()
+
+
+def test_generic_multi_bit_agrees_with_tuned_kernel(orc, keys_multibit, monkeypatch):
+    """PARAM_MULTI_BIT_MESSAGE_2_CARRY_2_GROUP_3 through the generic kernel against pbs_multibit_v8.cu: identical LUT rotation, one group step
+    within the FFT tolerance, identical decrypted values."""
+    import fhe_string_bounty_b200 as F
+    p, ck, sk = keys_multibit
+    acc, _ = sk.generate_lookup_table(lambda x: (11 * x + 5) % 16)
+
+    def make():
+        e = F.Engine(engine_params(p))
+        e.upload_ksk(sk.ksk)
+        e.upload_bsk_std(sk.bsk)
+        e.upload_luts(acc[None, :])
+        return e
+
+    tuned = make()
+    monkeypatch.setenv("TFHE_B200_PBS_KERNEL", "generic")
+    gen = make()
+    monkeypatch.delenv("TFHE_B200_PBS_KERNEL")
+    vals = np.arange(32) % 16
+    cts = ck.encrypt_batch(vals)
+    small = tuned.keyswitch_batch(cts)
+    assert np.array_equal(tuned.pbs_batch(small, None, n_iters=0), gen.pbs_batch(small, None, n_iters=0))
+    d = np.abs((tuned.pbs_batch(small, None, n_iters=1) - gen.pbs_batch(small, None, n_iters=1)).view(np.int64)).max()
+    assert d <= 2**44, np.log2(float(d))
+    want = [(11 * int(v) + 5) % 16 for v in vals]
+    assert list(ck.decrypt_batch(gen.ks_pbs_batch(cts, None))) == want
+    tuned.close()
+    gen.close()

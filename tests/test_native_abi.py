@@ -81,3 +81,25 @@ def test_cpu_mirror_of_four_warp_fft(tmp_path):
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout
     assert "OK" in out.stdout
+
+
+def test_parameter_tables_match_the_oracle_and_the_engine_envelope():
+    """The product's parameter tables (classic_params / multi_bit_params) against the oracle's independently typed copies of
+    shortint/parameters/{mod,multi_bit}.rs, and every set inside the envelope tfhe_b200_ctx_create accepts (c_api.cu check_params)."""
+    import fhe_string_bounty_b200 as F
+    from fhe_string_bounty_b200._native import _CLASSIC_SETS, _MULTI_BIT_SETS
+    from oracle import oracle as O
+    assert len(_CLASSIC_SETS) == 36 and len(_MULTI_BIT_SETS) == 6
+    assert F.classic_params("2_2") == dict(F.PARAM_MESSAGE_2_CARRY_2_KS_PBS)
+    assert F.multi_bit_params("2_2_g3") == dict(F.PARAM_MULTI_BIT_MESSAGE_2_CARRY_2_GROUP_3_KS_PBS)
+    fields = ("lwe_dim", "glwe_dim", "poly_size", "pbs_base_log", "pbs_level", "ks_base_log", "ks_level", "grouping_factor", "msg_mod", "carry_mod")
+    for name in O.OTHER_CLASSIC_SETS:
+        op, mine = O.params(name), F.classic_params(name)
+        assert all(getattr(op, f) == mine[f] for f in fields), name
+    for name in O.OTHER_MULTI_BIT_SETS:
+        op, mine = O.params(name), F.multi_bit_params(name.replace("multibit_", ""))
+        assert all(getattr(op, f) == mine[f] for f in fields), name
+    shapes = {(256, 5), (512, 3), (512, 2), (1024, 2), (2048, 1), (4096, 1), (8192, 1), (16384, 1), (32768, 1)}
+    for name, t in list(_CLASSIC_SETS.items()) + list(_MULTI_BIT_SETS.items()):
+        n, k, N, pb, pl, kb, kl = t[:7]
+        assert (N, k) in shapes and 2 <= kb <= 7 and kb * kl <= 31 and 2 <= pb <= 30 and pb * pl <= 52 and n <= 4096, name
