@@ -5,10 +5,10 @@
 // math/decomposition.rs:25-86 + iter.rs:120-127 (multi-level signed decomposition with carry), fft/mod.rs:220-326 (fold/twist) and
 // glwe_sample_extraction.rs:91-147, but with none of that kernel's shape assumptions:
 //
-//   * N <= 8192: one CTA per ciphertext, T = min(512, N/4) threads; the accumulator ((k+1) * N u64, <= 128 KiB) and ONE transform buffer
+//   * N <= 8192: one CTA per ciphertext, T = min(512, N/8) threads; the accumulator ((k+1) * N u64, <= 128 KiB) and ONE transform buffer
 //     (N/2 complex, <= 64 KiB) live in shared memory;
-//   * the size-N/2 complex FFT is a shared-memory radix-2 pass structure (forward DIF: natural -> bit-reversed, inverse DIT: back),
-//     so nothing is ever reordered -- the Fourier key is produced by the same device function and multiplied position by position;
+//   * the size-N/2 complex FFT runs in shared memory, two radix-2 stages per pass in registers (forward DIF: natural -> bit-reversed,
+//     inverse DIT: back) with the roots of unity in a shared table, so nothing is ever reordered -- the Fourier key is produced by the same device function and multiplied position by position;
 //   * every thread keeps the Fourier-domain output of "its" PER = (N/2)/T positions for all k+1 output polynomials in registers
 //     (<= 16 complex values), so the (k+1)(level) forward transforms of an iteration share the one buffer;
 //   * the Fourier key [ggsw][level][row][col][N/2] is read with coalesced 16-byte loads, once per ciphertext and iteration.
@@ -24,8 +24,9 @@ using tb::cplx;
 template <int LOGN>
 struct Shape {
     static constexpr int N = 1 << LOGN, M = N / 2;
-    static constexpr int PER = M > 1024 ? M / 512 : 2;
+    static constexpr int PER = M > 2048 ? M / 512 : 4;       // positions per thread = one radix-4 butterfly per FFT pass (two above N = 4096)
     static constexpr int T = M / PER;
+    static constexpr int MINB = M == 2048 ? 2 : 1;           // N = 4096: two 512-thread CTAs per SM (64 registers)
 };
 
 __device__ __forceinline__ cplx cmul(cplx a, cplx b) {
@@ -54,20 +55,56 @@ __device__ __forceinline__ cplx root(const cplx *__restrict__ tw, int e) {
     return r;
 }
 
-// forward: natural order in, bit-reversed positions out.  Ends with a barrier.
+// the same root from the shared-memory table rt[e] = W_M^e, e < M/4
+template <int M>
+__device__ __forceinline__ cplx sroot(const cplx *rt, int e) {
+    const bool hi = e >= M / 4;
+    const cplx t = rt[hi ? e - M / 4 : e];
+    cplx r;
+    r.x = hi ? t.y : t.x;          // (-i) * (x + iy) = y - ix
+    r.y = hi ? -t.x : t.y;
+    return r;
+}
+__device__ __forceinline__ cplx cadd(cplx a, cplx b) { cplx r; r.x = DADD(a.x, b.x); r.y = DADD(a.y, b.y); return r; }
+__device__ __forceinline__ cplx csub(cplx a, cplx b) { cplx r; r.x = DSUB(a.x, b.x); r.y = DSUB(a.y, b.y); return r; }
+__device__ __forceinline__ cplx mul_neg_i(cplx a) { cplx r; r.x = a.y; r.y = -a.x; return r; }
+__device__ __forceinline__ cplx mul_pos_i(cplx a) { cplx r; r.x = -a.y; r.y = a.x; return r; }
+
+template <int M> struct Log2 { static constexpr int v = 1 + Log2<M / 2>::v; };
+template <> struct Log2<1> { static constexpr int v = 0; };
+
+// forward: natural order in, bit-reversed positions out (radix-2 DIF stages taken two at a time).  Ends with a barrier.
 template <int M, int T>
-__device__ __forceinline__ void fft_fwd(cplx *buf, const cplx *__restrict__ tw) {
-    for (int half = M / 2; half >= 1; half >>= 1) {
+__device__ __forceinline__ void fft_fwd(cplx *buf, const cplx *rt) {
+    int half = M / 2;
+    if (Log2<M>::v & 1) {                      // odd stage count: one plain radix-2 stage first
         __syncthreads();
-        const int stride = M / 2 / half;
         for (int b = threadIdx.x; b < M / 2; b += T) {
-            const int j = b & (half - 1), i0 = ((b - j) << 1) + j, i1 = i0 + half;
-            const cplx u = buf[i0], v = buf[i1];
-            cplx s, d;
-            s.x = DADD(u.x, v.x); s.y = DADD(u.y, v.y);
-            d.x = DSUB(u.x, v.x); d.y = DSUB(u.y, v.y);
-            buf[i0] = s;
-            buf[i1] = half == 1 ? d : cmul(d, root<M>(tw, j * stride));
+            const cplx u = buf[b], v = buf[b + M / 2];
+            buf[b] = cadd(u, v);
+            buf[b + M / 2] = cmul(csub(u, v), sroot<M>(rt, b));
+        }
+        half >>= 1;
+    }
+    for (; half >= 2; half >>= 2) {            // stages `half` and `half / 2` in registers
+        __syncthreads();
+        const int q = half >> 1, s1 = M / (4 * q);
+        for (int b = threadIdx.x; b < M / 4; b += T) {
+            const int j = b & (q - 1), i0 = ((b - j) << 2) + j;
+            const cplx a0 = buf[i0], a1 = buf[i0 + q], a2 = buf[i0 + 2 * q], a3 = buf[i0 + 3 * q];
+            const cplx b0 = cadd(a0, a2), b1 = cadd(a1, a3);
+            cplx b2 = csub(a0, a2), b3 = mul_neg_i(csub(a1, a3));
+            cplx c1 = csub(b0, b1), c2 = cadd(b2, b3), c3 = csub(b2, b3);
+            if (q > 1) {
+                const cplx w1 = sroot<M>(rt, j * s1), w2 = sroot<M>(rt, 2 * j * s1);
+                c1 = cmul(c1, w2);
+                c2 = cmul(c2, w1);             // both halves of the first stage carry W_{4q}^j ...
+                c3 = cmul(cmul(c3, w1), w2);   // ... and the lower pair also the second stage's W_{2q}^j
+            }
+            buf[i0] = cadd(b0, b1);
+            buf[i0 + q] = c1;
+            buf[i0 + 2 * q] = c2;
+            buf[i0 + 3 * q] = c3;
         }
     }
     __syncthreads();
@@ -75,19 +112,32 @@ __device__ __forceinline__ void fft_fwd(cplx *buf, const cplx *__restrict__ tw) 
 
 // inverse (unscaled): bit-reversed positions in, natural order out.  Ends with a barrier.
 template <int M, int T>
-__device__ __forceinline__ void fft_inv(cplx *buf, const cplx *__restrict__ tw) {
-    for (int half = 1; half <= M / 2; half <<= 1) {
+__device__ __forceinline__ void fft_inv(cplx *buf, const cplx *rt) {
+    for (int q = 1; 4 * q <= M; q <<= 2) {     // stages `q` and `2q`
         __syncthreads();
-        const int stride = M / 2 / half;
+        const int s1 = M / (4 * q);
+        for (int b = threadIdx.x; b < M / 4; b += T) {
+            const int j = b & (q - 1), i0 = ((b - j) << 2) + j;
+            cplx c0 = buf[i0], c1 = buf[i0 + q], c2 = buf[i0 + 2 * q], c3 = buf[i0 + 3 * q];
+            if (q > 1) {
+                const cplx w1 = sroot<M>(rt, j * s1), w2 = sroot<M>(rt, 2 * j * s1);
+                c1 = cmul_conj(c1, w2);
+                c2 = cmul_conj(c2, w1);
+                c3 = cmul_conj(cmul_conj(c3, w1), w2);
+            }
+            const cplx b0 = cadd(c0, c1), b1 = csub(c0, c1), b2 = cadd(c2, c3), b3 = mul_pos_i(csub(c2, c3));
+            buf[i0] = cadd(b0, b2);
+            buf[i0 + 2 * q] = csub(b0, b2);
+            buf[i0 + q] = cadd(b1, b3);
+            buf[i0 + 3 * q] = csub(b1, b3);
+        }
+    }
+    if (Log2<M>::v & 1) {
+        __syncthreads();
         for (int b = threadIdx.x; b < M / 2; b += T) {
-            const int j = b & (half - 1), i0 = ((b - j) << 1) + j, i1 = i0 + half;
-            const cplx u = buf[i0];
-            const cplx v = half == 1 ? buf[i1] : cmul_conj(buf[i1], root<M>(tw, j * stride));
-            cplx s, d;
-            s.x = DADD(u.x, v.x); s.y = DADD(u.y, v.y);
-            d.x = DSUB(u.x, v.x); d.y = DSUB(u.y, v.y);
-            buf[i0] = s;
-            buf[i1] = d;
+            const cplx u = buf[b], v = cmul_conj(buf[b + M / 2], sroot<M>(rt, b));
+            buf[b] = cadd(u, v);
+            buf[b + M / 2] = csub(u, v);
         }
     }
     __syncthreads();
@@ -126,7 +176,7 @@ __device__ __forceinline__ cplx root2n(const cplx *__restrict__ tw, uint32_t e) 
 // `pos` of the transform holds the evaluation at zeta = w^(1 - 4*brev(pos)), so the monomial's spectrum there is w^(deg_j * (1 - 4*brev(pos)))
 // (fft/mod.rs:408-445).  n_iters counts groups.
 template <int LOGN, int K1, int GF>
-__global__ void __launch_bounds__(Shape<LOGN>::T)
+__global__ void __launch_bounds__(Shape<LOGN>::T, Shape<LOGN>::MINB)
 pbs_generic_kernel(const uint64_t *__restrict__ lwe_small, const uint32_t *__restrict__ lut_idx, const uint64_t *__restrict__ luts,
                    const cplx *__restrict__ bskf, const cplx *__restrict__ tw, uint64_t *__restrict__ out,
                    const uint32_t *__restrict__ out_slot, int n, int base_log, int levels, int n_iters) {
@@ -135,7 +185,9 @@ pbs_generic_kernel(const uint64_t *__restrict__ lwe_small, const uint32_t *__res
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t *acc = reinterpret_cast<uint64_t *>(smem_raw);                 // [K1][N]
     cplx *buf = reinterpret_cast<cplx *>(smem_raw + (size_t)K1 * N * 8);      // [M]
+    cplx *rt = buf + M;                                                       // [M/4]: W_M^e = conj(tw[4e])
     const int ct = blockIdx.x, t = threadIdx.x;
+    for (int e = t; e < M / 4; e += T) { const cplx w = __ldg(tw + 4 * e); rt[e].x = w.x; rt[e].y = -w.y; }
     const uint64_t *lwe = lwe_small + (size_t)ct * (n + 1);
     const auto mod_switch = [](uint64_t x) { return (uint32_t)(((x >> (64 - LOGN - 2)) + 1) >> 1) & (2 * N - 1); };
 
@@ -198,7 +250,7 @@ pbs_generic_kernel(const uint64_t *__restrict__ lwe_small, const uint32_t *__res
                     z.y = (double)signed_digit(v1, base_log, levels, lv);
                     buf[j] = cmul(z, __ldg(tw + j));
                 }
-                fft_fwd<M, T>(buf, tw);
+                fft_fwd<M, T>(buf, rt);
                 const cplx *g = ggsw + ((size_t)(lv - 1) * K1 + r) * K1 * M;
 #pragma unroll
                 for (int q = 0; q < PER; ++q) {
@@ -234,7 +286,7 @@ pbs_generic_kernel(const uint64_t *__restrict__ lwe_small, const uint32_t *__res
         for (int c = 0; c < K1; ++c) {
 #pragma unroll
             for (int q = 0; q < PER; ++q) buf[t + T * q] = o[c][q];
-            fft_inv<M, T>(buf, tw);
+            fft_inv<M, T>(buf, rt);
 #pragma unroll
             for (int q = 0; q < PER; ++q) {
                 const int j = t + T * q;
@@ -266,6 +318,8 @@ bsk_convert_generic_kernel(const uint64_t *__restrict__ bsk_std, cplx *__restric
     constexpr int N = S::N, M = S::M, PER = S::PER, T = S::T;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cplx *buf = reinterpret_cast<cplx *>(smem_raw);
+    cplx *rt = buf + M;
+    for (int e = threadIdx.x; e < M / 4; e += T) { const cplx w = __ldg(tw + 4 * e); rt[e].x = w.x; rt[e].y = -w.y; }
     const uint64_t *src = bsk_std + (size_t)blockIdx.x * N;
     const double scale = 1.0 / (18446744073709551616.0 * (double)M);
 #pragma unroll
@@ -276,7 +330,7 @@ bsk_convert_generic_kernel(const uint64_t *__restrict__ bsk_std, cplx *__restric
         z.y = DMUL((double)(long long)src[j + M], scale);
         buf[j] = cmul(z, __ldg(tw + j));
     }
-    fft_fwd<M, T>(buf, tw);
+    fft_fwd<M, T>(buf, rt);
 #pragma unroll
     for (int q = 0; q < PER; ++q) bskf[(size_t)blockIdx.x * M + threadIdx.x + T * q] = buf[threadIdx.x + T * q];
 }
@@ -285,7 +339,7 @@ template <int LOGN, int K1, int GF>
 cudaError_t launch(const uint64_t *lwe_small, const uint32_t *lut_idx, const uint64_t *luts, const void *bskf, const void *tw,
                    uint64_t *out, const uint32_t *out_slot, int batch, int n, int base_log, int levels, int n_iters, cudaStream_t stream) {
     using S = Shape<LOGN>;
-    const size_t smem = (size_t)K1 * S::N * 8 + (size_t)S::M * 16;
+    const size_t smem = (size_t)K1 * S::N * 8 + (size_t)S::M * 16 + (size_t)S::M * 4;
     // function attributes are per device: set on every launch (microseconds) rather than caching a process-wide flag
     cudaError_t e = cudaFuncSetAttribute(pbs_generic_kernel<LOGN, K1, GF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -297,7 +351,7 @@ cudaError_t launch(const uint64_t *lwe_small, const uint32_t *lut_idx, const uin
 template <int LOGN>
 cudaError_t convert(const uint64_t *bsk_std, void *bskf, const void *tw, size_t n_polys, cudaStream_t stream) {
     using S = Shape<LOGN>;
-    const size_t smem = (size_t)S::M * 16;
+    const size_t smem = (size_t)S::M * 16 + (size_t)S::M * 4;
     cudaError_t e = cudaFuncSetAttribute(bsk_convert_generic_kernel<LOGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     bsk_convert_generic_kernel<LOGN><<<(unsigned)n_polys, S::T, smem, stream>>>(bsk_std, reinterpret_cast<cplx *>(bskf),
