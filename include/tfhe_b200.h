@@ -25,8 +25,11 @@ extern "C" {
 
 typedef struct tfhe_b200_ctx tfhe_b200_ctx;
 
-/* shortint::ClassicPBSParameters / MultiBitPBSParameters (shortint/parameters/mod.rs:703-717,
- * multi_bit.rs:173-190); grouping_factor = 0 selects the classic PBS. */
+/* shortint::ClassicPBSParameters / MultiBitPBSParameters (shortint/parameters/mod.rs:598-1136,
+ * multi_bit.rs:96-209); grouping_factor = 0 selects the classic PBS, 2 or 3 the multi-bit PBS.
+ * Accepted: every PARAM_MESSAGE_m_CARRY_c_KS_PBS (N = 256 ... 32768, k = 1 ... 5, 1 ... 3 PBS levels) and
+ * every PARAM_MULTI_BIT_MESSAGE_m_CARRY_c_GROUP_g_KS_PBS (N <= 8192).  N = 2048, k = 1, one PBS level
+ * (classic, and multi-bit with g = 3) runs on the tuned kernels, everything else on the generic one. */
 typedef struct {
     uint32_t lwe_dim;        /* n   (small key)            */
     uint32_t glwe_dim;       /* k                           */
