@@ -368,63 +368,35 @@ cudaError_t convert(const uint64_t *bsk_std, void *bskf, const void *tw, size_t 
 // ---------------------------------------------------------------------------------------------------------------------------------
 constexpr int BIG_T = 512, BIG_CH = 4096;
 
+// The last log2(4096) DIF stages of a size-M transform are complete 4096-point transforms of each contiguous block (the stage twiddle
+// W_{2*half}^j does not depend on M), so the shared-memory part is fft_fwd / fft_inv of size BIG_CH with that size's root table.
 template <int M>
-__device__ __forceinline__ void fft_fwd_big(cplx *g, cplx *sm, const cplx *__restrict__ tw) {
+__device__ __forceinline__ void fft_fwd_big(cplx *g, cplx *sm, const cplx *rt, const cplx *__restrict__ tw) {
     for (int half = M / 2; half >= BIG_CH; half >>= 1) {
         __syncthreads();
         const int stride = M / 2 / half;
         for (int b = threadIdx.x; b < M / 2; b += BIG_T) {
             const int j = b & (half - 1), i0 = ((b - j) << 1) + j, i1 = i0 + half;
             const cplx u = g[i0], v = g[i1];
-            cplx s, d;
-            s.x = DADD(u.x, v.x); s.y = DADD(u.y, v.y);
-            d.x = DSUB(u.x, v.x); d.y = DSUB(u.y, v.y);
-            g[i0] = s;
-            g[i1] = cmul(d, root<M>(tw, j * stride));
+            g[i0] = cadd(u, v);
+            g[i1] = cmul(csub(u, v), root<M>(tw, j * stride));
         }
     }
     for (int c0 = 0; c0 < M; c0 += BIG_CH) {
         __syncthreads();
         for (int j = threadIdx.x; j < BIG_CH; j += BIG_T) sm[j] = g[c0 + j];
-        for (int half = BIG_CH / 2; half >= 1; half >>= 1) {
-            __syncthreads();
-            const int stride = M / 2 / half;
-            for (int b = threadIdx.x; b < BIG_CH / 2; b += BIG_T) {
-                const int j = b & (half - 1), i0 = ((b - j) << 1) + j, i1 = i0 + half;
-                const cplx u = sm[i0], v = sm[i1];
-                cplx s, d;
-                s.x = DADD(u.x, v.x); s.y = DADD(u.y, v.y);
-                d.x = DSUB(u.x, v.x); d.y = DSUB(u.y, v.y);
-                sm[i0] = s;
-                sm[i1] = half == 1 ? d : cmul(d, root<M>(tw, j * stride));
-            }
-        }
-        __syncthreads();
+        fft_fwd<BIG_CH, BIG_T>(sm, rt);
         for (int j = threadIdx.x; j < BIG_CH; j += BIG_T) g[c0 + j] = sm[j];
     }
     __syncthreads();
 }
 
 template <int M>
-__device__ __forceinline__ void fft_inv_big(cplx *g, cplx *sm, const cplx *__restrict__ tw) {
+__device__ __forceinline__ void fft_inv_big(cplx *g, cplx *sm, const cplx *rt, const cplx *__restrict__ tw) {
     for (int c0 = 0; c0 < M; c0 += BIG_CH) {
         __syncthreads();
         for (int j = threadIdx.x; j < BIG_CH; j += BIG_T) sm[j] = g[c0 + j];
-        for (int half = 1; half <= BIG_CH / 2; half <<= 1) {
-            __syncthreads();
-            const int stride = M / 2 / half;
-            for (int b = threadIdx.x; b < BIG_CH / 2; b += BIG_T) {
-                const int j = b & (half - 1), i0 = ((b - j) << 1) + j, i1 = i0 + half;
-                const cplx u = sm[i0];
-                const cplx v = half == 1 ? sm[i1] : cmul_conj(sm[i1], root<M>(tw, j * stride));
-                cplx s, d;
-                s.x = DADD(u.x, v.x); s.y = DADD(u.y, v.y);
-                d.x = DSUB(u.x, v.x); d.y = DSUB(u.y, v.y);
-                sm[i0] = s;
-                sm[i1] = d;
-            }
-        }
-        __syncthreads();
+        fft_inv<BIG_CH, BIG_T>(sm, rt);
         for (int j = threadIdx.x; j < BIG_CH; j += BIG_T) g[c0 + j] = sm[j];
     }
     for (int half = BIG_CH; half <= M / 2; half <<= 1) {
@@ -434,14 +406,17 @@ __device__ __forceinline__ void fft_inv_big(cplx *g, cplx *sm, const cplx *__res
             const int j = b & (half - 1), i0 = ((b - j) << 1) + j, i1 = i0 + half;
             const cplx u = g[i0];
             const cplx v = cmul_conj(g[i1], root<M>(tw, j * stride));
-            cplx s, d;
-            s.x = DADD(u.x, v.x); s.y = DADD(u.y, v.y);
-            d.x = DSUB(u.x, v.x); d.y = DSUB(u.y, v.y);
-            g[i0] = s;
-            g[i1] = d;
+            g[i0] = cadd(u, v);
+            g[i1] = csub(u, v);
         }
     }
     __syncthreads();
+}
+
+// rt[e] = W_4096^e = conj(tw[e * N / 2048]), e < 1024
+template <int N>
+__device__ __forceinline__ void big_root_table(cplx *rt, const cplx *__restrict__ tw) {
+    for (int e = threadIdx.x; e < BIG_CH / 4; e += BIG_T) { const cplx w = __ldg(tw + e * (N / 2048)); rt[e].x = w.x; rt[e].y = -w.y; }
 }
 
 template <int LOGN, int K1>
@@ -456,6 +431,8 @@ pbs_generic_big_kernel(const uint64_t *__restrict__ lwe_small, const uint32_t *_
     constexpr int N = 1 << LOGN, M = N / 2, T = BIG_T;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cplx *sm = reinterpret_cast<cplx *>(smem_raw);                                              // [BIG_CH]
+    cplx *rt = sm + BIG_CH;                                                                     // [BIG_CH / 4]
+    big_root_table<N>(rt, tw);
     unsigned char *mine = scratch + (size_t)blockIdx.x * big_scratch_bytes<LOGN, K1>();
     uint64_t *acc = reinterpret_cast<uint64_t *>(mine);                                         // [K1][N]
     cplx *buf = reinterpret_cast<cplx *>(mine + (size_t)K1 * N * 8);                            // [M]
@@ -494,7 +471,7 @@ pbs_generic_big_kernel(const uint64_t *__restrict__ lwe_small, const uint32_t *_
                         z.y = (double)signed_digit(v1, base_log, levels, lv);
                         buf[j] = cmul(z, __ldg(tw + j));
                     }
-                    fft_fwd_big<M>(buf, sm, tw);
+                    fft_fwd_big<M>(buf, sm, rt, tw);
                     const cplx *g = ggsw + ((size_t)(lv - 1) * K1 + r) * K1 * M;
                     for (int pos = t; pos < M; pos += T) {
                         const cplx f = buf[pos];
@@ -511,7 +488,7 @@ pbs_generic_big_kernel(const uint64_t *__restrict__ lwe_small, const uint32_t *_
                 }
             }
             for (int c = 0; c < K1; ++c) {
-                fft_inv_big<M>(o + c * M, sm, tw);
+                fft_inv_big<M>(o + c * M, sm, rt, tw);
                 for (int j = t; j < M; j += T) {
                     const cplx z = cmul_conj(o[c * M + j], __ldg(tw + j));
                     acc[c * N + j] += tb::from_torus_f64(z.x);
@@ -534,6 +511,8 @@ bsk_convert_generic_big_kernel(const uint64_t *__restrict__ bsk_std, cplx *bskf,
     constexpr int N = 1 << LOGN, M = N / 2;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cplx *sm = reinterpret_cast<cplx *>(smem_raw);
+    cplx *rt = sm + BIG_CH;
+    big_root_table<N>(rt, tw);
     const uint64_t *src = bsk_std + (size_t)blockIdx.x * N;
     cplx *dst = bskf + (size_t)blockIdx.x * M;            // transformed in place
     const double scale = 1.0 / (18446744073709551616.0 * (double)M);
@@ -543,13 +522,13 @@ bsk_convert_generic_big_kernel(const uint64_t *__restrict__ bsk_std, cplx *bskf,
         z.y = DMUL((double)(long long)src[j + M], scale);
         dst[j] = cmul(z, __ldg(tw + j));
     }
-    fft_fwd_big<M>(dst, sm, tw);
+    fft_fwd_big<M>(dst, sm, rt, tw);
 }
 
 template <int LOGN, int K1>
 cudaError_t launch_big(const uint64_t *lwe_small, const uint32_t *lut_idx, const uint64_t *luts, const void *bskf, const void *tw,
                        uint64_t *out, const uint32_t *out_slot, int batch, int n, int base_log, int levels, int n_iters, cudaStream_t stream) {
-    const size_t smem = (size_t)BIG_CH * 16;
+    const size_t smem = (size_t)BIG_CH * 16 + (size_t)BIG_CH * 4;
     cudaError_t e = cudaFuncSetAttribute(pbs_generic_big_kernel<LOGN, K1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int dev = 0, sms = 0;
@@ -568,7 +547,7 @@ cudaError_t launch_big(const uint64_t *lwe_small, const uint32_t *lut_idx, const
 
 template <int LOGN>
 cudaError_t convert_big(const uint64_t *bsk_std, void *bskf, const void *tw, size_t n_polys, cudaStream_t stream) {
-    const size_t smem = (size_t)BIG_CH * 16;
+    const size_t smem = (size_t)BIG_CH * 16 + (size_t)BIG_CH * 4;
     cudaError_t e = cudaFuncSetAttribute(bsk_convert_generic_big_kernel<LOGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     bsk_convert_generic_big_kernel<LOGN><<<(unsigned)n_polys, BIG_T, smem, stream>>>(bsk_std, reinterpret_cast<cplx *>(bskf),
