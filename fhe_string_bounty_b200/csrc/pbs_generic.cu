@@ -55,11 +55,41 @@ __device__ __forceinline__ cplx root(const cplx *__restrict__ tw, int e) {
     return r;
 }
 
-// the same root from the shared-memory table rt[e] = W_M^e, e < M/4
+// Shared-memory tables of one transform size M: wt = the radix-4 passes' first-stage twiddles W_{4q}^j (j < q) for q = 1, 4, 16, ...,
+// stored pass by pass (offset (q - 1) / 3) so that consecutive threads read consecutive entries; the second-stage twiddle is its
+// square.  When log2 M is odd one plain radix-2 stage remains, with W_M^b from rt[e] = W_M^e, e < M/4 (the upper half by symmetry).
+template <int M> struct Log2 { static constexpr int v = 1 + Log2<M / 2>::v; };
+template <> struct Log2<1> { static constexpr int v = 0; };
 template <int M>
-__device__ __forceinline__ cplx sroot(const cplx *rt, int e) {
+struct Tables {
+    static constexpr bool ODD = (Log2<M>::v & 1) != 0;
+    static constexpr int QMAX = ODD ? M / 8 : M / 4;
+    static constexpr int WT = (4 * QMAX - 1) / 3;
+    static constexpr int RT = ODD ? M / 4 : 0;
+    static constexpr int ENTRIES = WT + RT;
+};
+
+// tw[t] = exp(i*pi*t/N) with N = n_over_m * M: W_{4q}^j = conj(tw[j * N / (2q)]), W_M^e = conj(tw[2 * e * N / M])
+template <int M, int T>
+__device__ __forceinline__ void make_tables(cplx *tbl, const cplx *__restrict__ tw, int n_over_m) {
+    for (int q = 1; q <= Tables<M>::QMAX; q <<= 2)
+        for (int j = threadIdx.x; j < q; j += T) {
+            const cplx w = __ldg(tw + (size_t)j * (n_over_m * M / (2 * q)));
+            cplx r; r.x = w.x; r.y = -w.y;
+            tbl[(q - 1) / 3 + j] = r;
+        }
+    if (Tables<M>::ODD)
+        for (int e = threadIdx.x; e < M / 4; e += T) {
+            const cplx w = __ldg(tw + (size_t)e * 2 * n_over_m);
+            cplx r; r.x = w.x; r.y = -w.y;
+            tbl[Tables<M>::WT + e] = r;
+        }
+}
+
+template <int M>
+__device__ __forceinline__ cplx sroot(const cplx *tbl, int e) {      // W_M^e, e < M/2, for the radix-2 stage
     const bool hi = e >= M / 4;
-    const cplx t = rt[hi ? e - M / 4 : e];
+    const cplx t = tbl[Tables<M>::WT + (hi ? e - M / 4 : e)];
     cplx r;
     r.x = hi ? t.y : t.x;          // (-i) * (x + iy) = y - ix
     r.y = hi ? -t.x : t.y;
@@ -69,42 +99,47 @@ __device__ __forceinline__ cplx cadd(cplx a, cplx b) { cplx r; r.x = DADD(a.x, b
 __device__ __forceinline__ cplx csub(cplx a, cplx b) { cplx r; r.x = DSUB(a.x, b.x); r.y = DSUB(a.y, b.y); return r; }
 __device__ __forceinline__ cplx mul_neg_i(cplx a) { cplx r; r.x = a.y; r.y = -a.x; return r; }
 __device__ __forceinline__ cplx mul_pos_i(cplx a) { cplx r; r.x = -a.y; r.y = a.x; return r; }
+__device__ __forceinline__ cplx csqr(cplx a) { cplx r; r.x = DFMA(a.x, a.x, -DMUL(a.y, a.y)); r.y = DMUL(DADD(a.x, a.x), a.y); return r; }
 
-template <int M> struct Log2 { static constexpr int v = 1 + Log2<M / 2>::v; };
-template <> struct Log2<1> { static constexpr int v = 0; };
+// Element i of a transform buffer lives at slot SW(i): the low three slot bits are XOR-ed with bits 3-4 of i, which makes the
+// 16-byte accesses of every pass conflict free -- consecutive elements (q >= 8), the q = 4 pass (elements 16 g + j + 4 m) and the
+// q = 1 pass (elements 4 b + m) each spread a quarter-warp over all eight 16-byte bank groups.
+__device__ __forceinline__ int SW(int i) { return i ^ ((i >> 3) & 3) ^ ((i >> 2) & 4); }
 
 // forward: natural order in, bit-reversed positions out (radix-2 DIF stages taken two at a time).  Ends with a barrier.
 template <int M, int T>
-__device__ __forceinline__ void fft_fwd(cplx *buf, const cplx *rt) {
+__device__ __forceinline__ void fft_fwd(cplx *buf, const cplx *tbl) {
     int half = M / 2;
-    if (Log2<M>::v & 1) {                      // odd stage count: one plain radix-2 stage first
+    if (Tables<M>::ODD) {                      // odd stage count: one plain radix-2 stage first
         __syncthreads();
         for (int b = threadIdx.x; b < M / 2; b += T) {
-            const cplx u = buf[b], v = buf[b + M / 2];
-            buf[b] = cadd(u, v);
-            buf[b + M / 2] = cmul(csub(u, v), sroot<M>(rt, b));
+            const cplx u = buf[SW(b)], v = buf[SW(b + M / 2)];
+            buf[SW(b)] = cadd(u, v);
+            buf[SW(b + M / 2)] = cmul(csub(u, v), sroot<M>(tbl, b));
         }
         half >>= 1;
     }
     for (; half >= 2; half >>= 2) {            // stages `half` and `half / 2` in registers
         __syncthreads();
-        const int q = half >> 1, s1 = M / (4 * q);
+        const int q = half >> 1;
+        const cplx *wq = tbl + (q - 1) / 3;
         for (int b = threadIdx.x; b < M / 4; b += T) {
             const int j = b & (q - 1), i0 = ((b - j) << 2) + j;
-            const cplx a0 = buf[i0], a1 = buf[i0 + q], a2 = buf[i0 + 2 * q], a3 = buf[i0 + 3 * q];
+            const int p0 = SW(i0), p1 = SW(i0 + q), p2 = SW(i0 + 2 * q), p3 = SW(i0 + 3 * q);
+            const cplx a0 = buf[p0], a1 = buf[p1], a2 = buf[p2], a3 = buf[p3];
             const cplx b0 = cadd(a0, a2), b1 = cadd(a1, a3);
-            cplx b2 = csub(a0, a2), b3 = mul_neg_i(csub(a1, a3));
+            const cplx b2 = csub(a0, a2), b3 = mul_neg_i(csub(a1, a3));
             cplx c1 = csub(b0, b1), c2 = cadd(b2, b3), c3 = csub(b2, b3);
             if (q > 1) {
-                const cplx w1 = sroot<M>(rt, j * s1), w2 = sroot<M>(rt, 2 * j * s1);
+                const cplx w1 = wq[j], w2 = csqr(w1);
                 c1 = cmul(c1, w2);
                 c2 = cmul(c2, w1);             // both halves of the first stage carry W_{4q}^j ...
                 c3 = cmul(cmul(c3, w1), w2);   // ... and the lower pair also the second stage's W_{2q}^j
             }
-            buf[i0] = cadd(b0, b1);
-            buf[i0 + q] = c1;
-            buf[i0 + 2 * q] = c2;
-            buf[i0 + 3 * q] = c3;
+            buf[p0] = cadd(b0, b1);
+            buf[p1] = c1;
+            buf[p2] = c2;
+            buf[p3] = c3;
         }
     }
     __syncthreads();
@@ -112,32 +147,33 @@ __device__ __forceinline__ void fft_fwd(cplx *buf, const cplx *rt) {
 
 // inverse (unscaled): bit-reversed positions in, natural order out.  Ends with a barrier.
 template <int M, int T>
-__device__ __forceinline__ void fft_inv(cplx *buf, const cplx *rt) {
+__device__ __forceinline__ void fft_inv(cplx *buf, const cplx *tbl) {
     for (int q = 1; 4 * q <= M; q <<= 2) {     // stages `q` and `2q`
         __syncthreads();
-        const int s1 = M / (4 * q);
+        const cplx *wq = tbl + (q - 1) / 3;
         for (int b = threadIdx.x; b < M / 4; b += T) {
             const int j = b & (q - 1), i0 = ((b - j) << 2) + j;
-            cplx c0 = buf[i0], c1 = buf[i0 + q], c2 = buf[i0 + 2 * q], c3 = buf[i0 + 3 * q];
+            const int p0 = SW(i0), p1 = SW(i0 + q), p2 = SW(i0 + 2 * q), p3 = SW(i0 + 3 * q);
+            cplx c0 = buf[p0], c1 = buf[p1], c2 = buf[p2], c3 = buf[p3];
             if (q > 1) {
-                const cplx w1 = sroot<M>(rt, j * s1), w2 = sroot<M>(rt, 2 * j * s1);
+                const cplx w1 = wq[j], w2 = csqr(w1);
                 c1 = cmul_conj(c1, w2);
                 c2 = cmul_conj(c2, w1);
                 c3 = cmul_conj(cmul_conj(c3, w1), w2);
             }
             const cplx b0 = cadd(c0, c1), b1 = csub(c0, c1), b2 = cadd(c2, c3), b3 = mul_pos_i(csub(c2, c3));
-            buf[i0] = cadd(b0, b2);
-            buf[i0 + 2 * q] = csub(b0, b2);
-            buf[i0 + q] = cadd(b1, b3);
-            buf[i0 + 3 * q] = csub(b1, b3);
+            buf[p0] = cadd(b0, b2);
+            buf[p2] = csub(b0, b2);
+            buf[p1] = cadd(b1, b3);
+            buf[p3] = csub(b1, b3);
         }
     }
-    if (Log2<M>::v & 1) {
+    if (Tables<M>::ODD) {
         __syncthreads();
         for (int b = threadIdx.x; b < M / 2; b += T) {
-            const cplx u = buf[b], v = cmul_conj(buf[b + M / 2], sroot<M>(rt, b));
-            buf[b] = cadd(u, v);
-            buf[b + M / 2] = csub(u, v);
+            const cplx u = buf[SW(b)], v = cmul_conj(buf[SW(b + M / 2)], sroot<M>(tbl, b));
+            buf[SW(b)] = cadd(u, v);
+            buf[SW(b + M / 2)] = csub(u, v);
         }
     }
     __syncthreads();
@@ -185,9 +221,9 @@ pbs_generic_kernel(const uint64_t *__restrict__ lwe_small, const uint32_t *__res
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t *acc = reinterpret_cast<uint64_t *>(smem_raw);                 // [K1][N]
     cplx *buf = reinterpret_cast<cplx *>(smem_raw + (size_t)K1 * N * 8);      // [M]
-    cplx *rt = buf + M;                                                       // [M/4]: W_M^e = conj(tw[4e])
+    cplx *rt = buf + M;                                                       // [Tables<M>::ENTRIES] twiddle tables
     const int ct = blockIdx.x, t = threadIdx.x;
-    for (int e = t; e < M / 4; e += T) { const cplx w = __ldg(tw + 4 * e); rt[e].x = w.x; rt[e].y = -w.y; }
+    make_tables<M, T>(rt, tw, 2);
     const uint64_t *lwe = lwe_small + (size_t)ct * (n + 1);
     const auto mod_switch = [](uint64_t x) { return (uint32_t)(((x >> (64 - LOGN - 2)) + 1) >> 1) & (2 * N - 1); };
 
@@ -248,14 +284,14 @@ pbs_generic_kernel(const uint64_t *__restrict__ lwe_small, const uint32_t *__res
                     cplx z;
                     z.x = (double)signed_digit(v0, base_log, levels, lv);
                     z.y = (double)signed_digit(v1, base_log, levels, lv);
-                    buf[j] = cmul(z, __ldg(tw + j));
+                    buf[SW(j)] = cmul(z, __ldg(tw + j));
                 }
                 fft_fwd<M, T>(buf, rt);
                 const cplx *g = ggsw + ((size_t)(lv - 1) * K1 + r) * K1 * M;
 #pragma unroll
                 for (int q = 0; q < PER; ++q) {
                     const int pos = t + T * q;
-                    const cplx f = buf[pos];
+                    const cplx f = buf[SW(pos)];
                     if (GF == 0) {
 #pragma unroll
                         for (int c = 0; c < K1; ++c) {
@@ -285,12 +321,12 @@ pbs_generic_kernel(const uint64_t *__restrict__ lwe_small, const uint32_t *__res
 #pragma unroll
         for (int c = 0; c < K1; ++c) {
 #pragma unroll
-            for (int q = 0; q < PER; ++q) buf[t + T * q] = o[c][q];
+            for (int q = 0; q < PER; ++q) buf[SW(t + T * q)] = o[c][q];
             fft_inv<M, T>(buf, rt);
 #pragma unroll
             for (int q = 0; q < PER; ++q) {
                 const int j = t + T * q;
-                const cplx z = cmul_conj(buf[j], __ldg(tw + j));
+                const cplx z = cmul_conj(buf[SW(j)], __ldg(tw + j));
                 if (GF == 0) {
                     acc[c * N + j] += tb::from_torus_f64(z.x);
                     acc[c * N + j + M] += tb::from_torus_f64(z.y);
@@ -319,7 +355,7 @@ bsk_convert_generic_kernel(const uint64_t *__restrict__ bsk_std, cplx *__restric
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cplx *buf = reinterpret_cast<cplx *>(smem_raw);
     cplx *rt = buf + M;
-    for (int e = threadIdx.x; e < M / 4; e += T) { const cplx w = __ldg(tw + 4 * e); rt[e].x = w.x; rt[e].y = -w.y; }
+    make_tables<M, T>(rt, tw, 2);
     const uint64_t *src = bsk_std + (size_t)blockIdx.x * N;
     const double scale = 1.0 / (18446744073709551616.0 * (double)M);
 #pragma unroll
@@ -328,18 +364,18 @@ bsk_convert_generic_kernel(const uint64_t *__restrict__ bsk_std, cplx *__restric
         cplx z;
         z.x = DMUL((double)(long long)src[j], scale);
         z.y = DMUL((double)(long long)src[j + M], scale);
-        buf[j] = cmul(z, __ldg(tw + j));
+        buf[SW(j)] = cmul(z, __ldg(tw + j));
     }
     fft_fwd<M, T>(buf, rt);
 #pragma unroll
-    for (int q = 0; q < PER; ++q) bskf[(size_t)blockIdx.x * M + threadIdx.x + T * q] = buf[threadIdx.x + T * q];
+    for (int q = 0; q < PER; ++q) bskf[(size_t)blockIdx.x * M + threadIdx.x + T * q] = buf[SW(threadIdx.x + T * q)];
 }
 
 template <int LOGN, int K1, int GF>
 cudaError_t launch(const uint64_t *lwe_small, const uint32_t *lut_idx, const uint64_t *luts, const void *bskf, const void *tw,
                    uint64_t *out, const uint32_t *out_slot, int batch, int n, int base_log, int levels, int n_iters, cudaStream_t stream) {
     using S = Shape<LOGN>;
-    const size_t smem = (size_t)K1 * S::N * 8 + (size_t)S::M * 16 + (size_t)S::M * 4;
+    const size_t smem = (size_t)K1 * S::N * 8 + (size_t)S::M * 16 + (size_t)Tables<S::M>::ENTRIES * 16;
     // function attributes are per device: set on every launch (microseconds) rather than caching a process-wide flag
     cudaError_t e = cudaFuncSetAttribute(pbs_generic_kernel<LOGN, K1, GF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -351,7 +387,7 @@ cudaError_t launch(const uint64_t *lwe_small, const uint32_t *lut_idx, const uin
 template <int LOGN>
 cudaError_t convert(const uint64_t *bsk_std, void *bskf, const void *tw, size_t n_polys, cudaStream_t stream) {
     using S = Shape<LOGN>;
-    const size_t smem = (size_t)S::M * 16 + (size_t)S::M * 4;
+    const size_t smem = (size_t)S::M * 16 + (size_t)Tables<S::M>::ENTRIES * 16;
     cudaError_t e = cudaFuncSetAttribute(bsk_convert_generic_kernel<LOGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     bsk_convert_generic_kernel<LOGN><<<(unsigned)n_polys, S::T, smem, stream>>>(bsk_std, reinterpret_cast<cplx *>(bskf),
@@ -384,9 +420,9 @@ __device__ __forceinline__ void fft_fwd_big(cplx *g, cplx *sm, const cplx *rt, c
     }
     for (int c0 = 0; c0 < M; c0 += BIG_CH) {
         __syncthreads();
-        for (int j = threadIdx.x; j < BIG_CH; j += BIG_T) sm[j] = g[c0 + j];
+        for (int j = threadIdx.x; j < BIG_CH; j += BIG_T) sm[SW(j)] = g[c0 + j];
         fft_fwd<BIG_CH, BIG_T>(sm, rt);
-        for (int j = threadIdx.x; j < BIG_CH; j += BIG_T) g[c0 + j] = sm[j];
+        for (int j = threadIdx.x; j < BIG_CH; j += BIG_T) g[c0 + j] = sm[SW(j)];
     }
     __syncthreads();
 }
@@ -395,9 +431,9 @@ template <int M>
 __device__ __forceinline__ void fft_inv_big(cplx *g, cplx *sm, const cplx *rt, const cplx *__restrict__ tw) {
     for (int c0 = 0; c0 < M; c0 += BIG_CH) {
         __syncthreads();
-        for (int j = threadIdx.x; j < BIG_CH; j += BIG_T) sm[j] = g[c0 + j];
+        for (int j = threadIdx.x; j < BIG_CH; j += BIG_T) sm[SW(j)] = g[c0 + j];
         fft_inv<BIG_CH, BIG_T>(sm, rt);
-        for (int j = threadIdx.x; j < BIG_CH; j += BIG_T) g[c0 + j] = sm[j];
+        for (int j = threadIdx.x; j < BIG_CH; j += BIG_T) g[c0 + j] = sm[SW(j)];
     }
     for (int half = BIG_CH; half <= M / 2; half <<= 1) {
         __syncthreads();
@@ -413,12 +449,6 @@ __device__ __forceinline__ void fft_inv_big(cplx *g, cplx *sm, const cplx *rt, c
     __syncthreads();
 }
 
-// rt[e] = W_4096^e = conj(tw[e * N / 2048]), e < 1024
-template <int N>
-__device__ __forceinline__ void big_root_table(cplx *rt, const cplx *__restrict__ tw) {
-    for (int e = threadIdx.x; e < BIG_CH / 4; e += BIG_T) { const cplx w = __ldg(tw + e * (N / 2048)); rt[e].x = w.x; rt[e].y = -w.y; }
-}
-
 template <int LOGN, int K1>
 __host__ __device__ constexpr size_t big_scratch_bytes() { return (size_t)K1 * (1 << LOGN) * 8 + (size_t)(1 << (LOGN - 1)) * 16 * (1 + K1); }
 
@@ -431,8 +461,8 @@ pbs_generic_big_kernel(const uint64_t *__restrict__ lwe_small, const uint32_t *_
     constexpr int N = 1 << LOGN, M = N / 2, T = BIG_T;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cplx *sm = reinterpret_cast<cplx *>(smem_raw);                                              // [BIG_CH]
-    cplx *rt = sm + BIG_CH;                                                                     // [BIG_CH / 4]
-    big_root_table<N>(rt, tw);
+    cplx *rt = sm + BIG_CH;                                                                     // [Tables<BIG_CH>::ENTRIES]
+    make_tables<BIG_CH, BIG_T>(rt, tw, N / BIG_CH);
     unsigned char *mine = scratch + (size_t)blockIdx.x * big_scratch_bytes<LOGN, K1>();
     uint64_t *acc = reinterpret_cast<uint64_t *>(mine);                                         // [K1][N]
     cplx *buf = reinterpret_cast<cplx *>(mine + (size_t)K1 * N * 8);                            // [M]
@@ -512,7 +542,7 @@ bsk_convert_generic_big_kernel(const uint64_t *__restrict__ bsk_std, cplx *bskf,
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cplx *sm = reinterpret_cast<cplx *>(smem_raw);
     cplx *rt = sm + BIG_CH;
-    big_root_table<N>(rt, tw);
+    make_tables<BIG_CH, BIG_T>(rt, tw, N / BIG_CH);
     const uint64_t *src = bsk_std + (size_t)blockIdx.x * N;
     cplx *dst = bskf + (size_t)blockIdx.x * M;            // transformed in place
     const double scale = 1.0 / (18446744073709551616.0 * (double)M);
@@ -528,7 +558,7 @@ bsk_convert_generic_big_kernel(const uint64_t *__restrict__ bsk_std, cplx *bskf,
 template <int LOGN, int K1>
 cudaError_t launch_big(const uint64_t *lwe_small, const uint32_t *lut_idx, const uint64_t *luts, const void *bskf, const void *tw,
                        uint64_t *out, const uint32_t *out_slot, int batch, int n, int base_log, int levels, int n_iters, cudaStream_t stream) {
-    const size_t smem = (size_t)BIG_CH * 16 + (size_t)BIG_CH * 4;
+    const size_t smem = (size_t)BIG_CH * 16 + (size_t)Tables<BIG_CH>::ENTRIES * 16;
     cudaError_t e = cudaFuncSetAttribute(pbs_generic_big_kernel<LOGN, K1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int dev = 0, sms = 0;
@@ -547,7 +577,7 @@ cudaError_t launch_big(const uint64_t *lwe_small, const uint32_t *lut_idx, const
 
 template <int LOGN>
 cudaError_t convert_big(const uint64_t *bsk_std, void *bskf, const void *tw, size_t n_polys, cudaStream_t stream) {
-    const size_t smem = (size_t)BIG_CH * 16 + (size_t)BIG_CH * 4;
+    const size_t smem = (size_t)BIG_CH * 16 + (size_t)Tables<BIG_CH>::ENTRIES * 16;
     cudaError_t e = cudaFuncSetAttribute(bsk_convert_generic_big_kernel<LOGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     bsk_convert_generic_big_kernel<LOGN><<<(unsigned)n_polys, BIG_T, smem, stream>>>(bsk_std, reinterpret_cast<cplx *>(bskf),
