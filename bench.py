@@ -229,11 +229,14 @@ def bench_string_ops(eng, p, rank, world, local):
     out["eq_8char_ops_per_s"] = timed(lambda: MG.sharded_eq(execute, params, a8, b8, 8, rank, world, dev), 20)
     out["contains_256_16_ops_per_s"] = timed(lambda: MG.sharded_contains(execute, params, hay, pat, 256, 16, rank, world, dev), 3)
     # throughput mode: independent string pairs share each tree level's launches (each rank takes its own share of pairs)
-    n_pairs = 128
+    n_pairs = 512
     many = Program("string_eq_many", (8, 8, n_pairs), params=params)
     pairs = rng.integers(0, 2**64, size=(many.n_inputs, p.big_len), dtype=np.uint64)
     out["eq_8char_batched_ops_per_s"] = world * n_pairs * timed(lambda: many.run(eng, pairs), 3)
     out["eq_8char_batch"] = {"pairs_per_rank": n_pairs, "pbs": many.n_pbs, "levels": many.level_widths}
+    manyp = Program("string_eq_many_packed", (8, 8, n_pairs), params=params)    # one PBS per pair of blocks (comparator.rs:193-221)
+    out["eq_8char_batched_packed_ops_per_s"] = world * n_pairs * timed(lambda: manyp.run(eng, pairs), 3)
+    out["eq_8char_batch_packed"] = {"pairs_per_rank": n_pairs, "pbs": manyp.n_pbs, "levels": manyp.level_widths}
     if world == 1:
         cp = Program("string_contains_packed", (256, 16), params=params)
         ins_c = np.concatenate([hay, pat])
@@ -243,6 +246,9 @@ def bench_string_ops(eng, p, rank, world, local):
         ins = np.concatenate([hay, pat])
         out["find_256_16_ops_per_s"] = timed(lambda: find.run(eng, ins), 3)
         out["find_256_16_pbs"] = find.n_pbs
+        findp = Program("string_find_packed", (256, 16), params=params)
+        out["find_256_16_packed_ops_per_s"] = timed(lambda: findp.run(eng, ins), 3)
+        out["find_256_16_packed_pbs"] = findp.n_pbs
         low = Program("string_to_lowercase", (1024,), params=params)
         s1024 = rng.integers(0, 2**64, size=(4096, p.big_len), dtype=np.uint64)
         out["to_lowercase_1024_ops_per_s"] = timed(lambda: low.run(eng, s1024), 3)

@@ -191,6 +191,11 @@ def test_many_independent_pairs_share_levels(orc, toy_keys):
     ins = np.concatenate([np.concatenate([R.encrypt_string(ck, a), R.encrypt_string(ck, b)]) for a, b in pairs])
     out = R.run_program(PN.ir(), sk, ins)
     assert [ck.decrypt_message_and_carry(c) for c in out] == [int(a == b) for a, b in pairs]
+    # the same with packed block equalities (one PBS per pair of blocks): fewer PBS, same booleans
+    PP = Program("string_eq_many_packed", (3, 3, 5), params=engine_params(p))
+    assert PP.n_pbs < PN.n_pbs and PP.level_widths[0] * 2 == PN.level_widths[0]
+    out = R.run_program(PP.ir(), sk, ins)
+    assert [ck.decrypt_message_and_carry(c) for c in out] == [int(a == b) for a, b in pairs]
 
 
 def test_packed_equality_halves_the_pbs_and_agrees(orc, toy_keys):
