@@ -26,7 +26,10 @@ struct Shape {
     static constexpr int N = 1 << LOGN, M = N / 2;
     static constexpr int PER = M > 2048 ? M / 512 : 4;       // positions per thread = one radix-4 butterfly per FFT pass (two above N = 4096)
     static constexpr int T = M / PER;
-    static constexpr int MINB = M == 2048 ? 2 : 1;           // N = 4096: two 512-thread CTAs per SM (64 registers)
+    // resident CTAs per SM the register allocation must allow: N = 4096 two 512-thread CTAs (64 registers); N = 512 ... 2048 are capped
+    // at 128 registers, which doubles their occupancy (ncu: 234 registers, 8 warps per SM, latency bound; +2 ... +18 %).  N = 256 (k = 5,
+    // 24 complex accumulators per thread) is faster uncapped (measured: 80.7 k vs 56.7 k KS-PBS/s with a 168-register cap)
+    static constexpr int MINB = M == 2048 ? 2 : M == 1024 ? 2 : M == 512 ? 4 : M == 256 ? 8 : 1;
 };
 
 __device__ __forceinline__ cplx cmul(cplx a, cplx b) {
@@ -378,6 +381,8 @@ cudaError_t launch(const uint64_t *lwe_small, const uint32_t *lut_idx, const uin
     const size_t smem = (size_t)K1 * S::N * 8 + (size_t)S::M * 16 + (size_t)Tables<S::M>::ENTRIES * 16;
     // function attributes are per device: set on every launch (microseconds) rather than caching a process-wide flag
     cudaError_t e = cudaFuncSetAttribute(pbs_generic_kernel<LOGN, K1, GF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(pbs_generic_kernel<LOGN, K1, GF>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     pbs_generic_kernel<LOGN, K1, GF><<<batch, S::T, smem, stream>>>(lwe_small, lut_idx, luts, reinterpret_cast<const cplx *>(bskf),
                                                                  reinterpret_cast<const cplx *>(tw), out, out_slot, n, base_log, levels, n_iters);
