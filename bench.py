@@ -237,6 +237,12 @@ def bench_string_ops(eng, p, rank, world, local):
     manyp = Program("string_eq_many_packed", (8, 8, n_pairs), params=params)    # one PBS per pair of blocks (comparator.rs:193-221)
     out["eq_8char_batched_packed_ops_per_s"] = world * n_pairs * timed(lambda: manyp.run(eng, pairs), 3)
     out["eq_8char_batch_packed"] = {"pairs_per_rank": n_pairs, "pbs": manyp.n_pbs, "levels": manyp.level_widths}
+    if world > 1:
+        # the other shardings of SURVEY 8(e): find = windows split + all-gather of (found, index) + first-rank selection;
+        # to_lowercase = chars split + all-gather of the converted blocks
+        out["find_256_16_ops_per_s"] = timed(lambda: MG.sharded_find(execute, params, hay, pat, 256, 16, rank, world, dev), 3)
+        s1024 = rng.integers(0, 2**64, size=(4096, p.big_len), dtype=np.uint64)
+        out["to_lowercase_1024_ops_per_s"] = timed(lambda: MG.sharded_case(execute, params, "to_lowercase", s1024, 1024, rank, world, dev), 3)
     if world == 1:
         cp = Program("string_contains_packed", (256, 16), params=params)
         ins_c = np.concatenate([hay, pat])
@@ -259,7 +265,8 @@ def bench_string_ops(eng, p, rank, world, local):
         two = rng.integers(0, 2**64, size=(eic.n_inputs, p.big_len), dtype=np.uint64)
         out["eq_ignore_case_1024_ops_per_s"] = timed(lambda: eic.run(eng, two), 2)
         out["eq_ignore_case_1024_pbs"] = eic.n_pbs
-    out["note"] = "host buffers in/out; eq shards chars, contains shards windows across ranks + one all-reduce of a 2049-word LWE"
+    out["note"] = ("host buffers in/out; eq shards chars, contains shards windows across ranks + one all-reduce of a 2049-word LWE; "
+                   "with several ranks find shards windows (all-gather of found + index, 2 selection levels) and to_lowercase shards chars")
     return out
 
 

@@ -88,6 +88,52 @@ class StringServerKey {
     BooleanBlock gt(const FheString &a, const FheString &b) { return cmp(a, b, false, false); }
     BooleanBlock ge(const FheString &a, const FheString &b) { return cmp(a, b, false, true); }
 
+    // multi-GPU split of a comparison: a rank's share is the sign block of its char range ...
+    Ct compare_sign(const FheString &a, const FheString &b) {
+        if (a.len() != b.len() || a.len() == 0) throw std::invalid_argument("compare_sign: equal, non-zero lengths required");
+        return isk.unchecked_compare(lex_radix(a, a.len()), lex_radix(b, b.len()));
+    }
+    // ... and the gathered sign blocks (least significant range first) finish with the pairwise tree + the final map (comparator.rs:257-279,957-971)
+    BooleanBlock finish_signs(std::vector<Ct> signs, bool want_less, bool or_equal) {
+        Ct sign = isk.reduce_signs(std::move(signs));
+        return isk.map_sign_result(sign, [=](uint64_t x) {
+            if (x == IntegerServerKey::IS_EQUAL) return or_equal;
+            return want_less ? x == IntegerServerKey::IS_INFERIOR : x == IntegerServerKey::IS_SUPERIOR;
+        });
+    }
+    // multi-GPU split of find: every rank's (found, first index in its window range), ranges in ascending order -> the overall first match.
+    //   level 1   first_r = [found_r and no earlier rank found]        (leveled prefix count of the flags, one PBS per rank)
+    //             found   = [sum of the flags != 0]
+    //   level 2   index digit b = sum_r (first_r ? index_r[b] : 0)     (one PBS per rank and digit; at most one term is non-zero)
+    std::pair<BooleanBlock, Radix> combine_find(const std::vector<std::pair<BooleanBlock, Radix>> &parts) {
+        if (parts.empty()) throw std::invalid_argument("combine_find: no parts");
+        if (2 * parts.size() > p.total_mod()) throw std::invalid_argument("combine_find: too many parts for the message space");
+        const size_t nb = parts[0].second.size();
+        std::vector<Ct> flags, first;
+        Ct before = pg.create_trivial(0);
+        for (size_t r = 0; r < parts.size(); ++r) {
+            flags.push_back(parts[r].first);
+            // x = found_r + 2 * (#earlier ranks that found)  in [0, 15]
+            Ct x = pg.unchecked_add(parts[r].first, pg.unchecked_scalar_mul(before, 2));
+            first.push_back(r == 0 ? parts[r].first : pg.pbs(x, [](uint64_t v) { return uint64_t(v == 1); }));
+            before = pg.unchecked_add(before, parts[r].first);
+        }
+        Ct found = isk.is_at_least_one_comparisons_block_true(flags);
+        Radix index;
+        for (size_t b = 0; b < nb; ++b) {
+            Ct sum;
+            for (size_t r = 0; r < parts.size(); ++r) {
+                Ct y = pg.unchecked_add(pg.unchecked_scalar_mul(first[r], p.msg_mod), parts[r].second[b]);
+                const uint64_t mm = p.msg_mod;
+                Ct term = pg.pbs(y, [mm](uint64_t v) { return (v / mm) % 2 ? v % mm : uint64_t(0); });
+                sum = r == 0 ? term : pg.unchecked_add(sum, term);
+            }
+            sum.degree = p.msg_mod - 1;       // at most one term is non-zero
+            index.push_back(sum);
+        }
+        return {found, index};
+    }
+
     // ---- contains / starts_with / ends_with / find: config 3 -------------------------------------------------------------
     // match flag of every window: block equalities for all (window, pattern position) pairs in one level, then one
     // AND tree per window ([15424, 1205, 241] for 256/16)
@@ -121,15 +167,26 @@ class StringServerKey {
     }
     // find: (found, index of the first match as a radix of ceil(log4(W)) blocks; 0 when not found, like the
     // regex example's "no match" convention of returning a boolean separately)
-    std::pair<BooleanBlock, Radix> find(const FheString &hay, const FheString &pat) {
-        const size_t W = pat.len() <= hay.len() ? hay.len() - pat.len() + 1 : 0;
+    std::pair<BooleanBlock, Radix> find(const FheString &hay, const FheString &pat) { return find_range(hay, pat, 0, size_t(-1)); }
+    // number of radix blocks of a window index
+    static size_t index_blocks(size_t hay_len, size_t pat_len) {
+        const size_t W = pat_len <= hay_len ? hay_len - pat_len + 1 : 0;
         size_t idx_blocks = 1;
         while ((size_t(1) << (2 * idx_blocks)) < std::max<size_t>(W, 1)) ++idx_blocks;
+        return idx_blocks;
+    }
+    // the same over the windows [w0, w1) only (the multi-GPU split): first match inside the range, reported as its GLOBAL window index
+    std::pair<BooleanBlock, Radix> find_range(const FheString &hay, const FheString &pat, size_t w0, size_t w1) {
+        const size_t W_all = pat.len() <= hay.len() ? hay.len() - pat.len() + 1 : 0;
+        const size_t idx_blocks = index_blocks(hay.len(), pat.len());
         Radix zero_idx;
         for (size_t b = 0; b < idx_blocks; ++b) zero_idx.push_back(pg.create_trivial(0));
-        if (W == 0) return {pg.create_trivial(0), zero_idx};
-        if (pat.len() == 0) return {pg.create_trivial(1), zero_idx};
-        std::vector<Ct> m = window_matches(hay, pat);
+        if (W_all == 0) return {pg.create_trivial(0), zero_idx};
+        w1 = std::min(w1, W_all);
+        if (w0 >= w1) return {pg.create_trivial(0), zero_idx};
+        if (pat.len() == 0) return {pg.create_trivial(w0 == 0 ? 1 : 0), zero_idx};
+        const size_t W = w1 - w0;            // local window count; local window w is global window w0 + w
+        std::vector<Ct> m = window_matches(hay, pat, w0, w1);
         // one-hot first match in THREE levels instead of a log-depth prefix OR.  Windows are cut into blocks of 14:
         //   level 1   any_k   = [sum of the block's match flags != 0]                (leveled sum of <= 14 booleans + 1 PBS per block)
         //   level 2   before_k = [sum_{k' < k} any_k' != 0]                         (leveled prefix sums, chunks of <= 15, 1 PBS per block)
@@ -177,7 +234,7 @@ class StringServerKey {
         for (size_t b = 0; b < idx_blocks; ++b) {
             std::vector<Ct> terms;
             for (size_t w = 0; w < W; ++w) {
-                const uint64_t digit = (w >> (2 * b)) & 3;
+                const uint64_t digit = ((w0 + w) >> (2 * b)) & 3;
                 if (digit == 0) continue;
                 terms.push_back(pg.pbs(first[w], [digit](uint64_t x) { return (x & 1) ? digit : uint64_t(0); }));
             }

@@ -122,6 +122,30 @@ bool record(tfhe_b200_program &h, const std::string &op_in, const uint64_t *a, s
         pg.output(a[1] ? pg.pbs(s, [n](uint64_t x) { return uint64_t(x == n); }) : pg.pbs(s, [](uint64_t x) { return uint64_t(x != 0); }));
         return true;
     }
+    // ---- multi-GPU finishing programs: inputs are what the ranks exchanged -------------------------------------------------
+    if (op == "signs_finish") {                  // a = {count, want_less, or_equal}; inputs: count sign blocks, least significant range first
+        if (!need(3)) return false;
+        if (a[0] < 1) { err = "signs_finish: needs at least one sign block"; return false; }
+        std::vector<tbh::Ct> signs;
+        for (uint64_t r = 0; r < a[0]; ++r) signs.push_back(pg.input(2, 1));
+        pg.output(ssk.finish_signs(signs, a[1] != 0, a[2] != 0));
+        return true;
+    }
+    if (op == "find_combine") {                  // a = {count, index blocks}; inputs: count x (found flag, index radix), ascending window ranges
+        if (!need(2)) return false;
+        if (a[0] < 1 || 2 * a[0] > h.p.total_mod() || a[1] < 1) { err = "find_combine: 1..total_mod/2 parts, at least one index block"; return false; }
+        std::vector<std::pair<tbh::Ct, tbh::Radix>> parts;
+        for (uint64_t r = 0; r < a[0]; ++r) {
+            tbh::Ct f = pg.input(1, 1);
+            tbh::Radix idx;
+            for (uint64_t b = 0; b < a[1]; ++b) idx.push_back(pg.input(h.p.msg_mod - 1, 1));
+            parts.push_back({f, idx});
+        }
+        auto r = ssk.combine_find(parts);
+        pg.output(r.first);
+        output_radix(pg, r.second);
+        return true;
+    }
     // ---- many independent string pairs in one program (throughput mode): a = {len_a, len_b, count}; inputs are
     //      count x (string a, string b); one boolean per pair.  op = string_eq_many / string_lt_many / string_contains_many
     if (op.size() > 5 && op.rfind("string_", 0) == 0 && op.compare(op.size() - 5, 5, "_many") == 0) {
@@ -164,6 +188,12 @@ bool record(tfhe_b200_program &h, const std::string &op_in, const uint64_t *a, s
         else if (f == "starts_with") pg.output(ssk.starts_with(s, t));
         else if (f == "ends_with") pg.output(ssk.ends_with(s, t));
         else if (f == "find") { auto r = ssk.find(s, t); pg.output(r.first); output_radix(pg, r.second); }
+        else if (f == "find_windows") {           // multi-GPU shard: first match among windows [a[2], a[3]) as a global index
+            if (!need(4)) return false;
+            if (a[2] > a[3]) { err = "find_windows: bad window range"; return false; }
+            auto r = ssk.find_range(s, t, a[2], a[3]); pg.output(r.first); output_radix(pg, r.second);
+        }
+        else if (f == "cmp_sign") pg.output(ssk.compare_sign(s, t));     // multi-GPU shard of lt / le / gt / ge: the range's sign block
         else if (f == "contains_windows") {
             // multi-GPU shard: match flag OR-reduced over windows [a[2], a[3]) only -> one boolean block
             if (!need(4)) return false;

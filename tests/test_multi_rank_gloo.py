@@ -1,5 +1,7 @@
 """world_size-2 (and 3) gloo test of the multi-GPU sharding path on CPU: window / char partition, all-reduce(SUM) of the
-per-rank boolean LWE blocks (wrapping u64 add == homomorphic add), final LUT.  Programs are executed with the CPU oracle;
+per-rank boolean LWE blocks (wrapping u64 add == homomorphic add) + final LUT for eq / contains; all-gather of sign blocks + sign
+tree for lt / le / gt / ge; all-gather of converted chars for the case conversions; all-gather of (found, index) + first-rank
+selection for find.  Programs are executed with the CPU oracle;
 the sharding + collective code is the product's (fhe_string_bounty_b200/multi_gpu.py)."""
 import os
 import socket
@@ -46,6 +48,19 @@ def _worker(rank, world, port, ret):
     for a, b in [(b"abcdefg", b"abcdefg"), (b"abcdefg", b"abcdefh"), (b"x", b"x")]:
         out = MG.sharded_eq(execute, params, R.encrypt_string(ck, a), R.encrypt_string(ck, b), len(a), rank, world)
         results.append(("eq", a, b, ck.decrypt_message_and_carry(out), int(a == b)))
+    for a, b in [(b"abcdefg", b"abcdefg"), (b"abcdefg", b"abcdefh"), (b"bbcdefg", b"abcdefz"), (b"aaaaaab", b"aaaaaaa"), (b"q", b"r")]:
+        for op, w in (("lt", a < b), ("le", a <= b), ("gt", a > b), ("ge", a >= b)):
+            out = MG.sharded_compare(execute, params, op, R.encrypt_string(ck, a), R.encrypt_string(ck, b), len(a), rank, world)
+            results.append((op, a, b, ck.decrypt_message_and_carry(out), int(w)))
+    for s_ in [b"Hello Zama, how is it going?", b"aZ"]:
+        out = MG.sharded_case(execute, params, "to_uppercase", R.encrypt_string(ck, s_), len(s_), rank, world)
+        results.append(("upper", s_, b"", R.decrypt_string(ck, out), s_.upper()))
+        out = MG.sharded_case(execute, params, "to_lowercase", R.encrypt_string(ck, s_), len(s_), rank, world)
+        results.append(("lower", s_, b"", R.decrypt_string(ck, out), s_.lower()))
+    for hay, pat in [(b"the quick brown fox", b"quick"), (b"abcabcabc", b"abc"), (b"abcabcabc", b"cab"), (b"abcabcabd", b"abd"), (b"abcabc", b"xyz")]:
+        out = MG.sharded_find(execute, params, R.encrypt_string(ck, hay), R.encrypt_string(ck, pat), len(hay), len(pat), rank, world)
+        pos = hay.find(pat)
+        results.append(("find", hay, pat, (ck.decrypt_message_and_carry(out[0]), R.decrypt_radix(ck, out[1:])), (int(pos >= 0), max(pos, 0))))
     assert MG.shard_range(241, 0, 8) == (0, 31) and MG.shard_range(241, 7, 8) == (211, 241)
     ret[rank] = results
     dist.barrier()
