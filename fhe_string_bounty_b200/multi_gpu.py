@@ -115,18 +115,23 @@ def sharded_compare(execute, params: dict, op: str, a: np.ndarray, b: np.ndarray
 
 
 def sharded_case(execute, params: dict, op: str, s: np.ndarray, n_chars: int, rank: int, world: int,
-                 device: str | None = None) -> np.ndarray:
-    """to_lowercase / to_uppercase with the chars split over ranks: elementwise, so the only exchange is the all-gather of the
-    converted blocks (every rank returns the whole converted string)."""
+                 device: str | None = None, gather: bool = True) -> np.ndarray:
+    """to_lowercase / to_uppercase with the chars split over ranks: elementwise, so there is no exchange on the path.  With
+    gather=True every rank returns the whole converted string (one all-gather of the converted blocks, 16 KiB per block -- for a
+    1024-char string that is 67 MB and costs more than the conversion); with gather=False a rank returns its own chars
+    [shard_range(n_chars, rank, world)] only ("no exchange; optional all-gather")."""
     if world == 1 or n_chars == 0:
         return execute(cached_program("string_" + op, (n_chars,), params), s)
     active = min(world, n_chars)
     per = -(-n_chars // active)                                  # padded share, in chars
-    mine = np.zeros((4 * per, s.shape[1]), dtype=np.uint64)
     c0 = c1 = 0
     if rank < active:
         c0, c1 = shard_range(n_chars, rank, active)
-        mine[:4 * (c1 - c0)] = execute(cached_program("string_" + op, (c1 - c0,), params), s[4 * c0:4 * c1])
+    conv = execute(cached_program("string_" + op, (c1 - c0,), params), s[4 * c0:4 * c1]) if c1 > c0 else np.zeros((0, s.shape[1]), dtype=np.uint64)
+    if not gather:
+        return conv
+    mine = np.zeros((4 * per, s.shape[1]), dtype=np.uint64)
+    mine[:4 * (c1 - c0)] = conv
     parts = all_gather_lwe(mine, device)
     out = []
     for r in range(active):

@@ -57,6 +57,9 @@ def _worker(rank, world, port, ret):
         results.append(("upper", s_, b"", R.decrypt_string(ck, out), s_.upper()))
         out = MG.sharded_case(execute, params, "to_lowercase", R.encrypt_string(ck, s_), len(s_), rank, world)
         results.append(("lower", s_, b"", R.decrypt_string(ck, out), s_.lower()))
+        c0, c1 = MG.shard_range(len(s_), rank, min(world, len(s_))) if rank < min(world, len(s_)) else (0, 0)
+        out = MG.sharded_case(execute, params, "to_lowercase", R.encrypt_string(ck, s_), len(s_), rank, world, gather=False)
+        results.append(("lower-own-share", s_, b"", R.decrypt_string(ck, out), s_.lower()[c0:c1]))
     for hay, pat in [(b"the quick brown fox", b"quick"), (b"abcabcabc", b"abc"), (b"abcabcabc", b"cab"), (b"abcabcabd", b"abd"), (b"abcabc", b"xyz")]:
         out = MG.sharded_find(execute, params, R.encrypt_string(ck, hay), R.encrypt_string(ck, pat), len(hay), len(pat), rank, world)
         pos = hay.find(pat)
