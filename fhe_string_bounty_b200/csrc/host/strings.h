@@ -168,6 +168,8 @@ class StringServerKey {
     // find: (found, index of the first match as a radix of ceil(log4(W)) blocks; 0 when not found, like the
     // regex example's "no match" convention of returning a boolean separately)
     std::pair<BooleanBlock, Radix> find(const FheString &hay, const FheString &pat) { return find_range(hay, pat, 0, size_t(-1)); }
+    // rfind: the LAST match -- the same circuit over the windows in descending order
+    std::pair<BooleanBlock, Radix> rfind(const FheString &hay, const FheString &pat) { return find_range(hay, pat, 0, size_t(-1), true); }
     // number of radix blocks of a window index
     static size_t index_blocks(size_t hay_len, size_t pat_len) {
         const size_t W = pat_len <= hay_len ? hay_len - pat_len + 1 : 0;
@@ -176,7 +178,7 @@ class StringServerKey {
         return idx_blocks;
     }
     // the same over the windows [w0, w1) only (the multi-GPU split): first match inside the range, reported as its GLOBAL window index
-    std::pair<BooleanBlock, Radix> find_range(const FheString &hay, const FheString &pat, size_t w0, size_t w1) {
+    std::pair<BooleanBlock, Radix> find_range(const FheString &hay, const FheString &pat, size_t w0, size_t w1, bool last = false) {
         const size_t W_all = pat.len() <= hay.len() ? hay.len() - pat.len() + 1 : 0;
         const size_t idx_blocks = index_blocks(hay.len(), pat.len());
         Radix zero_idx;
@@ -184,9 +186,16 @@ class StringServerKey {
         if (W_all == 0) return {pg.create_trivial(0), zero_idx};
         w1 = std::min(w1, W_all);
         if (w0 >= w1) return {pg.create_trivial(0), zero_idx};
-        if (pat.len() == 0) return {pg.create_trivial(w0 == 0 ? 1 : 0), zero_idx};
-        const size_t W = w1 - w0;            // local window count; local window w is global window w0 + w
+        if (pat.len() == 0) {                // the empty pattern matches everywhere: first window 0, last window W_all - 1 (public)
+            if (!last) return {pg.create_trivial(w0 == 0 ? 1 : 0), zero_idx};
+            Radix idx;
+            for (size_t b = 0; b < idx_blocks; ++b) idx.push_back(pg.create_trivial(w1 == W_all ? ((W_all - 1) >> (2 * b)) & 3 : 0));
+            return {pg.create_trivial(w1 == W_all ? 1 : 0), idx};
+        }
+        const size_t W = w1 - w0;            // local window count; local window w is global window w0 + w (w1 - 1 - w for rfind)
         std::vector<Ct> m = window_matches(hay, pat, w0, w1);
+        if (last) std::reverse(m.begin(), m.end());
+        const auto global = [=](size_t w) { return last ? w1 - 1 - w : w0 + w; };
         // one-hot first match in THREE levels instead of a log-depth prefix OR.  Windows are cut into blocks of 14:
         //   level 1   any_k   = [sum of the block's match flags != 0]                (leveled sum of <= 14 booleans + 1 PBS per block)
         //   level 2   before_k = [sum_{k' < k} any_k' != 0]                         (leveled prefix sums, chunks of <= 15, 1 PBS per block)
@@ -234,7 +243,7 @@ class StringServerKey {
         for (size_t b = 0; b < idx_blocks; ++b) {
             std::vector<Ct> terms;
             for (size_t w = 0; w < W; ++w) {
-                const uint64_t digit = ((w0 + w) >> (2 * b)) & 3;
+                const uint64_t digit = (global(w) >> (2 * b)) & 3;
                 if (digit == 0) continue;
                 terms.push_back(pg.pbs(first[w], [digit](uint64_t x) { return (x & 1) ? digit : uint64_t(0); }));
             }

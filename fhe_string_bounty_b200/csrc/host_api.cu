@@ -188,6 +188,7 @@ bool record(tfhe_b200_program &h, const std::string &op_in, const uint64_t *a, s
         else if (f == "starts_with") pg.output(ssk.starts_with(s, t));
         else if (f == "ends_with") pg.output(ssk.ends_with(s, t));
         else if (f == "find") { auto r = ssk.find(s, t); pg.output(r.first); output_radix(pg, r.second); }
+        else if (f == "rfind") { auto r = ssk.rfind(s, t); pg.output(r.first); output_radix(pg, r.second); }
         else if (f == "find_windows") {           // multi-GPU shard: first match among windows [a[2], a[3]) as a global index
             if (!need(4)) return false;
             if (a[2] > a[3]) { err = "find_windows: bad window range"; return false; }

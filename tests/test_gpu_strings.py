@@ -62,6 +62,9 @@ def test_string_ops_small(orc, keys_2_2, eng):
         out = P.run(eng, ins)
         f = a.find(b)
         assert _bool(ck, out[0]) == int(f >= 0) and R.decrypt_radix(ck, out[1:]) == max(f, 0), (a, b)
+        out = Program("string_rfind", (len(a), len(b)), params=engine_params(p)).run(eng, ins)
+        f = a.rfind(b)
+        assert _bool(ck, out[0]) == int(f >= 0) and R.decrypt_radix(ck, out[1:]) == max(f, 0), ("rfind", a, b)
 
 
 def test_case_conversion_kat_gpu(orc, keys_2_2, eng):

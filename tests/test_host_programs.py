@@ -126,6 +126,11 @@ def test_find_and_contains_toy(orc, toy_keys):
         found, idx = _dec_bool(ck, out[0]), R.decrypt_radix(ck, out[1:])
         want = hay.find(pat)
         assert found == int(want >= 0) and idx == max(want, 0), (hay, pat, found, idx)
+        # rfind: the last match (same circuit over the windows in descending order), reference-shaped and packed
+        for op in ("string_rfind", "string_rfind_packed"):
+            out, _ = _run(orc, toy_keys, op, (len(hay), len(pat)), ins)
+            want_r = hay.rfind(pat)
+            assert (_dec_bool(ck, out[0]), R.decrypt_radix(ck, out[1:])) == (int(want_r >= 0), max(want_r, 0)), (op, hay, pat)
         # clear pattern variant: the pattern is a trivial string, equality against it still costs the same PBS
         out, _ = _run(orc, toy_keys, "string_contains", (len(hay),), R.encrypt_string(ck, hay), clear=pat.decode())
         assert _dec_bool(ck, out[0]) == int(pat in hay)
