@@ -176,6 +176,7 @@ def multi_bit_params(name: str) -> dict:
 EXPORTS = {
     "tfhe_b200_ctx_create": (C.c_int, [C.c_int, C.POINTER(Params), C.POINTER(C.c_void_p)]),
     "tfhe_b200_ctx_destroy": (C.c_int, [C.c_void_p]),
+    "tfhe_b200_set_ciphertext_modulus_log2": (C.c_int, [C.c_void_p, C.c_uint32]),
     "tfhe_b200_last_error": (C.c_char_p, []),
     "tfhe_b200_upload_ksk": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "tfhe_b200_upload_bsk_std": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
@@ -358,6 +359,10 @@ class Engine:
 
     def pbs_batch_device(self, d_small, d_idx, d_out, batch: int, stream: int | None = None):
         self._check(self.lib.tfhe_b200_pbs_batch_device(self.h, _ptr(d_small), _ptr(d_idx), _ptr(d_out), batch, stream))
+
+    def set_ciphertext_modulus_log2(self, log2_q: int):
+        """non-native power-of-two ciphertext modulus 2^log2_q (64 = native): PBS outputs are rounded like bootstrap.rs:318-330"""
+        self._check(self.lib.tfhe_b200_set_ciphertext_modulus_log2(self.h, log2_q))
 
     def synchronize(self):
         self._check(self.lib.tfhe_b200_synchronize(self.h))

@@ -67,8 +67,21 @@ int do_keyswitch(tfhe_b200_ctx *c, const uint64_t *d_in, uint64_t *d_small, size
     return 0;
 }
 
+static int do_pbs_kernels(tfhe_b200_ctx *c, const uint64_t *d_small, const uint32_t *d_idx, const uint64_t *d_luts, uint64_t *d_out, size_t batch,
+                          uint32_t n_iters, cudaStream_t s, const uint32_t *out_slot, bool fused);
+
 int do_pbs(tfhe_b200_ctx *c, const uint64_t *d_small, const uint32_t *d_idx, const uint64_t *d_luts, uint64_t *d_out, size_t batch,
            uint32_t n_iters, cudaStream_t s, const uint32_t *out_slot, bool fused) {
+    if (do_pbs_kernels(c, d_small, d_idx, d_luts, d_out, batch, n_iters, s, out_slot, fused)) return 1;
+    if (c->log2_q < 64 && batch) {
+        TB_CUDA(tbk::launch_round_pow2(d_out, out_slot, (int)batch, (int)c->p.poly_size, (int)c->big_len(), c->log2_q, s));
+        c->launches += 1;
+    }
+    return 0;
+}
+
+static int do_pbs_kernels(tfhe_b200_ctx *c, const uint64_t *d_small, const uint32_t *d_idx, const uint64_t *d_luts, uint64_t *d_out, size_t batch,
+                          uint32_t n_iters, cudaStream_t s, const uint32_t *out_slot, bool fused) {
     if (fused && !fused_supported(c)) return fail("internal: fused PBS input requested on an unsupported configuration");
     if (!c->have_bsk) return fail("bootstrap key not uploaded");
     if (!d_luts) return fail("no lookup tables uploaded");
@@ -225,6 +238,14 @@ int tfhe_b200_ctx_create(int cuda_device, const tfhe_b200_params *params, tfhe_b
     TB_CUDA(cudaMemcpyAsync(c->tbl8.p, tbl8.data(), tbl8.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     TB_CUDA(cudaStreamSynchronize(c->stream));
     *out = c;
+    return 0;
+}
+
+int tfhe_b200_set_ciphertext_modulus_log2(tfhe_b200_ctx *c, uint32_t log2_q) {
+    if (!c) return fail("null context");
+    if (log2_q < 2 || log2_q > 64) return fail("ciphertext modulus must be 2^2 ... 2^64");
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->log2_q = (int)log2_q;
     return 0;
 }
 

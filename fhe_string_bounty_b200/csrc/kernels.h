@@ -87,6 +87,8 @@ cudaError_t launch_pbs_generic(const uint64_t *lwe_small, const uint32_t *lut_id
                                cudaStream_t stream);
 cudaError_t launch_bsk_convert_generic(const uint64_t *bsk_std, void *bskf, const void *tw, size_t n_polys, int poly_size, cudaStream_t stream);
 
+// leveled.cu: rounding of PBS outputs to a non-native power-of-two ciphertext modulus (bootstrap.rs:318-330)
+cudaError_t launch_round_pow2(uint64_t *out, const uint32_t *out_slot, int batch, int poly_size, int lwe_len, int log2_q, cudaStream_t stream);
 cudaError_t launch_gather_rows(const uint64_t *arena, const uint32_t *slots, uint64_t *dst, int n_rows, int lwe_len, cudaStream_t stream);
 
 // seeded.cu: dst row g = [mask_len words of the AES-128 CTR stream of `seed` | body_len words copied from bodies]

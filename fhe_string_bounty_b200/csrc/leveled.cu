@@ -43,7 +43,32 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const uint64_t *__rest
 }
 }  // namespace tblin
 
+namespace tblin {
+// Non-native power-of-two ciphertext modulus 2^log2_q (bootstrap.rs:318-330): the reference rounds every accumulator coefficient with
+// SignedDecomposer(log2_q, 1).closest_representable BEFORE the sample extraction.  Applied to the extracted sample instead: the words
+// that sample extraction negated (glwe_sample_extraction.rs:91-147: every mask word except the first of each polynomial) are rounded as
+// -round(-x), the others as round(x), which is the same value bit for bit, ties included.
+__global__ void __launch_bounds__(256) round_pow2_kernel(uint64_t *__restrict__ out, const uint32_t *__restrict__ out_slot, int poly_size,
+                                                         int lwe_len, int log2_q) {
+    uint64_t *row = out + (size_t)(out_slot ? out_slot[blockIdx.x] : blockIdx.x) * lwe_len;
+    const int shift = 64 - log2_q - 1;
+    for (int j = threadIdx.x; j < lwe_len; j += blockDim.x) {
+        const bool negated = j != lwe_len - 1 && (j % poly_size) != 0;
+        uint64_t x = row[j];
+        if (negated) x = (uint64_t)0 - x;
+        x = (((x >> shift) + 1) & ~(uint64_t)1) << shift;
+        row[j] = negated ? (uint64_t)0 - x : x;
+    }
+}
+}  // namespace tblin
+
 namespace tbk {
+
+cudaError_t launch_round_pow2(uint64_t *out, const uint32_t *out_slot, int batch, int poly_size, int lwe_len, int log2_q, cudaStream_t stream) {
+    if (batch <= 0 || log2_q >= 64) return cudaSuccess;
+    tblin::round_pow2_kernel<<<batch, 256, 0, stream>>>(out, out_slot, poly_size, lwe_len, log2_q);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_gather_rows(const uint64_t *arena, const uint32_t *slots, uint64_t *dst, int n_rows, int lwe_len, cudaStream_t stream) {
     if (n_rows <= 0) return cudaSuccess;

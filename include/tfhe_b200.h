@@ -46,6 +46,10 @@ typedef struct {
 int tfhe_b200_ctx_create(int cuda_device, const tfhe_b200_params *params, tfhe_b200_ctx **out);
 int tfhe_b200_ctx_destroy(tfhe_b200_ctx *ctx);
 const char *tfhe_b200_last_error(void);
+/* CiphertextModulus (core_crypto/commons/ciphertext_modulus.rs): native 2^64 by default; a smaller power of two 2^log2_q keeps its
+ * values in the MSBs of each u64 word and makes every PBS output round to a multiple of 2^(64 - log2_q), exactly as
+ * fft64/crypto/bootstrap.rs:318-330 does.  The keyswitch is unchanged (lwe_keyswitch.rs:136-140: compatible with the native modulus). */
+int tfhe_b200_set_ciphertext_modulus_log2(tfhe_b200_ctx *ctx, uint32_t log2_q);
 
 /* Keys (host pointers, copied).
  * ksk: LweKeyswitchKey<u64> container, [k*N][ks_level (level l..1)][n+1]

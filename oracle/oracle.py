@@ -99,6 +99,7 @@ def lib():
         "orc_add_external_product_f64": (None, [_PP, C.c_void_p, C.c_size_t, _u64p, _u64p]),
         "orc_add_external_product_exact": (None, [_PP, _u64p, _u64p, _u64p]),
         "orc_pbs_f64": (None, [_PP, C.c_void_p, _u64p, _u64p, _u64p]),
+        "orc_pbs_f64_pow2_modulus": (None, [_PP, C.c_void_p, _u64p, _u64p, _u64p, C.c_uint32]),
         "orc_pbs_exact": (None, [_PP, _u64p, _u64p, _u64p, _u64p]),
         "orc_ks_pbs_batch": (C.c_int, [_PP, _u64p, C.c_void_p, _u64p, C.c_void_p, _u64p, _u64p, C.c_void_p, C.c_size_t, C.c_int]),
         "orc_max_threads": (C.c_int, []),
@@ -277,6 +278,12 @@ class ServerKey:
             lib().orc_pbs_exact(C.byref(self.p), self.bsk, np.ascontiguousarray(lwe_small), acc, out)
         else:
             lib().orc_pbs_f64(C.byref(self.p), self.fourier, np.ascontiguousarray(lwe_small), acc, out)
+        return out
+
+    def pbs_pow2_modulus(self, lwe_small: np.ndarray, acc: np.ndarray, log2_q: int) -> np.ndarray:
+        """PBS under a non-native power-of-two ciphertext modulus 2^log2_q (bootstrap.rs:318-330)."""
+        out = np.zeros(self.p.big_dim + 1, dtype=np.uint64)
+        lib().orc_pbs_f64_pow2_modulus(C.byref(self.p), self.fourier, np.ascontiguousarray(lwe_small), acc, out, log2_q)
         return out
 
     def ks_pbs_batch(self, cts: np.ndarray, luts: np.ndarray, lut_idx=None, threads: int = 0, want_ks: bool = False):

@@ -798,6 +798,21 @@ static void pbs_f64_with_scratch(const orc_params *p, const orc_fourier_bsk *f, 
     orc_sample_extract0(p, s->ct0, lwe_out);   /* bootstrap.rs:358-362 */
 }
 
+/* Non-native power-of-two ciphertext modulus q = 2^log2_q (values live in the MSBs): after the blind rotation every accumulator
+ * coefficient is rounded to a multiple of 2^(64 - log2_q) with SignedDecomposer(base_log = log2_q, level 1).closest_representable
+ * (fft64/crypto/bootstrap.rs:318-330), then the sample is extracted (:358-362). */
+void orc_pbs_f64_pow2_modulus(const orc_params *p, const orc_fourier_bsk *f, const uint64_t *lwe_in, const uint64_t *acc,
+                              uint64_t *lwe_out, uint32_t log2_q) {
+    size_t N = p->poly_size, k1 = p->glwe_dim + 1;
+    pbs_scratch s; scratch_init(&s, p);
+    memcpy(s.ct0, acc, k1 * N * 8);
+    blind_rotate_f64(p, f, lwe_in, &s);
+    if (log2_q < 64)
+        for (size_t j = 0; j < k1 * N; j++) s.ct0[j] = orc_closest_representable(s.ct0[j], log2_q, 1);
+    orc_sample_extract0(p, s.ct0, lwe_out);
+    scratch_free(&s);
+}
+
 void orc_pbs_f64(const orc_params *p, const orc_fourier_bsk *f, const uint64_t *lwe_in, const uint64_t *acc, uint64_t *lwe_out) {
     pbs_scratch s; scratch_init(&s, p);
     pbs_f64_with_scratch(p, f, lwe_in, acc, lwe_out, &s);

@@ -4,7 +4,7 @@ import ctypes as C
 import numpy as np
 
 
-def oracle_partial_pbs(orc, sk, lwe_small, lut, n_iters):
+def oracle_partial_pbs(orc, sk, lwe_small, lut, n_iters, log2_q=64):
     """bootstrap.rs:254-316 restated with the oracle primitives, stopping after n_iters mask elements;
     returns the sample-extracted LWE (same shape as a full PBS output)."""
     L = orc.lib()
@@ -27,8 +27,11 @@ def oracle_partial_pbs(orc, sk, lwe_small, lut, n_iters):
             L.orc_monomial_mul_and_subtract(tmp, np.ascontiguousarray(acc[q * N:(q + 1) * N]), N, a_hat)
             ct1[q * N:(q + 1) * N] = tmp
         L.orc_add_external_product_f64(C.byref(p), sk.fourier, i, acc, ct1)
+    if log2_q < 64:   # bootstrap.rs:318-330: SignedDecomposer(log2_q, 1).closest_representable on every coefficient, then extract
+        shift = np.uint64(64 - log2_q - 1)
+        acc = (((acc >> shift) + np.uint64(1)) & ~np.uint64(1)) << shift
     out = np.zeros(p.big_dim + 1, dtype=np.uint64)
-    L.orc_sample_extract0(C.byref(p), acc, out)
+    L.orc_sample_extract0(C.byref(p), np.ascontiguousarray(acc), out)
     return out
 
 

@@ -165,3 +165,52 @@ def test_every_kernel_instance_boundary(orc, keys_2_2, eng):
         family = "narrow" if batch <= 2 * sms else "wide"     # pbs_v8.cu / pbs_v4.cu: different FFT factorisations, different rounding
         first.setdefault(family, out[0].copy())
         assert np.array_equal(out[0], first[family]), f"ciphertext 0 differs between batch sizes (batch {batch})"
+
+
+@pytest.mark.parametrize("log2_q", [63, 32, 16])
+def test_power_of_two_ciphertext_modulus(orc, keys_2_2, log2_q):
+    """Non-native power-of-two ciphertext modulus (bootstrap.rs:318-330; the reference's own PBS tests run q = 2^63,
+    core_crypto/algorithms/test/mod.rs TEST_PARAMS_3_BITS_63_U64): every PBS output word is a multiple of 2^(64 - log2_q); LUT rotation
+    + rounding + sample extraction is bit-exact against the reference's order (round the accumulator, then extract), ties included;
+    one CMUX differs by at most one unit of the modulus or the FFT tolerance; full KS-PBS decrypts exactly and equals the oracle's
+    decryption."""
+    import fhe_string_bounty_b200 as F
+    p, ck, sk = keys_2_2
+    fs, luts = _luts(sk)
+    eng = F.Engine(engine_params(p))
+    eng.upload_ksk(sk.ksk)
+    eng.upload_bsk_std(sk.bsk)
+    eng.upload_luts(luts)
+    eng.set_ciphertext_modulus_log2(log2_q)
+    unit = 1 << (64 - log2_q)
+    shift = np.uint64(64 - log2_q - 1)
+    rnd = lambda x: (((x >> shift) + np.uint64(1)) & ~np.uint64(1)) << shift
+    vals = np.arange(32) % 16
+    idx = (np.arange(32) % len(fs)).astype(np.uint32)
+    cts = rnd(ck.encrypt_batch(vals))                    # ciphertexts modulo q live in the MSBs
+    small = np.stack([sk.keyswitch(c) for c in cts])
+    assert np.array_equal(eng.keyswitch_batch(cts), small)
+    # an accumulator whose words sit exactly on rounding ties, so that the order "round, then negate" matters
+    tie_lut = luts[0].copy()
+    tie_lut[p.poly_size:] = (np.arange(p.poly_size, dtype=np.uint64) << np.uint64(64 - log2_q)) + np.uint64(unit // 2)
+    eng.upload_luts(np.concatenate([luts, tie_lut[None, :]]))
+    all_luts = np.concatenate([luts, tie_lut[None, :]])
+    idx0 = np.array([len(fs), 0, 1, 2], dtype=np.uint32)
+    for n_iters in (0, 1):
+        got = eng.pbs_batch(small[:4], idx0, n_iters=n_iters)
+        assert not np.any(got & np.uint64(unit - 1)), "outputs must be multiples of 2^(64 - log2_q)"
+        for b in range(4):
+            want = oracle_partial_pbs(orc, sk, small[b], all_luts[idx0[b]], n_iters, log2_q)
+            d = int(np.abs((got[b] - want).view(np.int64)).max())
+            if n_iters == 0:
+                assert d == 0, (log2_q, b)
+            else:
+                assert d <= max(unit, 2**44), (log2_q, b, np.log2(max(d, 1)))
+    out = eng.ks_pbs_batch(cts, idx)
+    assert not np.any(out & np.uint64(unit - 1))
+    want = np.array([fs[i](int(v)) for v, i in zip(vals, idx)])
+    assert np.array_equal(ck.decrypt_batch(out), want)
+    ref = np.stack([sk.pbs_pow2_modulus(small[b], luts[idx[b]], log2_q) for b in range(8)])
+    assert not np.any(ref & np.uint64(unit - 1))
+    assert np.array_equal(ck.decrypt_batch(ref), want[:8])
+    eng.close()

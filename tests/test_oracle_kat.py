@@ -207,3 +207,17 @@ def test_batch_equals_sequential(orc, keys_2_2):
         ks = sk.keyswitch(cts[i])
         assert np.array_equal(ks, ks_b[i])
         assert np.array_equal(sk.pbs(ks, ident), out_b[i])
+
+
+def test_power_of_two_modulus_pbs_oracle(orc, toy_keys):
+    """bootstrap.rs:318-330 (the reference runs its PBS tests with q = 2^63 as well): outputs are multiples of 2^(64 - log2 q) and still
+    decrypt to the LUT value; with q = 2^64 the function is the plain PBS."""
+    p, ck, sk = toy_keys
+    acc, _ = sk.generate_lookup_table(lambda x: (x + 3) % 16)
+    for v in (0, 7, 15):
+        small = sk.keyswitch(ck.encrypt_with_carry(v))
+        assert np.array_equal(sk.pbs_pow2_modulus(small, acc, 64), sk.pbs(small, acc))
+        for log2_q in (63, 32, 20):
+            out = sk.pbs_pow2_modulus(small, acc, log2_q)
+            assert not np.any(out & np.uint64((1 << (64 - log2_q)) - 1))
+            assert ck.decrypt_message_and_carry(out) == (v + 3) % 16
