@@ -70,7 +70,7 @@ def _worker(rank, world, port, ret):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("world", [2, 3, 8])
 def test_sharded_string_ops_gloo(world):
     port = _free_port()
     mgr = mp.Manager()
