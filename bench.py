@@ -137,15 +137,20 @@ def run_param_sweep(args):
     """--param-sweep: KS-PBS/s of other classic parameter sets (pbs_generic.cu) on one GPU next to the CPU oracle on the
     same box.  Device-resident inputs, CUDA events on the launching stream, random key words (the arithmetic does not depend on the key
     values).  One JSON line; not the headline metric."""
+    rows = param_sweep_rows(args.param_sweep.split(","), args.cpu_sample > 0, 0)
+    print(json.dumps({"metric": "KS-PBS throughput per classic parameter set (1 GPU, device-resident)", "unit": "PBS/s", "sets": rows}))
+
+
+def param_sweep_rows(names, with_cpu: bool, device: int):
     import math
     import torch
     import fhe_string_bounty_b200 as F
-    torch.cuda.set_device(0)
-    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    torch.cuda.set_device(device)
+    sms = torch.cuda.get_device_properties(device).multi_processor_count
     rows = []
-    for name in args.param_sweep.split(","):
+    for name in names:
         p = F.Params(**F.classic_params(name))
-        eng = F.Engine(p, device=0)
+        eng = F.Engine(p, device=device)
         rng = np.random.default_rng(0xB200)
         eng.upload_ksk(rng.integers(0, 2**64, size=p.ksk_len, dtype=np.uint64))
         eng.upload_bsk_std(rng.integers(0, 2**64, size=p.bsk_len, dtype=np.uint64))
@@ -176,7 +181,7 @@ def run_param_sweep(args):
         row = {"params": f"PARAM_MESSAGE_{name.replace('_', '_CARRY_')}_KS_PBS", "N": p.poly_size, "k": p.glwe_dim, "pbs_level": l,
                "batch": B, "ms": ms, "keyswitch_ms": ks_ms, "pbs_ms": pbs_ms, "ks_pbs_per_s": B / (ms * 1e-3), "flop_per_pbs": flop,
                "pbs_tflops": B * flop / (pbs_ms * 1e-3) / 1e12}
-        if args.cpu_sample > 0:
+        if with_cpu:
             ref = CpuReference(1, params_name=name)
             n_cpu = ref.cores * (2 if small_n else 1)
             ref.close()
@@ -188,7 +193,7 @@ def run_param_sweep(args):
             row["cpu_cores"] = used
             row["gpu_over_cpu"] = row["ks_pbs_per_s"] / row["cpu_port_ks_pbs_per_s"]
         rows.append(row)
-    print(json.dumps({"metric": "KS-PBS throughput per classic parameter set (1 GPU, device-resident)", "unit": "PBS/s", "sets": rows}))
+    return rows
 
 
 def bench_string_ops(eng, p, rank, world, local):
@@ -435,6 +440,14 @@ def run_b200(args):
         }
         if string_ops is not None:
             line["string_ops"] = string_ops
+        if args.other_sets and world == 1:
+            # breadth, next to the headline: two other classic parameter sets on the generic kernel, this rank's GPU only
+            try:
+                line["other_parameter_sets"] = [
+                    {k: r[k] for k in ("params", "N", "k", "pbs_level", "batch", "ks_pbs_per_s", "pbs_ms", "pbs_tflops")}
+                    for r in param_sweep_rows(args.other_sets.split(","), False, local)]
+            except Exception as e:            # never lose the headline over the extra rows
+                line["other_parameter_sets"] = {"error": str(e)[:200]}
         if cpu_rate is not None and string_ops is not None:
             # the CPU path has no batching effect beyond its cores: a string op costs (its PBS count) / (CPU KS-PBS rate)
             string_ops["cpu_port_ops_per_s_derived"] = {
@@ -459,6 +472,7 @@ def main():
     ap.add_argument("--params", default="2_2", choices=["2_2", "multibit"], help="2_2 = PARAM_MESSAGE_2_CARRY_2_KS_PBS (headline); multibit = ..._GROUP_3_KS_PBS")
     ap.add_argument("--string-ops", type=int, default=1, help="also time FheString eq/contains/find through the host layer (0 = skip)")
     ap.add_argument("--param-sweep", default="", help="comma-separated classic sets (e.g. 1_1,3_3,4_4): per-set KS-PBS/s on one GPU + CPU oracle, then exit")
+    ap.add_argument("--other-sets", default="1_1,3_3", help="classic sets measured briefly after the headline and reported as other_parameter_sets ('' = skip)")
     ap.add_argument("--cpu-sample", type=int, default=8192, help="KS-PBS evaluated by the CPU baseline leg (0 = skip)")
     args = ap.parse_args()
     if args.param_sweep:
