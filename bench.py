@@ -227,50 +227,66 @@ def bench_string_ops(eng, p, rank, world, local):
             dt = float(t[0])
         return reps / dt
 
-    a8 = rng.integers(0, 2**64, size=(32, p.big_len), dtype=np.uint64)
-    b8 = rng.integers(0, 2**64, size=(32, p.big_len), dtype=np.uint64)
-    hay = rng.integers(0, 2**64, size=(1024, p.big_len), dtype=np.uint64)
-    pat = rng.integers(0, 2**64, size=(64, p.big_len), dtype=np.uint64)
+    _pinned = []
+
+    def pin(arr):
+        """page-locked copy of a host array (the e2e contract: inputs leave from pinned host memory)"""
+        t = torch.from_numpy(arr.view(np.int64)).pin_memory()
+        _pinned.append(t)
+        return t.numpy().view(np.uint64)
+
+    def run_pinned(prog, ins):
+        """single-GPU program through host buffers, both of them page-locked"""
+        key = id(prog)
+        if key not in run_pinned.out:
+            run_pinned.out[key] = pin(np.zeros((prog.n_outputs, p.big_len), dtype=np.uint64))
+        return prog.run(eng, ins, out=run_pinned.out[key])
+    run_pinned.out = {}
+
+    a8 = pin(rng.integers(0, 2**64, size=(32, p.big_len), dtype=np.uint64))
+    b8 = pin(rng.integers(0, 2**64, size=(32, p.big_len), dtype=np.uint64))
+    hay = pin(rng.integers(0, 2**64, size=(1024, p.big_len), dtype=np.uint64))
+    pat = pin(rng.integers(0, 2**64, size=(64, p.big_len), dtype=np.uint64))
     out["eq_8char_ops_per_s"] = timed(lambda: MG.sharded_eq(execute, params, a8, b8, 8, rank, world, dev), 20)
     out["contains_256_16_ops_per_s"] = timed(lambda: MG.sharded_contains(execute, params, hay, pat, 256, 16, rank, world, dev), 3)
     # throughput mode: independent string pairs share each tree level's launches (each rank takes its own share of pairs)
     n_pairs = 512
     many = Program("string_eq_many", (8, 8, n_pairs), params=params)
-    pairs = rng.integers(0, 2**64, size=(many.n_inputs, p.big_len), dtype=np.uint64)
-    out["eq_8char_batched_ops_per_s"] = world * n_pairs * timed(lambda: many.run(eng, pairs), 3)
+    pairs = pin(rng.integers(0, 2**64, size=(many.n_inputs, p.big_len), dtype=np.uint64))
+    out["eq_8char_batched_ops_per_s"] = world * n_pairs * timed(lambda: run_pinned(many, pairs), 3)
     out["eq_8char_batch"] = {"pairs_per_rank": n_pairs, "pbs": many.n_pbs, "levels": many.level_widths}
     manyp = Program("string_eq_many_packed", (8, 8, n_pairs), params=params)    # one PBS per pair of blocks (comparator.rs:193-221)
-    out["eq_8char_batched_packed_ops_per_s"] = world * n_pairs * timed(lambda: manyp.run(eng, pairs), 3)
+    out["eq_8char_batched_packed_ops_per_s"] = world * n_pairs * timed(lambda: run_pinned(manyp, pairs), 3)
     out["eq_8char_batch_packed"] = {"pairs_per_rank": n_pairs, "pbs": manyp.n_pbs, "levels": manyp.level_widths}
     if world > 1:
         # the other shardings of SURVEY 8(e): find = windows split + all-gather of (found, index) + first-rank selection;
         # to_lowercase = chars split + all-gather of the converted blocks
         out["find_256_16_ops_per_s"] = timed(lambda: MG.sharded_find(execute, params, hay, pat, 256, 16, rank, world, dev), 3)
-        s1024 = rng.integers(0, 2**64, size=(4096, p.big_len), dtype=np.uint64)
+        s1024 = pin(rng.integers(0, 2**64, size=(4096, p.big_len), dtype=np.uint64))
         out["to_lowercase_1024_ops_per_s"] = timed(lambda: MG.sharded_case(execute, params, "to_lowercase", s1024, 1024, rank, world, dev, gather=False), 3)
     if world == 1:
         cp = Program("string_contains_packed", (256, 16), params=params)
-        ins_c = np.concatenate([hay, pat])
-        out["contains_256_16_packed_ops_per_s"] = timed(lambda: cp.run(eng, ins_c), 3)
+        ins_c = pin(np.concatenate([hay, pat]))
+        out["contains_256_16_packed_ops_per_s"] = timed(lambda: run_pinned(cp, ins_c), 3)
         out["contains_256_16_packed_pbs"] = cp.n_pbs
         find = Program("string_find", (256, 16), params=params)
-        ins = np.concatenate([hay, pat])
-        out["find_256_16_ops_per_s"] = timed(lambda: find.run(eng, ins), 3)
+        ins = ins_c
+        out["find_256_16_ops_per_s"] = timed(lambda: run_pinned(find, ins), 3)
         out["find_256_16_pbs"] = find.n_pbs
         findp = Program("string_find_packed", (256, 16), params=params)
-        out["find_256_16_packed_ops_per_s"] = timed(lambda: findp.run(eng, ins), 3)
+        out["find_256_16_packed_ops_per_s"] = timed(lambda: run_pinned(findp, ins), 3)
         out["find_256_16_packed_pbs"] = findp.n_pbs
         low = Program("string_to_lowercase", (1024,), params=params)
-        s1024 = rng.integers(0, 2**64, size=(4096, p.big_len), dtype=np.uint64)
-        out["to_lowercase_1024_ops_per_s"] = timed(lambda: low.run(eng, s1024), 3)
+        s1024 = pin(rng.integers(0, 2**64, size=(4096, p.big_len), dtype=np.uint64))
+        out["to_lowercase_1024_ops_per_s"] = timed(lambda: run_pinned(low, s1024), 3)
         out["to_lowercase_1024_pbs"] = low.n_pbs
         up = Program("string_to_uppercase", (1024,), params=params)
-        out["to_uppercase_1024_ops_per_s"] = timed(lambda: up.run(eng, s1024), 3)
+        out["to_uppercase_1024_ops_per_s"] = timed(lambda: run_pinned(up, s1024), 3)
         eic = Program("string_eq_ignore_case", (1024, 1024), params=params)
-        two = rng.integers(0, 2**64, size=(eic.n_inputs, p.big_len), dtype=np.uint64)
-        out["eq_ignore_case_1024_ops_per_s"] = timed(lambda: eic.run(eng, two), 2)
+        two = pin(rng.integers(0, 2**64, size=(eic.n_inputs, p.big_len), dtype=np.uint64))
+        out["eq_ignore_case_1024_ops_per_s"] = timed(lambda: run_pinned(eic, two), 2)
         out["eq_ignore_case_1024_pbs"] = eic.n_pbs
-    out["note"] = ("host buffers in/out; eq shards chars, contains shards windows across ranks + one all-reduce of a 2049-word LWE; "
+    out["note"] = ("page-locked host buffers in/out; eq shards chars, contains shards windows across ranks + one all-reduce of a 2049-word LWE; "
                    "with several ranks find shards windows (all-gather of found + index, 2 selection levels) and to_lowercase shards chars (no exchange: each rank keeps its converted chars)")
     return out
 

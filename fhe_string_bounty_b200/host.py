@@ -99,12 +99,16 @@ class Program:
             self._check(self.lib.tfhe_b200_program_accumulators(self.h, acc.ctypes.data))
         return acc[: self.n_luts]
 
-    def run(self, eng: Engine, inputs: np.ndarray) -> np.ndarray:
-        """Execute on the GPU of `eng`; inputs [n_inputs, k*N+1] u64 (host) -> outputs [n_outputs, k*N+1]."""
+    def run(self, eng: Engine, inputs: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
+        """Execute on the GPU of `eng`; inputs [n_inputs, k*N+1] u64 (host) -> outputs [n_outputs, k*N+1].  `out` lets the caller
+        supply the result buffer (page-locked memory makes both copies DMA transfers instead of staged ones)."""
         inputs = np.ascontiguousarray(inputs, dtype=np.uint64).reshape(-1, self.p.big_len)
         if inputs.shape[0] != self.n_inputs:
             raise ValueError(f"{self.op}: expected {self.n_inputs} input blocks, got {inputs.shape[0]}")
-        out = np.empty((self.n_outputs, self.p.big_len), dtype=np.uint64)
+        if out is None:
+            out = np.empty((self.n_outputs, self.p.big_len), dtype=np.uint64)
+        elif out.dtype != np.uint64 or not out.flags.c_contiguous or out.size != self.n_outputs * self.p.big_len:
+            raise ValueError(f"{self.op}: out must be a C-contiguous uint64 array of {self.n_outputs} x {self.p.big_len} words")
         self._check(self.lib.tfhe_b200_program_run(eng.h, self.h, inputs.ctypes.data if inputs.size else None, out.ctypes.data if out.size else None))
         return out
 
