@@ -20,16 +20,24 @@
 // This is the coverage kernel, not the tuned one: N = 2048, k = 1, one level stays on pbs_v4.cu / pbs_v8.cu (TFHE_B200_PBS_KERNEL=generic
 // forces this one for cross-checks).  Measured 2.4 ... 6.1 TFLOP/s algorithmic against 15.8 for the tuned kernels.
 #include "kernels.h"
+#include <type_traits>
 #include "fft_core.cuh"
+#include "pbs16_common.cuh"      // Tensor Memory helpers (tcgen05.alloc / ld / st)
 
 namespace tbg {
 using tb::cplx;
 
-template <int LOGN>
+template <int LOGN, int K1 = 0>
 struct Shape {
     static constexpr int N = 1 << LOGN, M = N / 2;
-    static constexpr int PER = M > 2048 ? M / 512 : 4;       // positions per thread = one radix-4 butterfly per FFT pass (two above N = 4096)
+    static constexpr bool R8 = K1 == 2 && M >= 1024;          // k = 1: three stages per FFT pass (Fft8), 8 positions per thread
+    static constexpr int PER = R8 ? 8 : M > 2048 ? M / 512 : 4;   // otherwise one radix-4 butterfly per thread and pass (two above N = 4096)
     static constexpr int T = M / PER;
+    // N = 4096, 8192 with 8 positions per thread: the 16 complex Fourier accumulators of a thread (64 registers) are parked in its Tensor
+    // Memory lane while the FFT passes run (ncu on N = 8192: 1.0 G spill instructions, and with 208 KiB of shared memory there is no L1
+    // left, so every spill reload was an L2 round trip -- long_scoreboard 3.1 of 12.5 cycles per instruction)
+    static constexpr bool TM = R8 && M >= 2048;
+    static constexpr int TM_COLS = T / 128 * 64;              // warps sharing a lane quarter x 64 columns
     // resident CTAs per SM the register allocation must allow: N = 4096 two 512-thread CTAs (64 registers); N = 512 ... 2048 are capped
     // at 128 registers, which doubles their occupancy (ncu: 234 registers, 8 warps per SM, latency bound; +2 ... +18 %).  N = 256 (k = 5,
     // 24 complex accumulators per thread) is faster uncapped (measured: 80.7 k vs 56.7 k KS-PBS/s with a 168-register cap)
@@ -186,6 +194,206 @@ __device__ __forceinline__ void fft_inv(cplx *buf, const cplx *tbl) {
     __syncthreads();
 }
 
+// ---- the same transform with THREE radix-2 stages per shared-memory pass (8 points per thread) -----------------------------------
+// used where a thread's registers allow it (k = 1: 16 complex Fourier accumulators + 8 points): 4 passes instead of 6 at N = 4096 and
+// 8192.  log2(M) mod 3 leftover stages run first (one radix-2 or one radix-4 pass over the whole buffer), then passes with q = M'/8,
+// M'/64, ..., 1.  Inside a pass the stage twiddles W_{8q}^j, W_{4q}^j, W_{2q}^j are powers of w1 = W_{8q}^j and commute with the later
+// butterflies of their half, so they are applied once at the end as w1^brev3(a) on register a; only the constants W_8^r, W_4^r sit
+// between the stages.  Slot swizzle: low three bits XOR bits 3-5 (conflict free for consecutive elements, q = 8 and q = 1).
+constexpr double kInvSqrt2 = 0.70710678118654752440;
+
+template <int M, int T>
+struct Fft8 {
+    static constexpr int R = Log2<M>::v % 3;
+    static constexpr int MP = M >> R;              // size of the sub-transforms the radix-8 passes see
+    static constexpr int QMAX = MP / 8;
+    static constexpr int W8 = (8 * QMAX - 1) / 7;  // pass q = 8^i at offset (q - 1) / 7
+    static constexpr int LEFT = R == 0 ? 0 : M / 4;
+    static constexpr int ENTRIES = W8 + LEFT;
+    __device__ static __forceinline__ int sw(int i) { return i ^ ((i >> 3) & 7); }
+
+    __device__ static __forceinline__ void make(cplx *tbl, const cplx *__restrict__ tw, int n_over_m) {
+        for (int q = 1; q <= QMAX; q <<= 3)
+            for (int j = threadIdx.x; j < q; j += T) {
+                const cplx w = __ldg(tw + (size_t)j * (n_over_m * M / (4 * q)));      // W_{8q}^j = conj(tw[j N / (4q)])
+                cplx r; r.x = w.x; r.y = -w.y;
+                tbl[(q - 1) / 7 + j] = r;
+            }
+        if (R != 0)
+            for (int e = threadIdx.x; e < M / 4; e += T) {
+                const cplx w = __ldg(tw + (size_t)e * 2 * n_over_m);                  // W_M^e
+                cplx r; r.x = w.x; r.y = -w.y;
+                tbl[W8 + e] = r;
+            }
+    }
+    __device__ static __forceinline__ cplx left_root(const cplx *tbl, int e) {        // W_M^e, e < M/2
+        const bool hi = e >= M / 4;
+        const cplx t = tbl[W8 + (hi ? e - M / 4 : e)];
+        cplx r;
+        r.x = hi ? t.y : t.x;
+        r.y = hi ? -t.x : t.y;
+        return r;
+    }
+
+    __device__ static __forceinline__ void fwd(cplx *buf, const cplx *tbl) {
+        if (R == 1) {
+            __syncthreads();
+            for (int b = threadIdx.x; b < M / 2; b += T) {
+                const cplx u = buf[sw(b)], v = buf[sw(b + M / 2)];
+                buf[sw(b)] = cadd(u, v);
+                buf[sw(b + M / 2)] = cmul(csub(u, v), left_root(tbl, b));
+            }
+        } else if (R == 2) {
+            __syncthreads();
+            constexpr int q = M / 4;
+            for (int b = threadIdx.x; b < M / 4; b += T) {
+                const int p0 = sw(b), p1 = sw(b + q), p2 = sw(b + 2 * q), p3 = sw(b + 3 * q);
+                const cplx a0 = buf[p0], a1 = buf[p1], a2 = buf[p2], a3 = buf[p3];
+                const cplx b0 = cadd(a0, a2), b1 = cadd(a1, a3), b2 = csub(a0, a2), b3 = mul_neg_i(csub(a1, a3));
+                const cplx w1 = tbl[W8 + b], w2 = csqr(w1);
+                buf[p0] = cadd(b0, b1);
+                buf[p1] = cmul(csub(b0, b1), w2);
+                buf[p2] = cmul(cadd(b2, b3), w1);
+                buf[p3] = cmul(cmul(csub(b2, b3), w1), w2);
+            }
+        }
+        for (int q = QMAX; q >= 1; q >>= 3) {
+            __syncthreads();
+            const cplx *wq = tbl + (q - 1) / 7;
+            for (int b = threadIdx.x; b < M / 8; b += T) {
+                const int j = b & (q - 1), i0 = ((b - j) << 3) + j;
+                cplx x[8];
+#pragma unroll
+                for (int m = 0; m < 8; ++m) x[m] = buf[sw(i0 + m * q)];
+                // stage A: pairs (a, a + 4), constants W_8^a
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    const cplx u = x[a], d = csub(x[a], x[a + 4]);
+                    x[a] = cadd(u, x[a + 4]);
+                    cplx r;
+                    if (a == 0) r = d;
+                    else if (a == 1) { r.x = DMUL(DADD(d.x, d.y), kInvSqrt2); r.y = DMUL(DSUB(d.y, d.x), kInvSqrt2); }
+                    else if (a == 2) r = mul_neg_i(d);
+                    else { r.x = DMUL(DSUB(d.y, d.x), kInvSqrt2); r.y = -DMUL(DADD(d.x, d.y), kInvSqrt2); }
+                    x[a + 4] = r;
+                }
+                // stage B: pairs (a, a + 2) inside each half, constants W_4^a
+#pragma unroll
+                for (int base = 0; base < 8; base += 4) {
+                    const cplx u0 = x[base], u1 = x[base + 1];
+                    const cplx d0 = csub(u0, x[base + 2]), d1 = mul_neg_i(csub(u1, x[base + 3]));
+                    x[base] = cadd(u0, x[base + 2]);
+                    x[base + 1] = cadd(u1, x[base + 3]);
+                    x[base + 2] = d0;
+                    x[base + 3] = d1;
+                }
+                // stage C: pairs (a, a + 1)
+#pragma unroll
+                for (int base = 0; base < 8; base += 2) {
+                    const cplx u = x[base], v = x[base + 1];
+                    x[base] = cadd(u, v);
+                    x[base + 1] = csub(u, v);
+                }
+                if (q > 1) {                       // register a carries w1^brev3(a): a = 4 -> 1, 2 -> 2, 6 -> 3, 1 -> 4, 5 -> 5, 3 -> 6, 7 -> 7
+                    const cplx w1 = wq[j], w2 = csqr(w1), w3 = cmul(w1, w2), w4 = csqr(w2);
+                    x[4] = cmul(x[4], w1);
+                    x[2] = cmul(x[2], w2);
+                    x[6] = cmul(x[6], w3);
+                    x[1] = cmul(x[1], w4);
+                    x[5] = cmul(x[5], cmul(w4, w1));
+                    x[3] = cmul(x[3], cmul(w4, w2));
+                    x[7] = cmul(x[7], cmul(w4, w3));
+                }
+#pragma unroll
+                for (int m = 0; m < 8; ++m) buf[sw(i0 + m * q)] = x[m];
+            }
+        }
+        __syncthreads();
+    }
+
+    __device__ static __forceinline__ void inv(cplx *buf, const cplx *tbl) {
+        for (int q = 1; q <= QMAX; q <<= 3) {
+            __syncthreads();
+            const cplx *wq = tbl + (q - 1) / 7;
+            for (int b = threadIdx.x; b < M / 8; b += T) {
+                const int j = b & (q - 1), i0 = ((b - j) << 3) + j;
+                cplx x[8];
+#pragma unroll
+                for (int m = 0; m < 8; ++m) x[m] = buf[sw(i0 + m * q)];
+                if (q > 1) {
+                    const cplx w1 = wq[j], w2 = csqr(w1), w3 = cmul(w1, w2), w4 = csqr(w2);
+                    x[4] = cmul_conj(x[4], w1);
+                    x[2] = cmul_conj(x[2], w2);
+                    x[6] = cmul_conj(x[6], w3);
+                    x[1] = cmul_conj(x[1], w4);
+                    x[5] = cmul_conj(x[5], cmul(w4, w1));
+                    x[3] = cmul_conj(x[3], cmul(w4, w2));
+                    x[7] = cmul_conj(x[7], cmul(w4, w3));
+                }
+#pragma unroll
+                for (int base = 0; base < 8; base += 2) {
+                    const cplx u = x[base], v = x[base + 1];
+                    x[base] = cadd(u, v);
+                    x[base + 1] = csub(u, v);
+                }
+#pragma unroll
+                for (int base = 0; base < 8; base += 4) {
+                    const cplx u0 = x[base], u1 = x[base + 1], v0 = x[base + 2], v1 = mul_pos_i(x[base + 3]);
+                    x[base] = cadd(u0, v0);
+                    x[base + 2] = csub(u0, v0);
+                    x[base + 1] = cadd(u1, v1);
+                    x[base + 3] = csub(u1, v1);
+                }
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    const cplx u = x[a], d = x[a + 4];
+                    cplx v;                        // d * conj(W_8^a)
+                    if (a == 0) v = d;
+                    else if (a == 1) { v.x = DMUL(DSUB(d.x, d.y), kInvSqrt2); v.y = DMUL(DADD(d.x, d.y), kInvSqrt2); }
+                    else if (a == 2) v = mul_pos_i(d);
+                    else { v.x = -DMUL(DADD(d.x, d.y), kInvSqrt2); v.y = DMUL(DSUB(d.x, d.y), kInvSqrt2); }
+                    x[a] = cadd(u, v);
+                    x[a + 4] = csub(u, v);
+                }
+#pragma unroll
+                for (int m = 0; m < 8; ++m) buf[sw(i0 + m * q)] = x[m];
+            }
+        }
+        if (R == 1) {
+            __syncthreads();
+            for (int b = threadIdx.x; b < M / 2; b += T) {
+                const cplx u = buf[sw(b)], v = cmul_conj(buf[sw(b + M / 2)], left_root(tbl, b));
+                buf[sw(b)] = cadd(u, v);
+                buf[sw(b + M / 2)] = csub(u, v);
+            }
+        } else if (R == 2) {
+            __syncthreads();
+            constexpr int q = M / 4;
+            for (int b = threadIdx.x; b < M / 4; b += T) {
+                const int p0 = sw(b), p1 = sw(b + q), p2 = sw(b + 2 * q), p3 = sw(b + 3 * q);
+                const cplx w1 = tbl[W8 + b], w2 = csqr(w1);
+                const cplx c0 = buf[p0], c1 = cmul_conj(buf[p1], w2), c2 = cmul_conj(buf[p2], w1), c3 = cmul_conj(cmul_conj(buf[p3], w1), w2);
+                const cplx b0 = cadd(c0, c1), b1 = csub(c0, c1), b2 = cadd(c2, c3), b3 = mul_pos_i(csub(c2, c3));
+                buf[p0] = cadd(b0, b2);
+                buf[p2] = csub(b0, b2);
+                buf[p1] = cadd(b1, b3);
+                buf[p3] = csub(b1, b3);
+            }
+        }
+        __syncthreads();
+    }
+};
+
+// the two-stages-per-pass transform behind the same interface
+template <int M, int T>
+struct Fft4 {
+    static constexpr int ENTRIES = Tables<M>::ENTRIES;
+    __device__ static __forceinline__ int sw(int i) { return SW(i); }
+    __device__ static __forceinline__ void make(cplx *tbl, const cplx *__restrict__ tw, int n_over_m) { make_tables<M, T>(tbl, tw, n_over_m); }
+    __device__ static __forceinline__ void fwd(cplx *buf, const cplx *tbl) { fft_fwd<M, T>(buf, tbl); }
+    __device__ static __forceinline__ void inv(cplx *buf, const cplx *tbl) { fft_inv<M, T>(buf, tbl); }
+};
+
 // digit of level `lv` (1 = most significant) of the `levels`-level signed decomposition of x: closest representable
 // (decomposer.rs:98-118), then the carry chain from the least significant level up (iter.rs:120-127)
 __device__ __forceinline__ int64_t signed_digit(uint64_t x, int base_log, int levels, int lv) {
@@ -203,6 +411,43 @@ __device__ __forceinline__ int64_t signed_digit(uint64_t x, int base_log, int le
     return (int64_t)digit;
 }
 
+// a thread's K1 x PER complex accumulators in its own Tensor Memory lane (4 columns per value)
+template <int K1, int PER>
+struct TmemAcc {
+    uint32_t base;
+    __device__ __forceinline__ void store(const cplx (&o)[K1][PER]) const {
+#pragma unroll
+        for (int k = 0; k < K1 * PER / 4; ++k) {
+            uint32_t v[16];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const cplx z = o[(4 * k + e) / PER][(4 * k + e) % PER];
+                v[4 * e] = (uint32_t)__double2loint(z.x); v[4 * e + 1] = (uint32_t)__double2hiint(z.x);
+                v[4 * e + 2] = (uint32_t)__double2loint(z.y); v[4 * e + 3] = (uint32_t)__double2hiint(z.y);
+            }
+            tb16k::tmem_st16(base + 16 * k, v);
+        }
+        tb16k::tmem_wait_st();
+    }
+    __device__ __forceinline__ void load_col(int c, cplx (&oc)[PER]) const {
+#pragma unroll
+        for (int k = 0; k < PER / 4; ++k) {
+            uint32_t v[16];
+            tb16k::tmem_ld16(base + (uint32_t)(c * PER * 4 + 16 * k), v);
+            tb16k::tmem_wait_ld();
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                oc[4 * k + e].x = __hiloint2double((int)v[4 * e + 1], (int)v[4 * e]);
+                oc[4 * k + e].y = __hiloint2double((int)v[4 * e + 3], (int)v[4 * e + 2]);
+            }
+        }
+    }
+    __device__ __forceinline__ void load(cplx (&o)[K1][PER]) const {
+#pragma unroll
+        for (int c = 0; c < K1; ++c) load_col(c, o[c]);
+    }
+};
+
 // w^e = exp(i*pi*e/N) for e in [0, 2N) from the twist table (e < N/2) and the quadrant
 template <int N>
 __device__ __forceinline__ cplx root2n(const cplx *__restrict__ tw, uint32_t e) {
@@ -219,18 +464,29 @@ __device__ __forceinline__ cplx root2n(const cplx *__restrict__ tw, uint32_t e) 
 // `pos` of the transform holds the evaluation at zeta = w^(1 - 4*brev(pos)), so the monomial's spectrum there is w^(deg_j * (1 - 4*brev(pos)))
 // (fft/mod.rs:408-445).  n_iters counts groups.
 template <int LOGN, int K1, int GF>
-__global__ void __launch_bounds__(Shape<LOGN>::T, Shape<LOGN>::MINB)
+__global__ void __launch_bounds__(Shape<LOGN, K1>::T, Shape<LOGN, K1>::MINB)
 pbs_generic_kernel(const uint64_t *__restrict__ lwe_small, const uint32_t *__restrict__ lut_idx, const uint64_t *__restrict__ luts,
                    const cplx *__restrict__ bskf, const cplx *__restrict__ tw, uint64_t *__restrict__ out,
                    const uint32_t *__restrict__ out_slot, int n, int base_log, int levels, int n_iters) {
-    using S = Shape<LOGN>;
+    using S = Shape<LOGN, K1>;
     constexpr int N = S::N, M = S::M, PER = S::PER, T = S::T;
+    using F = typename std::conditional<S::R8, Fft8<M, T>, Fft4<M, T>>::type;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t *acc = reinterpret_cast<uint64_t *>(smem_raw);                 // [K1][N]
     cplx *buf = reinterpret_cast<cplx *>(smem_raw + (size_t)K1 * N * 8);      // [M]
-    cplx *rt = buf + M;                                                       // [Tables<M>::ENTRIES] twiddle tables
+    cplx *rt = buf + M;                                                       // [F::ENTRIES] twiddle tables
     const int ct = blockIdx.x, t = threadIdx.x;
-    make_tables<M, T>(rt, tw, 2);
+    F::make(rt, tw, 2);
+    constexpr bool TM = S::TM;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(rt + F::ENTRIES);
+    TmemAcc<K1, PER> tacc{0};
+    if (TM) {
+        if (t < 32) tb16k::tmem_alloc<S::TM_COLS>(tmem_slot);
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        tacc.base = *tmem_slot + ((uint32_t)(((t >> 5) & 3) * 32) << 16) + (uint32_t)((t >> 7) * 64);    // lane quarter = warp id % 4
+    }
     const uint64_t *lwe = lwe_small + (size_t)ct * (n + 1);
     const auto mod_switch = [](uint64_t x) { return (uint32_t)(((x >> (64 - LOGN - 2)) + 1) >> 1) & (2 * N - 1); };
 
@@ -264,12 +520,15 @@ pbs_generic_kernel(const uint64_t *__restrict__ lwe_small, const uint32_t *__res
             }
         }
         cplx o[K1][PER];
+        if (!S::TM) {
 #pragma unroll
-        for (int c = 0; c < K1; ++c)
+            for (int c = 0; c < K1; ++c)
 #pragma unroll
-            for (int q = 0; q < PER; ++q) { o[c][q].x = 0.0; o[c][q].y = 0.0; }
+                for (int q = 0; q < PER; ++q) { o[c][q].x = 0.0; o[c][q].y = 0.0; }
+        }
         const size_t ggsw_len = (size_t)levels * K1 * K1 * M;
         const cplx *ggsw = bskf + (size_t)i * (GF ? (1 << GF) : 1) * ggsw_len;
+        bool parked = false;                                                 // TM: the accumulators are in Tensor Memory
 
         for (int lv = levels; lv >= 1; --lv) {                               // ggsw.rs:524: level l first
             for (int r = 0; r < K1; ++r) {
@@ -291,14 +550,23 @@ pbs_generic_kernel(const uint64_t *__restrict__ lwe_small, const uint32_t *__res
                     cplx z;
                     z.x = (double)signed_digit(v0, base_log, levels, lv);
                     z.y = (double)signed_digit(v1, base_log, levels, lv);
-                    buf[SW(j)] = cmul(z, __ldg(tw + j));
+                    buf[F::sw(j)] = cmul(z, __ldg(tw + j));
                 }
-                fft_fwd<M, T>(buf, rt);
+                F::fwd(buf, rt);
                 const cplx *g = ggsw + ((size_t)(lv - 1) * K1 + r) * K1 * M;
+                if (TM) {                                                    // the accumulators live in registers only across this loop
+                    if (parked) tacc.load(o);
+                    else {
+#pragma unroll
+                        for (int c = 0; c < K1; ++c)
+#pragma unroll
+                            for (int q = 0; q < PER; ++q) { o[c][q].x = 0.0; o[c][q].y = 0.0; }
+                    }
+                }
 #pragma unroll
                 for (int q = 0; q < PER; ++q) {
                     const int pos = t + T * q;
-                    const cplx f = buf[SW(pos)];
+                    const cplx f = buf[F::sw(pos)];
                     if (GF == 0) {
 #pragma unroll
                         for (int c = 0; c < K1; ++c) {
@@ -321,6 +589,7 @@ pbs_generic_kernel(const uint64_t *__restrict__ lwe_small, const uint32_t *__res
                         }
                     }
                 }
+                if (TM) { tacc.store(o); parked = true; }
                 __syncthreads();                                             // the buffer is rewritten next
             }
         }
@@ -328,12 +597,14 @@ pbs_generic_kernel(const uint64_t *__restrict__ lwe_small, const uint32_t *__res
 #pragma unroll
         for (int c = 0; c < K1; ++c) {
 #pragma unroll
-            for (int q = 0; q < PER; ++q) buf[SW(t + T * q)] = o[c][q];
-            fft_inv<M, T>(buf, rt);
+            if (TM) tacc.load_col(c, o[c]);
+#pragma unroll
+            for (int q = 0; q < PER; ++q) buf[F::sw(t + T * q)] = o[c][q];
+            F::inv(buf, rt);
 #pragma unroll
             for (int q = 0; q < PER; ++q) {
                 const int j = t + T * q;
-                const cplx z = cmul_conj(buf[SW(j)], __ldg(tw + j));
+                const cplx z = cmul_conj(buf[F::sw(j)], __ldg(tw + j));
                 if (GF == 0) {
                     acc[c * N + j] += tb::from_torus_f64(z.x);
                     acc[c * N + j + M] += tb::from_torus_f64(z.y);
@@ -351,6 +622,11 @@ pbs_generic_kernel(const uint64_t *__restrict__ lwe_small, const uint32_t *__res
     for (int r = 0; r < K1 - 1; ++r)
         for (int j = t; j < N; j += T) dst[r * N + j] = j == 0 ? acc[r * N] : (uint64_t)0 - acc[r * N + N - j];
     if (t == 0) dst[(K1 - 1) * N] = acc[(K1 - 1) * N];
+    if (TM) {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (t < 32) tb16k::tmem_dealloc<S::TM_COLS>(*tmem_slot);
+    }
 }
 
 // std key polynomial (u64 torus, fft/mod.rs:197-218) -> the kernel's Fourier layout, scale 2^-64 / (N/2) folded in
@@ -381,8 +657,9 @@ bsk_convert_generic_kernel(const uint64_t *__restrict__ bsk_std, cplx *__restric
 template <int LOGN, int K1, int GF>
 cudaError_t launch(const uint64_t *lwe_small, const uint32_t *lut_idx, const uint64_t *luts, const void *bskf, const void *tw,
                    uint64_t *out, const uint32_t *out_slot, int batch, int n, int base_log, int levels, int n_iters, cudaStream_t stream) {
-    using S = Shape<LOGN>;
-    const size_t smem = (size_t)K1 * S::N * 8 + (size_t)S::M * 16 + (size_t)Tables<S::M>::ENTRIES * 16;
+    using S = Shape<LOGN, K1>;
+    using F = typename std::conditional<S::R8, Fft8<S::M, S::T>, Fft4<S::M, S::T>>::type;
+    const size_t smem = (size_t)K1 * S::N * 8 + (size_t)S::M * 16 + (size_t)F::ENTRIES * 16 + 16;   // + the Tensor Memory base address slot
     // function attributes are per device: set on every launch (microseconds) rather than caching a process-wide flag
     cudaError_t e = cudaFuncSetAttribute(pbs_generic_kernel<LOGN, K1, GF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -412,6 +689,7 @@ cudaError_t convert(const uint64_t *bsk_std, void *bskf, const void *tw, size_t 
 // over ciphertexts blockIdx.x, blockIdx.x + gridDim.x, ...
 // ---------------------------------------------------------------------------------------------------------------------------------
 constexpr int BIG_T = 512, BIG_CH = 4096;
+using BigFft = Fft8<BIG_CH, BIG_T>;
 
 // The last log2(4096) DIF stages of a size-M transform are complete 4096-point transforms of each contiguous block (the stage twiddle
 // W_{2*half}^j does not depend on M), so the shared-memory part is fft_fwd / fft_inv of size BIG_CH with that size's root table.
@@ -429,9 +707,9 @@ __device__ __forceinline__ void fft_fwd_big(cplx *g, cplx *sm, const cplx *rt, c
     }
     for (int c0 = 0; c0 < M; c0 += BIG_CH) {
         __syncthreads();
-        for (int j = threadIdx.x; j < BIG_CH; j += BIG_T) sm[SW(j)] = g[c0 + j];
-        fft_fwd<BIG_CH, BIG_T>(sm, rt);
-        for (int j = threadIdx.x; j < BIG_CH; j += BIG_T) g[c0 + j] = sm[SW(j)];
+        for (int j = threadIdx.x; j < BIG_CH; j += BIG_T) sm[BigFft::sw(j)] = g[c0 + j];
+        BigFft::fwd(sm, rt);
+        for (int j = threadIdx.x; j < BIG_CH; j += BIG_T) g[c0 + j] = sm[BigFft::sw(j)];
     }
     __syncthreads();
 }
@@ -440,9 +718,9 @@ template <int M>
 __device__ __forceinline__ void fft_inv_big(cplx *g, cplx *sm, const cplx *rt, const cplx *__restrict__ tw) {
     for (int c0 = 0; c0 < M; c0 += BIG_CH) {
         __syncthreads();
-        for (int j = threadIdx.x; j < BIG_CH; j += BIG_T) sm[SW(j)] = g[c0 + j];
-        fft_inv<BIG_CH, BIG_T>(sm, rt);
-        for (int j = threadIdx.x; j < BIG_CH; j += BIG_T) g[c0 + j] = sm[SW(j)];
+        for (int j = threadIdx.x; j < BIG_CH; j += BIG_T) sm[BigFft::sw(j)] = g[c0 + j];
+        BigFft::inv(sm, rt);
+        for (int j = threadIdx.x; j < BIG_CH; j += BIG_T) g[c0 + j] = sm[BigFft::sw(j)];
     }
     for (int half = BIG_CH; half <= M / 2; half <<= 1) {
         __syncthreads();
@@ -470,8 +748,8 @@ pbs_generic_big_kernel(const uint64_t *__restrict__ lwe_small, const uint32_t *_
     constexpr int N = 1 << LOGN, M = N / 2, T = BIG_T;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cplx *sm = reinterpret_cast<cplx *>(smem_raw);                                              // [BIG_CH]
-    cplx *rt = sm + BIG_CH;                                                                     // [Tables<BIG_CH>::ENTRIES]
-    make_tables<BIG_CH, BIG_T>(rt, tw, N / BIG_CH);
+    cplx *rt = sm + BIG_CH;                                                                     // [BigFft::ENTRIES]
+    BigFft::make(rt, tw, N / BIG_CH);
     unsigned char *mine = scratch + (size_t)blockIdx.x * big_scratch_bytes<LOGN, K1>();
     uint64_t *acc = reinterpret_cast<uint64_t *>(mine);                                         // [K1][N]
     cplx *buf = reinterpret_cast<cplx *>(mine + (size_t)K1 * N * 8);                            // [M]
@@ -551,7 +829,7 @@ bsk_convert_generic_big_kernel(const uint64_t *__restrict__ bsk_std, cplx *bskf,
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cplx *sm = reinterpret_cast<cplx *>(smem_raw);
     cplx *rt = sm + BIG_CH;
-    make_tables<BIG_CH, BIG_T>(rt, tw, N / BIG_CH);
+    BigFft::make(rt, tw, N / BIG_CH);
     const uint64_t *src = bsk_std + (size_t)blockIdx.x * N;
     cplx *dst = bskf + (size_t)blockIdx.x * M;            // transformed in place
     const double scale = 1.0 / (18446744073709551616.0 * (double)M);
@@ -567,7 +845,7 @@ bsk_convert_generic_big_kernel(const uint64_t *__restrict__ bsk_std, cplx *bskf,
 template <int LOGN, int K1>
 cudaError_t launch_big(const uint64_t *lwe_small, const uint32_t *lut_idx, const uint64_t *luts, const void *bskf, const void *tw,
                        uint64_t *out, const uint32_t *out_slot, int batch, int n, int base_log, int levels, int n_iters, cudaStream_t stream) {
-    const size_t smem = (size_t)BIG_CH * 16 + (size_t)Tables<BIG_CH>::ENTRIES * 16;
+    const size_t smem = (size_t)BIG_CH * 16 + (size_t)BigFft::ENTRIES * 16;
     cudaError_t e = cudaFuncSetAttribute(pbs_generic_big_kernel<LOGN, K1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int dev = 0, sms = 0;
@@ -586,7 +864,7 @@ cudaError_t launch_big(const uint64_t *lwe_small, const uint32_t *lut_idx, const
 
 template <int LOGN>
 cudaError_t convert_big(const uint64_t *bsk_std, void *bskf, const void *tw, size_t n_polys, cudaStream_t stream) {
-    const size_t smem = (size_t)BIG_CH * 16 + (size_t)Tables<BIG_CH>::ENTRIES * 16;
+    const size_t smem = (size_t)BIG_CH * 16 + (size_t)BigFft::ENTRIES * 16;
     cudaError_t e = cudaFuncSetAttribute(bsk_convert_generic_big_kernel<LOGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     bsk_convert_generic_big_kernel<LOGN><<<(unsigned)n_polys, BIG_T, smem, stream>>>(bsk_std, reinterpret_cast<cplx *>(bskf),
