@@ -37,7 +37,8 @@ struct Shape {
     // Memory lane while the FFT passes run (ncu on N = 8192: 1.0 G spill instructions, and with 208 KiB of shared memory there is no L1
     // left, so every spill reload was an L2 round trip -- long_scoreboard 3.1 of 12.5 cycles per instruction)
     static constexpr bool TM = R8 && M >= 2048;
-    static constexpr int TM_COLS = T / 128 * 64;              // warps sharing a lane quarter x 64 columns
+    static constexpr int TM_SLOT = 128;                       // columns per warp: 64 accumulator + 32 twist factors (+ 32 unused)
+    static constexpr int TM_COLS = T / 128 * TM_SLOT;         // warps sharing a lane quarter x slot
     // resident CTAs per SM the register allocation must allow: N = 4096 two 512-thread CTAs (64 registers); N = 512 ... 2048 are capped
     // at 128 registers, which doubles their occupancy (ncu: 234 registers, 8 warps per SM, latency bound; +2 ... +18 %).  N = 256 (k = 5,
     // 24 complex accumulators per thread) is faster uncapped (measured: 80.7 k vs 56.7 k KS-PBS/s with a 168-register cap)
@@ -485,8 +486,15 @@ pbs_generic_kernel(const uint64_t *__restrict__ lwe_small, const uint32_t *__res
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        tacc.base = *tmem_slot + ((uint32_t)(((t >> 5) & 3) * 32) << 16) + (uint32_t)((t >> 7) * 64);    // lane quarter = warp id % 4
+        tacc.base = *tmem_slot + ((uint32_t)(((t >> 5) & 3) * 32) << 16) + (uint32_t)((t >> 7) * S::TM_SLOT);    // lane quarter = warp id % 4
+        // the twist factors of this thread's positions never change: keep them in its Tensor Memory lane as well (ncu: with no L1 left
+        // beside the shared memory, every __ldg(tw + j) of the fold / unfold steps waited for L2)
+        cplx twv[1][PER];
+#pragma unroll
+        for (int q = 0; q < PER; ++q) twv[0][q] = __ldg(tw + t + T * q);
+        TmemAcc<1, PER>{tacc.base + K1 * PER * 4}.store(twv);
     }
+    const TmemAcc<1, PER> ttw{tacc.base + K1 * PER * 4};
     const uint64_t *lwe = lwe_small + (size_t)ct * (n + 1);
     const auto mod_switch = [](uint64_t x) { return (uint32_t)(((x >> (64 - LOGN - 2)) + 1) >> 1) & (2 * N - 1); };
 
@@ -535,6 +543,8 @@ pbs_generic_kernel(const uint64_t *__restrict__ lwe_small, const uint32_t *__res
                 // digits of (acc * X^a_hat - acc)[r] (bootstrap.rs:286-300; multi-bit: of acc[r] itself), folded (coefficient j +
                 // i * coefficient j+M) and twisted
                 const uint64_t *src = acc + r * N;
+                cplx twq[PER];
+                if (TM) ttw.load_col(0, twq);
 #pragma unroll
                 for (int q = 0; q < PER; ++q) {
                     const int j = t + T * q;
@@ -550,7 +560,7 @@ pbs_generic_kernel(const uint64_t *__restrict__ lwe_small, const uint32_t *__res
                     cplx z;
                     z.x = (double)signed_digit(v0, base_log, levels, lv);
                     z.y = (double)signed_digit(v1, base_log, levels, lv);
-                    buf[F::sw(j)] = cmul(z, __ldg(tw + j));
+                    buf[F::sw(j)] = cmul(z, TM ? twq[q] : __ldg(tw + j));
                 }
                 F::fwd(buf, rt);
                 const cplx *g = ggsw + ((size_t)(lv - 1) * K1 + r) * K1 * M;
@@ -601,10 +611,12 @@ pbs_generic_kernel(const uint64_t *__restrict__ lwe_small, const uint32_t *__res
 #pragma unroll
             for (int q = 0; q < PER; ++q) buf[F::sw(t + T * q)] = o[c][q];
             F::inv(buf, rt);
+            cplx twq[PER];
+            if (TM) ttw.load_col(0, twq);
 #pragma unroll
             for (int q = 0; q < PER; ++q) {
                 const int j = t + T * q;
-                const cplx z = cmul_conj(buf[F::sw(j)], __ldg(tw + j));
+                const cplx z = cmul_conj(buf[F::sw(j)], TM ? twq[q] : __ldg(tw + j));
                 if (GF == 0) {
                     acc[c * N + j] += tb::from_torus_f64(z.x);
                     acc[c * N + j + M] += tb::from_torus_f64(z.y);
