@@ -562,8 +562,15 @@ pbs_generic_kernel(const uint64_t *__restrict__ lwe_small, const uint32_t *__res
                     z.y = (double)signed_digit(v1, base_log, levels, lv);
                     buf[F::sw(j)] = cmul(z, TM ? twq[q] : __ldg(tw + j));
                 }
-                F::fwd(buf, rt);
                 const cplx *g = ggsw + ((size_t)(lv - 1) * K1 + r) * K1 * M;
+                if (TM && GF == 0 && LOGN >= 13) {                           // the key values this thread multiplies by after the transform: pull
+#pragma unroll                                                               // them into L2 while the FFT passes run (no registers held).  N = 8192
+                    // only: its key (453 MB) streams from HBM (3_3 +2.5 %); keys that fit the L2 lose 1.5 % to the extra instructions
+                    for (int q = 0; q < PER; ++q)
+#pragma unroll
+                        for (int c = 0; c < K1; ++c) asm volatile("prefetch.global.L2 [%0];" ::"l"(g + (size_t)c * M + t + T * q));
+                }
+                F::fwd(buf, rt);
                 if (TM) {                                                    // the accumulators live in registers only across this loop
                     if (parked) tacc.load(o);
                     else {
