@@ -261,9 +261,17 @@ def bench_string_ops(eng, p, rank, world, local):
     if world > 1:
         # the other shardings of SURVEY 8(e): find = windows split + all-gather of (found, index) + first-rank selection;
         # to_lowercase = chars split + all-gather of the converted blocks
-        out["find_256_16_ops_per_s"] = timed(lambda: MG.sharded_find(execute, params, hay, pat, 256, 16, rank, world, dev), 3)
-        s1024 = pin(rng.integers(0, 2**64, size=(4096, p.big_len), dtype=np.uint64))
-        out["to_lowercase_1024_ops_per_s"] = timed(lambda: MG.sharded_case(execute, params, "to_lowercase", s1024, 1024, rank, world, dev, gather=False), 3)
+        # (every rank takes the same path, so an error here is the same on all of them and cannot strand a collective; it must not cost
+        # the headline line)
+        try:
+            out["find_256_16_ops_per_s"] = timed(lambda: MG.sharded_find(execute, params, hay, pat, 256, 16, rank, world, dev), 3)
+        except Exception as e:
+            out["find_256_16_error"] = str(e)[:200]
+        try:
+            s1024 = pin(rng.integers(0, 2**64, size=(4096, p.big_len), dtype=np.uint64))
+            out["to_lowercase_1024_ops_per_s"] = timed(lambda: MG.sharded_case(execute, params, "to_lowercase", s1024, 1024, rank, world, dev, gather=False), 3)
+        except Exception as e:
+            out["to_lowercase_1024_error"] = str(e)[:200]
     if world == 1:
         cp = Program("string_contains_packed", (256, 16), params=params)
         ins_c = pin(np.concatenate([hay, pat]))
