@@ -347,9 +347,9 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
-        # NCCL prints its version banner on stdout when NCCL_DEBUG is VERSION (this image's default): keep stdout to the one JSON line
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # NCCL writes its version banner (any NCCL_DEBUG level from VERSION up, which the GPU boxes set) and its warnings to stdout by
+        # default: send them to stderr so that stdout stays the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     B = args.batch
