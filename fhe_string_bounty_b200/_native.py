@@ -14,7 +14,7 @@ import numpy as np
 
 _PKG = Path(__file__).resolve().parent
 _SO = _PKG / "libtfhe_b200.so"
-_SOURCES = ["csrc/pbs.cu", "csrc/pbs_v3.cu", "csrc/pbs_v4.cu", "csrc/pbs_v8.cu", "csrc/pbs_multibit.cu", "csrc/pbs_multibit_v4.cu", "csrc/pbs_multibit_v8.cu", "csrc/pbs_generic.cu", "csrc/keyswitch.cu", "csrc/keyswitch_mma.cu", "csrc/leveled.cu", "csrc/seeded.cu", "csrc/c_api.cu", "csrc/host_api.cu"]
+_SOURCES = ["csrc/pbs_v4.cu", "csrc/pbs_v8.cu", "csrc/pbs_multibit_v4.cu", "csrc/pbs_multibit_v8.cu", "csrc/pbs_generic.cu", "csrc/keyswitch.cu", "csrc/keyswitch_mma.cu", "csrc/leveled.cu", "csrc/seeded.cu", "csrc/probe.cu", "csrc/exchange.cu", "csrc/c_api.cu", "csrc/host_api.cu"]
 _HEADERS = ["csrc/fft_core.cuh", "csrc/fft16_core.cuh", "csrc/fft8_core.cuh", "csrc/pbs16_common.cuh", "csrc/pbs8_common.cuh", "csrc/ring_helpers.cuh", "csrc/kernels.h", "csrc/ctx.h", "csrc/host/program.h", "csrc/host/radix.h", "csrc/host/strings.h", "../include/tfhe_b200.h"]
 
 NVCC_FLAGS = [
@@ -198,6 +198,7 @@ EXPORTS = {
     "tfhe_b200_ks_pbs_batch_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "tfhe_b200_synchronize": (C.c_int, [C.c_void_p]),
     "tfhe_b200_pbs_batch_partial": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32]),
+    "tfhe_b200_set_tuning": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "tfhe_b200_kernel_launches": (C.c_uint64, [C.c_void_p]),
     "tfhe_b200_time_last_kernels": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "tfhe_b200_probe_fp64_tflops": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
@@ -208,7 +209,17 @@ EXPORTS = {
     "tfhe_b200_program_copy": (C.c_int, [C.c_void_p] + [C.c_void_p] * 11),
     "tfhe_b200_program_accumulators": (C.c_int, [C.c_void_p, C.c_void_p]),
     "tfhe_b200_program_run": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "tfhe_b200_program_run_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "tfhe_b200_program_last_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+    "tfhe_b200_exchange_create": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]),
+    "tfhe_b200_exchange_handle": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "tfhe_b200_exchange_attach": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "tfhe_b200_exchange_attach_local": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "tfhe_b200_exchange_send_rows": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "tfhe_b200_exchange_gather_stride": (C.c_size_t, [C.c_void_p, C.c_uint32]),
+    "tfhe_b200_exchange_all_gather": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "tfhe_b200_exchange_all_reduce_sum": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "tfhe_b200_exchange_destroy": (C.c_int, [C.c_void_p]),
 }
 
 _lib = None
@@ -366,6 +377,10 @@ class Engine:
 
     def synchronize(self):
         self._check(self.lib.tfhe_b200_synchronize(self.h))
+
+    def set_tuning(self, key: str, value: int):
+        """kernel selection at run time (include/tfhe_b200.h: narrow_kernel, narrow_max, ks_kernel)"""
+        self._check(self.lib.tfhe_b200_set_tuning(self.h, key.encode(), int(value)))
 
     # instrumentation -------------------------------------------------------------------------------------
     @property

@@ -1,6 +1,9 @@
 // c_api.cu -- extern "C" boundary of libtfhe_b200.so (see include/tfhe_b200.h for the reference
 // interfaces each entry point replaces).  Plain pointers and sizes only; no torch types.
 #include "ctx.h"
+
+#include <atomic>
+#include <memory>
 #include "host/wire.h"
 #include <chrono>
 
@@ -45,7 +48,7 @@ int check_params(const tfhe_b200_params &p) {
 
 namespace tbc {
 
-bool fused_supported(const tfhe_b200_ctx *c) { return c->ks_kernel == 1 && c->pbs_kernel >= 3 && c->p.grouping_factor == 0 && !c->generic; }
+bool fused_supported(const tfhe_b200_ctx *c) { return c->ks_kernel == 1 && c->p.grouping_factor == 0 && !c->generic; }
 
 int do_keyswitch(tfhe_b200_ctx *c, const uint64_t *d_in, uint64_t *d_small, size_t batch, cudaStream_t s, const uint32_t *in_slot,
                  DevBuf *digits, bool fused) {
@@ -53,7 +56,7 @@ int do_keyswitch(tfhe_b200_ctx *c, const uint64_t *d_in, uint64_t *d_small, size
     if (!digits) digits = &c->ks_digits;
     if (!c->have_ksk) return fail("keyswitch key not uploaded");
     if (c->ks_kernel == 1) {
-        TB_CUDA(digits->reserve(tbk::ks_mma_digits_bytes((int)batch, (int)(c->p.glwe_dim * c->p.poly_size), (int)c->p.ks_level)));
+        TB_CUDA(digits->reserve_on(tbk::ks_mma_digits_bytes((int)batch, (int)(c->p.glwe_dim * c->p.poly_size), (int)c->p.ks_level), s));
         TB_CUDA(tbk::launch_keyswitch_mma(d_in, in_slot, (uint8_t *)digits->p, (const uint8_t *)c->ksk_planes.p,
                                           (const uint64_t *)c->ksk_colsum.p, d_small, (int)batch, (int)(c->p.glwe_dim * c->p.poly_size),
                                           (int)c->p.lwe_dim, (int)c->p.ks_base_log, (int)c->p.ks_level, fused ? tb::kLogN + 1 : 0, s));
@@ -95,39 +98,33 @@ static int do_pbs_kernels(tfhe_b200_ctx *c, const uint64_t *d_small, const uint3
     }
     if (c->p.grouping_factor == 3) {
         const uint32_t groups = c->p.lwe_dim / 3;
-        if (c->mb_kernel == 4) {
-            // whole waves of 3 ciphertexts per SM, then the remainder on the 1- / 2-ciphertext instances if it fits them (the launcher
-            // picks the instance from the batch size); a remainder or a whole level of at most one ciphertext per SM runs on the
-            // 8-points-per-thread kernel pbs_multibit_v8.cu
-            const size_t wave = (size_t)3 * c->sms, rem = batch % wave;
-            const size_t tail = batch <= (size_t)2 * c->sms ? batch : (rem != 0 && rem <= (size_t)2 * c->sms) ? rem : 0, wide = batch - tail;
-            const int steps = (int)(n_iters < groups ? n_iters : groups);
-            if (wide) {
-                TB_CUDA(tbk::launch_pbs_multibit_v4(d_small, d_idx, d_luts, c->bskf.p, c->tbl16.p, c->roots.p, d_out, out_slot, (int)wide,
-                                                    (int)c->p.lwe_dim, (int)c->p.pbs_base_log, steps, s));
-                c->launches += 1;
-            }
-            if (tail) {
-                const uint64_t *t_small = d_small + wide * (size_t)(c->p.lwe_dim + 1);
-                uint64_t *t_out = out_slot ? d_out : d_out + wide * ((size_t)c->p.glwe_dim * c->p.poly_size + 1);
-                if (c->narrow_kernel == 8 && tail <= (size_t)(c->narrow_max ? c->narrow_max : c->sms))
-                    TB_CUDA(tbk::launch_pbs_multibit_v8(t_small, d_idx ? d_idx + wide : nullptr, d_luts, c->bskf8.p, c->tbl8.p, c->roots.p, t_out,
-                                                        out_slot ? out_slot + wide : nullptr, (int)tail, (int)c->p.lwe_dim,
-                                                        (int)c->p.pbs_base_log, steps, s));
-                else
-                    TB_CUDA(tbk::launch_pbs_multibit_v4(t_small, d_idx ? d_idx + wide : nullptr, d_luts, c->bskf.p, c->tbl16.p, c->roots.p, t_out,
-                                                        out_slot ? out_slot + wide : nullptr, (int)tail, (int)c->p.lwe_dim,
-                                                        (int)c->p.pbs_base_log, steps, s));
-                c->launches += 1;
-            }
-            return 0;
-        } else
-            TB_CUDA(tbk::launch_pbs_multibit(d_small, d_idx, d_luts, c->bskf.p, c->tbl.p, c->roots.p, d_out, out_slot, (int)batch,
-                                             (int)c->p.lwe_dim, (int)c->p.pbs_base_log, (int)(n_iters < groups ? n_iters : groups), s));
-        c->launches += 1;
+        // whole waves of 3 ciphertexts per SM, then the remainder on the 1- / 2-ciphertext instances if it fits them (the launcher
+        // picks the instance from the batch size); a remainder or a whole level of at most one ciphertext per SM runs on the
+        // 8-points-per-thread kernel pbs_multibit_v8.cu
+        const size_t wave = (size_t)3 * c->sms, rem = batch % wave;
+        const size_t tail = batch <= (size_t)2 * c->sms ? batch : (rem != 0 && rem <= (size_t)2 * c->sms) ? rem : 0, wide = batch - tail;
+        const int steps = (int)(n_iters < groups ? n_iters : groups);
+        if (wide) {
+            TB_CUDA(tbk::launch_pbs_multibit_v4(d_small, d_idx, d_luts, c->bskf.p, c->tbl16.p, c->roots.p, d_out, out_slot, (int)wide,
+                                                (int)c->p.lwe_dim, (int)c->p.pbs_base_log, steps, s));
+            c->launches += 1;
+        }
+        if (tail) {
+            const uint64_t *t_small = d_small + wide * (size_t)(c->p.lwe_dim + 1);
+            uint64_t *t_out = out_slot ? d_out : d_out + wide * ((size_t)c->p.glwe_dim * c->p.poly_size + 1);
+            if (c->narrow_kernel == 8 && tail <= (size_t)(c->narrow_max ? c->narrow_max : c->sms))
+                TB_CUDA(tbk::launch_pbs_multibit_v8(t_small, d_idx ? d_idx + wide : nullptr, d_luts, c->bskf8.p, c->tbl8.p, c->roots.p, t_out,
+                                                    out_slot ? out_slot + wide : nullptr, (int)tail, (int)c->p.lwe_dim,
+                                                    (int)c->p.pbs_base_log, steps, s));
+            else
+                TB_CUDA(tbk::launch_pbs_multibit_v4(t_small, d_idx ? d_idx + wide : nullptr, d_luts, c->bskf.p, c->tbl16.p, c->roots.p, t_out,
+                                                    out_slot ? out_slot + wide : nullptr, (int)tail, (int)c->p.lwe_dim,
+                                                    (int)c->p.pbs_base_log, steps, s));
+            c->launches += 1;
+        }
         return 0;
     }
-    if (c->pbs_kernel == 4) {
+    {
         // Wide part: whole waves of 4 ciphertexts per SM on pbs_v4.cu.  What is left over, if it fits two ciphertexts per SM, runs on
         // the narrow-level kernel pbs_v8.cu (2.9 ms for <= SM count, 4.4 ms for <= 2 x SM count) instead of a mostly empty 7.8 ms wave.
         const size_t wave = (size_t)4 * c->sms, narrow = c->narrow_kernel == 8 ? (size_t)(c->narrow_max ? c->narrow_max : 2 * c->sms) : 0;
@@ -150,16 +147,6 @@ static int do_pbs_kernels(tfhe_b200_ctx *c, const uint64_t *d_small, const uint3
         }
         return 0;
     }
-    if (c->pbs_kernel == 3) {
-        TB_CUDA(tbk::launch_pbs_classic_v3(d_small, d_idx, d_luts, c->bskf.p, c->tbl.p, d_out, out_slot, (int)batch, (int)c->p.lwe_dim,
-                                           (int)c->p.pbs_base_log, (int)n_iters, fused ? 1 : 0, s));
-        c->launches += 1;
-        return 0;
-    }
-    TB_CUDA(tbk::launch_pbs_classic(d_small, d_idx, d_luts, c->bskf.p, c->tbl.p, d_out, out_slot, (int)batch,
-                                    (int)c->p.lwe_dim, (int)c->p.pbs_base_log, (int)n_iters, s));
-    c->launches += 1;
-    return 0;
 }
 
 }  // namespace tbc
@@ -185,7 +172,11 @@ int tfhe_b200_ctx_create(int cuda_device, const tfhe_b200_params *params, tfhe_b
     TB_CUDA(cudaGetDeviceCount(&count));
     if (cuda_device < 0 || cuda_device >= count) return fail("no such CUDA device (this engine has no CPU fallback)");
     DeviceGuard g(cuda_device);
-    tfhe_b200_ctx *c = new tfhe_b200_ctx();
+    static std::atomic<uint64_t> next_id{1};
+    // every early return below (TB_CUDA) destroys the half-built context: streams, events and buffers do not leak
+    std::unique_ptr<tfhe_b200_ctx, int (*)(tfhe_b200_ctx *)> guard(new tfhe_b200_ctx(), tfhe_b200_ctx_destroy);
+    tfhe_b200_ctx *c = guard.get();
+    c->id = next_id.fetch_add(1);
     c->device = cuda_device;
     c->p = *params;
     TB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -193,7 +184,6 @@ int tfhe_b200_ctx_create(int cuda_device, const tfhe_b200_params *params, tfhe_b
     for (auto &L : c->lane) TB_CUDA(cudaStreamCreateWithFlags(&L.s, cudaStreamNonBlocking));
     if (const char *e = std::getenv("TFHE_B200_KS_KERNEL")) c->ks_kernel = (e[0] == 'i') ? 0 : 1;
     if (!tbk::ks_mma_supported((int)params->ks_level)) c->ks_kernel = 0;
-    if (const char *e = std::getenv("TFHE_B200_PBS_KERNEL")) c->pbs_kernel = (e[0] == '2') ? 2 : (e[0] == '3') ? 3 : 4;
     c->generic = !(params->poly_size == (uint32_t)tb::kN && params->glwe_dim == 1 && params->pbs_level == 1) || params->grouping_factor == 2;
     if (const char *e = std::getenv("TFHE_B200_PBS_KERNEL")) if (e[0] == 'g') c->generic = true;
     if (c->generic) {   // twist table of pbs_generic.cu: exp(i*pi*j/N), j < N/2 (fft/mod.rs:58-69)
@@ -204,15 +194,11 @@ int tfhe_b200_ctx_create(int cuda_device, const tfhe_b200_params *params, tfhe_b
         TB_CUDA(c->tw_generic.reserve(tw.size() * 8));
         TB_CUDA(cudaMemcpy(c->tw_generic.p, tw.data(), tw.size() * 8, cudaMemcpyHostToDevice));
     }
-    TB_CUDA(tbk::pbs_configure());
-    TB_CUDA(tbk::pbs_v3_configure());
     TB_CUDA(tbk::pbs_v4_configure());
     TB_CUDA(tbk::pbs_v8_configure());
     if (const char *e = std::getenv("TFHE_B200_NARROW_KERNEL")) c->narrow_kernel = (e[0] == '8') ? 8 : 0;
     if (const char *e = std::getenv("TFHE_B200_NARROW_MAX")) c->narrow_max = atoi(e);
     TB_CUDA(cudaDeviceGetAttribute(&c->sms, cudaDevAttrMultiProcessorCount, cuda_device));
-    if (const char *e = std::getenv("TFHE_B200_MB_KERNEL")) c->mb_kernel = (e[0] == '3') ? 3 : 4;
-    TB_CUDA(tbk::pbs_multibit_configure());
     TB_CUDA(tbk::pbs_multibit_v4_configure());
     TB_CUDA(tbk::pbs_multibit_v8_configure());
     {   // roots[e] = exp(i*pi*e/2048): monomial spectra of the multi-bit combine
@@ -223,11 +209,7 @@ int tfhe_b200_ctx_create(int cuda_device, const tfhe_b200_params *params, tfhe_b
         TB_CUDA(cudaMemcpy(c->roots.p, r.data(), r.size() * 8, cudaMemcpyHostToDevice));
     }
     TB_CUDA(tbk::ks_configure((int)params->ks_level));
-    // inter-pass twiddle table
-    std::vector<double> tbl(2 * tb::kM);
-    tb_make_twiddle_table(tbl.data());
-    TB_CUDA(c->tbl.reserve(tbl.size() * sizeof(double)));
-    TB_CUDA(cudaMemcpyAsync(c->tbl.p, tbl.data(), tbl.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    // twiddle tables of the 16- and 8-points-per-thread FFTs
     std::vector<double> tbl16(2 * (tb::kM + 64));
     tb16_make_tables(tbl16.data(), tbl16.data() + 2 * tb::kM);
     TB_CUDA(c->tbl16.reserve(tbl16.size() * sizeof(double)));
@@ -237,7 +219,7 @@ int tfhe_b200_ctx_create(int cuda_device, const tfhe_b200_params *params, tfhe_b
     TB_CUDA(c->tbl8.reserve(tbl8.size() * sizeof(double)));
     TB_CUDA(cudaMemcpyAsync(c->tbl8.p, tbl8.data(), tbl8.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     TB_CUDA(cudaStreamSynchronize(c->stream));
-    *out = c;
+    *out = guard.release();
     return 0;
 }
 
@@ -249,11 +231,31 @@ int tfhe_b200_set_ciphertext_modulus_log2(tfhe_b200_ctx *c, uint32_t log2_q) {
     return 0;
 }
 
+int tfhe_b200_set_tuning(tfhe_b200_ctx *c, const char *key, int value) {
+    if (!c || !key) return fail("null argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    const std::string k(key);
+    if (k == "narrow_kernel") {
+        if (value != 0 && value != 8) return fail("narrow_kernel must be 0 or 8");
+        c->narrow_kernel = value;
+    } else if (k == "narrow_max") {
+        if (value < 0) return fail("narrow_max must be >= 0");
+        c->narrow_max = value;
+    } else if (k == "ks_kernel") {
+        if (value != 0 && value != 1) return fail("ks_kernel must be 0 (IMAD) or 1 (tensor cores)");
+        if (value == 1 && !tbk::ks_mma_supported((int)c->p.ks_level)) return fail("tensor-core keyswitch does not support this level count");
+        if (value == 1 && c->have_ksk && !c->ksk_planes.p) return fail("the keyswitch key was uploaded for the IMAD kernel only: upload it again after selecting ks_kernel = 1");
+        c->ks_kernel = value;
+    } else
+        return fail("unknown tuning key '" + k + "'");
+    return 0;
+}
+
 int tfhe_b200_ctx_destroy(tfhe_b200_ctx *c) {
     if (!c) return 0;
     DeviceGuard g(c->device);
     cudaStreamSynchronize(c->stream);
-    for (DevBuf *b : {&c->ksk_packed, &c->ksk_colsum, &c->ksk_planes, &c->ks_digits, &c->bskf, &c->bskf8, &c->tbl, &c->tbl16, &c->tbl8, &c->tw_generic, &c->roots, &c->luts, &c->d_in, &c->d_small, &c->d_out, &c->d_idx})
+    for (DevBuf *b : {&c->ksk_packed, &c->ksk_colsum, &c->ksk_planes, &c->ks_digits, &c->bskf, &c->bskf8, &c->tbl16, &c->tbl8, &c->tw_generic, &c->roots, &c->luts, &c->d_in, &c->d_small, &c->d_out, &c->d_idx})
         b->release();
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     for (auto &L : c->lane) {
@@ -295,28 +297,19 @@ static int finish_bsk(tfhe_b200_ctx *c, const tbc::DevBuf &raw) {
     TB_CUDA(c->bskf.reserve(n_polys * (c->p.poly_size / 2) * sizeof(double) * 2));
     if (c->generic)
         TB_CUDA(tbk::launch_bsk_convert_generic((const uint64_t *)raw.p, c->bskf.p, c->tw_generic.p, n_polys, (int)c->p.poly_size, c->stream));
-    else if (c->p.grouping_factor == 3 && c->mb_kernel == 4)
-    {
+    else if (c->p.grouping_factor == 3) {
         TB_CUDA(tbk::launch_bsk_convert_multibit_v4((const uint64_t *)raw.p, c->bskf.p, c->tbl16.p, (int)n_polys, c->stream));
-        if (c->narrow_kernel == 8) {   // second copy of the key for the narrow-level kernel
-            TB_CUDA(c->bskf8.reserve(n_polys * tb::kM * sizeof(double) * 2));
-            TB_CUDA(tbk::launch_bsk_convert_multibit_v8((const uint64_t *)raw.p, c->bskf8.p, c->tbl8.p, (int)n_polys, c->stream));
-        }
-    }
-    else if (c->p.grouping_factor == 3)
-        TB_CUDA(tbk::launch_bsk_convert_multibit((const uint64_t *)raw.p, c->bskf.p, c->tbl.p, (int)n_polys, c->stream));
-    else if (c->pbs_kernel == 4) {
+        // second copy of the key for the narrow-level kernel (always built: the narrow-kernel choice can change per context at run time)
+        TB_CUDA(c->bskf8.reserve(n_polys * tb::kM * sizeof(double) * 2));
+        TB_CUDA(tbk::launch_bsk_convert_multibit_v8((const uint64_t *)raw.p, c->bskf8.p, c->tbl8.p, (int)n_polys, c->stream));
+        c->launches += 1;
+    } else {
         TB_CUDA(tbk::launch_bsk_convert_v4((const uint64_t *)raw.p, c->bskf.p, c->tbl16.p, (int)n_polys, c->stream));
-        if (c->narrow_kernel == 8) {   // second copy of the key, in the narrow-level kernel's (thread, register) order
-            TB_CUDA(c->bskf8.reserve(n_polys * tb::kM * sizeof(double) * 2));
-            TB_CUDA(tbk::launch_bsk_convert_v8((const uint64_t *)raw.p, c->bskf8.p, c->tbl8.p, (int)n_polys, c->stream));
-            c->launches += 1;
-        }
+        // second copy of the key, in the narrow-level kernel's (thread, register) order
+        TB_CUDA(c->bskf8.reserve(n_polys * tb::kM * sizeof(double) * 2));
+        TB_CUDA(tbk::launch_bsk_convert_v8((const uint64_t *)raw.p, c->bskf8.p, c->tbl8.p, (int)n_polys, c->stream));
+        c->launches += 1;
     }
-    else if (c->pbs_kernel == 3)
-        TB_CUDA(tbk::launch_bsk_convert_v3((const uint64_t *)raw.p, c->bskf.p, c->tbl.p, (int)n_polys, c->stream));
-    else
-        TB_CUDA(tbk::launch_bsk_convert((const uint64_t *)raw.p, c->bskf.p, c->tbl.p, (int)n_polys, c->stream));
     c->launches += 1;
     TB_CUDA(cudaStreamSynchronize(c->stream));
     c->have_bsk = true;
@@ -527,7 +520,7 @@ int tfhe_b200_ks_pbs_batch_device(tfhe_b200_ctx *c, const uint64_t *d_in, const 
     std::lock_guard<std::mutex> lk(c->mu);
     DeviceGuard g(c->device);
     cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
-    TB_CUDA(c->d_small.reserve(batch * c->small_len() * 8));
+    TB_CUDA(c->d_small.reserve_on(batch * c->small_len() * 8, s));
     TB_CUDA(cudaEventRecord(c->ev[0], s));
     const bool fused = tbc::fused_supported(c);
     if (tbc::do_keyswitch(c, d_in, (uint64_t *)c->d_small.p, batch, s, nullptr, nullptr, fused)) return 1;
@@ -540,6 +533,15 @@ int tfhe_b200_ks_pbs_batch_device(tfhe_b200_ctx *c, const uint64_t *d_in, const 
 }
 
 // ---- host-buffer entry points ---------------------------------------------------------------------
+
+// a LUT index past the uploaded table would be an out-of-bounds device read: reject it where the indices are host-visible
+static int check_lut_indices(const tfhe_b200_ctx *c, const uint32_t *idx, size_t batch) {
+    if (!idx) return 0;
+    for (size_t i = 0; i < batch; ++i)
+        if (idx[i] >= c->n_luts)
+            return fail("lut_idx[" + std::to_string(i) + "] = " + std::to_string(idx[i]) + " but only " + std::to_string(c->n_luts) + " lookup tables are uploaded");
+    return 0;
+}
 
 int tfhe_b200_keyswitch_batch(tfhe_b200_ctx *c, const uint64_t *in, uint64_t *out, size_t batch) {
     if (!c || (batch && (!in || !out))) return fail("null argument");
@@ -560,6 +562,7 @@ static int pbs_host(tfhe_b200_ctx *c, const uint64_t *in, const uint32_t *idx, u
     if (batch == 0) return 0;
     if (n_iters > c->p.lwe_dim) return fail("n_iters exceeds lwe_dim");
     std::lock_guard<std::mutex> lk(c->mu);
+    if (check_lut_indices(c, idx, batch)) return 1;
     DeviceGuard g(c->device);
     TB_CUDA(c->d_small.reserve(batch * c->small_len() * 8));
     TB_CUDA(c->d_out.reserve(batch * c->big_len() * 8));
@@ -593,12 +596,13 @@ int tfhe_b200_ks_pbs_batch(tfhe_b200_ctx *c, const uint64_t *in, const uint32_t 
     if (!c->have_bsk) return fail("bootstrap key not uploaded");
     if (c->n_luts == 0) return fail("no lookup tables uploaded");
     std::lock_guard<std::mutex> lk(c->mu);
+    if (check_lut_indices(c, idx, batch)) return 1;
     DeviceGuard g(c->device);
     // chunks of whole waves (classic: 4 ciphertexts per SM x 4 waves; multi-bit: 3 per SM x 5 waves), alternating between two lanes
     // (stream + staging buffers)
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
-    const size_t chunk = std::min<size_t>(batch, c->p.grouping_factor && c->mb_kernel == 4 ? (size_t)sms * 3 * 5 : (size_t)sms * 4 * 4);
+    const size_t chunk = std::min<size_t>(batch, c->p.grouping_factor ? (size_t)sms * 3 * 5 : (size_t)sms * 4 * 4);
     const size_t L = c->big_len();
     for (auto &ln : c->lane) {
         TB_CUDA(ln.in.reserve(chunk * L * 8));
@@ -631,6 +635,7 @@ int tfhe_b200_pbs_ks_batch(tfhe_b200_ctx *c, const uint64_t *in, const uint32_t 
     if (batch == 0) return 0;
     if (c->n_luts == 0) return fail("no lookup tables uploaded");
     std::lock_guard<std::mutex> lk(c->mu);
+    if (check_lut_indices(c, idx, batch)) return 1;
     DeviceGuard g(c->device);
     cudaStream_t s = c->stream;
     TB_CUDA(c->d_small.reserve(batch * c->small_len() * 8));

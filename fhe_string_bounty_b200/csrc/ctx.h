@@ -24,14 +24,28 @@ int fail(const std::string &msg);   // records the thread-local error string, re
             return tbc::fail(std::string(#expr) + ": " + cudaGetErrorString(e__));                 \
     } while (0)
 
-struct DevBuf {
+struct DevBuf {   // owning device allocation; freed on scope exit (error paths included).  The owner sets the device first.
     void *p = nullptr;
     size_t cap = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { release(); }
     cudaError_t reserve(size_t bytes) {
         if (bytes <= cap) return cudaSuccess;
         if (p) cudaFree(p);
         p = nullptr; cap = 0;
         cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    // stream-ordered growth for the per-call scratch of the device entry points: cudaFree would synchronise the whole device (and, with
+    // several ranks driven by one process, wait for a peer's exchange kernel that itself waits for this rank)
+    cudaError_t reserve_on(size_t bytes, cudaStream_t s) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaError_t e = cudaFreeAsync(p, s); if (e != cudaSuccess) return e; }
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMallocAsync(&p, bytes, s);
         if (e == cudaSuccess) cap = bytes;
         return e;
     }
@@ -47,23 +61,22 @@ struct DeviceGuard {
 }  // namespace tbc
 
 struct tfhe_b200_ctx {
+    uint64_t id = 0;      // unique per process: programs remember the id of the context they are bound to, not its address
     int device = 0;
     tfhe_b200_params p{};
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     bool timed = false;
     // keys
-    tbc::DevBuf ksk_packed, ksk_colsum, ksk_planes, ks_digits, bskf, bskf8, tbl, tbl16, tbl8, tw_generic, roots, luts;
+    tbc::DevBuf ksk_packed, ksk_colsum, ksk_planes, ks_digits, bskf, bskf8, tbl16, tbl8, tw_generic, roots, luts;
     int ks_kernel = 1;    // 1: tensor-core GEMM (keyswitch_mma.cu), 0: IMAD GEMM (keyswitch.cu); env TFHE_B200_KS_KERNEL=imad
     uint32_t n_luts = 0;
     bool have_ksk = false, have_bsk = false;
-    int narrow_kernel = 8;   // classic PBS, levels of <= 2 * SM count ciphertexts: 8 = pbs_v8.cu (8 FFT points per thread, 8 warps per ciphertext; keeps a second copy of the Fourier key in its own layout), 0 = the narrow instances of pbs_kernel; env TFHE_B200_NARROW_KERNEL
+    int narrow_kernel = 8;   // classic PBS, levels of <= 2 * SM count ciphertexts: 8 = pbs_v8.cu (8 FFT points per thread, 8 warps per ciphertext; keeps a second copy of the Fourier key in its own layout), 0 = the 1- / 2-ciphertext instances of pbs_v4.cu; env TFHE_B200_NARROW_KERNEL
     bool generic = false;    // parameter sets outside N = 2048, k = 1, l = 1 (or TFHE_B200_PBS_KERNEL=generic): pbs_generic.cu, no fused modulus switch
     int log2_q = 64;         // ciphertext modulus 2^log2_q; < 64: PBS outputs are rounded to multiples of 2^(64 - log2_q) (bootstrap.rs:318-330)
     int sms = 148;
     int narrow_max = 0;      // widest level the narrow kernel takes (0 = 2 * SM count); env TFHE_B200_NARROW_MAX
-    int mb_kernel = 4;    // multi-bit: 4 = pbs_multibit_v4.cu (16 points per thread), 3 = pbs_multibit.cu; env TFHE_B200_MB_KERNEL
-    int pbs_kernel = 4;   // 4: TMEM + TMA ring, 16 FFT points per thread (pbs_v4.cu); 3: same data path, 32 points per thread (pbs_v3.cu); 2: one CTA per ciphertext (pbs.cu); env TFHE_B200_PBS_KERNEL
     // staging for the host-pointer entry points
     tbc::DevBuf d_in, d_small, d_out, d_idx;
     // two copy/compute lanes for the host-buffer KS-PBS entry point: H2D of chunk k+1 and D2H of chunk k-1 overlap the

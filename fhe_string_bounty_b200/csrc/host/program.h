@@ -175,6 +175,11 @@ class Program {
     // ---- apply_lookup_table (server_key/mod.rs:457-476 -> 783-857) ---------------------------------------------
     Ct pbs(const Ct &a, uint32_t lut) {
         const Lut &l = luts_.lut(lut);
+        // the LUT only covers [0, total_mod): a larger value reaches the padding bit and comes back as -f(x - total_mod)
+        // (max_degree of shortint/server_key/mod.rs:91-103: msg_mod * carry_mod - 1)
+        if (a.degree >= p_.total_mod())
+            throw std::logic_error("apply_lookup_table on a ciphertext of degree " + std::to_string(a.degree) + " >= message space " +
+                                   std::to_string(p_.total_mod()));
         if (a.is_trivial()) {  // mod.rs:788-791 trivial short cut: pure table lookup, no crypto
             Ct r; r.body = luts_.trivial_pbs(lut, a.body); r.degree = l.degree; r.noise = 0; r.ready = a.ready;
             ++n_trivial_pbs_;

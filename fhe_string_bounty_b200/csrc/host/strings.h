@@ -210,19 +210,23 @@ class StringServerKey {
             for (size_t i = k * BLK + 1; i < std::min(W, (k + 1) * BLK); ++i) sum = pg.unchecked_add(sum, m[i]);
             any[k] = pg.pbs(sum, [](uint64_t x) { return uint64_t(x != 0); });
         }
-        // before_k: "some earlier block matched".  Prefix sums of booleans overflow after 15 terms, so carry a cleaned flag
-        // forward every 15 blocks (one extra PBS per 15 blocks, still the same level for the first 15).
+        // before_k: "some earlier block matched".  A prefix sum of booleans must stay <= total_mod - 1 = 15 (the next value would reach
+        // the padding bit and the LUT would return -f(0)), so a cleaned flag is carried forward from group to group: the first group
+        // sums 15 blocks, every later group its carry + 14 blocks (one extra PBS per group, still the same level for the first group).
         std::vector<Ct> before(n_blk);
         before[0] = pg.create_trivial(0);
         {
-            Ct carry = pg.create_trivial(0);   // cleaned "matched before this group of 15 blocks"
-            for (size_t g0 = 0; g0 < n_blk; g0 += 15) {
+            const size_t max_sum = p.total_mod() - 1;
+            Ct carry = pg.create_trivial(0);   // cleaned "matched before this group of blocks"
+            for (size_t g0 = 0; g0 < n_blk;) {
+                const size_t g1 = std::min(n_blk, g0 + (g0 == 0 ? max_sum : max_sum - 1));
                 Ct run = carry;
-                for (size_t k = g0; k < std::min(n_blk, g0 + 15); ++k) {
+                for (size_t k = g0; k < g1; ++k) {
                     if (k > 0) before[k] = pg.pbs(run, [](uint64_t x) { return uint64_t(x != 0); });
                     run = pg.unchecked_add(run, any[k]);
                 }
-                if (g0 + 15 < n_blk) carry = pg.pbs(run, [](uint64_t x) { return uint64_t(x != 0); });
+                if (g1 < n_blk) carry = pg.pbs(run, [](uint64_t x) { return uint64_t(x != 0); });
+                g0 = g1;
             }
         }
         std::vector<Ct> first(W);

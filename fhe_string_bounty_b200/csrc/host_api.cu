@@ -17,8 +17,10 @@ struct tfhe_b200_program {
     std::unique_ptr<tbh::LutRegistry> luts;
     std::unique_ptr<tbh::Program> prog;
     std::string op;
-    // device copies (valid for `owner`)
-    tfhe_b200_ctx *owner = nullptr;
+    // device copies, valid for the context with id `owner_id` on CUDA device `device` (ids are unique per process, so a destroyed
+    // context whose address is reused is never mistaken for the owner; the buffers are plain device memory and outlive the context)
+    uint64_t owner_id = 0;
+    int device = -1;
     DevBuf d_luts, d_lin, d_terms, d_pbs_in, d_pbs_out, d_pbs_lut, d_arena, d_out_slots, d_out_rows;
     std::vector<uint32_t> lin_off, pbs_off;   // per level offsets
     float last_ms = 0.f;
@@ -210,6 +212,97 @@ bool record(tfhe_b200_program &h, const std::string &op_in, const uint64_t *a, s
     return false;
 }
 
+// frees the device copy of a program on the device it was uploaded to (no context needed: the owner may already be gone)
+void release_device_state(tfhe_b200_program &h) {
+    if (h.device < 0) return;
+    DeviceGuard g(h.device);
+    for (DevBuf *b : {&h.d_luts, &h.d_lin, &h.d_terms, &h.d_pbs_in, &h.d_pbs_out, &h.d_pbs_lut, &h.d_arena, &h.d_out_slots, &h.d_out_rows}) b->release();
+    if (h.ev0) cudaEventDestroy(h.ev0);
+    if (h.ev1) cudaEventDestroy(h.ev1);
+    h.ev0 = h.ev1 = nullptr;
+    h.owner_id = 0;
+    h.device = -1;
+}
+
+bool same_params(const tfhe_b200_params &q, const tbh::Params &p) {
+    return q.lwe_dim == p.lwe_dim && q.glwe_dim == p.glwe_dim && q.poly_size == p.poly_size && q.pbs_base_log == p.pbs_base_log &&
+           q.pbs_level == p.pbs_level && q.ks_base_log == p.ks_base_log && q.ks_level == p.ks_level &&
+           q.grouping_factor == p.grouping_factor && q.msg_mod == p.msg_mod && q.carry_mod == p.carry_mod;
+}
+
+// first run on this context: upload the program (accumulators, instruction arrays) and size its arena.  A program bound to another
+// context is re-bound (its old device copy is dropped); `owner_id` is only set once every upload has succeeded.
+int bind_program(tfhe_b200_ctx *c, tfhe_b200_program *h) {
+    if (h->owner_id == c->id) return 0;
+    release_device_state(*h);
+    const tbh::Program &pg = *h->prog;
+    cudaStream_t s = c->stream;
+    const size_t L = c->big_len();
+    h->device = c->device;            // from here on release_device_state() knows where the partial uploads live
+    TB_CUDA(cudaEventCreate(&h->ev0));
+    TB_CUDA(cudaEventCreate(&h->ev1));
+    std::vector<uint64_t> accs(std::max<size_t>(h->luts->size(), 1) * h->p.lut_len());
+    for (size_t u = 0; u < h->luts->size(); ++u) h->luts->fill_accumulator(uint32_t(u), accs.data() + u * h->p.lut_len());
+    TB_CUDA(h->d_luts.reserve(accs.size() * 8));
+    TB_CUDA(cudaMemcpyAsync(h->d_luts.p, accs.data(), accs.size() * 8, cudaMemcpyHostToDevice, s));
+    std::vector<tbk::LinInstr> lin;
+    std::vector<uint32_t> pin, pout, plut;
+    for (auto &l : pg.levels()) {
+        for (auto &i : l.lin) lin.push_back({i.out_slot, i.term_begin, i.term_end, 0u, i.body_add});
+        for (auto &j : l.pbs) { pin.push_back(j.in_slot); pout.push_back(j.out_slot); plut.push_back(j.lut); }
+    }
+    std::vector<tbk::LinTerm> terms;
+    for (auto &t : pg.terms()) terms.push_back({t.slot, 0u, t.coef});
+    auto up = [&](DevBuf &b, const void *src, size_t bytes) -> cudaError_t {
+        cudaError_t e = b.reserve(std::max<size_t>(bytes, 16));
+        if (e != cudaSuccess || bytes == 0) return e;
+        return cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, s);
+    };
+    TB_CUDA(up(h->d_lin, lin.data(), lin.size() * sizeof(tbk::LinInstr)));
+    TB_CUDA(up(h->d_terms, terms.data(), terms.size() * sizeof(tbk::LinTerm)));
+    TB_CUDA(up(h->d_pbs_in, pin.data(), pin.size() * 4));
+    TB_CUDA(up(h->d_pbs_out, pout.data(), pout.size() * 4));
+    TB_CUDA(up(h->d_pbs_lut, plut.data(), plut.size() * 4));
+    TB_CUDA(up(h->d_out_slots, pg.outputs().data(), pg.outputs().size() * 4));
+    TB_CUDA(h->d_out_rows.reserve(std::max<size_t>(pg.outputs().size(), 1) * L * 8));
+    TB_CUDA(h->d_arena.reserve(std::max<size_t>(pg.n_slots(), 1) * L * 8));
+    TB_CUDA(cudaStreamSynchronize(s));   // the staging vectors above go out of scope
+    h->owner_id = c->id;
+    return 0;
+}
+
+// enqueues every level of the program on stream `s`: inputs are already in arena rows [0, n_inputs); the output rows end up in `d_out`
+int enqueue_levels(tfhe_b200_ctx *c, tfhe_b200_program *h, uint64_t *d_out, cudaStream_t s) {
+    const tbh::Program &pg = *h->prog;
+    const size_t L = c->big_len();
+    uint64_t *arena = (uint64_t *)h->d_arena.p;
+    TB_CUDA(cudaEventRecord(h->ev0, s));
+    size_t max_w = 0;
+    for (auto &l : pg.levels()) max_w = std::max(max_w, l.pbs.size());
+    TB_CUDA(c->d_small.reserve_on(std::max<size_t>(max_w, 1) * c->small_len() * 8, s));
+    for (size_t lv = 0; lv < pg.levels().size(); ++lv) {
+        const uint32_t l0 = h->lin_off[lv], l1 = h->lin_off[lv + 1], p0 = h->pbs_off[lv], p1 = h->pbs_off[lv + 1];
+        if (l1 > l0) {
+            TB_CUDA(tbk::launch_linear(arena, (const tbk::LinInstr *)h->d_lin.p + l0, (const tbk::LinTerm *)h->d_terms.p, int(l1 - l0), int(L), s));
+            c->launches += 1;
+        }
+        if (p1 > p0) {
+            const size_t w = p1 - p0;
+            const bool fused = tbc::fused_supported(c);
+            if (tbc::do_keyswitch(c, arena, (uint64_t *)c->d_small.p, w, s, (const uint32_t *)h->d_pbs_in.p + p0, nullptr, fused)) return 1;
+            if (tbc::do_pbs(c, (const uint64_t *)c->d_small.p, (const uint32_t *)h->d_pbs_lut.p + p0, (const uint64_t *)h->d_luts.p, arena, w,
+                            c->p.lwe_dim, s, (const uint32_t *)h->d_pbs_out.p + p0, fused))
+                return 1;
+        }
+    }
+    TB_CUDA(cudaEventRecord(h->ev1, s));
+    if (!pg.outputs().empty()) {   // gather the output rows on the device
+        TB_CUDA(tbk::launch_gather_rows(arena, (const uint32_t *)h->d_out_slots.p, d_out, (int)pg.outputs().size(), (int)L, s));
+        c->launches += 1;
+    }
+    return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -244,12 +337,7 @@ int tfhe_b200_program_build(const tfhe_b200_params *params, const char *op, cons
 
 int tfhe_b200_program_destroy(tfhe_b200_program *h) {
     if (!h) return 0;
-    if (h->owner) {
-        DeviceGuard g(h->owner->device);
-        for (DevBuf *b : {&h->d_luts, &h->d_lin, &h->d_terms, &h->d_pbs_in, &h->d_pbs_out, &h->d_pbs_lut, &h->d_arena, &h->d_out_slots, &h->d_out_rows}) b->release();
-        if (h->ev0) cudaEventDestroy(h->ev0);
-        if (h->ev1) cudaEventDestroy(h->ev1);
-    }
+    release_device_state(*h);
     delete h;
     return 0;
 }
@@ -313,80 +401,49 @@ int tfhe_b200_program_run(tfhe_b200_ctx *c, tfhe_b200_program *h, const uint64_t
     if (!c || !h) return fail("null argument");
     const tbh::Program &pg = *h->prog;
     if ((pg.n_inputs() && !inputs) || (!pg.outputs().empty() && !outputs)) return fail("null buffer");
-    if (to_host_params(c->p).poly_size != h->p.poly_size || c->p.lwe_dim != h->p.lwe_dim || c->p.msg_mod != h->p.msg_mod ||
-        c->p.carry_mod != h->p.carry_mod)
-        return fail("program was recorded for other parameters than the context");
+    if (!same_params(c->p, h->p)) return fail("program was recorded for other parameters than the context");
     std::lock_guard<std::mutex> lk(c->mu);
     DeviceGuard g(c->device);
     cudaStream_t s = c->stream;
     const size_t L = c->big_len();
-    if (h->owner != c) {   // first run on this context: upload the program once
-        if (h->owner) return fail("program already bound to another context");
-        h->owner = c;
-        TB_CUDA(cudaEventCreate(&h->ev0));
-        TB_CUDA(cudaEventCreate(&h->ev1));
-        std::vector<uint64_t> accs(std::max<size_t>(h->luts->size(), 1) * h->p.lut_len());
-        for (size_t u = 0; u < h->luts->size(); ++u) h->luts->fill_accumulator(uint32_t(u), accs.data() + u * h->p.lut_len());
-        TB_CUDA(h->d_luts.reserve(accs.size() * 8));
-        TB_CUDA(cudaMemcpyAsync(h->d_luts.p, accs.data(), accs.size() * 8, cudaMemcpyHostToDevice, s));
-        std::vector<tbk::LinInstr> lin;
-        std::vector<uint32_t> pin, pout, plut;
-        for (auto &l : pg.levels()) {
-            for (auto &i : l.lin) lin.push_back({i.out_slot, i.term_begin, i.term_end, 0u, i.body_add});
-            for (auto &j : l.pbs) { pin.push_back(j.in_slot); pout.push_back(j.out_slot); plut.push_back(j.lut); }
-        }
-        std::vector<tbk::LinTerm> terms;
-        for (auto &t : pg.terms()) terms.push_back({t.slot, 0u, t.coef});
-        auto up = [&](DevBuf &b, const void *src, size_t bytes) -> cudaError_t {
-            cudaError_t e = b.reserve(std::max<size_t>(bytes, 16));
-            if (e != cudaSuccess || bytes == 0) return e;
-            return cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, s);
-        };
-        TB_CUDA(up(h->d_lin, lin.data(), lin.size() * sizeof(tbk::LinInstr)));
-        TB_CUDA(up(h->d_terms, terms.data(), terms.size() * sizeof(tbk::LinTerm)));
-        TB_CUDA(up(h->d_pbs_in, pin.data(), pin.size() * 4));
-        TB_CUDA(up(h->d_pbs_out, pout.data(), pout.size() * 4));
-        TB_CUDA(up(h->d_pbs_lut, plut.data(), plut.size() * 4));
-        TB_CUDA(up(h->d_out_slots, pg.outputs().data(), pg.outputs().size() * 4));
-        TB_CUDA(h->d_out_rows.reserve(std::max<size_t>(pg.outputs().size(), 1) * L * 8));
-        TB_CUDA(h->d_arena.reserve(std::max<size_t>(pg.n_slots(), 1) * L * 8));
-        TB_CUDA(cudaStreamSynchronize(s));   // the staging vectors above go out of scope
-    }
-    uint64_t *arena = (uint64_t *)h->d_arena.p;
-    if (pg.n_inputs()) TB_CUDA(cudaMemcpyAsync(arena, inputs, (size_t)pg.n_inputs() * L * 8, cudaMemcpyHostToDevice, s));
-    TB_CUDA(cudaEventRecord(h->ev0, s));
-    size_t max_w = 0;
-    for (auto &l : pg.levels()) max_w = std::max(max_w, l.pbs.size());
-    TB_CUDA(c->d_small.reserve(std::max<size_t>(max_w, 1) * c->small_len() * 8));
-    for (size_t lv = 0; lv < pg.levels().size(); ++lv) {
-        const uint32_t l0 = h->lin_off[lv], l1 = h->lin_off[lv + 1], p0 = h->pbs_off[lv], p1 = h->pbs_off[lv + 1];
-        if (l1 > l0) {
-            TB_CUDA(tbk::launch_linear(arena, (const tbk::LinInstr *)h->d_lin.p + l0, (const tbk::LinTerm *)h->d_terms.p, int(l1 - l0), int(L), s));
-            c->launches += 1;
-        }
-        if (p1 > p0) {
-            const size_t w = p1 - p0;
-            const bool fused = tbc::fused_supported(c);
-            if (tbc::do_keyswitch(c, arena, (uint64_t *)c->d_small.p, w, s, (const uint32_t *)h->d_pbs_in.p + p0, nullptr, fused)) return 1;
-            if (tbc::do_pbs(c, (const uint64_t *)c->d_small.p, (const uint32_t *)h->d_pbs_lut.p + p0, (const uint64_t *)h->d_luts.p, arena, w,
-                            c->p.lwe_dim, s, (const uint32_t *)h->d_pbs_out.p + p0, fused))
-                return 1;
-        }
-    }
-    TB_CUDA(cudaEventRecord(h->ev1, s));
-    if (!pg.outputs().empty()) {   // gather the output rows on the device, one copy back
-        TB_CUDA(tbk::launch_gather_rows(arena, (const uint32_t *)h->d_out_slots.p, (uint64_t *)h->d_out_rows.p, (int)pg.outputs().size(), (int)L, s));
-        c->launches += 1;
+    if (bind_program(c, h)) return 1;
+    if (pg.n_inputs()) TB_CUDA(cudaMemcpyAsync(h->d_arena.p, inputs, (size_t)pg.n_inputs() * L * 8, cudaMemcpyHostToDevice, s));
+    if (enqueue_levels(c, h, (uint64_t *)h->d_out_rows.p, s)) return 1;
+    if (!pg.outputs().empty())     // one copy back
         TB_CUDA(cudaMemcpyAsync(outputs, h->d_out_rows.p, pg.outputs().size() * L * 8, cudaMemcpyDeviceToHost, s));
-    }
     TB_CUDA(cudaStreamSynchronize(s));
     TB_CUDA(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
     return 0;
 }
 
+/* The same on DEVICE buffers of the context's GPU, enqueued on `cuda_stream` (NULL = the context's own stream) WITHOUT synchronising:
+ * d_inputs n_inputs x (k*N+1) words, d_outputs n_outputs x (k*N+1) words.  This is what chains a rank's share of a sharded string
+ * operation, the exchange of the narrow-end blocks and the finishing program without a host round trip (multi_gpu.py).
+ * One stream at a time per context: the keyswitch scratch and the program's arena are per context / per program. */
+int tfhe_b200_program_run_device(tfhe_b200_ctx *c, tfhe_b200_program *h, const uint64_t *d_inputs, uint64_t *d_outputs, void *cuda_stream) {
+    if (!c || !h) return fail("null argument");
+    const tbh::Program &pg = *h->prog;
+    if ((pg.n_inputs() && !d_inputs) || (!pg.outputs().empty() && !d_outputs)) return fail("null buffer");
+    if (!same_params(c->p, h->p)) return fail("program was recorded for other parameters than the context");
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : c->stream;
+    const size_t L = c->big_len();
+    if (bind_program(c, h)) return 1;
+    if (pg.n_inputs()) TB_CUDA(cudaMemcpyAsync(h->d_arena.p, d_inputs, (size_t)pg.n_inputs() * L * 8, cudaMemcpyDeviceToDevice, s));
+    h->last_ms = -1.f;    // not synchronised: tfhe_b200_program_last_ms reads the events on demand
+    return enqueue_levels(c, h, d_outputs, s);
+}
+
 /* Device time (ms, CUDA events on the context stream) of the kernels of the last tfhe_b200_program_run. */
 int tfhe_b200_program_last_ms(const tfhe_b200_program *h, float *ms) {
     if (!h || !ms) return fail("null argument");
+    if (h->last_ms < 0.f && h->ev1) {   // last run was tfhe_b200_program_run_device: wait for its end event
+        DeviceGuard g(h->device);
+        TB_CUDA(cudaEventSynchronize(h->ev1));
+        TB_CUDA(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+        return 0;
+    }
     *ms = h->last_ms;
     return 0;
 }

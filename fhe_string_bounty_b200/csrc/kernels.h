@@ -21,30 +21,13 @@ cudaError_t launch_keyswitch_mma(const uint64_t *lwe_in, const uint32_t *in_slot
                                  int ms_log2_2n, cudaStream_t stream);
 size_t ks_mma_digits_bytes(int batch, int in_dim, int level);
 
-// pbs.cu
-cudaError_t pbs_configure();
-cudaError_t launch_pbs_classic(const uint64_t *lwe_small, const uint32_t *lut_idx, const uint64_t *luts, const void *bskf,
-                               const void *tbl, uint64_t *out, const uint32_t *out_slot, int batch, int n, int base_log,
-                               int n_iters, cudaStream_t stream);
-cudaError_t launch_bsk_convert(const uint64_t *bsk_std, void *bskf, const void *tbl, int n_polys, cudaStream_t stream);
-// pbs_v3.cu
-cudaError_t pbs_v3_configure();
-cudaError_t launch_pbs_classic_v3(const uint64_t *lwe_small, const uint32_t *lut_idx, const uint64_t *luts, const void *bskf3,
-                                  const void *tbl, uint64_t *out, const uint32_t *out_slot, int batch, int n, int base_log,
-                                  int n_iters, int small_is_u16, cudaStream_t stream);
-cudaError_t launch_bsk_convert_v3(const uint64_t *bsk_std, void *bskf3, const void *tbl, int n_polys, cudaStream_t stream);
 // pbs_v4.cu (tbl16 = the two twiddle tables of fft16_core.cuh, 1024 + 64 complex values)
 cudaError_t pbs_v4_configure();
 cudaError_t launch_pbs_classic_v4(const uint64_t *lwe_small, const uint32_t *lut_idx, const uint64_t *luts, const void *bskf4,
                                   const void *tbl16, uint64_t *out, const uint32_t *out_slot, int batch, int n, int base_log,
                                   int n_iters, int small_is_u16, cudaStream_t stream);
 cudaError_t launch_bsk_convert_v4(const uint64_t *bsk_std, void *bskf4, const void *tbl16, int n_polys, cudaStream_t stream);
-// pbs_multibit.cu
-cudaError_t pbs_multibit_configure();
-cudaError_t launch_pbs_multibit(const uint64_t *lwe_small, const uint32_t *lut_idx, const uint64_t *luts, const void *bskm,
-                                const void *tbl, const void *roots, uint64_t *out, const uint32_t *out_slot, int batch, int n,
-                                int base_log, int n_groups, cudaStream_t stream);
-cudaError_t launch_bsk_convert_multibit(const uint64_t *bsk_std, void *bskm, const void *tbl, int n_polys, cudaStream_t stream);
+// probe.cu
 cudaError_t launch_fp64_peak(double *sink, int blocks, int iters, cudaStream_t stream);
 
 // leveled.cu

@@ -165,7 +165,41 @@ int tfhe_b200_program_copy(const tfhe_b200_program *prog, uint32_t *level_lin_of
                            uint64_t *output_degree_noise);
 int tfhe_b200_program_accumulators(const tfhe_b200_program *prog, uint64_t *accs);
 int tfhe_b200_program_run(tfhe_b200_ctx *ctx, tfhe_b200_program *prog, const uint64_t *inputs, uint64_t *outputs);
+/* Same on DEVICE buffers of the context's GPU, enqueued on `cuda_stream` (NULL = the context's stream) without synchronising; chains a
+ * rank's share of a sharded operation, the exchange below and the finishing program with no host round trip in between. */
+int tfhe_b200_program_run_device(tfhe_b200_ctx *ctx, tfhe_b200_program *prog, const uint64_t *d_inputs, uint64_t *d_outputs,
+                                 void *cuda_stream);
 int tfhe_b200_program_last_ms(const tfhe_b200_program *prog, float *ms);
+
+/* ---- multi-GPU: the one exchange step of a sharded string operation, over NVLink peer memory ------------------------------------
+ * One process per GPU; keys replicated; haystack windows / chars partitioned.  Where the wide levels are sharded, the
+ * narrow end of the reduction tree -- which the CPU reference hands over through shared memory inside one rayon reduction
+ * (are_all_comparisons_block_true / is_at_least_one_comparisons_block_true, integer/server_key/radix_parallel/scalar_comparison.rs:
+ * 147-240; the sign tree, integer/server_key/comparator.rs:257-279,957-971) -- crosses GPUs exactly once.  The engine does that
+ * exchange itself: every rank owns a symmetric buffer (CUDA IPC), a rank's last tree level writes its rows straight into its send
+ * area, and ONE kernel publishes a flag to every peer, waits for all peers' flags and pulls their rows with peer loads, concatenating
+ * (all_gather) or summing them modulo 2^64 = homomorphic addition (all_reduce_sum).  No NCCL call and no host synchronisation sit
+ * between a rank's share, the exchange and the finishing program (fhe_string_bounty_b200/csrc/exchange.cu).
+ *   create -> handle (64-byte CUDA IPC handle; ship it to every peer by any transport) -> attach (all handles, rank order)
+ *   send_rows: where the NEXT exchange's local rows go (max_rows x (k*N+1) words) -- pass it as d_outputs of program_run_device
+ *   all_gather: d_out = world parts of gather_stride(rows) words each;  all_reduce_sum: d_out = rows x (k*N+1) words (+1 pad if odd)
+ * d_out must be 16-byte aligned.  Destroy the exchange before its context.  attach_local serves several GPUs driven by one process. */
+typedef struct tfhe_b200_exchange tfhe_b200_exchange;
+int tfhe_b200_exchange_create(tfhe_b200_ctx *ctx, uint32_t rank, uint32_t world, uint32_t max_rows, tfhe_b200_exchange **out);
+int tfhe_b200_exchange_handle(tfhe_b200_exchange *ex, uint8_t handle[64]);
+int tfhe_b200_exchange_attach(tfhe_b200_exchange *ex, const uint8_t *handles);
+int tfhe_b200_exchange_attach_local(tfhe_b200_exchange *ex, tfhe_b200_exchange *const *peers);
+int tfhe_b200_exchange_send_rows(tfhe_b200_exchange *ex, uint64_t **d_rows);
+size_t tfhe_b200_exchange_gather_stride(const tfhe_b200_exchange *ex, uint32_t rows);
+int tfhe_b200_exchange_all_gather(tfhe_b200_exchange *ex, uint32_t rows, uint64_t *d_out, void *cuda_stream);
+int tfhe_b200_exchange_all_reduce_sum(tfhe_b200_exchange *ex, uint32_t rows, uint64_t *d_out, void *cuda_stream);
+int tfhe_b200_exchange_destroy(tfhe_b200_exchange *ex);
+
+/* Kernel selection (A/B comparisons and the parity tests that pin one kernel instance); the same keys are read from the environment at
+ * context creation as TFHE_B200_<KEY>.  Keys: "narrow_kernel" (8 = pbs_v8.cu / pbs_multibit_v8.cu serve levels of at most narrow_max
+ * ciphertexts and level tails, 0 = the 1- / 2-ciphertext instances of the wide kernels), "narrow_max" (0 = default: 2 x SM count
+ * classic, SM count multi-bit), "ks_kernel" (1 = tensor-core keyswitch, 0 = IMAD keyswitch). */
+int tfhe_b200_set_tuning(tfhe_b200_ctx *ctx, const char *key, int value);
 
 /* Instrumentation. */
 uint64_t tfhe_b200_kernel_launches(const tfhe_b200_ctx *ctx);   /* kernels launched by this context so far */

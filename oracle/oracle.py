@@ -100,6 +100,7 @@ def lib():
         "orc_add_external_product_exact": (None, [_PP, _u64p, _u64p, _u64p]),
         "orc_pbs_f64": (None, [_PP, C.c_void_p, _u64p, _u64p, _u64p]),
         "orc_pbs_f64_pow2_modulus": (None, [_PP, C.c_void_p, _u64p, _u64p, _u64p, C.c_uint32]),
+        "orc_pbs_f64_partial": (None, [_PP, C.c_void_p, _u64p, _u64p, _u64p, C.c_size_t]),
         "orc_pbs_exact": (None, [_PP, _u64p, _u64p, _u64p, _u64p]),
         "orc_ks_pbs_batch": (C.c_int, [_PP, _u64p, C.c_void_p, _u64p, C.c_void_p, _u64p, _u64p, C.c_void_p, C.c_size_t, C.c_int]),
         "orc_max_threads": (C.c_int, []),
@@ -278,6 +279,12 @@ class ServerKey:
             lib().orc_pbs_exact(C.byref(self.p), self.bsk, np.ascontiguousarray(lwe_small), acc, out)
         else:
             lib().orc_pbs_f64(C.byref(self.p), self.fourier, np.ascontiguousarray(lwe_small), acc, out)
+        return out
+
+    def pbs_partial(self, lwe_small: np.ndarray, acc: np.ndarray, n_steps: int) -> np.ndarray:
+        """PBS stopped after n_steps mask elements (classic) / groups (multi-bit): what tfhe_b200_pbs_batch_partial computes."""
+        out = np.zeros(self.p.big_dim + 1, dtype=np.uint64)
+        lib().orc_pbs_f64_partial(C.byref(self.p), self.fourier, np.ascontiguousarray(lwe_small), np.ascontiguousarray(acc), out, n_steps)
         return out
 
     def pbs_pow2_modulus(self, lwe_small: np.ndarray, acc: np.ndarray, log2_q: int) -> np.ndarray:

@@ -760,8 +760,10 @@ static void prepare_multi_bit_ggsw(const orc_params *p, const orc_fourier_bsk *f
     }
 }
 
-static void blind_rotate_f64(const orc_params *p, const orc_fourier_bsk *f, const uint64_t *lwe_in,
-                             pbs_scratch *s) {
+/* max_steps bounds the number of mask elements (classic) / groups (multi-bit) that are processed: the test hook behind
+ * orc_pbs_f64_partial, mirroring tfhe_b200_pbs_batch_partial; SIZE_MAX = the whole blind rotation */
+static void blind_rotate_f64_steps(const orc_params *p, const orc_fourier_bsk *f, const uint64_t *lwe_in,
+                                   pbs_scratch *s, size_t max_steps) {
     size_t N = p->poly_size, M = N / 2, k1 = p->glwe_dim + 1, n = p->lwe_dim;
     uint32_t lgN = ilog2(N);
     size_t plane = f->ggsw_polys * M;
@@ -770,7 +772,7 @@ static void blind_rotate_f64(const orc_params *p, const orc_fourier_bsk *f, cons
     for (size_t q = 0; q < k1; q++) orc_monomial_div(s->ct1 + q * N, s->ct0 + q * N, N, b_hat);
     memcpy(s->ct0, s->ct1, k1 * N * 8);
     if (p->grouping_factor == 0) {
-        for (size_t i = 0; i < n; i++) { /* bootstrap.rs:279-316 */
+        for (size_t i = 0; i < n && i < max_steps; i++) { /* bootstrap.rs:279-316 */
             if (lwe_in[i] == 0) continue;
             size_t a_hat = (size_t)orc_modulus_switch(lwe_in[i], lgN);
             for (size_t q = 0; q < k1; q++) orc_monomial_mul_and_subtract(s->ct1 + q * N, s->ct0 + q * N, N, a_hat);
@@ -780,7 +782,7 @@ static void blind_rotate_f64(const orc_params *p, const orc_fourier_bsk *f, cons
         /* deterministic order (lwe_multi_bit_programmable_bootstrapping.rs:755-800): dst = 0; dst += G (x) src */
         size_t g = p->grouping_factor, groups = n / g;
         uint64_t *src = s->ct0, *dst = s->ct1;
-        for (size_t grp = 0; grp < groups; grp++) {
+        for (size_t grp = 0; grp < groups && grp < max_steps; grp++) {
             prepare_multi_bit_ggsw(p, f, grp, lwe_in + grp * g, s);
             memset(dst, 0, k1 * N * 8);
             add_external_product_f64_planes(p, s->g_re, s->g_im, dst, src, s);
@@ -788,6 +790,10 @@ static void blind_rotate_f64(const orc_params *p, const orc_fourier_bsk *f, cons
         }
         if (src != s->ct0) memcpy(s->ct0, src, k1 * N * 8);
     }
+}
+
+static void blind_rotate_f64(const orc_params *p, const orc_fourier_bsk *f, const uint64_t *lwe_in, pbs_scratch *s) {
+    blind_rotate_f64_steps(p, f, lwe_in, s, (size_t)-1);
 }
 
 static void pbs_f64_with_scratch(const orc_params *p, const orc_fourier_bsk *f, const uint64_t *lwe_in,
@@ -816,6 +822,18 @@ void orc_pbs_f64_pow2_modulus(const orc_params *p, const orc_fourier_bsk *f, con
 void orc_pbs_f64(const orc_params *p, const orc_fourier_bsk *f, const uint64_t *lwe_in, const uint64_t *acc, uint64_t *lwe_out) {
     pbs_scratch s; scratch_init(&s, p);
     pbs_f64_with_scratch(p, f, lwe_in, acc, lwe_out, &s);
+    scratch_free(&s);
+}
+
+/* PBS that stops after n_steps blind-rotation steps (mask elements, or groups for the multi-bit PBS), then extracts the sample:
+ * n_steps = 0 is LUT rotation + extraction (integer only), n_steps = 1 one external product (ggsw.rs:477-598). */
+void orc_pbs_f64_partial(const orc_params *p, const orc_fourier_bsk *f, const uint64_t *lwe_in, const uint64_t *acc, uint64_t *lwe_out,
+                         size_t n_steps) {
+    size_t N = p->poly_size, k1 = p->glwe_dim + 1;
+    pbs_scratch s; scratch_init(&s, p);
+    memcpy(s.ct0, acc, k1 * N * 8);
+    blind_rotate_f64_steps(p, f, lwe_in, &s, n_steps);
+    orc_sample_extract0(p, s.ct0, lwe_out);
     scratch_free(&s);
 }
 

@@ -108,6 +108,9 @@ void orc_add_external_product_exact(const orc_params *p, const uint64_t *ggsw_st
 /* PBS (bootstrap.rs:242-364 classic; lwe_multi_bit_programmable_bootstrapping.rs deterministic order).
  * lwe_in: n+1 words under the small key; acc: (k+1)*N LUT; lwe_out: k*N+1 words. */
 void orc_pbs_f64(const orc_params *p, const orc_fourier_bsk *f, const uint64_t *lwe_in, const uint64_t *acc, uint64_t *lwe_out);
+/* test hook mirroring tfhe_b200_pbs_batch_partial: stop after n_steps mask elements (classic) / groups (multi-bit) */
+void orc_pbs_f64_partial(const orc_params *p, const orc_fourier_bsk *f, const uint64_t *lwe_in, const uint64_t *acc, uint64_t *lwe_out,
+                         size_t n_steps);
 void orc_pbs_exact(const orc_params *p, const uint64_t *bsk_std, const uint64_t *lwe_in, const uint64_t *acc, uint64_t *lwe_out);
 
 /* shortint/server_key/mod.rs:783-857: batched KS -> PBS, one independent ciphertext per OpenMP thread

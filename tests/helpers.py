@@ -50,3 +50,38 @@ def phase_error(ck, cts, expected_values):
         d = (ph - (int(v) << 59)) % 2**64
         errs.append(min(d, 2**64 - d))
     return np.array(errs, dtype=np.float64)
+
+
+def simulate_program_clear(ir, inputs_clear, total_mod):
+    """Noise-free execution of a recorded program on PLAINTEXT values: a slot holds its value modulo 2 * total_mod (message space plus
+    the padding bit), leveled instructions are exact, a PBS is the table lookup the blind rotation performs -- f(x) below the padding
+    bit, -f(x - total_mod) above it (negacyclic LUT, shortint/server_key/mod.rs:763-781).  Any operand that reaches the padding bit is
+    reported: returns (outputs, n_padding_hits).  Used for programs far too large for the CPU oracle's real PBS."""
+    M = 2 * total_mod
+    delta = (1 << 63) // total_mod
+    val = np.zeros(ir.n_slots, dtype=np.int64)
+    val[: ir.n_inputs] = np.asarray(inputs_clear, dtype=np.int64)
+    hits = 0
+    for lv in range(len(ir.level_lin_off) - 1):
+        for li in range(int(ir.level_lin_off[lv]), int(ir.level_lin_off[lv + 1])):
+            out, tb, te = (int(v) for v in ir.lin[li])
+            body = int(ir.lin_body[li])
+            assert body % delta == 0, "plaintext bodies are multiples of delta"
+            acc = body // delta
+            for t in range(tb, te):
+                acc += int(ir.term_coef[t]) * int(val[ir.term_slot[t]])
+            val[out] = acc % M
+        for j in range(int(ir.level_pbs_off[lv]), int(ir.level_pbs_off[lv + 1])):
+            src, dst, lut = (int(v) for v in ir.pbs[j])
+            x = int(val[src])
+            if x >= total_mod:
+                hits += 1
+                val[dst] = (-int(ir.lut_tables[lut][x - total_mod])) % M
+            else:
+                val[dst] = int(ir.lut_tables[lut][x])
+    return val[ir.outputs], hits
+
+
+def string_blocks_clear(s: bytes):
+    """4 little-endian 2-bit blocks per char"""
+    return [(ch >> (2 * b)) & 3 for ch in s for b in range(4)]

@@ -41,31 +41,37 @@ def test_missing_keys_and_bad_arguments_fail_loudly(orc, keys_2_2):
     eng.close()
 
 
-def test_both_keyswitch_kernels_and_all_pbs_kernels_agree(orc, keys_2_2, monkeypatch):
-    """The IMAD keyswitch and the tensor-core keyswitch are bit-identical; the v2, v3 and v4 blind-rotation kernels decrypt to
-    the same values.  v2 and v3 share the 32 x 32 FFT of fft_core.cuh and produce identical words; v4 evaluates the same
-    transform as 16 x 4 x 16 (fft16_core.cuh), so only its rounding differs."""
+def test_both_keyswitch_kernels_and_both_pbs_kernel_families_agree(orc, keys_2_2):
+    """The IMAD keyswitch and the tensor-core keyswitch are bit-identical (exact integer arithmetic, different association order of
+    wrapping sums); the narrow-level kernel (pbs_v8.cu, 8 x 8 x 4 x 4 FFT) and the 1-ciphertext instance of the wide kernel
+    (pbs_v4.cu, 16 x 4 x 16 FFT) evaluate the same transform with different rounding: identical LUT rotation, one CMUX within the
+    stated 2^44, same decrypted values.  Kernel selection through tfhe_b200_set_tuning (the wide instances are pinned in
+    tests/test_gpu_wide_kernels.py)."""
     import fhe_string_bounty_b200 as F
     p, ck, sk = keys_2_2
     acc, _ = sk.generate_lookup_table(lambda x: (7 * x + 2) % 16)
     cts = ck.encrypt_batch(np.arange(37) % 16)
-    outs, kss = {}, {}
-    for ks_k, pbs_k in (("imad", "2"), ("mma", "3"), ("mma", "2"), ("mma", "4")):
-        monkeypatch.setenv("TFHE_B200_KS_KERNEL", ks_k)
-        monkeypatch.setenv("TFHE_B200_PBS_KERNEL", pbs_k)
-        eng = F.Engine(engine_params(p))
-        eng.upload_ksk(sk.ksk)
-        eng.upload_bsk_std(sk.bsk)
-        eng.upload_luts(acc[None, :])
-        kss[(ks_k, pbs_k)] = eng.keyswitch_batch(cts)
-        outs[(ks_k, pbs_k)] = eng.ks_pbs_batch(cts, None)
-        eng.close()
-    assert np.array_equal(kss[("imad", "2")], kss[("mma", "3")])
+    eng = F.Engine(engine_params(p))
+    eng.upload_ksk(sk.ksk)
+    eng.upload_bsk_std(sk.bsk)
+    eng.upload_luts(acc[None, :])
+    outs, kss, part = {}, {}, {}
+    for ks_k, narrow in ((0, 8), (1, 8), (1, 0)):
+        eng.set_tuning("ks_kernel", ks_k)
+        eng.set_tuning("narrow_kernel", narrow)
+        kss[(ks_k, narrow)] = eng.keyswitch_batch(cts)
+        outs[(ks_k, narrow)] = eng.ks_pbs_batch(cts, None)
+        part[(ks_k, narrow)] = [eng.pbs_batch(kss[(ks_k, narrow)], None, n_iters=n) for n in (0, 1)]
+    eng.close()
+    assert np.array_equal(kss[(0, 8)], kss[(1, 8)]) and np.array_equal(kss[(0, 8)], np.stack([sk.keyswitch(c) for c in cts]))
     want = [(7 * int(v) + 2) % 16 for v in np.arange(37) % 16]
     for k, o in outs.items():
         assert list(ck.decrypt_batch(o)) == want, k
-    # same FFT arithmetic (fft_core.cuh) in both kernels => identical words, not just identical plaintexts
-    assert np.array_equal(outs[("mma", "2")], outs[("mma", "3")])
+    # the unfused path (IMAD keyswitch, u64 hand-off) and the fused one (tensor-core keyswitch, u16 hand-off) feed the same PBS kernel
+    assert np.array_equal(outs[(0, 8)], outs[(1, 8)])
+    assert np.array_equal(part[(1, 8)][0], part[(1, 0)][0])
+    d = np.abs((part[(1, 8)][1] - part[(1, 0)][1]).view(np.int64)).max()
+    assert d <= 2**44, f"v8 vs v4<1> after one CMUX: 2^{np.log2(max(int(d), 1)):.1f}"
 
 
 def test_kernels_do_not_write_outside_their_buffers(orc, keys_2_2):

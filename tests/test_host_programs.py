@@ -248,3 +248,31 @@ def test_find_full_size_first_match_positions(orc, toy_keys):
         want = hay.find(pat)
         assert ck.decrypt_message_and_carry(out[0]) == int(want >= 0), positions
         assert R.decrypt_radix(ck, out[1:]) == max(want, 0), positions
+
+
+@pytest.mark.parametrize("hay,pat", [
+    (b"ab" * 300, b"ab"),                    # 599 windows, a match in every block of 14: the carry of the block-prefix sums is live
+    (b"b" * 1024, b"b"),                     # 1024 windows, every window matches
+    (b"a" * 700 + b"b", b"ab"),              # single match in the last group
+    (b"xy" * 256 + b"ab" * 256, b"ab"),      # first match exactly at a group boundary region
+    (b"a" * 900, b"b"),                      # no match at all
+])
+def test_find_long_haystack_dense_matches(hay, pat):
+    """More than 30 blocks of 14 windows (> 420 windows): the cleaned carry of the 'some earlier block matched' prefix sums must never
+    push a PBS operand past total_mod - 1 (round-1 bug: carry + 15 flags = 16 reached the padding bit and the carry was lost, so a
+    later window was reported as first).  Executed noise-free on plaintexts (the program is far too large for the CPU oracle)."""
+    from helpers import simulate_program_clear, string_blocks_clear
+    for op, want_pos in (("string_find", hay.find(pat)), ("string_rfind", hay.rfind(pat))):
+        P = Program(op, (len(hay), len(pat)))
+        out, hits = simulate_program_clear(P.ir(), string_blocks_clear(hay) + string_blocks_clear(pat), 16)
+        assert hits == 0, f"{op}: {hits} PBS operands reached the padding bit"
+        found, idx = int(out[0]), sum(int(d) << (2 * i) for i, d in enumerate(out[1:]))
+        assert (found, idx) == (int(want_pos >= 0), max(want_pos, 0)), (op, found, idx, want_pos)
+
+
+def test_pbs_rejects_operand_past_message_space():
+    """Program::pbs refuses a ciphertext whose degree exceeds total_mod - 1 instead of recording a wrong LUT evaluation"""
+    from fhe_string_bounty_b200 import NativeError
+    with pytest.raises(NativeError, match="degree"):
+        Program("bool_sum_finish", (16, 0))
+    Program("bool_sum_finish", (15, 1))
