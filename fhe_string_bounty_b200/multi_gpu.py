@@ -52,6 +52,8 @@ class HostComm:
         return self._programs[key]
 
     def run(self, prog: Program, inputs):
+        if isinstance(inputs, (list, tuple)):          # pieces of the input block array, in order
+            inputs = np.concatenate([np.asarray(x, dtype=np.uint64).reshape(len(x), -1) for x in inputs])
         return self.execute(prog, np.ascontiguousarray(inputs, dtype=np.uint64))
 
     def zeros(self, rows: int, lwe_len: int):
@@ -139,6 +141,7 @@ class DeviceComm:
         self.L = eng.p.big_len
         self._programs: dict = {}
         self._pending_send: tuple | None = None     # (rows,) of the result just written into the exchange send area
+        self._host_out: dict = {}                    # page-locked result buffers, by shape
         self.peer = PeerExchange(eng, self.rank, self.world, max_rows) if (exchange == "peer" and self.world > 1) else None
 
     @classmethod
@@ -171,10 +174,27 @@ class DeviceComm:
         return torch.cuda.current_stream(self.dev).cuda_stream
 
     def _to_device(self, x):
+        """host array (numpy, ideally a view of page-locked memory: the copy is then one asynchronous DMA) or tensor -> CUDA tensor.  A
+        list of pieces is assembled on the device, piece by piece, without a host-side concatenation."""
+        if isinstance(x, (list, tuple)):
+            pieces = [self._as_tensor(q) for q in x]
+            out = torch.empty((sum(q.shape[0] for q in pieces), self.L), dtype=torch.int64, device=self.dev)
+            r = 0
+            for q in pieces:
+                out[r:r + q.shape[0]].copy_(q.reshape(-1, self.L), non_blocking=True)
+                r += q.shape[0]
+            return out
+        t = self._as_tensor(x)
+        return t if t.is_cuda else t.to(self.dev, non_blocking=True)
+
+    @staticmethod
+    def _as_tensor(x):
         if isinstance(x, torch.Tensor):
-            return x if x.is_cuda else x.to(self.dev, non_blocking=True)
-        x = np.ascontiguousarray(x, dtype=np.uint64)
-        return torch.from_numpy(x.view(np.int64)).to(self.dev, non_blocking=True)
+            return x
+        x = np.asarray(x)
+        if x.dtype != np.uint64 or not x.flags.c_contiguous:
+            x = np.ascontiguousarray(x, dtype=np.uint64)
+        return torch.from_numpy(x.view(np.int64))
 
     def run(self, prog: Program, inputs, to_send_area: bool = False):
         """rows of `inputs` (host numpy / pinned tensor: uploaded here; CUDA tensor: used in place) -> CUDA tensor of the outputs.  With
@@ -237,10 +257,19 @@ class DeviceComm:
         return x[sel].contiguous()
 
     def to_host(self, x) -> np.ndarray:
-        """the one device -> host copy of an operation (synchronises the stream)"""
+        """the one device -> host copy of an operation (synchronises the stream), through a page-locked buffer.  Results above 1 MiB are
+        returned as a view of that buffer (valid until the next result of the same shape); small ones are copied out."""
         if x.dim() == 1:
             x = x[None, :]
-        return x.contiguous().cpu().numpy().view(np.uint64)
+        x = x.contiguous()
+        key = tuple(x.shape)
+        if key not in self._host_out:
+            self._host_out[key] = torch.empty(x.shape, dtype=torch.int64).pin_memory()
+        buf = self._host_out[key]
+        buf.copy_(x, non_blocking=True)
+        torch.cuda.current_stream(self.dev).synchronize()
+        out = buf.numpy().view(np.uint64)
+        return out if out.nbytes > (1 << 20) else out.copy()
 
     def close(self):
         if self.peer is not None:
@@ -282,19 +311,17 @@ def sharded_contains(comm, params: dict, hay, pat, hay_len: int, pat_len: int, r
     comm = _comm(comm)
     rank, world = comm.rank, comm.world
     n_win = hay_len - pat_len + 1
-    inputs = np.concatenate([hay, pat])
     if n_win <= 0 or pat_len == 0 or world == 1:   # nothing to split: the plain single-GPU program
-        return comm.to_host(comm.run(comm.program("string_contains", (hay_len, pat_len), params), inputs))[0]
+        return comm.to_host(comm.run(comm.program("string_contains", (hay_len, pat_len), params), [hay, pat]))[0]
     total_mod = params["msg_mod"] * params["carry_mod"]
     active = min(world, n_win, total_mod - 1)       # the summed flags must stay below the padding bit; surplus ranks contribute zero
     if rank < active:
         w0, w1 = shard_range(n_win, rank, active)
         # a rank only needs the haystack chars its windows touch: upload hay[w0 : w1 - 1 + pat_len] and the pattern
         lo, hi = w0, w1 - 1 + pat_len
-        mine = _share(comm, comm.program("string_contains_windows", (hi - lo, pat_len, 0, w1 - w0), params),
-                      np.concatenate([hay[4 * lo:4 * hi], pat]))
+        mine = _share(comm, comm.program("string_contains_windows", (hi - lo, pat_len, 0, w1 - w0), params), [hay[4 * lo:4 * hi], pat])
     else:
-        mine = comm.zeros(1, inputs.shape[1])
+        mine = comm.zeros(1, hay.shape[1])
     total = comm.all_reduce(mine)
     return comm.to_host(comm.run(comm.program("bool_sum_finish", (active, 0), params), total))[0]
 
@@ -307,12 +334,12 @@ def sharded_eq(comm, params: dict, a, b, n_chars: int, rank: int | None = None, 
     if n_chars == 0:
         return comm.to_host(comm.run(comm.program("string_eq", (0, 0), params), np.zeros((0, 1), dtype=np.uint64)))[0]
     if world == 1:
-        return comm.to_host(comm.run(comm.program("string_eq", (n_chars, n_chars), params), np.concatenate([a, b])))[0]
+        return comm.to_host(comm.run(comm.program("string_eq", (n_chars, n_chars), params), [a, b]))[0]
     total_mod = params["msg_mod"] * params["carry_mod"]
     active = max(1, min(world, n_chars, total_mod - 1))
     if rank < active:
         c0, c1 = shard_range(n_chars, rank, active)
-        mine = _share(comm, comm.program("string_eq", (c1 - c0, c1 - c0), params), np.concatenate([a[4 * c0:4 * c1], b[4 * c0:4 * c1]]))
+        mine = _share(comm, comm.program("string_eq", (c1 - c0, c1 - c0), params), [a[4 * c0:4 * c1], b[4 * c0:4 * c1]])
     else:
         mine = comm.zeros(1, a.shape[1])
     total = comm.all_reduce(mine)
@@ -332,10 +359,10 @@ def sharded_compare(comm, params: dict, op: str, a, b, n_chars: int, rank: int |
     want_less, or_equal = _CMP[op]
     active = max(1, min(world, n_chars))
     if world == 1 or n_chars == 0:
-        return comm.to_host(comm.run(comm.program("string_" + op, (n_chars, n_chars), params), np.concatenate([a, b])))[0]
+        return comm.to_host(comm.run(comm.program("string_" + op, (n_chars, n_chars), params), [a, b]))[0]
     if rank < active:
         c0, c1 = shard_range(n_chars, rank, active)
-        mine = _share(comm, comm.program("string_cmp_sign", (c1 - c0, c1 - c0), params), np.concatenate([a[4 * c0:4 * c1], b[4 * c0:4 * c1]]))
+        mine = _share(comm, comm.program("string_cmp_sign", (c1 - c0, c1 - c0), params), [a[4 * c0:4 * c1], b[4 * c0:4 * c1]])
     else:
         mine = comm.zeros(1, a.shape[1])
     signs = comm.all_gather(mine)[:active, 0]
@@ -381,7 +408,7 @@ def sharded_find(comm, params: dict, hay, pat, hay_len: int, pat_len: int, rank:
     comm = _comm(comm)
     rank, world = comm.rank, comm.world
     n_win = hay_len - pat_len + 1
-    inputs = np.concatenate([hay, pat])
+    inputs = [hay, pat]
     if n_win <= 1 or pat_len == 0 or world == 1:
         return comm.to_host(comm.run(comm.program("string_find", (hay_len, pat_len), params), inputs))
     total_mod = params["msg_mod"] * params["carry_mod"]
@@ -393,6 +420,6 @@ def sharded_find(comm, params: dict, hay, pat, hay_len: int, pat_len: int, rank:
         w0, w1 = shard_range(n_win, rank, active)
         mine = _share(comm, comm.program("string_find_windows", (hay_len, pat_len, w0, w1), params), inputs)
     else:
-        mine = comm.zeros(1 + nb, inputs.shape[1])
+        mine = comm.zeros(1 + nb, hay.shape[1])
     parts = comm.all_gather(mine)[:active]
     return comm.to_host(comm.run(comm.program("find_combine", (active, nb), params), parts.reshape(active * (1 + nb), -1)))
