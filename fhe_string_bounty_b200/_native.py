@@ -219,6 +219,7 @@ EXPORTS = {
     "tfhe_b200_exchange_gather_stride": (C.c_size_t, [C.c_void_p, C.c_uint32]),
     "tfhe_b200_exchange_all_gather": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]),
     "tfhe_b200_exchange_all_reduce_sum": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "tfhe_b200_exchange_group_run": (C.c_int, [C.POINTER(C.c_void_p), C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p), C.c_int, C.c_void_p]),
     "tfhe_b200_exchange_destroy": (C.c_int, [C.c_void_p]),
 }
 

@@ -35,8 +35,10 @@ struct tfhe_b200_exchange {
     std::vector<void *> peer;                  // peer[r] = rank r's buffer as mapped into this process (peer[rank] = local.p)
     std::vector<bool> opened;                  // mapped through cudaIpcOpenMemHandle (must be closed)
     DevBuf d_peers;                            // device copy of `peer`
+    DevBuf d_group;                            // per-rank arguments of a single-GPU group launch
     uint64_t epoch = 0;
     bool attached = false;
+    bool shares_device = false;                // some peer lives on this very GPU: only tfhe_b200_exchange_group_run may run the exchange
 };
 
 namespace {
@@ -57,9 +59,8 @@ __device__ __forceinline__ ulonglong2 ld_relaxed_sys_v2(const ulonglong2 *p) {
 }
 
 // words16 = number of 16-byte units per rank (rows * lwe_len words rounded up to even, / 2); out is 16-byte aligned
-__global__ void __launch_bounds__(256)
-exchange_kernel(void *const *__restrict__ peers, uint32_t rank, uint32_t world, uint64_t epoch, size_t flags_bytes, size_t area_bytes,
-                size_t words16, int reduce, ulonglong2 *__restrict__ out) {
+__device__ __forceinline__ void exchange_body(void *const *__restrict__ peers, uint32_t rank, uint32_t world, uint64_t epoch, size_t flags_bytes,
+                                              size_t area_bytes, size_t words16, int reduce, ulonglong2 *__restrict__ out) {
     // 1. publish (one CTA): everything the previous kernels of this stream wrote to my send area is visible system-wide first
     if (blockIdx.x == 0 && threadIdx.x < world) {
         __threadfence_system();
@@ -91,11 +92,28 @@ exchange_kernel(void *const *__restrict__ peers, uint32_t rank, uint32_t world, 
     }
 }
 
+__global__ void __launch_bounds__(256)
+exchange_kernel(void *const *__restrict__ peers, uint32_t rank, uint32_t world, uint64_t epoch, size_t flags_bytes, size_t area_bytes,
+                size_t words16, int reduce, ulonglong2 *__restrict__ out) {
+    exchange_body(peers, rank, world, epoch, flags_bytes, area_bytes, words16, reduce, out);
+}
+
+// Several ranks on ONE GPU (one process driving all of them: the single-GPU tests).  Kernels that wait on one another must not be
+// separate launches on one device -- nothing guarantees that they run at the same time -- so the ranks' exchanges run as ONE cooperative
+// launch, blockIdx.y = rank, every rank executing exactly the code of the multi-GPU kernel on its own buffers.
+struct GroupRank { void *const *peers; ulonglong2 *out; uint64_t epoch; };
+__global__ void __launch_bounds__(256)
+exchange_group_kernel(const GroupRank *__restrict__ ranks, uint32_t world, size_t flags_bytes, size_t area_bytes, size_t words16, int reduce) {
+    const GroupRank g = ranks[blockIdx.y];
+    exchange_body(g.peers, blockIdx.y, world, g.epoch, flags_bytes, area_bytes, words16, reduce, g.out);
+}
+
 size_t round_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 int run_exchange(tfhe_b200_exchange *ex, uint32_t rows, uint64_t *d_out, void *stream, int reduce) {
     if (!ex || !d_out) return fail("null argument");
     if (!ex->attached) return fail("exchange: peers not attached yet (tfhe_b200_exchange_attach)");
+    if (ex->shares_device) return fail("exchange: ranks that share a GPU must use tfhe_b200_exchange_group_run (kernels that wait on one another cannot be separate launches on one device)");
     if (rows == 0 || rows > ex->max_rows) return fail("exchange: row count outside [1, max_rows]");
     if ((reinterpret_cast<uintptr_t>(d_out) & 15) != 0) return fail("exchange: output buffer must be 16-byte aligned");
     std::lock_guard<std::mutex> lk(ex->ctx->mu);
@@ -185,6 +203,7 @@ int tfhe_b200_exchange_attach_local(tfhe_b200_exchange *ex, tfhe_b200_exchange *
         if (r == ex->rank) continue;
         if (!peers[r] || peers[r]->world != ex->world || peers[r]->rank != r || peers[r]->max_rows != ex->max_rows)
             return fail("exchange: peer " + std::to_string(r) + " does not match");
+        if (peers[r]->device == ex->device) ex->shares_device = true;
         if (peers[r]->device != ex->device) {
             int can = 0;
             TB_CUDA(cudaDeviceCanAccessPeer(&can, ex->device, peers[r]->device));
@@ -220,6 +239,42 @@ size_t tfhe_b200_exchange_gather_stride(const tfhe_b200_exchange *ex, uint32_t r
 /* d_out: rows x (k*N+1) words (+ one pad word if that count is odd) = sum over ranks modulo 2^64, i.e. the homomorphic sum. */
 int tfhe_b200_exchange_all_reduce_sum(tfhe_b200_exchange *ex, uint32_t rows, uint64_t *d_out, void *cuda_stream) {
     return run_exchange(ex, rows, d_out, cuda_stream, 1);
+}
+
+/* One process, several ranks on the same GPU: performs the exchange of EVERY rank of `group` (rank order) in one cooperative launch
+ * on `cuda_stream`; d_outs[r] is rank r's output as in all_gather / all_reduce_sum.  The caller orders the stream after every rank's
+ * producer work. */
+int tfhe_b200_exchange_group_run(tfhe_b200_exchange *const *group, uint32_t world, uint32_t rows, uint64_t *const *d_outs, int reduce,
+                                 void *cuda_stream) {
+    if (!group || !d_outs || world < 1) return fail("null argument");
+    tfhe_b200_exchange *lead = group[0];
+    if (!lead) return fail("null exchange");
+    for (uint32_t r = 0; r < world; ++r) {
+        tfhe_b200_exchange *ex = group[r];
+        if (!ex || !ex->attached || ex->world != world || ex->rank != r || ex->device != lead->device || ex->max_rows != lead->max_rows)
+            return fail("exchange group: rank " + std::to_string(r) + " does not belong to this single-GPU group");
+        if (!d_outs[r] || (reinterpret_cast<uintptr_t>(d_outs[r]) & 15) != 0) return fail("exchange group: outputs must be 16-byte aligned");
+    }
+    if (rows == 0 || rows > lead->max_rows) return fail("exchange: row count outside [1, max_rows]");
+    DeviceGuard g(lead->device);
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : lead->ctx->stream;
+    std::vector<GroupRank> h(world);
+    for (uint32_t r = 0; r < world; ++r) {
+        group[r]->epoch += 1;
+        h[r] = GroupRank{(void *const *)group[r]->d_peers.p, reinterpret_cast<ulonglong2 *>(d_outs[r]), group[r]->epoch};
+    }
+    TB_CUDA(lead->d_group.reserve_on(world * sizeof(GroupRank), s));
+    TB_CUDA(cudaMemcpyAsync(lead->d_group.p, h.data(), world * sizeof(GroupRank), cudaMemcpyHostToDevice, s));
+    TB_CUDA(cudaStreamSynchronize(s));      // h goes out of scope (test path: a synchronisation here is harmless)
+    const size_t words = (size_t)rows * lead->lwe_len;
+    size_t words16 = (words + 1) / 2;
+    const GroupRank *d_ranks = (const GroupRank *)lead->d_group.p;
+    int reduce_i = reduce;
+    const unsigned bx = (unsigned)std::max<size_t>(1, std::min<size_t>((size_t)lead->ctx->sms / world, (words16 + 255) / 256));
+    void *args[] = {(void *)&d_ranks, (void *)&world, (void *)&lead->flags_bytes, (void *)&lead->area_bytes, (void *)&words16, (void *)&reduce_i};
+    TB_CUDA(cudaLaunchCooperativeKernel((const void *)exchange_group_kernel, dim3(bx, world), dim3(256), args, 0, s));
+    lead->ctx->launches += 1;
+    return 0;
 }
 
 int tfhe_b200_exchange_destroy(tfhe_b200_exchange *ex) {

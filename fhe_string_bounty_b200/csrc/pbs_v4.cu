@@ -20,27 +20,33 @@ namespace tb4 {
 using namespace tb16k;
 
 constexpr int QPP = 4;                 // frequencies (registers) per ring piece
-constexpr int PIECE_CPLX = 2 * 2 * QPP * 64;   // [out poly 2][sel 2][q QPP][thread 64]
+constexpr int PIECE_CPLX = 2 * QPP * 64;       // one output polynomial's share of a chunk: [sel 2][q QPP][thread 64] = 8 KiB
 constexpr int PIECE_BYTES = PIECE_CPLX * 16;
-constexpr int PIECES_PER_ITER = 16 / QPP;
-constexpr int NSLOT = 81920 / (PIECE_CPLX * 16);   // 80 KiB of ring
+constexpr int CHUNKS_PER_ITER = 16 / QPP;
+// ring slots PER OUTPUT POLYNOMIAL: the warps of polynomial w only ever read the c = w half of a chunk, so the key streams through two
+// interleaved rings (slot 2 k + w) whose pieces are consumed by 2 * CTS warps each.  1..4 ciphertexts per CTA: 5 + 5 slots = 80 KiB;
+// 5 ciphertexts: 3 + 3 slots = 48 KiB next to ten 17 KiB tiles.
+constexpr int ring_slots(int cts) { return cts == 5 ? 3 : 5; }
 
 template <int CTS>
 struct Smem {
+    static constexpr int NS = ring_slots(CTS);
     cplx tile[2 * CTS][kTileCplx];         // 17 KiB per polynomial
-    cplx ring[NSLOT][PIECE_CPLX];          // 80 KiB
-    unsigned long long full_bar[NSLOT];
-    unsigned int consumed[NSLOT];
+    cplx ring[2 * NS][PIECE_CPLX];
+    unsigned long long full_bar[2 * NS];
+    unsigned int consumed[2 * NS];
     uint32_t tmem_base;
 };
 static_assert(sizeof(Smem<4>) <= 227 * 1024, "shared memory budget");
+static_assert(sizeof(Smem<5>) <= 227 * 1024, "shared memory budget");
 
 // Fourier key, v4 layout: [ggsw i][chunk 16/QPP][out poly c][sel: 0 = row c, 1 = row 1-c][q QPP][thread 64]; register g = QPP*chunk + q
-// (QPP = 4: 16 KiB pieces, 5 ring slots, measured 101.9 ms per 8192 against 104.1 ms for QPP = 2; QPP = 8 leaves two slots, which cannot
-// hold the ciphertexts' quarter-iteration stagger: the kernel deadlocks into its spin-limit trap)
+// (QPP = 4 measured 101.9 ms per 8192 against 104.1 ms for QPP = 2; QPP = 8 leaves too few slots for the ciphertexts' stagger)
 __device__ __forceinline__ size_t bskf4_index(int i, int chunk, int c, int sel, int q) {
-    return ((((size_t)(i * PIECES_PER_ITER + chunk) * 2 + c) * 2 + sel) * QPP + q) * 64;
+    return ((((size_t)(i * CHUNKS_PER_ITER + chunk) * 2 + c) * 2 + sel) * QPP + q) * 64;
 }
+// piece k of output polynomial w (k = i * CHUNKS_PER_ITER + chunk): 8 KiB, contiguous in the layout above
+__device__ __forceinline__ const cplx *piece_src(const cplx *bskf4, int k, int w) { return bskf4 + ((size_t)k * 2 + w) * PIECE_CPLX; }
 
 template <int CTS>
 __global__ void __launch_bounds__(128 * CTS, 1)
@@ -48,7 +54,10 @@ pbs_classic_kernel_v4(const uint64_t *__restrict__ lwe_small, const uint32_t *__
                       const cplx *__restrict__ bskf4, const cplx *__restrict__ tbl16, uint64_t *__restrict__ out,
                       const uint32_t *__restrict__ out_slot, int batch, int n, int base_log, int n_iters, int small_is_u16) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    constexpr int WARPS = 4 * CTS, TMEM_COLS = CTS == 4 ? 512 : 256, TW_COL = 64 * CTS;
+    constexpr int TMEM_COLS = CTS >= 4 ? 512 : 256, TW_COL = 64 * CTS, NS = Smem<CTS>::NS, CONSUMERS = 2 * CTS;
+    constexpr bool PER_CHUNK = NS <= CHUNKS_PER_ITER;    // the ring cannot hold a whole iteration plus the chunk being waited for
+    static_assert(TW_COL + 80 <= TMEM_COLS, "TMEM columns");
+    static_assert(3 * CTS <= 15, "named barriers: 1 .. 2 CTS per polynomial, 2 CTS + 1 .. 3 CTS per ciphertext");
     Smem<CTS> &sm = *reinterpret_cast<Smem<CTS> *>(smem_raw);
     const int W = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // warp -> (ciphertext, polynomial, half): the four warps of a ciphertext sit on the four schedulers (warp id % 4), so every
@@ -61,14 +70,14 @@ pbs_classic_kernel_v4(const uint64_t *__restrict__ lwe_small, const uint32_t *__
     const cplx *otile = sm.tile[P ^ 1];
     uint64_t *pb = reinterpret_cast<uint64_t *>(tile);   // the polynomial (2048 words) for the rotated gather
     const PolySync poly_sync{1 + P};
-    const int ct_bar = 9 + ctl;
+    const int ct_bar = 1 + 2 * CTS + ctl;
     const uint64_t *lwe = lwe_small + (size_t)ct * (n + 1);
     const uint16_t *lwe16 = reinterpret_cast<const uint16_t *>(lwe_small) + (size_t)ct * (n + 1);
-    const int total_pieces = n_iters * PIECES_PER_ITER;
+    const int total_pieces = n_iters * CHUNKS_PER_ITER;      // per output polynomial
 
     // ---- one-time setup: twiddle tables, barriers, TMEM, first ring fill ---------------------------------------------------
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NSLOT; ++s) { mbar_init(&sm.full_bar[s], 1); sm.consumed[s] = 0; }
+        for (int s = 0; s < 2 * NS; ++s) { mbar_init(&sm.full_bar[s], 1); sm.consumed[s] = 0; }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_proxy_async();
     }
@@ -92,11 +101,12 @@ pbs_classic_kernel_v4(const uint64_t *__restrict__ lwe_small, const uint32_t *__
         }
     }
     if (threadIdx.x == 0) {
-        const int first = total_pieces < NSLOT ? total_pieces : NSLOT;
-        for (int g = 0; g < first; ++g) {
-            mbar_expect_tx(&sm.full_bar[g], PIECE_BYTES);
-            tma_load_1d(sm.ring[g], bskf4 + (size_t)g * PIECE_CPLX, PIECE_BYTES, &sm.full_bar[g]);
-        }
+        const int first = total_pieces < NS ? total_pieces : NS;
+        for (int k = 0; k < first; ++k)
+            for (int c = 0; c < 2; ++c) {
+                mbar_expect_tx(&sm.full_bar[2 * k + c], PIECE_BYTES);
+                tma_load_1d(sm.ring[2 * k + c], piece_src(bskf4, k, c), PIECE_BYTES, &sm.full_bar[2 * k + c]);
+            }
     }
 
     // ---- acc <- LUT * X^(-b_hat): registers (own coefficients as u64 bit patterns in re/im), TMEM, shared ------------------------
@@ -133,10 +143,14 @@ pbs_classic_kernel_v4(const uint64_t *__restrict__ lwe_small, const uint32_t *__
         tmem_wait_st();
     }
 
-    // stagger: ciphertext k starts when ciphertext 0 reaches the k-th quarter of its first iteration
-    if (CTS == 4 && ctl >= 1 && n_iters > 0) bar_sync(12 + ctl, 256);
+    // stagger: ciphertext k starts k / CTS of an iteration after ciphertext 0, so that the FP64-heavy and the shared-memory-heavy phases
+    // of the ciphertexts sharing a scheduler do not coincide (a clock-based delay measured the same as a barrier hand-shake)
+    if (CTS >= 4 && ctl >= 1 && n_iters > 0) {
+        const long long t0 = clock64(), delay = (long long)ctl * (20000 / CTS);
+        while (clock64() - t0 < delay) { }
+    }
 
-    int slot = 0;            // ring position of this iteration's first piece
+    int slot = 0;            // this polynomial's ring position (0 .. NS-1) of this iteration's first piece
     uint32_t phase = 0;
 
     for (int i = 0; i < n_iters; ++i) {
@@ -156,10 +170,8 @@ pbs_classic_kernel_v4(const uint64_t *__restrict__ lwe_small, const uint32_t *__
             re[m] = (double)signed_digit_l1(r0 - o0, base_log);
             im[m] = (double)signed_digit_l1(r1 - o1, base_log);
         }
-        if (CTS == 4 && i == 0 && ctl == 0) bar_arrive(13, 256);
 
         fft16_fwd(re, im, tile, twd, T, poly_sync);
-        if (CTS == 4 && i == 0 && ctl == 0) bar_arrive(14, 256);
 
         // spectrum exchange between the two polynomials of the ciphertext: park my 16 values in my own exchange-B reader slots
         {
@@ -169,17 +181,18 @@ pbs_classic_kernel_v4(const uint64_t *__restrict__ lwe_small, const uint32_t *__
         }
         bar_sync(ct_bar, 128);
 
-        // out_fft[w] = F_w * G[w][w] + F_{1-w} * G[1-w][w], GGSW pieces from the ring.  Nothing is synchronised inside the loop (the
-        // compiler is free to run chunk c+1's loads under chunk c's arithmetic); after it lane c counts this warp out of piece c's slot,
-        // and the last of the WARPS warps to leave a slot re-arms it with the piece NSLOT ahead (measured against releasing each slot
-        // right after its chunk: 104.7 vs 106.0 ms per 8192).
+        // out_fft[w] = F_w * G[w][w] + F_{1-w} * G[1-w][w], GGSW pieces from this polynomial's ring.  Nothing is synchronised inside the loop
+        // (the compiler is free to run chunk c+1's loads under chunk c's arithmetic); after it lane c counts this warp out of piece c's
+        // slot, and the last of the 2 * CTS warps to leave a slot re-arms it with the piece NS chunks ahead (measured against releasing
+        // each slot right after its chunk: 104.7 vs 106.0 ms per 8192).
         {
             const cplx *fop = otile + xb_rbase(T);
             int my_slot = 0;
 #pragma unroll
-            for (int c = 0; c < PIECES_PER_ITER; ++c) {
-                if (!mbar_try_wait(&sm.full_bar[slot], phase)) mbar_wait(&sm.full_bar[slot], phase);
-                const cplx *pc = sm.ring[slot] + (w * 2) * QPP * 64 + T;
+            for (int c = 0; c < CHUNKS_PER_ITER; ++c) {
+                const int rs = 2 * slot + w;
+                if (!mbar_try_wait(&sm.full_bar[rs], phase)) mbar_wait(&sm.full_bar[rs], phase);
+                const cplx *pc = sm.ring[rs] + T;
 #pragma unroll
                 for (int q = 0; q < QPP; ++q) {
                     const int g = QPP * c + q;
@@ -195,23 +208,38 @@ pbs_classic_kernel_v4(const uint64_t *__restrict__ lwe_small, const uint32_t *__
                     oi = DFMA(F.y, B.x, oi);
                     re[g] = orr; im[g] = oi;
                 }
-                if (lane == c) my_slot = slot;
-                if (++slot == NSLOT) { slot = 0; phase ^= 1u; }
+                if (PER_CHUNK) {
+                    // fewer slots than chunks per iteration (5 ciphertexts per CTA): a slot has to be handed back before the next chunk can
+                    // arrive, so this warp counts itself out right away (shared-memory accesses of a warp complete in order: the atomic
+                    // follows every lane's loads of this chunk)
+                    __syncwarp();
+                    if (lane == 0 && atomicAdd(&sm.consumed[rs], 1u) == CONSUMERS - 1) {
+                        sm.consumed[rs] = 0;
+                        const int k2 = i * CHUNKS_PER_ITER + c + NS;
+                        if (k2 < total_pieces) {
+                            __threadfence_block();
+                            fence_proxy_async();
+                            mbar_expect_tx(&sm.full_bar[rs], PIECE_BYTES);
+                            tma_load_1d(sm.ring[rs], piece_src(bskf4, k2, w), PIECE_BYTES, &sm.full_bar[rs]);
+                        }
+                    }
+                }
+                if (lane == c) my_slot = rs;
+                if (++slot == NS) { slot = 0; phase ^= 1u; }
             }
             __syncwarp();     // every lane's loads from the ring have returned (their values fed the arithmetic above)
-            if (lane < PIECES_PER_ITER && atomicAdd(&sm.consumed[my_slot], 1u) == WARPS - 1) {
+            if (!PER_CHUNK && lane < CHUNKS_PER_ITER && atomicAdd(&sm.consumed[my_slot], 1u) == CONSUMERS - 1) {
                 sm.consumed[my_slot] = 0;
-                const int g2 = i * PIECES_PER_ITER + lane + NSLOT;
-                if (g2 < total_pieces) {
+                const int k2 = i * CHUNKS_PER_ITER + lane + NS;
+                if (k2 < total_pieces) {
                     __threadfence_block();
                     fence_proxy_async();
                     mbar_expect_tx(&sm.full_bar[my_slot], PIECE_BYTES);
-                    tma_load_1d(sm.ring[my_slot], bskf4 + (size_t)g2 * PIECE_CPLX, PIECE_BYTES, &sm.full_bar[my_slot]);
+                    tma_load_1d(sm.ring[my_slot], piece_src(bskf4, k2, w), PIECE_BYTES, &sm.full_bar[my_slot]);
                 }
             }
         }
         bar_sync(ct_bar, 128);   // the partner polynomial has read my spectrum: the tile is mine again
-        if (CTS == 4 && i == 0 && ctl == 0) bar_arrive(15, 256);
 
         fft16_inv(re, im, tile, twd, T, poly_sync);
         poly_sync();    // everyone has read the last exchange: the tile becomes the accumulator polynomial again
@@ -291,7 +319,9 @@ bsk_convert_kernel_v4(const uint64_t *__restrict__ bsk_std, cplx *__restrict__ b
 namespace tbk {
 
 cudaError_t pbs_v4_configure() {
-    cudaError_t e = cudaFuncSetAttribute(tb4::pbs_classic_kernel_v4<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tb4::Smem<4>));
+    cudaError_t e = cudaFuncSetAttribute(tb4::pbs_classic_kernel_v4<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tb4::Smem<5>));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(tb4::pbs_classic_kernel_v4<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tb4::Smem<4>));
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(tb4::pbs_classic_kernel_v4<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tb4::Smem<2>));
     if (e != cudaSuccess) return e;
@@ -300,7 +330,7 @@ cudaError_t pbs_v4_configure() {
 
 cudaError_t launch_pbs_classic_v4(const uint64_t *lwe_small, const uint32_t *lut_idx, const uint64_t *luts, const void *bskf4,
                                   const void *tbl16, uint64_t *out, const uint32_t *out_slot, int batch, int n, int base_log,
-                                  int n_iters, int small_is_u16, cudaStream_t stream) {
+                                  int n_iters, int small_is_u16, int wide_cts, cudaStream_t stream) {
     if (batch <= 0) return cudaSuccess;
     int sms = 148, dev = 0;
     cudaGetDevice(&dev);
@@ -311,6 +341,9 @@ cudaError_t launch_pbs_classic_v4(const uint64_t *lwe_small, const uint32_t *lut
                                                                                   base_log, n_iters, small_is_u16);
     else if (batch <= 2 * sms)
         tb4::pbs_classic_kernel_v4<2><<<(batch + 1) / 2, 256, sizeof(tb4::Smem<2>), stream>>>(lwe_small, lut_idx, luts, bk, tb, out, out_slot,
+                                                                                            batch, n, base_log, n_iters, small_is_u16);
+    else if (wide_cts == 5)
+        tb4::pbs_classic_kernel_v4<5><<<(batch + 4) / 5, 640, sizeof(tb4::Smem<5>), stream>>>(lwe_small, lut_idx, luts, bk, tb, out, out_slot,
                                                                                             batch, n, base_log, n_iters, small_is_u16);
     else
         tb4::pbs_classic_kernel_v4<4><<<(batch + 3) / 4, 512, sizeof(tb4::Smem<4>), stream>>>(lwe_small, lut_idx, luts, bk, tb, out, out_slot,

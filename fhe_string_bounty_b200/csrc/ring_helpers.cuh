@@ -22,9 +22,9 @@ __device__ __forceinline__ bool mbar_try_wait(void *bar, uint32_t parity) {
     return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(void *bar, uint32_t parity) {
-    uint32_t spins = 0;
+    const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 26)) __trap();   // never hang the GPU: a lost arrival becomes a launch failure
+        if (clock64() - t0 > 4000000000LL) __trap();   // ~2 s: never hang the GPU, a lost arrival becomes a launch failure
     }
 }
 __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, void *bar) {

@@ -142,13 +142,16 @@ class DeviceComm:
         self._programs: dict = {}
         self._pending_send: tuple | None = None     # (rows,) of the result just written into the exchange send area
         self._host_out: dict = {}                    # page-locked result buffers, by shape
+        self._group = None                           # set by local_group(): several ranks of one process on one GPU
         self.peer = PeerExchange(eng, self.rank, self.world, max_rows) if (exchange == "peer" and self.world > 1) else None
 
     @classmethod
     def local_group(cls, engines: list, max_rows: int = 16) -> list:
-        """several ranks driven by ONE process (one Engine per rank, on the same or on different GPUs): the exchange buffers are
-        attached by pointer (tfhe_b200_exchange_attach_local) instead of CUDA IPC.  Each rank must then be driven from its own thread
-        on its own CUDA stream (an exchange waits for every peer's kernel)."""
+        """several ranks driven by ONE process on ONE GPU (one Engine per rank; the single-GPU tests): the exchange buffers are attached
+        by pointer (tfhe_b200_exchange_attach_local) and every exchange runs as one cooperative launch over all ranks
+        (tfhe_b200_exchange_group_run) -- kernels that wait on one another must never be separate launches on one device.  Each rank is
+        driven from its own thread on its own CUDA stream; the threads meet at a host barrier around the group launch."""
+        import threading
         world = len(engines)
         comms = [cls(e, rank=r, world=world, exchange="nccl", max_rows=max_rows) for r, e in enumerate(engines)]
         if world > 1:
@@ -162,7 +165,36 @@ class DeviceComm:
             arr = (C.c_void_p * world)(*[c.peer.h for c in comms])
             for c in comms:
                 c.eng._check(c.eng.lib.tfhe_b200_exchange_attach_local(c.peer.h, arr))
+            group = {"barrier": threading.Barrier(world), "handles": arr, "events": [None] * world, "outs": [None] * world, "done": None,
+                     "error": None}
+            for c in comms:
+                c._group = group
         return comms
+
+    def _group_exchange(self, rows: int, out: torch.Tensor, reduce: bool):
+        """single-GPU group: every rank's thread records "my rows are staged", all meet, rank 0 launches the one cooperative kernel after
+        every rank's stream, all meet again and order their streams after it"""
+        g = self._group
+        stream = torch.cuda.current_stream(self.dev)
+        ev = torch.cuda.Event()
+        ev.record(stream)
+        g["events"][self.rank], g["outs"][self.rank] = ev, out
+        g["barrier"].wait()
+        if self.rank == 0:
+            try:
+                for e in g["events"]:
+                    stream.wait_event(e)
+                outs = (C.c_void_p * self.world)(*[o.data_ptr() for o in g["outs"]])
+                self.eng._check(self.eng.lib.tfhe_b200_exchange_group_run(g["handles"], self.world, rows, outs, int(reduce), stream.cuda_stream))
+                done = torch.cuda.Event()
+                done.record(stream)
+                g["done"], g["error"] = done, None
+            except Exception as e:      # the other ranks' threads must not be left at the barrier
+                g["error"] = e
+        g["barrier"].wait()
+        if g["error"] is not None:
+            raise NativeError(f"group exchange failed: {g['error']}")
+        stream.wait_event(g["done"])
 
     def program(self, op: str, args: tuple, params: dict) -> Program:
         key = (op, tuple(args), tuple(sorted(params.items())))      # per DeviceComm = per engine: a program is bound to one context
@@ -235,7 +267,10 @@ class DeviceComm:
         if self.peer is not None and (blocks is None or blocks.shape[0] <= self.max_rows):
             rows = self._stage_for_peer(blocks)
             out = torch.empty((rows * self.L + 1) // 2 * 2, dtype=torch.int64, device=self.dev)
-            self.peer.all_reduce_sum(rows, out.data_ptr(), self._stream())
+            if self._group is not None:
+                self._group_exchange(rows, out, True)
+            else:
+                self.peer.all_reduce_sum(rows, out.data_ptr(), self._stream())
             return out[: rows * self.L].reshape(rows, self.L)
         t = blocks.contiguous()
         dist.all_reduce(t, op=dist.ReduceOp.SUM)      # NCCL on the current stream; int64 wrap-around == u64 wrap-around
@@ -246,7 +281,10 @@ class DeviceComm:
             rows = self._stage_for_peer(blocks)
             stride = self.peer.gather_stride(rows)
             out = torch.empty((self.world, stride), dtype=torch.int64, device=self.dev)
-            self.peer.all_gather(rows, out.data_ptr(), self._stream())
+            if self._group is not None:
+                self._group_exchange(rows, out, False)
+            else:
+                self.peer.all_gather(rows, out.data_ptr(), self._stream())
             return out[:, : rows * self.L].reshape(self.world, rows, self.L)
         t = blocks.contiguous()
         out = torch.empty((self.world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=self.dev)

@@ -183,7 +183,8 @@ int tfhe_b200_program_last_ms(const tfhe_b200_program *prog, float *ms);
  *   create -> handle (64-byte CUDA IPC handle; ship it to every peer by any transport) -> attach (all handles, rank order)
  *   send_rows: where the NEXT exchange's local rows go (max_rows x (k*N+1) words) -- pass it as d_outputs of program_run_device
  *   all_gather: d_out = world parts of gather_stride(rows) words each;  all_reduce_sum: d_out = rows x (k*N+1) words (+1 pad if odd)
- * d_out must be 16-byte aligned.  Destroy the exchange before its context.  attach_local serves several GPUs driven by one process. */
+ * d_out must be 16-byte aligned.  Destroy the exchange before its context.  attach_local serves several ranks driven by one process
+ * (on one GPU use group_run instead of the per-rank calls). */
 typedef struct tfhe_b200_exchange tfhe_b200_exchange;
 int tfhe_b200_exchange_create(tfhe_b200_ctx *ctx, uint32_t rank, uint32_t world, uint32_t max_rows, tfhe_b200_exchange **out);
 int tfhe_b200_exchange_handle(tfhe_b200_exchange *ex, uint8_t handle[64]);
@@ -193,12 +194,17 @@ int tfhe_b200_exchange_send_rows(tfhe_b200_exchange *ex, uint64_t **d_rows);
 size_t tfhe_b200_exchange_gather_stride(const tfhe_b200_exchange *ex, uint32_t rows);
 int tfhe_b200_exchange_all_gather(tfhe_b200_exchange *ex, uint32_t rows, uint64_t *d_out, void *cuda_stream);
 int tfhe_b200_exchange_all_reduce_sum(tfhe_b200_exchange *ex, uint32_t rows, uint64_t *d_out, void *cuda_stream);
+/* several ranks on ONE GPU (attach_local; the single-GPU tests): all ranks' exchanges as one cooperative launch -- kernels that wait
+ * on one another must never be separate launches on one device */
+int tfhe_b200_exchange_group_run(tfhe_b200_exchange *const *group, uint32_t world, uint32_t rows, uint64_t *const *d_outs, int reduce,
+                                 void *cuda_stream);
 int tfhe_b200_exchange_destroy(tfhe_b200_exchange *ex);
 
 /* Kernel selection (A/B comparisons and the parity tests that pin one kernel instance); the same keys are read from the environment at
  * context creation as TFHE_B200_<KEY>.  Keys: "narrow_kernel" (8 = pbs_v8.cu / pbs_multibit_v8.cu serve levels of at most narrow_max
  * ciphertexts and level tails, 0 = the 1- / 2-ciphertext instances of the wide kernels), "narrow_max" (0 = default: 2 x SM count
- * classic, SM count multi-bit), "ks_kernel" (1 = tensor-core keyswitch, 0 = IMAD keyswitch). */
+ * classic, SM count multi-bit), "wide_cts" (ciphertexts per SM of the wide classic kernel: 5 or 4), "ks_kernel" (1 = tensor-core
+ * keyswitch, 0 = IMAD keyswitch). */
 int tfhe_b200_set_tuning(tfhe_b200_ctx *ctx, const char *key, int value);
 
 /* Instrumentation. */

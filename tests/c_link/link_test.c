@@ -22,7 +22,7 @@ int main(void) {
     ADDR(tfhe_b200_program_accumulators); ADDR(tfhe_b200_program_run); ADDR(tfhe_b200_program_run_device); ADDR(tfhe_b200_program_last_ms);
     ADDR(tfhe_b200_exchange_create); ADDR(tfhe_b200_exchange_handle); ADDR(tfhe_b200_exchange_attach); ADDR(tfhe_b200_exchange_attach_local);
     ADDR(tfhe_b200_exchange_send_rows); ADDR(tfhe_b200_exchange_gather_stride); ADDR(tfhe_b200_exchange_all_gather);
-    ADDR(tfhe_b200_exchange_all_reduce_sum); ADDR(tfhe_b200_exchange_destroy);
+    ADDR(tfhe_b200_exchange_all_reduce_sum); ADDR(tfhe_b200_exchange_group_run); ADDR(tfhe_b200_exchange_destroy);
     ADDR(tfhe_b200_set_tuning); ADDR(tfhe_b200_kernel_launches); ADDR(tfhe_b200_time_last_kernels); ADDR(tfhe_b200_probe_fp64_tflops);
     ADDR(tfhe_b200_version);
 

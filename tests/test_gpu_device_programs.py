@@ -4,8 +4,9 @@
     scalar radix comparisons (radix_parallel/scalar_comparison.rs:366-458, comparator.rs:474-502) on real keys;
   * find / rfind on a haystack with more than 420 windows and dense matches (the carry of the block-prefix sums, ADVICE r1);
   * every sharded string operation with two ranks driven from one process on ONE GPU: the ranks' exchange buffers are attached by
-    pointer, each rank runs on its own stream, and the publish / wait / pull kernel does the sum / gather -- decrypted results against
-    clear text (scalar_comparison.rs:147-240 for the boolean trees, comparator.rs:257-279 for the sign tree).
+    pointer, each rank runs on its own stream, and the publish / wait / pull code of the exchange kernel runs for both ranks in one
+    cooperative launch (ranks that share a GPU must not spin in separate launches) -- decrypted results against clear text
+    (scalar_comparison.rs:147-240 for the boolean trees, comparator.rs:257-279 for the sign tree).
 The two-GPU NCCL / CUDA-IPC variant is tests/test_gpu_multi_rank.py (skipped on a one-GPU box)."""
 from concurrent.futures import ThreadPoolExecutor
 
@@ -101,7 +102,7 @@ def test_find_more_than_420_windows_gpu(orc, keys_2_2, eng):
 
 
 def test_sharded_ops_two_ranks_one_gpu(orc, keys_2_2):
-    """world = 2 on one GPU: two engines, two threads, two streams; exchange through the engine's peer-memory kernel"""
+    """world = 2 on one GPU: two engines, two threads, two streams; exchange through the engine's peer-memory kernel (group launch)"""
     import torch
     from oracle import radix as R
     from fhe_string_bounty_b200 import multi_gpu as MG

@@ -96,23 +96,27 @@ def classic(keys_2_2):
     e.close()
 
 
-def test_classic_v4_four_per_sm(orc, classic):
-    """batch = 4 * SMs + 3: pbs_classic_kernel_v4<4> takes the 4 * SMs wide part, the remainder of 3 goes to pbs_v8.cu"""
+@pytest.mark.parametrize("per_sm", [5, 4])
+def test_classic_v4_wide_instances(orc, classic, per_sm):
+    """batch = per_sm * SMs + 3: pbs_classic_kernel_v4<per_sm> takes the per_sm * SMs wide part (5 per SM is the default: 20 warps of
+    96 registers; 4 per SM = 16 warps of 128), the remainder of 3 goes to pbs_v8.cu"""
     p, ck, sk, luts, eng = classic
     sms = _sms()
-    batch = 4 * sms + 3
+    batch = per_sm * sms + 3
+    eng.set_tuning("wide_cts", per_sm)
     cts, vals, idx = _batch(ck, batch, len(FS), 101)
     small = eng.keyswitch_batch(cts)
     assert np.array_equal(small[:64], np.stack([sk.keyswitch(c) for c in cts[:64]]))
-    rows = _probe_rows(4 * sms, 4) + [batch - 3, batch - 2, batch - 1]
-    _check_partial(eng, sk, small, idx, luts, rows, "pbs_classic_kernel_v4<4> (+ v8 tail)")
-    out = _check_full(eng, ck, sk, cts, vals, idx, luts, FS, rows[:32], "pbs_classic_kernel_v4<4> (+ v8 tail)")
+    rows = _probe_rows(per_sm * sms, per_sm) + [batch - 3, batch - 2, batch - 1]
+    _check_partial(eng, sk, small, idx, luts, rows, f"pbs_classic_kernel_v4<{per_sm}> (+ v8 tail)")
+    out = _check_full(eng, ck, sk, cts, vals, idx, luts, FS, rows[:32], f"pbs_classic_kernel_v4<{per_sm}> (+ v8 tail)")
     # the fused u16 hand-off (keyswitch epilogue applies the modulus switch) against the unfused two-call path: same kernels, same words
     assert np.array_equal(out, eng.pbs_batch(small, idx)), "fused KS->PBS hand-off differs from keyswitch_batch + pbs_batch"
     # a ciphertext's result does not depend on its position in the wide launch (rows 0 and 64 hold the same input and LUT index when 64 | 7*64)
-    same = [b for b in range(64, 4 * sms) if idx[b] == idx[b % 64]][:16]
+    same = [b for b in range(64, per_sm * sms) if idx[b] == idx[b % 64]][:16]
     for b in same:
         assert np.array_equal(out[b], out[b % 64]), f"row {b} differs from row {b % 64} (same input, same LUT)"
+    eng.set_tuning("wide_cts", 5)
 
 
 @pytest.mark.parametrize("per_cta", [2, 1])
