@@ -127,13 +127,13 @@ static int do_pbs_kernels(tfhe_b200_ctx *c, const uint64_t *d_small, const uint3
     {
         // Wide part: whole waves of 4 ciphertexts per SM on pbs_v4.cu.  What is left over, if it fits two ciphertexts per SM, runs on
         // the narrow-level kernel pbs_v8.cu (2.9 ms for <= SM count, 4.4 ms for <= 2 x SM count) instead of a mostly empty 7.8 ms wave.
-        const size_t wave = (size_t)c->wide_cts * c->sms, narrow = c->narrow_kernel == 8 ? (size_t)(c->narrow_max ? c->narrow_max : 2 * c->sms) : 0;
+        const size_t wave = (size_t)4 * c->sms, narrow = c->narrow_kernel == 8 ? (size_t)(c->narrow_max ? c->narrow_max : 2 * c->sms) : 0;
         const size_t rem = batch % wave;
         const size_t tail = batch <= narrow ? batch : (rem != 0 && rem <= narrow) ? rem : 0;
         const size_t wide = batch - tail;
         if (wide) {
             TB_CUDA(tbk::launch_pbs_classic_v4(d_small, d_idx, d_luts, c->bskf.p, c->tbl16.p, d_out, out_slot, (int)wide, (int)c->p.lwe_dim,
-                                               (int)c->p.pbs_base_log, (int)n_iters, fused ? 1 : 0, c->wide_cts, s));
+                                               (int)c->p.pbs_base_log, (int)n_iters, fused ? 1 : 0, s));
             c->launches += 1;
         }
         if (tail) {
@@ -198,7 +198,6 @@ int tfhe_b200_ctx_create(int cuda_device, const tfhe_b200_params *params, tfhe_b
     TB_CUDA(tbk::pbs_v8_configure());
     if (const char *e = std::getenv("TFHE_B200_NARROW_KERNEL")) c->narrow_kernel = (e[0] == '8') ? 8 : 0;
     if (const char *e = std::getenv("TFHE_B200_NARROW_MAX")) c->narrow_max = atoi(e);
-    if (const char *e = std::getenv("TFHE_B200_WIDE_CTS")) c->wide_cts = (e[0] == '4') ? 4 : 5;
     TB_CUDA(cudaDeviceGetAttribute(&c->sms, cudaDevAttrMultiProcessorCount, cuda_device));
     TB_CUDA(tbk::pbs_multibit_v4_configure());
     TB_CUDA(tbk::pbs_multibit_v8_configure());
@@ -242,9 +241,6 @@ int tfhe_b200_set_tuning(tfhe_b200_ctx *c, const char *key, int value) {
     } else if (k == "narrow_max") {
         if (value < 0) return fail("narrow_max must be >= 0");
         c->narrow_max = value;
-    } else if (k == "wide_cts") {
-        if (value != 4 && value != 5) return fail("wide_cts must be 4 or 5");
-        c->wide_cts = value;
     } else if (k == "ks_kernel") {
         if (value != 0 && value != 1) return fail("ks_kernel must be 0 (IMAD) or 1 (tensor cores)");
         if (value == 1 && !tbk::ks_mma_supported((int)c->p.ks_level)) return fail("tensor-core keyswitch does not support this level count");
@@ -606,7 +602,7 @@ int tfhe_b200_ks_pbs_batch(tfhe_b200_ctx *c, const uint64_t *in, const uint32_t 
     // (stream + staging buffers)
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
-    const size_t chunk = std::min<size_t>(batch, c->p.grouping_factor ? (size_t)sms * 3 * 5 : (size_t)sms * c->wide_cts * 4);
+    const size_t chunk = std::min<size_t>(batch, c->p.grouping_factor ? (size_t)sms * 3 * 5 : (size_t)sms * 4 * 4);
     const size_t L = c->big_len();
     for (auto &ln : c->lane) {
         TB_CUDA(ln.in.reserve(chunk * L * 8));

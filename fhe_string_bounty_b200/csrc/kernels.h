@@ -25,8 +25,7 @@ size_t ks_mma_digits_bytes(int batch, int in_dim, int level);
 cudaError_t pbs_v4_configure();
 cudaError_t launch_pbs_classic_v4(const uint64_t *lwe_small, const uint32_t *lut_idx, const uint64_t *luts, const void *bskf4,
                                   const void *tbl16, uint64_t *out, const uint32_t *out_slot, int batch, int n, int base_log,
-                                  int n_iters, int small_is_u16, int wide_cts /* ciphertexts per SM of the wide instance: 4 or 5 */,
-                                  cudaStream_t stream);
+                                  int n_iters, int small_is_u16, cudaStream_t stream);
 cudaError_t launch_bsk_convert_v4(const uint64_t *bsk_std, void *bskf4, const void *tbl16, int n_polys, cudaStream_t stream);
 // probe.cu
 cudaError_t launch_fp64_peak(double *sink, int blocks, int iters, cudaStream_t stream);

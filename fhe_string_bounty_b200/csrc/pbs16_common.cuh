@@ -12,9 +12,13 @@ using namespace tbr;
 __device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
-struct PolySync {
+struct PolySync {      // named barrier over the 64 threads of one polynomial
     int id;
     __device__ __forceinline__ void operator()() const { bar_sync(id, 64); }
+};
+struct CtSync {        // named barrier over the 128 threads of one ciphertext (both polynomials)
+    int id;
+    __device__ __forceinline__ void operator()() const { bar_sync(id, 128); }
 };
 struct BlockSync {
     __device__ __forceinline__ void operator()() const { __syncthreads(); }
@@ -188,5 +192,11 @@ __device__ __forceinline__ void fft16_inv(double (&re)[16], double (&im)[16], cp
     posttwist16_inv(re, im);
 }
 
+__device__ __forceinline__ void pack_cplx(double r, double i, uint32_t (&v)[16], int q) {
+    v[4 * q] = (uint32_t)__double2loint(r); v[4 * q + 1] = (uint32_t)__double2hiint(r);
+    v[4 * q + 2] = (uint32_t)__double2loint(i); v[4 * q + 3] = (uint32_t)__double2hiint(i);
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
 }  // namespace tb16k

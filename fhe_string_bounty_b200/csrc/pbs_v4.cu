@@ -1,18 +1,23 @@
-// pbs_v4.cu -- blind rotation, fourth generation: the v3 data path (Fourier key streamed once per SM through a TMA-fed
-// shared-memory ring, accumulator master copy in Tensor Memory) with HALF the work per thread: two warps per polynomial,
-// 16 FFT points per thread (fft16_core.cuh), so a 4-ciphertext CTA has 16 warps -- 4 per scheduler instead of 2.
+// pbs_v4.cu -- blind rotation for wide levels: the Fourier key streamed once per SM through a TMA-fed shared-memory ring, the
+// accumulator's master copy in Tensor Memory, 16 FFT points per thread (fft16_core.cuh): four warps per ciphertext, lanes 0-15 of a
+// warp on the mask polynomial and lanes 16-31 on the body polynomial, four ciphertexts (16 warps) per SM.
 //
-// Why: ncu on v3 (profiles/r01_pbs_v3_final_b8192_summary.txt) shows FP64 pipe 45 %, LSU 52 %, issue slots 46 %: nothing is
-// saturated, the two 255-register warps per scheduler simply cannot cover each other's dependency stalls.  With 16 points
-// per thread the kernel fits 128 registers, and the schedulers get twice the warps to pick from, at the price of one more shared-memory exchange per FFT (16 x 16 x 4 instead of 32 x 32).
+// Same arithmetic definition as the reference (bootstrap.rs:242-364, ggsw.rs:477-598, fft/mod.rs:197-326); the FFT evaluates the same
+// 1024 frequencies as concrete-fft, only the butterfly order (hence FP64 rounding) differs.
 //
-// Same arithmetic definition as pbs_v3.cu (bootstrap.rs:242-364, ggsw.rs:477-598, fft/mod.rs:197-326): the FFT evaluates
-// the same 1024 frequencies, only the butterfly order (hence FP64 rounding) differs.
-//
-// Shared memory per 4-ciphertext CTA: 8 x 17 KiB polynomial tiles (rotated-gather source, then exchange tile, then spectrum
-// exchange) + 5 x 16 KiB ring = 216 KiB.  TMEM: 64 columns per ciphertext (accumulator master copy) + 80 columns of
-// per-thread FFT twiddles (ncu: the kernel is bound by the LSU pipe, tcgen05.ld is not on it).
-// Named barriers: 1..8 one per polynomial (64 threads), 9..12 one per ciphertext (128), 13..15 start-up stagger.
+// What bounds the kernel (ncu, scripts/microbench/pipes.cu and fp64.cu, profiles/r02_*): every variant tried in round 2 -- four or
+// five ciphertexts per SM, spectrum exchange through shared memory or through shuffles, exchange A through shared memory or through
+// Tensor Memory -- ends at the same 0.52-0.56 instructions per cycle and scheduler, i.e. the run time follows the INSTRUCTION COUNT
+// (2.65 k per warp and iteration, half of them FP64 at two dispatch cycles each), not the shared-memory pipe (46-76 % busy) and not the
+// FP64 pipe (44-55 %).  Measured pipe costs: LDS.128 4.25, STS.128 4.73, SHFL 2.4 cycles per warp instruction on ONE shared pipe;
+// tcgen05.ld / st 11.3 / 6.9 cycles per 2 KiB on a separate, concurrent path.  Tried and dropped: a fifth ciphertext per SM (96
+// registers: +9 % time), exchange A through Tensor Memory with a ciphertext's four warps in one lane quarter (shared-memory pipe 76 ->
+// 47 %, but +31 % instructions for uniform-register address moves, warp-part twiddles and spills: +34 % time).  Kept: the two
+// polynomials of a ciphertext in the two halves of each warp, so that the spectrum exchange of the external product is a lane ^ 16
+// shuffle (two barriers and 32 shared-memory instructions per thread and iteration fewer).
+// Shared memory per 4-ciphertext CTA: 8 x 17 KiB polynomial tiles (rotated-gather source, then exchange tile) + 5 x 16 KiB ring.
+// TMEM: 64 columns per ciphertext (accumulator master copy) + 80 columns of per-thread FFT twiddles.
+// Named barriers: one per ciphertext (128 threads).
 #include "kernels.h"
 #include "pbs16_common.cuh"
 
@@ -20,33 +25,28 @@ namespace tb4 {
 using namespace tb16k;
 
 constexpr int QPP = 4;                 // frequencies (registers) per ring piece
-constexpr int PIECE_CPLX = 2 * QPP * 64;       // one output polynomial's share of a chunk: [sel 2][q QPP][thread 64] = 8 KiB
+constexpr int PIECE_CPLX = 2 * 2 * QPP * 64;   // one chunk: [out poly 2][sel 2][q QPP][thread 64] = 16 KiB
 constexpr int PIECE_BYTES = PIECE_CPLX * 16;
 constexpr int CHUNKS_PER_ITER = 16 / QPP;
-// ring slots PER OUTPUT POLYNOMIAL: the warps of polynomial w only ever read the c = w half of a chunk, so the key streams through two
-// interleaved rings (slot 2 k + w) whose pieces are consumed by 2 * CTS warps each.  1..4 ciphertexts per CTA: 5 + 5 slots = 80 KiB;
-// 5 ciphertexts: 3 + 3 slots = 48 KiB next to ten 17 KiB tiles.
-constexpr int ring_slots(int cts) { return cts == 5 ? 3 : 5; }
+constexpr int NS = 5;                  // ring slots: 80 KiB = 1.25 iterations of key
 
 template <int CTS>
 struct Smem {
-    static constexpr int NS = ring_slots(CTS);
-    cplx tile[2 * CTS][kTileCplx];         // 17 KiB per polynomial
-    cplx ring[2 * NS][PIECE_CPLX];
-    unsigned long long full_bar[2 * NS];
-    unsigned int consumed[2 * NS];
+    cplx tile[2 * CTS][kTileCplx];     // 17 KiB per polynomial
+    cplx ring[NS][PIECE_CPLX];
+    unsigned long long full_bar[NS];
+    unsigned int consumed[NS];
     uint32_t tmem_base;
 };
 static_assert(sizeof(Smem<4>) <= 227 * 1024, "shared memory budget");
-static_assert(sizeof(Smem<5>) <= 227 * 1024, "shared memory budget");
 
 // Fourier key, v4 layout: [ggsw i][chunk 16/QPP][out poly c][sel: 0 = row c, 1 = row 1-c][q QPP][thread 64]; register g = QPP*chunk + q
 // (QPP = 4 measured 101.9 ms per 8192 against 104.1 ms for QPP = 2; QPP = 8 leaves too few slots for the ciphertexts' stagger)
 __device__ __forceinline__ size_t bskf4_index(int i, int chunk, int c, int sel, int q) {
     return ((((size_t)(i * CHUNKS_PER_ITER + chunk) * 2 + c) * 2 + sel) * QPP + q) * 64;
 }
-// piece k of output polynomial w (k = i * CHUNKS_PER_ITER + chunk): 8 KiB, contiguous in the layout above
-__device__ __forceinline__ const cplx *piece_src(const cplx *bskf4, int k, int w) { return bskf4 + ((size_t)k * 2 + w) * PIECE_CPLX; }
+// piece k = i * CHUNKS_PER_ITER + chunk: 16 KiB, contiguous in the layout above
+__device__ __forceinline__ const cplx *piece_src(const cplx *bskf4, int k) { return bskf4 + (size_t)k * PIECE_CPLX; }
 
 template <int CTS>
 __global__ void __launch_bounds__(128 * CTS, 1)
@@ -54,59 +54,57 @@ pbs_classic_kernel_v4(const uint64_t *__restrict__ lwe_small, const uint32_t *__
                       const cplx *__restrict__ bskf4, const cplx *__restrict__ tbl16, uint64_t *__restrict__ out,
                       const uint32_t *__restrict__ out_slot, int batch, int n, int base_log, int n_iters, int small_is_u16) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    constexpr int TMEM_COLS = CTS >= 4 ? 512 : 256, TW_COL = 64 * CTS, NS = Smem<CTS>::NS, CONSUMERS = 2 * CTS;
-    constexpr bool PER_CHUNK = NS <= CHUNKS_PER_ITER;    // the ring cannot hold a whole iteration plus the chunk being waited for
-    static_assert(TW_COL + 80 <= TMEM_COLS, "TMEM columns");
-    static_assert(3 * CTS <= 15, "named barriers: 1 .. 2 CTS per polynomial, 2 CTS + 1 .. 3 CTS per ciphertext");
+    constexpr int TMEM_COLS = CTS == 4 ? 512 : 256, CONSUMERS = 4 * CTS;   // every warp reads every ring piece
+    constexpr int TW_COL = 64 * CTS;                                        // per-thread twiddles after the accumulators
     Smem<CTS> &sm = *reinterpret_cast<Smem<CTS> *>(smem_raw);
     const int W = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // warp -> (ciphertext, polynomial, half): the four warps of a ciphertext sit on the four schedulers (warp id % 4), so every
-    // scheduler hosts one warp of each ciphertext; the ciphertexts are started a quarter iteration apart (stagger below)
-    const int ctl = W >> 2, w = (W >> 1) & 1, T = ((W & 1) << 5) | lane, P = W >> 1;
+    // warp -> (ciphertext, quarter of the FFT threads); HALF-warp -> polynomial: lanes 0-15 work on the mask polynomial, lanes 16-31 on
+    // the body polynomial, both as the FFT threads T = 16 k + (lane & 15).  Lane l and lane l ^ 16 hold the two polynomials' spectra
+    // at the SAME frequencies.  Every scheduler (warp id % 4) hosts one warp of each ciphertext; the ciphertexts are started a fraction
+    // of an iteration apart (stagger below).
+    const int ctl = W >> 2, k = W & 3;
+    const int w = lane >> 4, T = (k << 4) | (lane & 15), P = 2 * ctl + w;
     const int ct_raw = blockIdx.x * CTS + ctl;
     const bool live = ct_raw < batch;
     const int ct = live ? ct_raw : batch - 1;        // ragged tail: recompute the last ciphertext, skip the store
     cplx *tile = sm.tile[P];
-    const cplx *otile = sm.tile[P ^ 1];
     uint64_t *pb = reinterpret_cast<uint64_t *>(tile);   // the polynomial (2048 words) for the rotated gather
-    const PolySync poly_sync{1 + P};
-    const int ct_bar = 1 + 2 * CTS + ctl;
+    const CtSync ct_sync{1 + ctl};        // exchange A crosses the ciphertext's four warps (both polynomials travel together)
     const uint64_t *lwe = lwe_small + (size_t)ct * (n + 1);
     const uint16_t *lwe16 = reinterpret_cast<const uint16_t *>(lwe_small) + (size_t)ct * (n + 1);
-    const int total_pieces = n_iters * CHUNKS_PER_ITER;      // per output polynomial
+    const int total_pieces = n_iters * CHUNKS_PER_ITER;
 
     // ---- one-time setup: twiddle tables, barriers, TMEM, first ring fill ---------------------------------------------------
     if (threadIdx.x == 0) {
-        for (int s = 0; s < 2 * NS; ++s) { mbar_init(&sm.full_bar[s], 1); sm.consumed[s] = 0; }
+        for (int s = 0; s < NS; ++s) { mbar_init(&sm.full_bar[s], 1); sm.consumed[s] = 0; }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_proxy_async();
     }
     if (W == 0) tmem_alloc<TMEM_COLS>(&sm.tmem_base);
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    tc_fence_before();
     __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_mine = sm.tmem_base + ((uint32_t)((W & 3) * 32) << 16) + (uint32_t)(ctl * 64);   // lane quarter = warp id % 4
-    const TmemTwiddles twd{sm.tmem_base + ((uint32_t)((W & 3) * 32) << 16) + (uint32_t)TW_COL};
+    tc_fence_after();
+    const uint32_t quarter = sm.tmem_base + ((uint32_t)((W & 3) * 32) << 16);       // lane quarter = warp id % 4
+    const uint32_t tmem_mine = quarter + (uint32_t)(ctl * 64);                      // this warp's accumulator columns
+    const TmemTwiddles twd{quarter + (uint32_t)TW_COL};
     {   // this thread's twiddles -> TMEM (5 x 16 columns: T1[p][T], p = 0..15, then the three pass-2 twiddles)
 #pragma unroll
-        for (int k = 0; k < 5; ++k) {
+        for (int kk = 0; kk < 5; ++kk) {
             uint32_t v[16];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const cplx t = k < 4 ? __ldg(tbl16 + (4 * k + q) * 64 + T) : __ldg(tbl16 + kM + 16 * (q < 3 ? q : 0) + (T & 15));
-                v[4 * q] = (uint32_t)__double2loint(t.x); v[4 * q + 1] = (uint32_t)__double2hiint(t.x);
-                v[4 * q + 2] = (uint32_t)__double2loint(t.y); v[4 * q + 3] = (uint32_t)__double2hiint(t.y);
+                const cplx t = kk < 4 ? __ldg(tbl16 + (4 * kk + q) * 64 + T) : __ldg(tbl16 + kM + 16 * (q < 3 ? q : 0) + (T & 15));
+                pack_cplx(t.x, t.y, v, q);
             }
-            tmem_st16(twd.col + 16 * k, v);
+            tmem_st16(twd.col + 16 * kk, v);
         }
     }
     if (threadIdx.x == 0) {
         const int first = total_pieces < NS ? total_pieces : NS;
-        for (int k = 0; k < first; ++k)
-            for (int c = 0; c < 2; ++c) {
-                mbar_expect_tx(&sm.full_bar[2 * k + c], PIECE_BYTES);
-                tma_load_1d(sm.ring[2 * k + c], piece_src(bskf4, k, c), PIECE_BYTES, &sm.full_bar[2 * k + c]);
-            }
+        for (int g = 0; g < first; ++g) {
+            mbar_expect_tx(&sm.full_bar[g], PIECE_BYTES);
+            tma_load_1d(sm.ring[g], piece_src(bskf4, g), PIECE_BYTES, &sm.full_bar[g]);
+        }
     }
 
     // ---- acc <- LUT * X^(-b_hat): registers (own coefficients as u64 bit patterns in re/im), TMEM, shared ------------------------
@@ -129,33 +127,28 @@ pbs_classic_kernel_v4(const uint64_t *__restrict__ lwe_small, const uint32_t *__
             im[m] = __longlong_as_double((long long)v1);
         }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int kk = 0; kk < 4; ++kk) {
             uint32_t v[16];
 #pragma unroll
-            for (int mm = 0; mm < 4; ++mm) {
-                const unsigned long long a = (unsigned long long)__double_as_longlong(re[4 * k + mm]);
-                const unsigned long long b = (unsigned long long)__double_as_longlong(im[4 * k + mm]);
-                v[4 * mm] = (uint32_t)a; v[4 * mm + 1] = (uint32_t)(a >> 32);
-                v[4 * mm + 2] = (uint32_t)b; v[4 * mm + 3] = (uint32_t)(b >> 32);
-            }
-            tmem_st16(tmem_mine + 16 * k, v);
+            for (int mm = 0; mm < 4; ++mm) pack_cplx(re[4 * kk + mm], im[4 * kk + mm], v, mm);
+            tmem_st16(tmem_mine + 16 * kk, v);
         }
         tmem_wait_st();
     }
 
-    // stagger: ciphertext k starts k / CTS of an iteration after ciphertext 0, so that the FP64-heavy and the shared-memory-heavy phases
-    // of the ciphertexts sharing a scheduler do not coincide (a clock-based delay measured the same as a barrier hand-shake)
+    // stagger: ciphertext c starts c / CTS of an iteration after ciphertext 0, so that the FP64-heavy and the shared-memory-heavy phases
+    // of the ciphertexts do not coincide (a clock-based delay measured the same as a barrier hand-shake)
     if (CTS >= 4 && ctl >= 1 && n_iters > 0) {
         const long long t0 = clock64(), delay = (long long)ctl * (20000 / CTS);
         while (clock64() - t0 < delay) { }
     }
 
-    int slot = 0;            // this polynomial's ring position (0 .. NS-1) of this iteration's first piece
+    int slot = 0;            // ring position (0 .. NS-1) of this iteration's first piece
     uint32_t phase = 0;
 
     for (int i = 0; i < n_iters; ++i) {
         const uint32_t a = (small_is_u16 ? (uint32_t)__ldg(lwe16 + i) : modulus_switch_2n(__ldg(lwe + i))) & (2 * kN - 1);   // a == 0 is NOT skipped
-        poly_sync();    // the accumulator polynomial is complete in shared memory
+        ct_sync();      // the accumulator polynomial is complete in shared memory
 
         // ct1 = acc * X^a - acc, level-1 signed digit, folded (own coefficients come from the registers)
 #pragma unroll
@@ -170,34 +163,26 @@ pbs_classic_kernel_v4(const uint64_t *__restrict__ lwe_small, const uint32_t *__
             re[m] = (double)signed_digit_l1(r0 - o0, base_log);
             im[m] = (double)signed_digit_l1(r1 - o1, base_log);
         }
+        fft16_fwd(re, im, tile, twd, T, ct_sync);    // its first barrier also ends the rotated gather: nobody writes the tile before it
 
-        fft16_fwd(re, im, tile, twd, T, poly_sync);
-
-        // spectrum exchange between the two polynomials of the ciphertext: park my 16 values in my own exchange-B reader slots
+        // out_fft[w] = F_w * G[w][w] + F_{1-w} * G[1-w][w], GGSW pieces from the ring, the other polynomial's spectrum from lane ^ 16.
+        // Nothing is synchronised inside the loop (the compiler is free to run chunk c+1's loads under chunk c's arithmetic); after it
+        // lane c counts this warp out of piece c's slot, and the last of the 4 * CTS warps to leave a slot re-arms it with the piece NS
+        // chunks ahead (measured against releasing each slot right after its chunk: 104.7 vs 106.0 ms per 8192).
         {
-            cplx *wp = tile + xb_rbase(T);
-#pragma unroll
-            for (int g = 0; g < 16; ++g) { cplx v; v.x = re[g]; v.y = im[g]; wp[xb_roff(g)] = v; }
-        }
-        bar_sync(ct_bar, 128);
-
-        // out_fft[w] = F_w * G[w][w] + F_{1-w} * G[1-w][w], GGSW pieces from this polynomial's ring.  Nothing is synchronised inside the loop
-        // (the compiler is free to run chunk c+1's loads under chunk c's arithmetic); after it lane c counts this warp out of piece c's
-        // slot, and the last of the 2 * CTS warps to leave a slot re-arms it with the piece NS chunks ahead (measured against releasing
-        // each slot right after its chunk: 104.7 vs 106.0 ms per 8192).
-        {
-            const cplx *fop = otile + xb_rbase(T);
             int my_slot = 0;
 #pragma unroll
             for (int c = 0; c < CHUNKS_PER_ITER; ++c) {
-                const int rs = 2 * slot + w;
-                if (!mbar_try_wait(&sm.full_bar[rs], phase)) mbar_wait(&sm.full_bar[rs], phase);
-                const cplx *pc = sm.ring[rs] + T;
+                if (!mbar_try_wait(&sm.full_bar[slot], phase)) mbar_wait(&sm.full_bar[slot], phase);
+                const cplx *pc = sm.ring[slot] + (w * 2) * QPP * 64 + T;
 #pragma unroll
                 for (int q = 0; q < QPP; ++q) {
                     const int g = QPP * c + q;
-                    const cplx A = pc[q * 64], B = pc[(QPP + q) * 64], F = fop[xb_roff(g)];
+                    const cplx A = pc[q * 64], B = pc[(QPP + q) * 64];
                     const double fr = re[g], fi = im[g];
+                    cplx F;       // the other polynomial's spectrum at this frequency: lane ^ 16
+                    F.x = __shfl_xor_sync(0xffffffffu, fr, 16);
+                    F.y = __shfl_xor_sync(0xffffffffu, fi, 16);
                     double orr = DMUL(fr, A.x);
                     orr = DFMA(-fi, A.y, orr);
                     orr = DFMA(F.x, B.x, orr);
@@ -208,51 +193,34 @@ pbs_classic_kernel_v4(const uint64_t *__restrict__ lwe_small, const uint32_t *__
                     oi = DFMA(F.y, B.x, oi);
                     re[g] = orr; im[g] = oi;
                 }
-                if (PER_CHUNK) {
-                    // fewer slots than chunks per iteration (5 ciphertexts per CTA): a slot has to be handed back before the next chunk can
-                    // arrive, so this warp counts itself out right away (shared-memory accesses of a warp complete in order: the atomic
-                    // follows every lane's loads of this chunk)
-                    __syncwarp();
-                    if (lane == 0 && atomicAdd(&sm.consumed[rs], 1u) == CONSUMERS - 1) {
-                        sm.consumed[rs] = 0;
-                        const int k2 = i * CHUNKS_PER_ITER + c + NS;
-                        if (k2 < total_pieces) {
-                            __threadfence_block();
-                            fence_proxy_async();
-                            mbar_expect_tx(&sm.full_bar[rs], PIECE_BYTES);
-                            tma_load_1d(sm.ring[rs], piece_src(bskf4, k2, w), PIECE_BYTES, &sm.full_bar[rs]);
-                        }
-                    }
-                }
-                if (lane == c) my_slot = rs;
+                if (lane == c) my_slot = slot;
                 if (++slot == NS) { slot = 0; phase ^= 1u; }
             }
             __syncwarp();     // every lane's loads from the ring have returned (their values fed the arithmetic above)
-            if (!PER_CHUNK && lane < CHUNKS_PER_ITER && atomicAdd(&sm.consumed[my_slot], 1u) == CONSUMERS - 1) {
+            if (lane < CHUNKS_PER_ITER && atomicAdd(&sm.consumed[my_slot], 1u) == CONSUMERS - 1) {
                 sm.consumed[my_slot] = 0;
                 const int k2 = i * CHUNKS_PER_ITER + lane + NS;
                 if (k2 < total_pieces) {
                     __threadfence_block();
                     fence_proxy_async();
                     mbar_expect_tx(&sm.full_bar[my_slot], PIECE_BYTES);
-                    tma_load_1d(sm.ring[my_slot], piece_src(bskf4, k2, w), PIECE_BYTES, &sm.full_bar[my_slot]);
+                    tma_load_1d(sm.ring[my_slot], piece_src(bskf4, k2), PIECE_BYTES, &sm.full_bar[my_slot]);
                 }
             }
         }
-        bar_sync(ct_bar, 128);   // the partner polynomial has read my spectrum: the tile is mine again
 
-        fft16_inv(re, im, tile, twd, T, poly_sync);
-        poly_sync();    // everyone has read the last exchange: the tile becomes the accumulator polynomial again
+        fft16_inv(re, im, tile, twd, T, ct_sync);
+        ct_sync();      // everyone is past its exchange-B reads: the tile becomes the accumulator polynomial again
 
         // acc += from_torus(.): master copy in TMEM, new values to registers (next gather's "own") and shared (next rotation)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int kk = 0; kk < 4; ++kk) {
             uint32_t v[16];
-            tmem_ld16(tmem_mine + 16 * k, v);
+            tmem_ld16(tmem_mine + 16 * kk, v);
             tmem_wait_ld();
 #pragma unroll
             for (int mm = 0; mm < 4; ++mm) {
-                const int m = 4 * k + mm, j = T + 64 * m;
+                const int m = 4 * kk + mm, j = T + 64 * m;
                 uint64_t o0 = ((uint64_t)v[4 * mm + 1] << 32) | v[4 * mm];
                 uint64_t o1 = ((uint64_t)v[4 * mm + 3] << 32) | v[4 * mm + 2];
                 o0 += from_torus_f64(re[m]);
@@ -263,7 +231,7 @@ pbs_classic_kernel_v4(const uint64_t *__restrict__ lwe_small, const uint32_t *__
                 re[m] = __longlong_as_double((long long)o0);
                 im[m] = __longlong_as_double((long long)o1);
             }
-            tmem_st16(tmem_mine + 16 * k, v);
+            tmem_st16(tmem_mine + 16 * kk, v);
         }
         tmem_wait_st();
     }
@@ -284,7 +252,7 @@ pbs_classic_kernel_v4(const uint64_t *__restrict__ lwe_small, const uint32_t *__
         }
     }
 
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    tc_fence_before();
     __syncthreads();
     if (W == 0) tmem_dealloc<TMEM_COLS>(sm.tmem_base);
 }
@@ -319,9 +287,7 @@ bsk_convert_kernel_v4(const uint64_t *__restrict__ bsk_std, cplx *__restrict__ b
 namespace tbk {
 
 cudaError_t pbs_v4_configure() {
-    cudaError_t e = cudaFuncSetAttribute(tb4::pbs_classic_kernel_v4<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tb4::Smem<5>));
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(tb4::pbs_classic_kernel_v4<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tb4::Smem<4>));
+    cudaError_t e = cudaFuncSetAttribute(tb4::pbs_classic_kernel_v4<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tb4::Smem<4>));
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(tb4::pbs_classic_kernel_v4<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tb4::Smem<2>));
     if (e != cudaSuccess) return e;
@@ -330,7 +296,7 @@ cudaError_t pbs_v4_configure() {
 
 cudaError_t launch_pbs_classic_v4(const uint64_t *lwe_small, const uint32_t *lut_idx, const uint64_t *luts, const void *bskf4,
                                   const void *tbl16, uint64_t *out, const uint32_t *out_slot, int batch, int n, int base_log,
-                                  int n_iters, int small_is_u16, int wide_cts, cudaStream_t stream) {
+                                  int n_iters, int small_is_u16, cudaStream_t stream) {
     if (batch <= 0) return cudaSuccess;
     int sms = 148, dev = 0;
     cudaGetDevice(&dev);
@@ -341,9 +307,6 @@ cudaError_t launch_pbs_classic_v4(const uint64_t *lwe_small, const uint32_t *lut
                                                                                   base_log, n_iters, small_is_u16);
     else if (batch <= 2 * sms)
         tb4::pbs_classic_kernel_v4<2><<<(batch + 1) / 2, 256, sizeof(tb4::Smem<2>), stream>>>(lwe_small, lut_idx, luts, bk, tb, out, out_slot,
-                                                                                            batch, n, base_log, n_iters, small_is_u16);
-    else if (wide_cts == 5)
-        tb4::pbs_classic_kernel_v4<5><<<(batch + 4) / 5, 640, sizeof(tb4::Smem<5>), stream>>>(lwe_small, lut_idx, luts, bk, tb, out, out_slot,
                                                                                             batch, n, base_log, n_iters, small_is_u16);
     else
         tb4::pbs_classic_kernel_v4<4><<<(batch + 3) / 4, 512, sizeof(tb4::Smem<4>), stream>>>(lwe_small, lut_idx, luts, bk, tb, out, out_slot,

@@ -14,8 +14,7 @@ eng.upload_luts(rng.integers(0, 2**64, size=(16, p.lut_len), dtype=np.uint64))
 sms = torch.cuda.get_device_properties(0).multi_processor_count
 ts = torch.cuda.Stream(); torch.cuda.set_stream(ts)
 rows = []
-for cts in [int(x) for x in (sys.argv[1] if len(sys.argv) > 1 else "4,5").split(",")]:
-    eng.set_tuning("wide_cts", cts)
+for cts in [4]:
     for B in (8192, cts * sms * 8):
         d_in = torch.randint(-2**63, 2**63 - 1, (B, p.big_len), dtype=torch.int64, device="cuda")
         d_idx = (torch.arange(B, device="cuda", dtype=torch.int32) % 16).contiguous()

@@ -96,14 +96,13 @@ def classic(keys_2_2):
     e.close()
 
 
-@pytest.mark.parametrize("per_sm", [5, 4])
-def test_classic_v4_wide_instances(orc, classic, per_sm):
-    """batch = per_sm * SMs + 3: pbs_classic_kernel_v4<per_sm> takes the per_sm * SMs wide part (5 per SM is the default: 20 warps of
-    96 registers; 4 per SM = 16 warps of 128), the remainder of 3 goes to pbs_v8.cu"""
+def test_classic_v4_four_per_sm(orc, classic):
+    """batch = 4 * SMs + 3: pbs_classic_kernel_v4<4> (exchange A through Tensor Memory) takes the 4 * SMs wide part, the remainder of 3
+    goes to pbs_v8.cu"""
     p, ck, sk, luts, eng = classic
     sms = _sms()
+    per_sm = 4
     batch = per_sm * sms + 3
-    eng.set_tuning("wide_cts", per_sm)
     cts, vals, idx = _batch(ck, batch, len(FS), 101)
     small = eng.keyswitch_batch(cts)
     assert np.array_equal(small[:64], np.stack([sk.keyswitch(c) for c in cts[:64]]))
@@ -116,7 +115,6 @@ def test_classic_v4_wide_instances(orc, classic, per_sm):
     same = [b for b in range(64, per_sm * sms) if idx[b] == idx[b % 64]][:16]
     for b in same:
         assert np.array_equal(out[b], out[b % 64]), f"row {b} differs from row {b % 64} (same input, same LUT)"
-    eng.set_tuning("wide_cts", 5)
 
 
 @pytest.mark.parametrize("per_cta", [2, 1])
