@@ -246,6 +246,30 @@ class IntegerServerKey {
         }
         return out;
     }
+    // full_propagate_parallelized on blocks of ANY degree < total_mod (radix_parallel/mod.rs:88-156, parallel branch): message_extract
+    // and carry_extract of every block in one level, the carries added one block up (message + carry <= 2 (msg_mod - 1)), then the
+    // single-carry propagation above.  Blocks whose degree already allows a single carry go straight to it.
+    Radix full_propagate_any_degree(const Radix &in) {
+        const uint64_t m = p.msg_mod;
+        uint64_t worst = 0;
+        for (auto &b : in) worst = std::max(worst, b.degree);
+        if (worst <= 2 * m - 1) return full_propagate(in);       // x <= 2 msg_mod - 1: at most one carry out of every block
+        Radix msg(in.size()), carry(in.size());
+        for (size_t i = 0; i < in.size(); ++i) {
+            msg[i] = pg.pbs(in[i], [m](uint64_t x) { return x % m; });
+            if (i + 1 < in.size()) carry[i] = pg.pbs(in[i], [m](uint64_t x) { return x / m; });
+        }
+        Radix sum(in.size());
+        for (size_t i = 0; i < in.size(); ++i) sum[i] = i == 0 ? msg[i] : pg.unchecked_add(msg[i], carry[i - 1]);
+        return full_propagate(sum);
+    }
+    bool block_carries_are_empty(const Radix &r) const {      // integer/ciphertext/base.rs: every degree < msg_mod
+        for (auto &b : r) if (b.degree >= p.msg_mod) return false;
+        return true;
+    }
+    // the default (non-"unchecked") comparisons: propagate an operand first if its carries are not empty (comparison.rs:200-260)
+    Radix cleaned(const Radix &r) { return block_carries_are_empty(r) ? r : full_propagate_any_degree(r); }
+
     // add_parallelized on clean inputs (radix_parallel/add.rs:206-243): leveled add then propagate
     Radix add(const Radix &a, const Radix &b) {
         if (a.size() != b.size()) throw std::invalid_argument("add: radix size mismatch");

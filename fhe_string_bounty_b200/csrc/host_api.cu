@@ -4,7 +4,7 @@
 // This is the restructuring of the reference's per-block rayon fan-out
 // (integer/server_key/radix_parallel/*.rs -> shortint apply_lookup_table) that north_star asks for.
 #include "ctx.h"
-#include "host/strings.h"
+#include "host/padded.h"
 
 #include <memory>
 
@@ -91,6 +91,26 @@ bool record(tfhe_b200_program &h, const std::string &op_in, const uint64_t *a, s
             pg.output(f == "scalar_eq" ? isk.unchecked_scalar_eq(x, a[1]) : f == "scalar_lt" ? isk.unchecked_scalar_lt(x, a[1]) : isk.unchecked_scalar_gt(x, a[1]));
             return true;
         }
+        // default (propagating) forms on operands whose blocks carry up to a[1] (e.g. 6 after one unchecked_add): what the reference's
+        // comparison tests exercise (radix_parallel/tests_cases_comparisons.rs:81-97)
+        if (f.rfind("default_", 0) == 0 || f == "full_propagate") {
+            if (!need(2)) return false;
+            if (a[1] >= h.p.total_mod()) { err = op + ": block degree must stay below the message space"; return false; }
+            auto dirty = [&](size_t n) { tbh::Radix r; for (size_t i = 0; i < n; ++i) r.push_back(pg.input(a[1], 2)); return r; };
+            tbh::Radix x = dirty(nb);
+            if (f == "full_propagate") { output_radix(pg, isk.full_propagate_any_degree(x)); return true; }
+            tbh::Radix y = dirty(nb);
+            x = isk.cleaned(x); y = isk.cleaned(y);
+            const std::string g = f.substr(8);
+            if (g == "eq") pg.output(isk.unchecked_eq(x, y));
+            else if (g == "ne") pg.output(isk.unchecked_ne(x, y));
+            else if (g == "lt") pg.output(isk.unchecked_lt(x, y));
+            else if (g == "le") pg.output(isk.unchecked_le(x, y));
+            else if (g == "gt") pg.output(isk.unchecked_gt(x, y));
+            else if (g == "ge") pg.output(isk.unchecked_ge(x, y));
+            else { err = "unknown radix op: " + op; return false; }
+            return true;
+        }
         if (f == "if_then_else") {
             tbh::Ct cond = pg.input(1, 1);
             tbh::Radix x = input_radix(pg, nb), y = input_radix(pg, nb);
@@ -167,6 +187,40 @@ bool record(tfhe_b200_program &h, const std::string &op_in, const uint64_t *a, s
             else if (f == "contains") pg.output(ssk.contains(st.first, st.second));
             else { err = "unknown batched string op: " + op; return false; }
         }
+        return true;
+    }
+    // ---- null-padded strings (secret length, host/padded.h): a = {capacity_a[, capacity_b | count]}; a clear pattern comes through `clear` -----
+    if (op.rfind("pstring_", 0) == 0) {
+        if (!need(1)) return false;
+        tbh::PaddedStringServerKey psk(pg);
+        const std::string f = op.substr(8);
+        tbh::FheString s = ssk.input_string(a[0]);
+        if (f == "len") { output_radix(pg, psk.len(s)); return true; }
+        if (f == "is_empty") { pg.output(psk.is_empty(s)); return true; }
+        if (f == "trim_start") { output_string(pg, psk.trim_start(s)); return true; }
+        if (f == "trim_end") { output_string(pg, psk.trim_end(s)); return true; }
+        if (f == "trim") { output_string(pg, psk.trim(s)); return true; }
+        if (f == "strip_prefix" || f == "strip_suffix") {
+            if (!clear) { err = op + ": needs a clear pattern"; return false; }
+            auto r = f == "strip_prefix" ? psk.strip_prefix(s, cl) : psk.strip_suffix(s, cl);
+            pg.output(r.first);
+            output_string(pg, r.second);
+            return true;
+        }
+        if (f == "repeat") { if (!need(2)) return false; output_string(pg, psk.repeat(s, a[1])); return true; }
+        if (!need(2)) return false;
+        tbh::FheString t = ssk.input_string(a[1]);
+        if (f == "eq") pg.output(psk.eq(s, t));
+        else if (f == "ne") pg.output(psk.ne(s, t));
+        else if (f == "lt") pg.output(psk.lt(s, t));
+        else if (f == "le") pg.output(psk.le(s, t));
+        else if (f == "gt") pg.output(psk.gt(s, t));
+        else if (f == "ge") pg.output(psk.ge(s, t));
+        else if (f == "contains") pg.output(psk.contains(s, t));
+        else if (f == "starts_with") pg.output(psk.starts_with(s, t));
+        else if (f == "ends_with") pg.output(psk.ends_with(s, t));
+        else if (f == "concat") output_string(pg, psk.concat(s, t));
+        else { err = "unknown padded string op: " + op; return false; }
         return true;
     }
     // ---- strings: a = {len_a[, len_b]}; with a non-empty `clear` the second operand is a clear (trivial) string ----------------------------------

@@ -146,10 +146,16 @@ int tfhe_b200_pbs_batch_partial(tfhe_b200_ctx *ctx, const uint64_t *lwe_small, c
  * fhe_string_bounty_b200/csrc/host/strings.h).  `op` is one of:
  *   shortint_apply_lut {n, f(0..15)}      shortint_bivariate_lut {n, f(x,y) row-major}
  *   radix_{eq,ne,lt,le,gt,ge,add} {n_blocks}   radix_scalar_{eq,lt,gt} {n_blocks, scalar}   radix_if_then_else {n_blocks}
+ *   radix_default_{eq,ne,lt,le,gt,ge} {n_blocks, block_degree} / radix_full_propagate {n_blocks, block_degree}: operands whose carries
+ *     are not empty (degree up to msg_mod*carry_mod - 1) are propagated first, as the non-"unchecked" reference methods do
  *   bool_all_true / bool_any_true {n}     bool_sum_finish {n_summed, want_all}
  *   string_{eq,ne,lt,le,gt,ge,eq_ignore_case,contains,starts_with,ends_with,find} {len_a, len_b}
  *   string_{to_lowercase,to_uppercase} {len}     string_contains_windows {len_a, len_b, w0, w1}
  *   string_{eq,ne,lt,le,contains}_many {len_a, len_b, count}   (count independent pairs in one program)
+ *   pstring_{len,is_empty,trim_start,trim_end,trim} {capacity}     pstring_{strip_prefix,strip_suffix} {capacity} + clear pattern
+ *   pstring_{eq,ne,lt,le,gt,ge,contains,starts_with,ends_with,concat} {capacity_a, capacity_b}     pstring_repeat {capacity, count}
+ *     -- NULL-PADDED strings: public capacity, secret length, content followed by zero bytes (host/padded.h); len returns a radix of
+ *        ceil(log4(capacity + 1)) blocks, the string-valued ops return 4 blocks per char of the result capacity
  * Appending "_packed" to a string op (or radix_eq) selects packed block equalities: one PBS per PAIR of blocks built from
  * pack_block_chunk + lwe_sub + LUT[x == 0] (the Comparator's own trick, comparator.rs:193-221); same decrypted results.
  * With clear_operand != NULL the second string operand is that clear (trivial) string instead of an input.

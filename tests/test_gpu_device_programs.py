@@ -91,6 +91,30 @@ def test_radix_scalar_comparisons_gpu(orc, keys_2_2, eng):
                 assert _bool(ck, out[0]) == int(w), (op, x, y)
 
 
+def test_default_comparisons_dirty_carries_gpu(orc, keys_2_2, eng):
+    """tests_cases_comparisons.rs:81-97: raise the degree of both operands with unchecked_add (carries not empty), then compare with the
+    default (propagating) forms; also full_propagate on blocks filled up to the whole message space"""
+    from oracle import radix as R
+    p, ck, sk = keys_2_2
+    rng = np.random.default_rng(91)
+    nb = 16
+    for trial in range(3):
+        xs = [int(rng.integers(0, 2**32)) for _ in range(2)]
+        ys = xs if trial == 0 else [int(rng.integers(0, 2**32)) for _ in range(2)]
+        cx = np.stack(R.encrypt_radix(ck, xs[0], nb)) + np.stack(R.encrypt_radix(ck, xs[1], nb))     # wrapping u64 add == unchecked_add
+        cy = np.stack(R.encrypt_radix(ck, ys[0], nb)) + np.stack(R.encrypt_radix(ck, ys[1], nb))
+        vx, vy = sum(xs) % 2**32, sum(ys) % 2**32
+        out = Program("radix_full_propagate", (nb, 6), params=engine_params(p)).run(eng, cx)
+        assert R.decrypt_radix(ck, out) == vx
+        for op, w in (("eq", vx == vy), ("ne", vx != vy), ("lt", vx < vy), ("le", vx <= vy), ("gt", vx > vy), ("ge", vx >= vy)):
+            out = Program("radix_default_" + op, (nb, 6), params=engine_params(p)).run(eng, np.concatenate([cx, cy]))
+            assert _bool(ck, out[0]) == int(w), (op, vx, vy)
+    five = [np.stack(R.encrypt_radix(ck, int(v), nb)) for v in rng.integers(0, 2**32, size=5)]     # degree 15
+    vals = [R.decrypt_radix(ck, f) for f in five]
+    out = Program("radix_full_propagate", (nb, 15), params=engine_params(p)).run(eng, sum(five[1:], five[0]))
+    assert R.decrypt_radix(ck, out) == sum(vals) % 2**32
+
+
 def test_find_more_than_420_windows_gpu(orc, keys_2_2, eng):
     from oracle import radix as R
     p, ck, sk = keys_2_2

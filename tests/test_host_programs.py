@@ -276,3 +276,26 @@ def test_pbs_rejects_operand_past_message_space():
     with pytest.raises(NativeError, match="degree"):
         Program("bool_sum_finish", (16, 0))
     Program("bool_sum_finish", (15, 1))
+
+
+@pytest.mark.parametrize("degree", [3, 6, 9, 15])
+def test_default_comparisons_on_dirty_carries(degree):
+    """Operands with non-empty carries (tests_cases_comparisons.rs:81-97 raises the degree with unchecked_add before comparing): the
+    default forms propagate first (message / carry extraction, shifted add, single-carry propagation) and then run the unchecked
+    circuit.  Noise-free execution on plaintext blocks holding up to `degree`; the compared VALUE is sum_i block_i 4^i mod 4^B."""
+    from helpers import simulate_program_clear
+    rng = np.random.default_rng(degree)
+    nb = 8
+    for trial in range(12):
+        x = rng.integers(0, degree + 1, size=nb)
+        y = x.copy() if trial % 3 == 0 else rng.integers(0, degree + 1, size=nb)
+        vx = sum(int(v) << (2 * i) for i, v in enumerate(x)) % 4**nb
+        vy = sum(int(v) << (2 * i) for i, v in enumerate(y)) % 4**nb
+        out, _ = simulate_program_clear(Program("radix_full_propagate", (nb, degree)).ir(), list(x), 16)
+        assert all(int(d) < 4 for d in out) and sum(int(d) << (2 * i) for i, d in enumerate(out)) == vx
+        for op, w in (("eq", vx == vy), ("ne", vx != vy), ("lt", vx < vy), ("le", vx <= vy), ("gt", vx > vy), ("ge", vx >= vy)):
+            out, _ = simulate_program_clear(Program("radix_default_" + op, (nb, degree)).ir(), list(x) + list(y), 16)
+            assert int(out[0]) == int(w), (op, degree, list(x), list(y))
+    # fresh operands take the no-propagation branch (comparison.rs:213-214): same program as the unchecked form
+    assert Program("radix_default_lt", (nb, 3)).n_pbs == Program("radix_lt", (nb,)).n_pbs
+    assert Program("radix_default_lt", (nb, 6)).n_pbs > Program("radix_lt", (nb,)).n_pbs
