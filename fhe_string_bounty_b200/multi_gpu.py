@@ -41,6 +41,7 @@ class HostComm:
 
     def __init__(self, execute, rank: int | None = None, world: int | None = None):
         self.execute = execute
+        self.min_shard_width = 0          # the CPU tests shard everything: they test the sharding logic, not its pay-off
         self.rank = dist.get_rank() if rank is None else rank
         self.world = dist.get_world_size() if world is None else world
         self._programs: dict = {}
@@ -125,15 +126,34 @@ class PeerExchange:
             pass
 
 
+def _on_own_stream(method):
+    """run a DeviceComm method on the comm's own CUDA stream, ordered after whatever the caller's current stream has enqueued (the C ABI
+    reads a NULL stream handle as "the context's stream", so torch's default stream must never be passed down)"""
+    import functools
+
+    @functools.wraps(method)
+    def wrapper(self, *args, **kwargs):
+        cur = torch.cuda.current_stream(self.dev)
+        if cur != self.stream:
+            self.stream.wait_stream(cur)
+        with torch.cuda.stream(self.stream):
+            return method(self, *args, **kwargs)
+    return wrapper
+
+
 class DeviceComm:
     """Device-resident execution on one Engine per rank.  Blocks are int64 CUDA tensors of shape (rows, k*N+1) (the bit pattern of the
-    u64 words); everything is enqueued on torch's current stream of the engine's device and nothing synchronises until to_host()."""
+    u64 words); everything is enqueued on the comm's own CUDA stream and nothing synchronises until to_host()."""
 
     def __init__(self, eng: Engine, rank: int | None = None, world: int | None = None, exchange: str = "peer", max_rows: int = 16):
         if exchange not in ("peer", "nccl"):
             raise ValueError("exchange must be 'peer' or 'nccl'")
         self.eng = eng
         self.dev = torch.device(f"cuda:{eng.device}")
+        self.stream = torch.cuda.Stream(device=self.dev)
+        # A tree whose widest level fits one ciphertext per SM is a chain of narrow-level launches whatever its width: splitting it
+        # over ranks only adds the exchange and the finishing level (round 1: eq of 8-char strings 113 ops/s on one GPU, 84 on two).
+        self.min_shard_width = torch.cuda.get_device_properties(self.dev).multi_processor_count
         self.rank = (dist.get_rank() if dist.is_initialized() else 0) if rank is None else rank
         self.world = (dist.get_world_size() if dist.is_initialized() else 1) if world is None else world
         self.exchange = exchange
@@ -175,7 +195,7 @@ class DeviceComm:
         """single-GPU group: every rank's thread records "my rows are staged", all meet, rank 0 launches the one cooperative kernel after
         every rank's stream, all meet again and order their streams after it"""
         g = self._group
-        stream = torch.cuda.current_stream(self.dev)
+        stream = self.stream
         ev = torch.cuda.Event()
         ev.record(stream)
         g["events"][self.rank], g["outs"][self.rank] = ev, out
@@ -203,7 +223,7 @@ class DeviceComm:
         return self._programs[key]
 
     def _stream(self) -> int:
-        return torch.cuda.current_stream(self.dev).cuda_stream
+        return self.stream.cuda_stream
 
     def _to_device(self, x):
         """host array (numpy, ideally a view of page-locked memory: the copy is then one asynchronous DMA) or tensor -> CUDA tensor.  A
@@ -228,6 +248,7 @@ class DeviceComm:
             x = np.ascontiguousarray(x, dtype=np.uint64)
         return torch.from_numpy(x.view(np.int64))
 
+    @_on_own_stream
     def run(self, prog: Program, inputs, to_send_area: bool = False):
         """rows of `inputs` (host numpy / pinned tensor: uploaded here; CUDA tensor: used in place) -> CUDA tensor of the outputs.  With
         to_send_area the rows are written straight into the exchange buffer (the collective that follows reads them there)."""
@@ -245,6 +266,7 @@ class DeviceComm:
         self._keep = d_in          # the upload must outlive the enqueued copy
         return out
 
+    @_on_own_stream
     def zeros(self, rows: int, lwe_len: int):
         return torch.zeros((rows, lwe_len), dtype=torch.int64, device=self.dev)
 
@@ -261,6 +283,7 @@ class DeviceComm:
         _tensor_from_ptr(self.peer.send_rows_ptr(), rows * self.L, self.dev).copy_(blocks.reshape(-1))
         return rows
 
+    @_on_own_stream
     def all_reduce(self, blocks):
         if self.world == 1:
             return blocks
@@ -276,6 +299,7 @@ class DeviceComm:
         dist.all_reduce(t, op=dist.ReduceOp.SUM)      # NCCL on the current stream; int64 wrap-around == u64 wrap-around
         return t
 
+    @_on_own_stream
     def all_gather(self, blocks):
         if self.peer is not None and (blocks is None or blocks.shape[0] <= self.max_rows):
             rows = self._stage_for_peer(blocks)
@@ -291,9 +315,11 @@ class DeviceComm:
         dist.all_gather_into_tensor(out, t)
         return out.reshape((self.world,) + tuple(t.shape))
 
+    @_on_own_stream
     def rows(self, x, sel):
         return x[sel].contiguous()
 
+    @_on_own_stream
     def to_host(self, x) -> np.ndarray:
         """the one device -> host copy of an operation (synchronises the stream), through a page-locked buffer.  Results above 1 MiB are
         returned as a view of that buffer (valid until the next result of the same shape); small ones are copied out."""
@@ -305,7 +331,7 @@ class DeviceComm:
             self._host_out[key] = torch.empty(x.shape, dtype=torch.int64).pin_memory()
         buf = self._host_out[key]
         buf.copy_(x, non_blocking=True)
-        torch.cuda.current_stream(self.dev).synchronize()
+        self.stream.synchronize()
         out = buf.numpy().view(np.uint64)
         return out if out.nbytes > (1 << 20) else out.copy()
 
@@ -339,6 +365,11 @@ def _share(comm, prog, inputs):
     return comm.run(prog, inputs)
 
 
+def _worth_sharding(comm, first_level_width: int) -> bool:
+    """shard only when the widest (first) level of the tree is wider than what one GPU runs as a single narrow-level launch"""
+    return comm.world > 1 and first_level_width > comm.min_shard_width
+
+
 # ---- the sharded operations -----------------------------------------------------------------------------------------------------
 # `comm` is a DeviceComm / HostComm (or a bare execute callable -> HostComm).  hay / pat / a / b / s are the encrypted blocks, 4 per
 # char, as host arrays (numpy or pinned tensors); only a rank's own share is uploaded.  The result is returned as a host array.
@@ -349,7 +380,7 @@ def sharded_contains(comm, params: dict, hay, pat, hay_len: int, pat_len: int, r
     comm = _comm(comm)
     rank, world = comm.rank, comm.world
     n_win = hay_len - pat_len + 1
-    if n_win <= 0 or pat_len == 0 or world == 1:   # nothing to split: the plain single-GPU program
+    if n_win <= 0 or pat_len == 0 or not _worth_sharding(comm, n_win * 4 * pat_len):   # nothing to split: the plain single-GPU program
         return comm.to_host(comm.run(comm.program("string_contains", (hay_len, pat_len), params), [hay, pat]))[0]
     total_mod = params["msg_mod"] * params["carry_mod"]
     active = min(world, n_win, total_mod - 1)       # the summed flags must stay below the padding bit; surplus ranks contribute zero
@@ -371,7 +402,7 @@ def sharded_eq(comm, params: dict, a, b, n_chars: int, rank: int | None = None, 
     rank, world = comm.rank, comm.world
     if n_chars == 0:
         return comm.to_host(comm.run(comm.program("string_eq", (0, 0), params), np.zeros((0, 1), dtype=np.uint64)))[0]
-    if world == 1:
+    if not _worth_sharding(comm, 4 * n_chars):
         return comm.to_host(comm.run(comm.program("string_eq", (n_chars, n_chars), params), [a, b]))[0]
     total_mod = params["msg_mod"] * params["carry_mod"]
     active = max(1, min(world, n_chars, total_mod - 1))
@@ -396,7 +427,7 @@ def sharded_compare(comm, params: dict, op: str, a, b, n_chars: int, rank: int |
     rank, world = comm.rank, comm.world
     want_less, or_equal = _CMP[op]
     active = max(1, min(world, n_chars))
-    if world == 1 or n_chars == 0:
+    if n_chars == 0 or not _worth_sharding(comm, 2 * n_chars):       # first level: one sign block per pair of blocks
         return comm.to_host(comm.run(comm.program("string_" + op, (n_chars, n_chars), params), [a, b]))[0]
     if rank < active:
         c0, c1 = shard_range(n_chars, rank, active)
@@ -417,8 +448,12 @@ def sharded_case(comm, params: dict, op: str, s, n_chars: int, rank: int | None 
     [shard_range(n_chars, rank, world)] only ("no exchange; optional all-gather")."""
     comm = _comm(comm)
     rank, world = comm.rank, comm.world
-    if world == 1 or n_chars == 0:
-        return comm.to_host(comm.run(comm.program("string_" + op, (n_chars,), params), s))
+    if n_chars == 0 or not _worth_sharding(comm, 2 * n_chars):
+        out = comm.to_host(comm.run(comm.program("string_" + op, (n_chars,), params), s))
+        if gather or world == 1:
+            return out
+        c0, c1 = shard_range(n_chars, rank, min(world, n_chars)) if rank < min(world, n_chars) else (0, 0)
+        return out[4 * c0:4 * c1]
     active = min(world, n_chars)
     per = -(-n_chars // active)                                  # padded share, in chars
     c0 = c1 = 0
@@ -447,7 +482,7 @@ def sharded_find(comm, params: dict, hay, pat, hay_len: int, pat_len: int, rank:
     rank, world = comm.rank, comm.world
     n_win = hay_len - pat_len + 1
     inputs = [hay, pat]
-    if n_win <= 1 or pat_len == 0 or world == 1:
+    if n_win <= 1 or pat_len == 0 or not _worth_sharding(comm, n_win * 4 * pat_len):
         return comm.to_host(comm.run(comm.program("string_find", (hay_len, pat_len), params), inputs))
     total_mod = params["msg_mod"] * params["carry_mod"]
     active = min(world, n_win, total_mod // 2)
