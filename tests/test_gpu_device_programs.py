@@ -134,6 +134,8 @@ def test_sharded_ops_two_ranks_one_gpu(orc, keys_2_2):
     params = engine_params(p)
     engines = [_engine(p, sk) for _ in range(2)]
     comms = MG.DeviceComm.local_group(engines)
+    for c in comms:
+        c.min_shard_width = 0                        # shard even these small trees: the test is about the sharded path
     streams = [torch.cuda.Stream() for _ in comms]
 
     def both(fn):

@@ -47,6 +47,7 @@ def _worker(rank, world, port, ret):
     results, raw = [], {}
     for mode in ("peer", "nccl"):
         comm = MG.DeviceComm(eng, exchange=mode)
+        comm.min_shard_width = 0                     # shard even these small trees: the test is about the sharded path
         rng = np.random.default_rng(0xB200 + 3)      # same strings on every rank and in both modes
         hay = bytes(rng.integers(ord("a"), ord("z") + 1, size=64).tolist())
         for pat in (hay[37:45], b"zzzzzzzq"):
