@@ -48,13 +48,21 @@ int check_params(const tfhe_b200_params &p) {
 
 namespace tbc {
 
-bool fused_supported(const tfhe_b200_ctx *c) { return c->ks_kernel == 1 && c->p.grouping_factor == 0 && !c->generic; }
+bool fused_supported(const tfhe_b200_ctx *c) { return c->ks_kernel >= 1 && c->p.grouping_factor == 0 && !c->generic; }
 
 int do_keyswitch(tfhe_b200_ctx *c, const uint64_t *d_in, uint64_t *d_small, size_t batch, cudaStream_t s, const uint32_t *in_slot,
                  DevBuf *digits, bool fused) {
     if (fused && !fused_supported(c)) return fail("internal: fused keyswitch requested on an unsupported configuration");
     if (!digits) digits = &c->ks_digits;
     if (!c->have_ksk) return fail("keyswitch key not uploaded");
+    if (c->ks_kernel == 2) {   // tcgen05.mma kind::i8 (keyswitch_tc.cu)
+        TB_CUDA(digits->reserve_on(tbk::ks_tc_digits_bytes((int)batch, (int)(c->p.glwe_dim * c->p.poly_size), (int)c->p.ks_level), s));
+        TB_CUDA(tbk::launch_keyswitch_tc(d_in, in_slot, (uint8_t *)digits->p, (const uint8_t *)c->ksk_planes.p,
+                                         (const uint64_t *)c->ksk_colsum.p, d_small, (int)batch, (int)(c->p.glwe_dim * c->p.poly_size),
+                                         (int)c->p.lwe_dim, (int)c->p.ks_base_log, (int)c->p.ks_level, fused ? tb::kLogN + 1 : 0, s));
+        c->launches += 2;
+        return 0;
+    }
     if (c->ks_kernel == 1) {
         TB_CUDA(digits->reserve_on(tbk::ks_mma_digits_bytes((int)batch, (int)(c->p.glwe_dim * c->p.poly_size), (int)c->p.ks_level), s));
         TB_CUDA(tbk::launch_keyswitch_mma(d_in, in_slot, (uint8_t *)digits->p, (const uint8_t *)c->ksk_planes.p,
@@ -182,7 +190,8 @@ int tfhe_b200_ctx_create(int cuda_device, const tfhe_b200_params *params, tfhe_b
     TB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (auto &e : c->ev) TB_CUDA(cudaEventCreate(&e));
     for (auto &L : c->lane) TB_CUDA(cudaStreamCreateWithFlags(&L.s, cudaStreamNonBlocking));
-    if (const char *e = std::getenv("TFHE_B200_KS_KERNEL")) c->ks_kernel = (e[0] == 'i') ? 0 : 1;
+    if (const char *e = std::getenv("TFHE_B200_KS_KERNEL")) c->ks_kernel = (e[0] == 'i') ? 0 : (e[0] == 'm') ? 1 : 2;   // imad / mma / tc
+    if (c->ks_kernel == 2 && !tbk::ks_tc_supported((int)(params->glwe_dim * params->poly_size), (int)params->ks_level)) c->ks_kernel = 1;
     if (!tbk::ks_mma_supported((int)params->ks_level)) c->ks_kernel = 0;
     c->generic = !(params->poly_size == (uint32_t)tb::kN && params->glwe_dim == 1 && params->pbs_level == 1) || params->grouping_factor == 2;
     if (const char *e = std::getenv("TFHE_B200_PBS_KERNEL")) if (e[0] == 'g') c->generic = true;
@@ -242,9 +251,11 @@ int tfhe_b200_set_tuning(tfhe_b200_ctx *c, const char *key, int value) {
         if (value < 0) return fail("narrow_max must be >= 0");
         c->narrow_max = value;
     } else if (k == "ks_kernel") {
-        if (value != 0 && value != 1) return fail("ks_kernel must be 0 (IMAD) or 1 (tensor cores)");
-        if (value == 1 && !tbk::ks_mma_supported((int)c->p.ks_level)) return fail("tensor-core keyswitch does not support this level count");
-        if (value == 1 && c->have_ksk && !c->ksk_planes.p) return fail("the keyswitch key was uploaded for the IMAD kernel only: upload it again after selecting ks_kernel = 1");
+        if (value < 0 || value > 2) return fail("ks_kernel must be 0 (IMAD), 1 (tensor cores, mma.sync) or 2 (tensor cores, tcgen05)");
+        if (value >= 1 && !tbk::ks_mma_supported((int)c->p.ks_level)) return fail("tensor-core keyswitch does not support this level count");
+        if (value == 2 && !tbk::ks_tc_supported((int)(c->p.glwe_dim * c->p.poly_size), (int)c->p.ks_level))
+            return fail("tcgen05 keyswitch: glwe_dim * poly_size * ks_level must be a multiple of 128 (and the driver must export cuTensorMapEncodeTiled)");
+        if (value >= 1 && c->have_ksk && !c->ksk_planes.p) return fail("the keyswitch key was uploaded for the IMAD kernel only: upload it again after selecting ks_kernel = 1");
         c->ks_kernel = value;
     } else
         return fail("unknown tuning key '" + k + "'");
@@ -276,7 +287,7 @@ static int finish_ksk(tfhe_b200_ctx *c, const tbc::DevBuf &raw) {
     TB_CUDA(tbk::launch_ksk_pack((const uint64_t *)raw.p, (uint64_t *)c->ksk_packed.p, (uint64_t *)c->ksk_colsum.p, (int)rows,
                                  (int)c->p.lwe_dim, c->stream));
     c->launches += 2;
-    if (c->ks_kernel == 1) {
+    if (c->ks_kernel >= 1) {
         TB_CUDA(c->ksk_planes.reserve(rows * (size_t)ldk * 8));
         TB_CUDA(tbk::launch_ksk_planes((const uint64_t *)c->ksk_packed.p, (uint8_t *)c->ksk_planes.p, (int)rows, ldk, c->stream));
         c->launches += 1;

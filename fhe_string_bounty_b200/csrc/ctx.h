@@ -69,7 +69,7 @@ struct tfhe_b200_ctx {
     bool timed = false;
     // keys
     tbc::DevBuf ksk_packed, ksk_colsum, ksk_planes, ks_digits, bskf, bskf8, tbl16, tbl8, tw_generic, roots, luts;
-    int ks_kernel = 1;    // 1: tensor-core GEMM (keyswitch_mma.cu), 0: IMAD GEMM (keyswitch.cu); env TFHE_B200_KS_KERNEL=imad
+    int ks_kernel = 2;    // 2: tcgen05 GEMM (keyswitch_tc.cu), 1: mma.sync GEMM (keyswitch_mma.cu), 0: IMAD GEMM (keyswitch.cu); env TFHE_B200_KS_KERNEL=tc|mma|imad
     uint32_t n_luts = 0;
     bool have_ksk = false, have_bsk = false;
     int narrow_kernel = 8;   // classic PBS, levels of <= 2 * SM count ciphertexts: 8 = pbs_v8.cu (8 FFT points per thread, 8 warps per ciphertext; keeps a second copy of the Fourier key in its own layout), 0 = the 1- / 2-ciphertext instances of pbs_v4.cu; env TFHE_B200_NARROW_KERNEL

@@ -20,6 +20,15 @@ cudaError_t launch_keyswitch_mma(const uint64_t *lwe_in, const uint32_t *in_slot
                                  const uint64_t *colsum, uint64_t *lwe_out, int batch, int in_dim, int n, int base_log, int level,
                                  int ms_log2_2n, cudaStream_t stream);
 size_t ks_mma_digits_bytes(int batch, int in_dim, int level);
+cudaError_t launch_ks_digits(const uint64_t *lwe_in, const uint32_t *in_slot, uint8_t *digits, int batch, int batch_pad, int in_dim,
+                             int base_log, int level, cudaStream_t stream);
+
+// keyswitch_tc.cu: the same GEMM on tcgen05.mma kind::i8 (TMA operands, accumulator in Tensor Memory); same digit matrix and key planes
+bool ks_tc_supported(int in_dim, int level);
+size_t ks_tc_digits_bytes(int batch, int in_dim, int level);
+cudaError_t launch_keyswitch_tc(const uint64_t *lwe_in, const uint32_t *in_slot, uint8_t *digits_scratch, const uint8_t *bmat,
+                                const uint64_t *colsum, uint64_t *lwe_out, int batch, int in_dim, int n, int base_log, int level,
+                                int ms_log2_2n, cudaStream_t stream);
 
 // pbs_v4.cu (tbl16 = the two twiddle tables of fft16_core.cuh, 1024 + 64 complex values)
 cudaError_t pbs_v4_configure();

@@ -191,6 +191,14 @@ cudaError_t launch_ksk_planes(const uint64_t *packed, uint8_t *bmat, int rows, i
     return cudaGetLastError();
 }
 
+cudaError_t launch_ks_digits(const uint64_t *lwe_in, const uint32_t *in_slot, uint8_t *digits, int batch, int batch_pad, int in_dim,
+                             int base_log, int level, cudaStream_t stream) {
+    const size_t total = (size_t)batch_pad * in_dim;
+    const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+    tbkm::ks_digits_kernel<<<blocks, 256, 0, stream>>>(lwe_in, in_slot, digits, batch, batch_pad, in_dim, base_log, level);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_keyswitch_mma(const uint64_t *lwe_in, const uint32_t *in_slot, uint8_t *digits_scratch, const uint8_t *bmat,
                                  const uint64_t *colsum, uint64_t *lwe_out, int batch, int in_dim, int n, int base_log, int level,
                                  int ms_log2_2n, cudaStream_t stream) {
@@ -198,10 +206,7 @@ cudaError_t launch_keyswitch_mma(const uint64_t *lwe_in, const uint32_t *in_slot
     const int ldk = ks_padded_cols(n);
     const int K = in_dim * level;
     const int batch_pad = ((batch + tbkm::BM - 1) / tbkm::BM) * tbkm::BM;
-    const size_t total = (size_t)batch_pad * in_dim;
-    const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
-    tbkm::ks_digits_kernel<<<blocks, 256, 0, stream>>>(lwe_in, in_slot, digits_scratch, batch, batch_pad, in_dim, base_log, level);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = launch_ks_digits(lwe_in, in_slot, digits_scratch, batch, batch_pad, in_dim, base_log, level, stream);
     if (e != cudaSuccess) return e;
     const int half_b = 1 << (base_log - 1);
     const int ms_shift = ms_log2_2n ? 64 - ms_log2_2n - 1 : 0;   // 0: raw u64 output; else u16 round(x / 2^(64 - log2(2N)))

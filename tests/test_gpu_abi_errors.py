@@ -42,7 +42,7 @@ def test_missing_keys_and_bad_arguments_fail_loudly(orc, keys_2_2):
 
 
 def test_both_keyswitch_kernels_and_both_pbs_kernel_families_agree(orc, keys_2_2):
-    """The IMAD keyswitch and the tensor-core keyswitch are bit-identical (exact integer arithmetic, different association order of
+    """The IMAD keyswitch and the two tensor-core keyswitches (mma.sync, tcgen05.mma kind::i8) are bit-identical (exact integer arithmetic, different association order of
     wrapping sums); the narrow-level kernel (pbs_v8.cu, 8 x 8 x 4 x 4 FFT) and the 1-ciphertext instance of the wide kernel
     (pbs_v4.cu, 16 x 4 x 16 FFT) evaluate the same transform with different rounding: identical LUT rotation, one CMUX within the
     stated 2^44, same decrypted values.  Kernel selection through tfhe_b200_set_tuning (the wide instances are pinned in
@@ -56,7 +56,7 @@ def test_both_keyswitch_kernels_and_both_pbs_kernel_families_agree(orc, keys_2_2
     eng.upload_bsk_std(sk.bsk)
     eng.upload_luts(acc[None, :])
     outs, kss, part = {}, {}, {}
-    for ks_k, narrow in ((0, 8), (1, 8), (1, 0)):
+    for ks_k, narrow in ((0, 8), (1, 8), (1, 0), (2, 8)):
         eng.set_tuning("ks_kernel", ks_k)
         eng.set_tuning("narrow_kernel", narrow)
         kss[(ks_k, narrow)] = eng.keyswitch_batch(cts)
@@ -64,6 +64,8 @@ def test_both_keyswitch_kernels_and_both_pbs_kernel_families_agree(orc, keys_2_2
         part[(ks_k, narrow)] = [eng.pbs_batch(kss[(ks_k, narrow)], None, n_iters=n) for n in (0, 1)]
     eng.close()
     assert np.array_equal(kss[(0, 8)], kss[(1, 8)]) and np.array_equal(kss[(0, 8)], np.stack([sk.keyswitch(c) for c in cts]))
+    assert np.array_equal(kss[(0, 8)], kss[(2, 8)]), "tcgen05 keyswitch differs from the IMAD keyswitch"
+    assert np.array_equal(outs[(1, 8)], outs[(2, 8)]), "fused u16 hand-off: tcgen05 vs mma.sync keyswitch"
     want = [(7 * int(v) + 2) % 16 for v in np.arange(37) % 16]
     for k, o in outs.items():
         assert list(ck.decrypt_batch(o)) == want, k
