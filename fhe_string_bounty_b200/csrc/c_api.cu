@@ -150,7 +150,7 @@ static int do_pbs_kernels(tfhe_b200_ctx *c, const uint64_t *d_small, const uint3
             uint64_t *t_out = out_slot ? d_out : d_out + wide * ((size_t)c->p.glwe_dim * c->p.poly_size + 1);
             TB_CUDA(tbk::launch_pbs_classic_v8(t_small, d_idx ? d_idx + wide : nullptr, d_luts, c->bskf8.p, c->tbl8.p, t_out,
                                                out_slot ? out_slot + wide : nullptr, (int)tail, (int)c->p.lwe_dim, (int)c->p.pbs_base_log,
-                                               (int)n_iters, fused ? 1 : 0, s));
+                                               (int)n_iters, fused ? 1 : 0, c->narrow_cluster ? c->sms / 2 : 0, s));
             c->launches += 1;
         }
         return 0;
@@ -250,6 +250,9 @@ int tfhe_b200_set_tuning(tfhe_b200_ctx *c, const char *key, int value) {
     } else if (k == "narrow_max") {
         if (value < 0) return fail("narrow_max must be >= 0");
         c->narrow_max = value;
+    } else if (k == "narrow_cluster") {
+        if (value != 0 && value != 1) return fail("narrow_cluster must be 0 or 1");
+        c->narrow_cluster = value;
     } else if (k == "ks_kernel") {
         if (value < 0 || value > 2) return fail("ks_kernel must be 0 (IMAD), 1 (tensor cores, mma.sync) or 2 (tensor cores, tcgen05)");
         if (value >= 1 && !tbk::ks_mma_supported((int)c->p.ks_level)) return fail("tensor-core keyswitch does not support this level count");

@@ -55,7 +55,8 @@ cudaError_t launch_linear(uint64_t *arena, const LinInstr *instrs, const LinTerm
 cudaError_t pbs_v8_configure();
 cudaError_t launch_pbs_classic_v8(const uint64_t *lwe_small, const uint32_t *lut_idx, const uint64_t *luts, const void *bskf8,
                                   const void *tbl8, uint64_t *out, const uint32_t *out_slot, int batch, int n, int base_log,
-                                  int n_iters, int small_is_u16, cudaStream_t stream);
+                                  int n_iters, int small_is_u16, int cluster_max /* levels of at most this many ciphertexts: one per 2-SM cluster */,
+                                  cudaStream_t stream);
 cudaError_t launch_bsk_convert_v8(const uint64_t *bsk_std, void *bskf8, const void *tbl8, int n_polys, cudaStream_t stream);
 // pbs_multibit_v4.cu (16 FFT points per thread, 1/2/4 ciphertexts per CTA; tbl16 = fft16_core.cuh tables)
 cudaError_t pbs_multibit_v4_configure();

@@ -18,6 +18,8 @@
 // Shared memory per 4-ciphertext CTA: 8 x 17 KiB polynomial tiles (rotated-gather source, then exchange tile) + 5 x 16 KiB ring.
 // TMEM: 64 columns per ciphertext (accumulator master copy) + 80 columns of per-thread FFT twiddles.
 // Named barriers: one per ciphertext (128 threads).
+#include <cstdlib>
+
 #include "kernels.h"
 #include "pbs16_common.cuh"
 
@@ -28,10 +30,11 @@ constexpr int QPP = 4;                 // frequencies (registers) per ring piece
 constexpr int PIECE_CPLX = 2 * 2 * QPP * 64;   // one chunk: [out poly 2][sel 2][q QPP][thread 64] = 16 KiB
 constexpr int PIECE_BYTES = PIECE_CPLX * 16;
 constexpr int CHUNKS_PER_ITER = 16 / QPP;
-constexpr int NS = 5;                  // ring slots: 80 KiB = 1.25 iterations of key
+template <int CTS> struct RingSlots { static constexpr int value = CTS == 3 ? 7 : 5; };   // 80 KiB = 1.25 iterations of key (112 KiB beside three ciphertexts)
 
 template <int CTS>
 struct Smem {
+    static constexpr int NS = RingSlots<CTS>::value;
     cplx tile[2 * CTS][kTileCplx];     // 17 KiB per polynomial
     cplx ring[NS][PIECE_CPLX];
     unsigned long long full_bar[NS];
@@ -54,7 +57,8 @@ pbs_classic_kernel_v4(const uint64_t *__restrict__ lwe_small, const uint32_t *__
                       const cplx *__restrict__ bskf4, const cplx *__restrict__ tbl16, uint64_t *__restrict__ out,
                       const uint32_t *__restrict__ out_slot, int batch, int n, int base_log, int n_iters, int small_is_u16) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    constexpr int TMEM_COLS = CTS == 4 ? 512 : 256, CONSUMERS = 4 * CTS;   // every warp reads every ring piece
+    constexpr int TMEM_COLS = CTS >= 3 ? 512 : 256, CONSUMERS = 4 * CTS;   // every warp reads every ring piece
+    constexpr int NS = Smem<CTS>::NS;
     constexpr int TW_COL = 64 * CTS;                                        // per-thread twiddles after the accumulators
     Smem<CTS> &sm = *reinterpret_cast<Smem<CTS> *>(smem_raw);
     const int W = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -138,7 +142,7 @@ pbs_classic_kernel_v4(const uint64_t *__restrict__ lwe_small, const uint32_t *__
 
     // stagger: ciphertext c starts c / CTS of an iteration after ciphertext 0, so that the FP64-heavy and the shared-memory-heavy phases
     // of the ciphertexts do not coincide (a clock-based delay measured the same as a barrier hand-shake)
-    if (CTS >= 4 && ctl >= 1 && n_iters > 0) {
+    if (CTS >= 3 && ctl >= 1 && n_iters > 0) {
         const long long t0 = clock64(), delay = (long long)ctl * (20000 / CTS);
         while (clock64() - t0 < delay) { }
     }
@@ -289,6 +293,8 @@ namespace tbk {
 cudaError_t pbs_v4_configure() {
     cudaError_t e = cudaFuncSetAttribute(tb4::pbs_classic_kernel_v4<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tb4::Smem<4>));
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(tb4::pbs_classic_kernel_v4<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tb4::Smem<3>));
+    if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(tb4::pbs_classic_kernel_v4<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tb4::Smem<2>));
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(tb4::pbs_classic_kernel_v4<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tb4::Smem<1>));
@@ -307,6 +313,9 @@ cudaError_t launch_pbs_classic_v4(const uint64_t *lwe_small, const uint32_t *lut
                                                                                   base_log, n_iters, small_is_u16);
     else if (batch <= 2 * sms)
         tb4::pbs_classic_kernel_v4<2><<<(batch + 1) / 2, 256, sizeof(tb4::Smem<2>), stream>>>(lwe_small, lut_idx, luts, bk, tb, out, out_slot,
+                                                                                            batch, n, base_log, n_iters, small_is_u16);
+    else if (std::getenv("TFHE_B200_WIDE_CTS") && std::getenv("TFHE_B200_WIDE_CTS")[0] == '3')   // experiment: 3 ciphertexts x 168 registers
+        tb4::pbs_classic_kernel_v4<3><<<(batch + 2) / 3, 384, sizeof(tb4::Smem<3>), stream>>>(lwe_small, lut_idx, luts, bk, tb, out, out_slot,
                                                                                             batch, n, base_log, n_iters, small_is_u16);
     else
         tb4::pbs_classic_kernel_v4<4><<<(batch + 3) / 4, 512, sizeof(tb4::Smem<4>), stream>>>(lwe_small, lut_idx, luts, bk, tb, out, out_slot,

@@ -256,6 +256,173 @@ pbs_classic_kernel_v8(const uint64_t *__restrict__ lwe_small, const uint32_t *__
     if (!REGS && W == 0) tmem_dealloc<TMEM_COLS>(sm.tmem_base);
 }
 
+
+// ---- the narrowest levels (at most SM count / 2 ciphertexts): ONE ciphertext on a CLUSTER of two SMs -------------------------------
+// ncu on the one-ciphertext instance above (profiles/r01_pbs_v8_narrow_level_summary.txt): its eight warps run in lockstep between
+// barriers, so an iteration costs the SUM of its shared-memory phases (4.2 k wavefronts on the SM-wide pipe) and its FP64 phases (2 warps
+// per scheduler), 7.4 k cycles, with nothing to overlap.  Both halve when each polynomial gets an SM of its own: CTA rank w of the cluster
+// owns polynomial w (accumulator, gather, forward FFT, the output polynomial w of the external product, inverse FFT), streams only the
+// half of the Fourier key that feeds output w (8 x 4 KiB pieces per iteration into a four-deep ring), and the two CTAs swap spectra once
+// per iteration: each thread stores its 8 values straight into the partner's shared memory (st.shared::cluster, double buffered) and one
+// cluster barrier (arrive.release / wait.acquire) publishes them -- the only cross-SM synchronisation of the iteration.
+constexpr int NBUFX = 4;
+constexpr int HALF_ITER_CPLX = PIECES_PER_ITER * 256;      // [register g 8][sel 2][thread 128] = 32 KiB
+struct SmemX2 {
+    cplx tile[tb8::kTileCplx];
+    cplx recv[2][PIECES_PER_ITER * 128];
+    cplx ring[NBUFX][HALF_ITER_CPLX];
+    unsigned long long full_bar[NBUFX];
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_cluster(uint32_t addr, double x, double y) {
+    asm volatile("st.shared::cluster.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(x), "d"(y) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
+pbs_classic_kernel_v8x2(const uint64_t *__restrict__ lwe_small, const uint32_t *__restrict__ lut_idx, const uint64_t *__restrict__ luts,
+                        const cplx *__restrict__ bskf8, const cplx *__restrict__ tbl8, uint64_t *__restrict__ out,
+                        const uint32_t *__restrict__ out_slot, int batch, int n, int base_log, int n_iters, int small_is_u16) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    SmemX2 &sm = *reinterpret_cast<SmemX2 *>(smem_raw);
+    const int T = threadIdx.x;
+    const int w = (int)cluster_ctarank();                 // polynomial of this CTA: 0 = mask, 1 = body
+    const int ct = blockIdx.x >> 1;                       // grid = 2 * batch: every cluster has a live ciphertext
+    cplx *tile = sm.tile;
+    uint64_t *pb = reinterpret_cast<uint64_t *>(tile);
+    const PolySync128 poly_sync{1};
+    const uint64_t *lwe = lwe_small + (size_t)ct * (n + 1);
+    const uint16_t *lwe16 = reinterpret_cast<const uint16_t *>(lwe_small) + (size_t)ct * (n + 1);
+    const uint32_t peer_recv = map_to_cta(smem_u32(&sm.recv[0][T]), (uint32_t)(w ^ 1));
+
+    auto fill = [&](int it) {      // this CTA's half of GGSW `it`: for every register g the [sel 2][thread 128] block of output polynomial w
+        const int buf = it & (NBUFX - 1);
+        mbar_expect_tx(&sm.full_bar[buf], HALF_ITER_CPLX * 16);
+#pragma unroll
+        for (int g = 0; g < PIECES_PER_ITER; ++g)
+            tma_load_1d(sm.ring[buf] + g * 256, bskf8 + bskf8_index(it, g, w, 0), 256 * 16, &sm.full_bar[buf]);
+    };
+    if (T == 0) {
+        for (int s = 0; s < NBUFX; ++s) mbar_init(&sm.full_bar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_proxy_async();
+        for (int g = 0; g < NBUFX && g < n_iters; ++g) fill(g);
+    }
+    cplx twr[24];
+    uint64_t accr[16];
+    const RegTw8 twd_r{twr};
+#pragma unroll
+    for (int k = 0; k < 24; ++k) twr[k] = __ldg(tbl8 + 24 * T + k);
+
+    double re[8], im[8];
+    {
+        const uint32_t b_hat = (small_is_u16 ? (uint32_t)__ldg(lwe16 + n) : modulus_switch_2n(__ldg(lwe + n))) & (2 * kN - 1);
+        const uint32_t a0 = (2 * kN - b_hat) & (2 * kN - 1);
+        const uint64_t *lut = luts + ((size_t)(lut_idx ? lut_idx[ct] : 0) * 2 + w) * kN;
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            const int j = T + 128 * m;
+            int s0, s1; bool n0, n1;
+            rot_src(j, a0, s0, n0);
+            rot_src(j + kM, a0, s1, n1);
+            uint64_t v0 = __ldg(lut + s0), v1 = __ldg(lut + s1);
+            v0 = n0 ? (uint64_t)0 - v0 : v0;
+            v1 = n1 ? (uint64_t)0 - v1 : v1;
+            pb[j] = v0; pb[j + kM] = v1;
+            re[m] = __longlong_as_double((long long)v0);
+            im[m] = __longlong_as_double((long long)v1);
+            accr[2 * m] = v0; accr[2 * m + 1] = v1;
+        }
+    }
+    cluster_sync_all();     // both CTAs are resident and their barriers initialised before anyone stores into the partner's shared memory
+
+    for (int i = 0; i < n_iters; ++i) {
+        const uint32_t a = (small_is_u16 ? (uint32_t)__ldg(lwe16 + i) : modulus_switch_2n(__ldg(lwe + i))) & (2 * kN - 1);
+        poly_sync();    // the accumulator polynomial is complete in shared memory; everyone is past the previous iteration's MAC
+        if (T == 0 && i >= 1 && i - 1 + NBUFX < n_iters) {     // so the ring buffer of iteration i - 1 can take GGSW i - 1 + NBUFX
+            fence_proxy_async();
+            fill(i - 1 + NBUFX);
+        }
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            const int j = T + 128 * m;
+            const uint32_t s0 = ((uint32_t)j - a) & (2 * kN - 1);
+            const uint32_t s1 = (s0 + kM) & (2 * kN - 1);
+            uint64_t r0 = pb[s0 & (kN - 1)], r1 = pb[s1 & (kN - 1)];
+            r0 = (s0 >= (uint32_t)kN) ? (uint64_t)0 - r0 : r0;
+            r1 = (s1 >= (uint32_t)kN) ? (uint64_t)0 - r1 : r1;
+            const uint64_t o0 = (uint64_t)__double_as_longlong(re[m]), o1 = (uint64_t)__double_as_longlong(im[m]);
+            re[m] = (double)signed_digit_l1(r0 - o0, base_log);
+            im[m] = (double)signed_digit_l1(r1 - o1, base_log);
+        }
+        fft8_fwd(re, im, tile, twd_r, T, poly_sync);
+
+        // my spectrum -> the partner's receive buffer i & 1 (the partner read buffer i & 1 last in iteration i - 2, i.e. before the
+        // cluster barrier of iteration i - 1 that I have already passed), then one cluster barrier
+        {
+            const uint32_t dst = peer_recv + (uint32_t)((i & 1) * PIECES_PER_ITER * 128 * 16);
+#pragma unroll
+            for (int c = 0; c < PIECES_PER_ITER; ++c) st_cluster(dst + (uint32_t)(c * 128 * 16), re[c], im[c]);
+        }
+        cluster_sync_all();
+
+        {
+            const int buf = i & (NBUFX - 1);
+            const uint32_t ph = (uint32_t)(i / NBUFX) & 1u;
+            if (!mbar_try_wait(&sm.full_bar[buf], ph)) mbar_wait(&sm.full_bar[buf], ph);
+            const cplx *fop = sm.recv[i & 1] + T;
+            const cplx *pc = sm.ring[buf] + T;
+#pragma unroll
+            for (int c = 0; c < PIECES_PER_ITER; ++c) {
+                const cplx A = pc[c * 256], B = pc[c * 256 + 128], F = fop[c * 128];
+                const double fr = re[c], fi = im[c];
+                double orr = DMUL(fr, A.x);
+                orr = DFMA(-fi, A.y, orr);
+                orr = DFMA(F.x, B.x, orr);
+                orr = DFMA(-F.y, B.y, orr);
+                double oi = DMUL(fr, A.y);
+                oi = DFMA(fi, A.x, oi);
+                oi = DFMA(F.x, B.y, oi);
+                oi = DFMA(F.y, B.x, oi);
+                re[c] = orr; im[c] = oi;
+            }
+        }
+        fft8_inv(re, im, tile, twd_r, T, poly_sync);
+        poly_sync();    // everyone has read the last exchange: the tile becomes the accumulator polynomial again
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            const int j = T + 128 * m;
+            const uint64_t o0 = accr[2 * m] + from_torus_f64(re[m]), o1 = accr[2 * m + 1] + from_torus_f64(im[m]);
+            accr[2 * m] = o0; accr[2 * m + 1] = o1;
+            pb[j] = o0; pb[j + kM] = o1;
+            re[m] = __longlong_as_double((long long)o0);
+            im[m] = __longlong_as_double((long long)o1);
+        }
+    }
+
+    uint64_t *o = out + (size_t)(out_slot ? out_slot[ct] : ct) * (kN + 1);
+    if (w == 0) {
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            const int j = T + 128 * m;
+            const uint64_t v0 = (uint64_t)__double_as_longlong(re[m]), v1 = (uint64_t)__double_as_longlong(im[m]);
+            if (j == 0) o[0] = v0; else o[kN - j] = (uint64_t)0 - v0;
+            o[kN - (j + kM)] = (uint64_t)0 - v1;
+        }
+    } else if (T == 0) {
+        o[kN] = (uint64_t)__double_as_longlong(re[0]);
+    }
+    cluster_sync_all();     // nobody leaves while the partner could still address its shared memory
+}
+
 // std -> Fourier key in the v8 ring layout (128 threads per polynomial; same forward transform as the kernel above)
 __global__ void __launch_bounds__(128)
 bsk_convert_kernel_v8(const uint64_t *__restrict__ bsk_std, cplx *__restrict__ bskf8, const cplx *__restrict__ tbl8, int n_polys) {
@@ -288,19 +455,24 @@ namespace tbk {
 cudaError_t pbs_v8_configure() {
     cudaError_t e = cudaFuncSetAttribute(tb8k::pbs_classic_kernel_v8<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tb8k::Smem<2>));
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(tb8k::pbs_classic_kernel_v8x2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tb8k::SmemX2));
+    if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(tb8k::pbs_classic_kernel_v8<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tb8k::Smem<1>));
 }
 
 // batch <= 2 * SM count only (the caller dispatches wider levels to launch_pbs_classic_v4)
 cudaError_t launch_pbs_classic_v8(const uint64_t *lwe_small, const uint32_t *lut_idx, const uint64_t *luts, const void *bskf8,
                                   const void *tbl8, uint64_t *out, const uint32_t *out_slot, int batch, int n, int base_log,
-                                  int n_iters, int small_is_u16, cudaStream_t stream) {
+                                  int n_iters, int small_is_u16, int cluster_max, cudaStream_t stream) {
     if (batch <= 0) return cudaSuccess;
     int sms = 148, dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const tb::cplx *bk = reinterpret_cast<const tb::cplx *>(bskf8), *tb = reinterpret_cast<const tb::cplx *>(tbl8);
-    if (batch <= sms)
+    if (batch <= cluster_max && batch <= sms / 2)      // one ciphertext per two-SM cluster
+        tb8k::pbs_classic_kernel_v8x2<<<2 * batch, 128, sizeof(tb8k::SmemX2), stream>>>(lwe_small, lut_idx, luts, bk, tb, out, out_slot, batch, n,
+                                                                                     base_log, n_iters, small_is_u16);
+    else if (batch <= sms)
         tb8k::pbs_classic_kernel_v8<1><<<batch, 256, sizeof(tb8k::Smem<1>), stream>>>(lwe_small, lut_idx, luts, bk, tb, out, out_slot, batch, n,
                                                                                    base_log, n_iters, small_is_u16);
     else

@@ -12,7 +12,9 @@ rng = np.random.default_rng(1)
 eng.upload_ksk(rng.integers(0, 2**64, size=p.ksk_len, dtype=np.uint64))
 eng.upload_bsk_std(rng.integers(0, 2**64, size=p.bsk_len, dtype=np.uint64))
 eng.upload_luts(rng.integers(0, 2**64, size=(4, p.lut_len), dtype=np.uint64))
-for op, args in [("shortint_apply_lut", [1] + list(range(16))), ("shortint_apply_lut", [32] + list(range(16))),
+import os
+if os.environ.get("NARROW_CLUSTER"): eng.set_tuning("narrow_cluster", int(os.environ["NARROW_CLUSTER"]))
+for op, args in [("shortint_apply_lut", [1] + list(range(16))), ("shortint_apply_lut", [32] + list(range(16))), ("shortint_apply_lut", [74] + list(range(16))),
                  ("shortint_apply_lut", [148] + list(range(16))), ("shortint_apply_lut", [592] + list(range(16))),
                  ("string_eq", (8, 8)), ("string_lt", (128, 128)), ("string_contains", (256, 16))]:
     P = Program(op, args)

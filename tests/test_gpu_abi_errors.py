@@ -76,6 +76,32 @@ def test_both_keyswitch_kernels_and_both_pbs_kernel_families_agree(orc, keys_2_2
     assert d <= 2**44, f"v8 vs v4<1> after one CMUX: 2^{np.log2(max(int(d), 1)):.1f}"
 
 
+def test_two_sm_cluster_instance_is_bit_identical_to_the_one_sm_instance(orc, keys_2_2):
+    """Levels of at most SM count / 2 ciphertexts put ONE ciphertext on a cluster of two SMs (pbs_classic_kernel_v8x2: a polynomial per
+    CTA, spectra swapped through distributed shared memory).  Same FFT, same order of every floating-point operation as the one-SM
+    instance pbs_classic_kernel_v8<1>: outputs are identical words, for 0 / 1 / all blind-rotation iterations, fused and unfused."""
+    import fhe_string_bounty_b200 as F
+    p, ck, sk = keys_2_2
+    accs = np.stack([sk.generate_lookup_table(f)[0] for f in (lambda x: (3 * x + 1) % 16, lambda x: int(x >= 8))])
+    eng = F.Engine(engine_params(p))
+    eng.upload_ksk(sk.ksk)
+    eng.upload_bsk_std(sk.bsk)
+    eng.upload_luts(accs)
+    for batch in (1, 37, 74):
+        cts = ck.encrypt_batch(np.arange(batch) % 16)
+        idx = (np.arange(batch) % 2).astype(np.uint32)
+        res = {}
+        for cl in (0, 1):
+            eng.set_tuning("narrow_cluster", cl)
+            small = eng.keyswitch_batch(cts)
+            res[cl] = [eng.pbs_batch(small, idx, n_iters=n) for n in (0, 1, None)] + [eng.ks_pbs_batch(cts, idx)]
+        for a, b in zip(res[0], res[1]):
+            assert np.array_equal(a, b), f"batch {batch}"
+        want = [[(3 * int(v) + 1) % 16, int(v >= 8)][i] for v, i in zip(np.arange(batch) % 16, idx)]
+        assert list(ck.decrypt_batch(res[1][3])) == want
+    eng.close()
+
+
 def test_kernels_do_not_write_outside_their_buffers(orc, keys_2_2):
     """compute-sanitizer is closed on this pool, so bounds are checked with canaries: device input/output/small buffers are
     embedded in larger sentinel-filled allocations; after KS, PBS and KS-PBS on ragged batch sizes the sentinels must be intact
