@@ -123,7 +123,7 @@ static int do_pbs_kernels(tfhe_b200_ctx *c, const uint64_t *d_small, const uint3
             if (c->narrow_kernel == 8 && tail <= (size_t)(c->narrow_max ? c->narrow_max : c->sms))
                 TB_CUDA(tbk::launch_pbs_multibit_v8(t_small, d_idx ? d_idx + wide : nullptr, d_luts, c->bskf8.p, c->tbl8.p, c->roots.p, t_out,
                                                     out_slot ? out_slot + wide : nullptr, (int)tail, (int)c->p.lwe_dim,
-                                                    (int)c->p.pbs_base_log, steps, s));
+                                                    (int)c->p.pbs_base_log, steps, c->narrow_cluster ? c->sms / 2 : 0, s));
             else
                 TB_CUDA(tbk::launch_pbs_multibit_v4(t_small, d_idx ? d_idx + wide : nullptr, d_luts, c->bskf.p, c->tbl16.p, c->roots.p, t_out,
                                                     out_slot ? out_slot + wide : nullptr, (int)tail, (int)c->p.lwe_dim,

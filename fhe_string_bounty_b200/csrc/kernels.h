@@ -69,7 +69,7 @@ cudaError_t launch_bsk_convert_multibit_v4(const uint64_t *bsk_std, void *bskm, 
 cudaError_t pbs_multibit_v8_configure();
 cudaError_t launch_pbs_multibit_v8(const uint64_t *lwe_small, const uint32_t *lut_idx, const uint64_t *luts, const void *bskm8,
                                    const void *tbl8, const void *roots, uint64_t *out, const uint32_t *out_slot, int batch, int n,
-                                   int base_log, int n_groups, cudaStream_t stream);
+                                   int base_log, int n_groups, int cluster_max, cudaStream_t stream);
 cudaError_t launch_bsk_convert_multibit_v8(const uint64_t *bsk_std, void *bskm8, const void *tbl8, int n_polys, cudaStream_t stream);
 
 // pbs_generic.cu: classic PBS for any (poly_size <= 8192, glwe_dim, pbs_level) of shortint/parameters/mod.rs; tw = exp(i*pi*j/N), j < N/2

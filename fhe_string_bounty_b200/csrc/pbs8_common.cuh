@@ -109,6 +109,39 @@ __device__ __forceinline__ void exchange_c_inv(double (&re)[8], double (&im)[8],
     for (int r = 0; r < 8; ++r) { re[r] = ore[r]; im[r] = oim[r]; }
 }
 
+// ---- two-SM cluster instances (pbs_classic_kernel_v8x2, pbs_multibit_kernel_v8x2): mbarrier hand-offs inside and across the CTAs ----
+__device__ __forceinline__ void mbar_arrive(void *bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(void *bar, uint32_t parity) {     // acquire at cluster scope: the partner's remote stores are visible after it
+    const long long t0 = clock64();
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (!ok && clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_cluster(uint32_t addr, double x, double y) {
+    asm volatile("st.shared::cluster.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(x), "d"(y) : "memory");
+}
+// remote store that signals the destination CTA's mbarrier with the bytes it delivered (complete_tx): no fence, no separate arrival
+__device__ __forceinline__ void st_async_cluster(uint32_t addr, double x, double y, uint32_t remote_bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f64 [%0], {%1, %2}, [%3];" ::"r"(addr), "d"(x), "d"(y), "r"(remote_bar)
+                 : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // forward: on entry the tile may still be read by other threads (the first sync covers that); on exit thread t holds register r =
 // frequency freq_of8(t, r) and nobody but t touches t's exchange-C reader slots.
 template <class Tw, class Sync>

@@ -218,6 +218,228 @@ pbs_multibit_kernel_v8(const uint64_t *__restrict__ lwe_small, const uint32_t *_
     }
 }
 
+
+// ---- the narrowest levels (at most SM count / 2 ciphertexts): one ciphertext on a cluster of TWO SMs, warp-specialised -----------------
+// ncu on the one-SM kernel above and on a first two-SM version: a narrow multi-bit step is one long dependency chain per warp (2.7 k
+// instructions at 5 cycles each: mbarrier probe -> key loads -> 7-term combination, 32 times, between two FFTs), not a bandwidth problem.
+// But the combination G = G_0 + sum_j G_j * M_j depends only on the step's monomial degrees (mask elements of the input), not on the
+// accumulator, so it need not sit on the accumulator's critical path:
+//   * CTA rank w of the cluster owns polynomial w (pbs_classic_kernel_v8x2 in pbs_v8.cu has the reasoning and the same spectrum swap
+//     through distributed shared memory) and streams only the half of the key that feeds output polynomial w;
+//   * warps 4-7 ("combine warps") run ONE STEP AHEAD: they pull the key through the ring and leave the combined GGSW values of their
+//     frequencies (Ga, Gb per register and thread, 32 KiB per step, double buffered) in shared memory;
+//   * warps 0-3 ("FFT warps") do what a classic blind-rotation step does -- decompose, forward FFT, swap spectra, 2 x 2 multiply-accumulate
+//     against the combined values, inverse FFT, round.
+// Hand-offs are mbarriers (combined values full / empty inside the CTA; "spectrum landed" = the 16 KiB of st.async stores reported to an
+// mbarrier in the receiving CTA).  The floating-point operations and their order are those of the one-SM kernel: identical words.
+constexpr int NSLOTX = 3;
+constexpr int HALF_REG_CPLX = 2048;            // one FFT register's worth of this CTA's key half: [j 8][sel 2][thread 128] = 32 KiB behind ONE barrier
+struct SmemX2 {
+    cplx tile[tb8::kTileCplx];
+    cplx recv[2][8 * 128];
+    cplx comb[2][8 * 256];                     // [step parity][register g][Ga, Gb][thread 128]
+    cplx ring[NSLOTX][HALF_REG_CPLX];
+    cplx root_hi[64], root_lo[64];
+    unsigned long long full_bar[NSLOTX], comb_full[2], comb_empty[2], spec_full[2];
+    unsigned int consumed[NSLOTX];
+};
+static_assert(sizeof(SmemX2) <= 227 * 1024, "shared memory budget");
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+pbs_multibit_kernel_v8x2(const uint64_t *__restrict__ lwe_small, const uint32_t *__restrict__ lut_idx, const uint64_t *__restrict__ luts,
+                         const cplx *__restrict__ bskm, const cplx *__restrict__ tbl8, const cplx *__restrict__ roots,
+                         uint64_t *__restrict__ out, const uint32_t *__restrict__ out_slot, int batch, int n, int base_log, int n_groups) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    SmemX2 &sm = *reinterpret_cast<SmemX2 *>(smem_raw);
+    const int T = threadIdx.x & 127, lane = threadIdx.x & 31;
+    const bool combiner = threadIdx.x >= 128;
+    uint32_t rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    const int w = (int)rank;
+    const int ct = blockIdx.x >> 1;
+    const uint64_t *lwe = lwe_small + (size_t)ct * (n + 1);
+    const int total_regs = n_groups * 8;
+
+    if (threadIdx.x < 64) {
+        sm.root_hi[threadIdx.x] = __ldg(roots + 64 * threadIdx.x);
+        sm.root_lo[threadIdx.x] = __ldg(roots + threadIdx.x);
+    }
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSLOTX; ++s) { mbar_init(&sm.full_bar[s], 1); sm.consumed[s] = 0; }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&sm.comb_full[s], 128); mbar_init(&sm.comb_empty[s], 128);
+            mbar_init(&sm.spec_full[s], 1); mbar_expect_tx(&sm.spec_full[s], 8 * 128 * 16);     // armed for steps 0 and 1
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_proxy_async();
+    }
+    __syncthreads();
+    // both CTAs resident, barriers initialised, before anybody signals or stores into the partner's shared memory
+    asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
+
+    if (combiner) {
+        // ================= combine warps: G = G_0 + sum_j G_j * M_j for the frequencies of FFT thread T, one step ahead ==================
+        auto fill = [&](int slot, int r) {     // register-piece r = grp * 8 + g: the [out poly w][sel 2][thread 128] blocks of its four key pieces
+            mbar_expect_tx(&sm.full_bar[slot], HALF_REG_CPLX * 16);
+#pragma unroll
+            for (int q = 0; q < 8; ++q)           // q = j = pc * 2 + jl
+                tma_load_1d(sm.ring[slot] + q * 256, bskm + (size_t)(r * PIECES_PER_REG + (q >> 1)) * PIECE_CPLX + (((q & 1) * 2 + w) * 2) * 128,
+                            256 * 16, &sm.full_bar[slot]);
+        };
+        if (threadIdx.x == 128) {
+            const int first = total_regs < NSLOTX ? total_regs : NSLOTX;
+            for (int g = 0; g < first; ++g) fill(g, g);
+        }
+        const int rot_t = (1 - 4 * freq_of8(T, 0)) & (2 * kN - 1);
+        int slot = 0;
+        uint32_t phase = 0;
+        for (int grp = 0; grp < n_groups; ++grp) {
+            cplx A[NGGSW];
+            uint32_t deg3 = 0;
+            {
+                const uint64_t a0v = __ldg(lwe + GF * grp), a1v = __ldg(lwe + GF * grp + 1), a2v = __ldg(lwe + GF * grp + 2);
+#pragma unroll
+                for (int j = 1; j < NGGSW; ++j) {
+                    const uint64_t s = ((j & 4) ? a0v : 0) + ((j & 2) ? a1v : 0) + ((j & 1) ? a2v : 0);
+                    const uint32_t deg = modulus_switch_2n(s) & (2 * kN - 1);
+                    deg3 |= (deg & 7u) << (3 * j);
+                    const uint32_t e = (deg * (uint32_t)rot_t) & (2 * kN - 1);
+                    const cplx hi = sm.root_hi[e >> 6], lo = sm.root_lo[e & 63];
+                    A[j].x = DFMA(hi.x, lo.x, -DMUL(hi.y, lo.y));
+                    A[j].y = DFMA(hi.x, lo.y, DMUL(hi.y, lo.x));
+                }
+            }
+            const int b = grp & 1;
+            cplx *dst = sm.comb[b] + T;
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+                cplx Ga, Gb;
+                const uint32_t x = (uint32_t)((g >> 2) + 2 * brev2(g & 3));
+                if (!mbar_try_wait(&sm.full_bar[slot], phase)) mbar_wait(&sm.full_bar[slot], phase);
+#pragma unroll
+                for (int j = 0; j < NGGSW; ++j) {
+                    const cplx *base = sm.ring[slot] + j * 256 + T;
+                    const cplx ga = base[0], gb = base[128];
+                    if (j == 0) {
+                        Ga = ga; Gb = gb;
+                    } else {
+                        const uint32_t e = (((deg3 >> (3 * j)) & 7u) * x) & 7u;
+                        const double br = c_w8[e][0], bi = c_w8[e][1];
+                        const double mr = DFMA(A[j].x, br, -DMUL(A[j].y, bi));
+                        const double mi = DFMA(A[j].x, bi, DMUL(A[j].y, br));
+                        Ga.x = DFMA(ga.x, mr, DFMA(-ga.y, mi, Ga.x));
+                        Ga.y = DFMA(ga.x, mi, DFMA(ga.y, mr, Ga.y));
+                        Gb.x = DFMA(gb.x, mr, DFMA(-gb.y, mi, Gb.x));
+                        Gb.y = DFMA(gb.x, mi, DFMA(gb.y, mr, Gb.y));
+                    }
+                }
+                if (g == 0 && grp >= 2) mbar_wait(&sm.comb_empty[b], (uint32_t)((grp >> 1) - 1) & 1u);   // the FFT warps are done with step grp - 2's values
+                dst[g * 256] = Ga;
+                dst[g * 256 + 128] = Gb;
+                __syncwarp();
+                if (lane == 0 && atomicAdd(&sm.consumed[slot], 1u) == 4 - 1) {
+                    sm.consumed[slot] = 0;
+                    const int r2 = grp * 8 + g + NSLOTX;
+                    if (r2 < total_regs) {
+                        __threadfence_block();
+                        fence_proxy_async();
+                        fill(slot, r2);
+                    }
+                }
+                if (++slot == NSLOTX) { slot = 0; phase ^= 1u; }
+            }
+            mbar_arrive(&sm.comb_full[b]);
+        }
+    } else {
+        // ================= FFT warps: the accumulator's critical path ===================================================================
+        cplx *tile = sm.tile;
+        const PolySync128 poly_sync{1};
+        uint32_t peer_recv, peer_bar;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(peer_recv) : "r"(smem_u32(&sm.recv[0][T])), "r"((uint32_t)(w ^ 1)));
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(peer_bar) : "r"(smem_u32(&sm.spec_full[0])), "r"((uint32_t)(w ^ 1)));
+        cplx twr[24];
+#pragma unroll
+        for (int k = 0; k < 24; ++k) twr[k] = __ldg(tbl8 + 24 * T + k);
+        const RegTw8 twd{twr};
+        double re[8], im[8];
+        {
+            const uint32_t b_hat = modulus_switch_2n(__ldg(lwe + n)) & (2 * kN - 1);
+            const uint32_t a0 = (2 * kN - b_hat) & (2 * kN - 1);
+            const uint64_t *lut = luts + ((size_t)(lut_idx ? lut_idx[ct] : 0) * 2 + w) * kN;
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                const int j = T + 128 * m;
+                int s0, s1; bool n0, n1;
+                rot_src(j, a0, s0, n0);
+                rot_src(j + kM, a0, s1, n1);
+                uint64_t v0 = __ldg(lut + s0), v1 = __ldg(lut + s1);
+                v0 = n0 ? (uint64_t)0 - v0 : v0;
+                v1 = n1 ? (uint64_t)0 - v1 : v1;
+                re[m] = __longlong_as_double((long long)v0);
+                im[m] = __longlong_as_double((long long)v1);
+            }
+        }
+        for (int grp = 0; grp < n_groups; ++grp) {
+            const int b = grp & 1;
+            const uint32_t par = (uint32_t)(grp >> 1) & 1u;
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                re[m] = (double)signed_digit_l1((uint64_t)__double_as_longlong(re[m]), base_log);
+                im[m] = (double)signed_digit_l1((uint64_t)__double_as_longlong(im[m]), base_log);
+            }
+            fft8_fwd(re, im, tile, twd, T, poly_sync);
+            {   // my spectrum -> the partner's receive buffer b: the partner read it last in step grp - 2, and it finished that step's
+                // multiply-accumulate before it sent me the spectrum of step grp - 1, which I have consumed
+                const uint32_t dst = peer_recv + (uint32_t)(b * 8 * 128 * 16);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) st_async_cluster(dst + (uint32_t)(c * 128 * 16), re[c], im[c], peer_bar + (uint32_t)(b * 8));
+            }
+            if (!mbar_try_wait(&sm.comb_full[b], par)) mbar_wait(&sm.comb_full[b], par);
+            const cplx *cg = sm.comb[b] + T;
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {         // the half of the product that needs only my own spectrum, while the partner's is in flight
+                const cplx Ga = cg[g * 256];
+                const double fr = re[g], fi = im[g];
+                re[g] = DFMA(-fi, Ga.y, DMUL(fr, Ga.x));
+                im[g] = DFMA(fi, Ga.x, DMUL(fr, Ga.y));
+            }
+            if (!mbar_try_wait(&sm.spec_full[b], par)) mbar_wait(&sm.spec_full[b], par);
+            if (T == 0) mbar_expect_tx(&sm.spec_full[b], 8 * 128 * 16);     // re-armed for step grp + 2 (the partner sends that only after my step grp + 1)
+            const cplx *fop = sm.recv[b] + T;
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+                const cplx Gb = cg[g * 256 + 128], F = fop[g * 128];
+                double orr = DFMA(F.x, Gb.x, re[g]);
+                orr = DFMA(-F.y, Gb.y, orr);
+                double oi = DFMA(F.x, Gb.y, im[g]);
+                oi = DFMA(F.y, Gb.x, oi);
+                re[g] = orr; im[g] = oi;
+            }
+            mbar_arrive(&sm.comb_empty[b]);
+            fft8_inv(re, im, tile, twd, T, poly_sync);
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                re[m] = __longlong_as_double((long long)from_torus_f64(re[m]));
+                im[m] = __longlong_as_double((long long)from_torus_f64(im[m]));
+            }
+        }
+        uint64_t *o = out + (size_t)(out_slot ? out_slot[ct] : ct) * (kN + 1);
+        if (w == 0) {
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                const int j = T + 128 * m;
+                const uint64_t v0 = (uint64_t)__double_as_longlong(re[m]), v1 = (uint64_t)__double_as_longlong(im[m]);
+                if (j == 0) o[0] = v0; else o[kN - j] = (uint64_t)0 - v0;
+                o[kN - (j + kM)] = (uint64_t)0 - v1;
+            }
+        } else if (T == 0) {
+            o[kN] = (uint64_t)__double_as_longlong(re[0]);
+        }
+    }
+    // nobody leaves while the partner could still address its shared memory
+    asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // std multi-bit key [group][j 8][level 1][row r][col c][N] (entities/lwe_multi_bit_bootstrap_key.rs:11-62) -> ring layout
 __global__ void __launch_bounds__(128)
 bsk_convert_multibit_kernel_v8(const uint64_t *__restrict__ bsk_std, cplx *__restrict__ bskm, const cplx *__restrict__ tbl8, int n_polys) {
@@ -256,14 +478,22 @@ cudaError_t pbs_multibit_v8_configure() {
     }
     cudaError_t err = cudaMemcpyToSymbol(tbm8::c_w8, h, sizeof(h));
     if (err != cudaSuccess) return err;
+    err = cudaFuncSetAttribute(tbm8::pbs_multibit_kernel_v8x2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tbm8::SmemX2));
+    if (err != cudaSuccess) return err;
     return cudaFuncSetAttribute(tbm8::pbs_multibit_kernel_v8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tbm8::Smem));
 }
 
 // one ciphertext per CTA: for batch <= SM count (the caller dispatches wider levels to launch_pbs_multibit_v4)
 cudaError_t launch_pbs_multibit_v8(const uint64_t *lwe_small, const uint32_t *lut_idx, const uint64_t *luts, const void *bskm8,
                                    const void *tbl8, const void *roots, uint64_t *out, const uint32_t *out_slot, int batch, int n,
-                                   int base_log, int n_groups, cudaStream_t stream) {
+                                   int base_log, int n_groups, int cluster_max, cudaStream_t stream) {
     if (batch <= 0) return cudaSuccess;
+    if (batch <= cluster_max) {
+        tbm8::pbs_multibit_kernel_v8x2<<<2 * batch, 256, sizeof(tbm8::SmemX2), stream>>>(
+            lwe_small, lut_idx, luts, reinterpret_cast<const tb::cplx *>(bskm8), reinterpret_cast<const tb::cplx *>(tbl8),
+            reinterpret_cast<const tb::cplx *>(roots), out, out_slot, batch, n, base_log, n_groups);
+        return cudaGetLastError();
+    }
     tbm8::pbs_multibit_kernel_v8<<<batch, 256, sizeof(tbm8::Smem), stream>>>(
         lwe_small, lut_idx, luts, reinterpret_cast<const tb::cplx *>(bskm8), reinterpret_cast<const tb::cplx *>(tbl8),
         reinterpret_cast<const tb::cplx *>(roots), out, out_slot, batch, n, base_log, n_groups);

@@ -263,29 +263,19 @@ pbs_classic_kernel_v8(const uint64_t *__restrict__ lwe_small, const uint32_t *__
 // per scheduler), 7.4 k cycles, with nothing to overlap.  Both halve when each polynomial gets an SM of its own: CTA rank w of the cluster
 // owns polynomial w (accumulator, gather, forward FFT, the output polynomial w of the external product, inverse FFT), streams only the
 // half of the Fourier key that feeds output w (8 x 4 KiB pieces per iteration into a four-deep ring), and the two CTAs swap spectra once
-// per iteration: each thread stores its 8 values straight into the partner's shared memory (st.shared::cluster, double buffered) and one
-// cluster barrier (arrive.release / wait.acquire) publishes them -- the only cross-SM synchronisation of the iteration.
+// per iteration: each thread stores its 8 values straight into the partner's shared memory (st.shared::cluster, double buffered) and
+// every store reports its bytes to an mbarrier in the partner's shared memory (st.async ... mbarrier::complete_tx): 16 KiB received = the
+// spectrum has landed.  No fence, no cluster barrier inside the loop (a cluster barrier per iteration, or 128 release.cluster arrivals,
+// put a MEMBAR.ALL.GPU + ERRBAR on every thread's path: ncu, profiles/r02_pbs_v8x2_*).
 constexpr int NBUFX = 4;
+constexpr int SPEC_BYTES = 8 * 128 * 16;     // one polynomial's spectrum
 constexpr int HALF_ITER_CPLX = PIECES_PER_ITER * 256;      // [register g 8][sel 2][thread 128] = 32 KiB
 struct SmemX2 {
     cplx tile[tb8::kTileCplx];
     cplx recv[2][PIECES_PER_ITER * 128];
     cplx ring[NBUFX][HALF_ITER_CPLX];
-    unsigned long long full_bar[NBUFX];
+    unsigned long long full_bar[NBUFX], spec_full[2];
 };
-
-__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ uint32_t map_to_cta(uint32_t saddr, uint32_t rank) {
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
-    return r;
-}
-__device__ __forceinline__ void st_cluster(uint32_t addr, double x, double y) {
-    asm volatile("st.shared::cluster.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(x), "d"(y) : "memory");
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
 pbs_classic_kernel_v8x2(const uint64_t *__restrict__ lwe_small, const uint32_t *__restrict__ lut_idx, const uint64_t *__restrict__ luts,
@@ -302,6 +292,7 @@ pbs_classic_kernel_v8x2(const uint64_t *__restrict__ lwe_small, const uint32_t *
     const uint64_t *lwe = lwe_small + (size_t)ct * (n + 1);
     const uint16_t *lwe16 = reinterpret_cast<const uint16_t *>(lwe_small) + (size_t)ct * (n + 1);
     const uint32_t peer_recv = map_to_cta(smem_u32(&sm.recv[0][T]), (uint32_t)(w ^ 1));
+    const uint32_t peer_bar = map_to_cta(smem_u32(&sm.spec_full[0]), (uint32_t)(w ^ 1));
 
     auto fill = [&](int it) {      // this CTA's half of GGSW `it`: for every register g the [sel 2][thread 128] block of output polynomial w
         const int buf = it & (NBUFX - 1);
@@ -312,6 +303,7 @@ pbs_classic_kernel_v8x2(const uint64_t *__restrict__ lwe_small, const uint32_t *
     };
     if (T == 0) {
         for (int s = 0; s < NBUFX; ++s) mbar_init(&sm.full_bar[s], 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(&sm.spec_full[s], 1); mbar_expect_tx(&sm.spec_full[s], SPEC_BYTES); }   // armed for iterations 0 and 1
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_proxy_async();
         for (int g = 0; g < NBUFX && g < n_iters; ++g) fill(g);
@@ -365,15 +357,17 @@ pbs_classic_kernel_v8x2(const uint64_t *__restrict__ lwe_small, const uint32_t *
         }
         fft8_fwd(re, im, tile, twd_r, T, poly_sync);
 
-        // my spectrum -> the partner's receive buffer i & 1 (the partner read buffer i & 1 last in iteration i - 2, i.e. before the
-        // cluster barrier of iteration i - 1 that I have already passed), then one cluster barrier
+        // my spectrum -> the partner's receive buffer i & 1: the partner read that buffer last in iteration i - 2, i.e. before it sent
+        // me the spectrum of iteration i - 1 (its arrivals are releases), which I have waited for
         {
             const uint32_t dst = peer_recv + (uint32_t)((i & 1) * PIECES_PER_ITER * 128 * 16);
 #pragma unroll
-            for (int c = 0; c < PIECES_PER_ITER; ++c) st_cluster(dst + (uint32_t)(c * 128 * 16), re[c], im[c]);
+            const uint32_t bar = peer_bar + (uint32_t)((i & 1) * 8);      // every store reports its 16 bytes there: 16 KiB = the spectrum has landed
+#pragma unroll
+            for (int c = 0; c < PIECES_PER_ITER; ++c) st_async_cluster(dst + (uint32_t)(c * 128 * 16), re[c], im[c], bar);
         }
-        cluster_sync_all();
 
+        // out_fft[w] = F_w * G[w][w] + F_{1-w} * G[1-w][w]: the half that needs only my own spectrum runs while the partner's is in flight
         {
             const int buf = i & (NBUFX - 1);
             const uint32_t ph = (uint32_t)(i / NBUFX) & 1u;
@@ -382,15 +376,21 @@ pbs_classic_kernel_v8x2(const uint64_t *__restrict__ lwe_small, const uint32_t *
             const cplx *pc = sm.ring[buf] + T;
 #pragma unroll
             for (int c = 0; c < PIECES_PER_ITER; ++c) {
-                const cplx A = pc[c * 256], B = pc[c * 256 + 128], F = fop[c * 128];
+                const cplx A = pc[c * 256];
                 const double fr = re[c], fi = im[c];
-                double orr = DMUL(fr, A.x);
-                orr = DFMA(-fi, A.y, orr);
-                orr = DFMA(F.x, B.x, orr);
+                re[c] = DFMA(-fi, A.y, DMUL(fr, A.x));
+                im[c] = DFMA(fi, A.x, DMUL(fr, A.y));
+            }
+            if (!mbar_try_wait(&sm.spec_full[i & 1], (uint32_t)(i >> 1) & 1u)) mbar_wait(&sm.spec_full[i & 1], (uint32_t)(i >> 1) & 1u);
+            // re-arm for iteration i + 2: the partner cannot send that spectrum before it has received mine of iteration i + 1, which I
+            // send only after this point
+            if (T == 0) mbar_expect_tx(&sm.spec_full[i & 1], SPEC_BYTES);
+#pragma unroll
+            for (int c = 0; c < PIECES_PER_ITER; ++c) {
+                const cplx B = pc[c * 256 + 128], F = fop[c * 128];
+                double orr = DFMA(F.x, B.x, re[c]);
                 orr = DFMA(-F.y, B.y, orr);
-                double oi = DMUL(fr, A.y);
-                oi = DFMA(fi, A.x, oi);
-                oi = DFMA(F.x, B.y, oi);
+                double oi = DFMA(F.x, B.y, im[c]);
                 oi = DFMA(F.y, B.x, oi);
                 re[c] = orr; im[c] = oi;
             }

@@ -12,8 +12,10 @@ rng = np.random.default_rng(1)
 eng.upload_ksk(rng.integers(0, 2**64, size=p.ksk_len, dtype=np.uint64))
 eng.upload_bsk_std(rng.integers(0, 2**64, size=p.bsk_len, dtype=np.uint64))
 eng.upload_luts(rng.integers(0, 2**64, size=(4, p.lut_len), dtype=np.uint64))
+import os
+if os.environ.get("NARROW_CLUSTER"): eng.set_tuning("narrow_cluster", int(os.environ["NARROW_CLUSTER"]))
 s = torch.cuda.Stream()
-for batch in (1, 8, 16, 32, 64, 128, 148, 296, 592):
+for batch in (1, 8, 16, 32, 64, 74, 128, 148, 296, 592):
     d_in = torch.from_numpy(rng.integers(0, 2**63, size=(batch, p.big_len), dtype=np.int64)).cuda()
     d_out = torch.empty_like(d_in)
     idx = torch.zeros(batch, dtype=torch.int32, device="cuda")

@@ -170,6 +170,10 @@ def test_multibit_narrow_level_kernel(orc, keys_multibit, monkeypatch):
         assert list(ck.decrypt_batch(out8)) == want, batch
         assert list(ck.decrypt_batch(e4.ks_pbs_batch(cts, idx))) == want, batch
         assert np.array_equal(out8, e8.ks_pbs_batch(cts, idx))          # deterministic
+        if batch <= sms // 2:    # default: one ciphertext per two-SM cluster (pbs_multibit_kernel_v8x2); identical words on one SM
+            e8.set_tuning("narrow_cluster", 0)
+            assert np.array_equal(out8, e8.ks_pbs_batch(cts, idx)), f"cluster instance differs from the one-SM instance, batch {batch}"
+            e8.set_tuning("narrow_cluster", 1)
         err = phase_error(ck, out8, np.array(want))
         assert err.max() < 2**55
         small = e8.keyswitch_batch(cts)
