@@ -227,45 +227,49 @@ pbs_multibit_kernel_v8(const uint64_t *__restrict__ lwe_small, const uint32_t *_
 //   * CTA rank w of the cluster owns polynomial w (pbs_classic_kernel_v8x2 in pbs_v8.cu has the reasoning and the same spectrum swap
 //     through distributed shared memory) and streams only the half of the key that feeds output polynomial w;
 //   * warps 4-7 ("combine warps") run ONE STEP AHEAD: they pull the key through the ring and leave the combined GGSW values of their
-//     frequencies (Ga, Gb per register and thread, 32 KiB per step, double buffered) in shared memory;
+//     frequencies (Ga, Gb per register and thread, double buffered) in the Tensor Memory lane they share with the FFT thread of the same
+//     index (tcgen05.st / tcgen05.ld: lane-private hand-over off the shared-memory pipe; the 64 KiB it would take in shared memory go to
+//     the key ring, whose depth -- bytes in flight against a 2 us refill turn-around -- is what bounds a step);
 //   * warps 0-3 ("FFT warps") do what a classic blind-rotation step does -- decompose, forward FFT, swap spectra, 2 x 2 multiply-accumulate
 //     against the combined values, inverse FFT, round.
 // Hand-offs are mbarriers (combined values full / empty inside the CTA; "spectrum landed" = the 16 KiB of st.async stores reported to an
 // mbarrier in the receiving CTA).  The floating-point operations and their order are those of the one-SM kernel: identical words.
-constexpr int NSLOTX = 3;
-constexpr int HALF_REG_CPLX = 2048;            // one FFT register's worth of this CTA's key half: [j 8][sel 2][thread 128] = 32 KiB behind ONE barrier
+constexpr int NSLOTX = 5;
+constexpr int HALF_REG_CPLX = 2048;            // one ring slot: [register of the pair 2][jj 4][sel 2][thread 128] = 32 KiB behind ONE barrier
 struct SmemX2 {
     cplx tile[tb8::kTileCplx];
     cplx recv[2][8 * 128];
-    cplx comb[2][8 * 256];                     // [step parity][register g][Ga, Gb][thread 128]
     cplx ring[NSLOTX][HALF_REG_CPLX];
     cplx root_hi[64], root_lo[64];
-    unsigned long long full_bar[NSLOTX], comb_full[2], comb_empty[2], spec_full[2];
+    unsigned long long full_bar[NSLOTX], empty_bar[NSLOTX], comb_full[2], comb_empty[2], spec_full[2];
     unsigned int consumed[NSLOTX];
+    uint32_t tmem_base;
 };
 static_assert(sizeof(SmemX2) <= 227 * 1024, "shared memory budget");
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+constexpr int COMB_COLS = 128;     // Tensor Memory: [step parity 2][register g 8][Ga.x Ga.y Gb.x Gb.y as 8 words] per lane (= FFT thread T)
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(288, 1)
 pbs_multibit_kernel_v8x2(const uint64_t *__restrict__ lwe_small, const uint32_t *__restrict__ lut_idx, const uint64_t *__restrict__ luts,
                          const cplx *__restrict__ bskm, const cplx *__restrict__ tbl8, const cplx *__restrict__ roots,
                          uint64_t *__restrict__ out, const uint32_t *__restrict__ out_slot, int batch, int n, int base_log, int n_groups) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SmemX2 &sm = *reinterpret_cast<SmemX2 *>(smem_raw);
     const int T = threadIdx.x & 127, lane = threadIdx.x & 31;
-    const bool combiner = threadIdx.x >= 128;
+    const bool combiner = threadIdx.x >= 128 && threadIdx.x < 256, producer = threadIdx.x >= 256;
     uint32_t rank;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
     const int w = (int)rank;
     const int ct = blockIdx.x >> 1;
     const uint64_t *lwe = lwe_small + (size_t)ct * (n + 1);
-    const int total_regs = n_groups * 8;
+    const int total_uses = n_groups * 8;      // ring slot uses: 4 register pairs x 2 halves per step
 
     if (threadIdx.x < 64) {
         sm.root_hi[threadIdx.x] = __ldg(roots + 64 * threadIdx.x);
         sm.root_lo[threadIdx.x] = __ldg(roots + threadIdx.x);
     }
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NSLOTX; ++s) { mbar_init(&sm.full_bar[s], 1); sm.consumed[s] = 0; }
+        for (int s = 0; s < NSLOTX; ++s) { mbar_init(&sm.full_bar[s], 1); mbar_init(&sm.empty_bar[s], 4); sm.consumed[s] = 0; }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&sm.comb_full[s], 128); mbar_init(&sm.comb_empty[s], 128);
             mbar_init(&sm.spec_full[s], 1); mbar_expect_tx(&sm.spec_full[s], 8 * 128 * 16);     // armed for steps 0 and 1
@@ -273,23 +277,43 @@ pbs_multibit_kernel_v8x2(const uint64_t *__restrict__ lwe_small, const uint32_t 
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_proxy_async();
     }
+    if (threadIdx.x < 32) tb16k::tmem_alloc<COMB_COLS>(&sm.tmem_base);
+    tb16k::tc_fence_before();
     __syncthreads();
+    tb16k::tc_fence_after();
+    // combine thread and FFT thread of the same T sit in the same TMEM lane (warp id % 4 = T / 32, same lane): the combined values are
+    // handed over there, lane-private, off the shared-memory pipe and out of the shared-memory budget (which goes to a deeper key ring)
+    const uint32_t comb_t = sm.tmem_base + ((uint32_t)((T >> 5) * 32) << 16);
     // both CTAs resident, barriers initialised, before anybody signals or stores into the partner's shared memory
     asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
 
-    if (combiner) {
-        // ================= combine warps: G = G_0 + sum_j G_j * M_j for the frequencies of FFT thread T, one step ahead ==================
-        auto fill = [&](int slot, int r) {     // register-piece r = grp * 8 + g: the [out poly w][sel 2][thread 128] blocks of its four key pieces
-            mbar_expect_tx(&sm.full_bar[slot], HALF_REG_CPLX * 16);
+    if (producer) {
+        // ================= producer warp: one lane keeps the key ring full (the refill is ~100 single-lane instructions per slot: on a
+        // combine warp it made that warp the slowest, and the ring moves at the pace of the slowest reader) ==================================
+        if (lane == 0) {
+        // ring slot = half the key of a PAIR of FFT registers: use u = (grp * 4 + pair) * 2 + h holds, for registers g = 2 pair + cw (cw = 0, 1)
+            // and GGSWs j = 4 h + jj, the [sel 2][thread 128] blocks of output polynomial w: [cw][jj][sel][thread] = 32 KiB behind one barrier.
+            auto fill = [&](int slot, int u) {
+                mbar_expect_tx(&sm.full_bar[slot], HALF_REG_CPLX * 16);
+                const int h = u & 1, gbase = (u >> 1) * 2;           // gbase = grp * 8 + 2 * pair
 #pragma unroll
-            for (int q = 0; q < 8; ++q)           // q = j = pc * 2 + jl
-                tma_load_1d(sm.ring[slot] + q * 256, bskm + (size_t)(r * PIECES_PER_REG + (q >> 1)) * PIECE_CPLX + (((q & 1) * 2 + w) * 2) * 128,
-                            256 * 16, &sm.full_bar[slot]);
-        };
-        if (threadIdx.x == 128) {
-            const int first = total_regs < NSLOTX ? total_regs : NSLOTX;
-            for (int g = 0; g < first; ++g) fill(g, g);
+                for (int q = 0; q < 8; ++q) {                        // q = cw * 4 + jj
+                    const int j = 4 * h + (q & 3);
+                    tma_load_1d(sm.ring[slot] + q * 256, bskm + (size_t)((gbase + (q >> 2)) * PIECES_PER_REG + (j >> 1)) * PIECE_CPLX + (((j & 1) * 2 + w) * 2) * 128,
+                                256 * 16, &sm.full_bar[slot]);
+                }
+            };
+            for (int u = 0; u < total_uses; ++u) {
+                const int slot = u % NSLOTX;
+                if (u >= NSLOTX) {
+                    mbar_wait(&sm.empty_bar[slot], (uint32_t)(u / NSLOTX - 1) & 1u);
+                    fence_proxy_async();
+                }
+                fill(slot, u);
+            }
         }
+    } else if (combiner) {
+        // ================= combine warps: G = G_0 + sum_j G_j * M_j for the frequencies of FFT thread T, one step ahead ==================
         const int rot_t = (1 - 4 * freq_of8(T, 0)) & (2 * kN - 1);
         int slot = 0;
         uint32_t phase = 0;
@@ -310,44 +334,55 @@ pbs_multibit_kernel_v8x2(const uint64_t *__restrict__ lwe_small, const uint32_t 
                 }
             }
             const int b = grp & 1;
-            cplx *dst = sm.comb[b] + T;
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {
-                cplx Ga, Gb;
-                const uint32_t x = (uint32_t)((g >> 2) + 2 * brev2(g & 3));
-                if (!mbar_try_wait(&sm.full_bar[slot], phase)) mbar_wait(&sm.full_bar[slot], phase);
+            for (int pair = 0; pair < 4; ++pair) {      // the two registers of a pair side by side: two independent accumulation chains
+                cplx Ga[2], Gb[2];
 #pragma unroll
-                for (int j = 0; j < NGGSW; ++j) {
-                    const cplx *base = sm.ring[slot] + j * 256 + T;
-                    const cplx ga = base[0], gb = base[128];
-                    if (j == 0) {
-                        Ga = ga; Gb = gb;
-                    } else {
-                        const uint32_t e = (((deg3 >> (3 * j)) & 7u) * x) & 7u;
-                        const double br = c_w8[e][0], bi = c_w8[e][1];
-                        const double mr = DFMA(A[j].x, br, -DMUL(A[j].y, bi));
-                        const double mi = DFMA(A[j].x, bi, DMUL(A[j].y, br));
-                        Ga.x = DFMA(ga.x, mr, DFMA(-ga.y, mi, Ga.x));
-                        Ga.y = DFMA(ga.x, mi, DFMA(ga.y, mr, Ga.y));
-                        Gb.x = DFMA(gb.x, mr, DFMA(-gb.y, mi, Gb.x));
-                        Gb.y = DFMA(gb.x, mi, DFMA(gb.y, mr, Gb.y));
+                for (int h = 0; h < 2; ++h) {
+                    if (!mbar_try_wait(&sm.full_bar[slot], phase)) mbar_wait(&sm.full_bar[slot], phase);
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const int j = 4 * h + jj;
+#pragma unroll
+                        for (int c2 = 0; c2 < 2; ++c2) {
+                            const int g = 2 * pair + c2;
+                            const uint32_t x = (uint32_t)((g >> 2) + 2 * brev2(g & 3));
+                            const cplx *base = sm.ring[slot] + (c2 * 4 + jj) * 256 + T;
+                            const cplx ga = base[0], gb = base[128];
+                            if (j == 0) {
+                                Ga[c2] = ga; Gb[c2] = gb;
+                            } else {
+                                const uint32_t e = (((deg3 >> (3 * j)) & 7u) * x) & 7u;
+                                const double br = c_w8[e][0], bi = c_w8[e][1];
+                                const double mr = DFMA(A[j].x, br, -DMUL(A[j].y, bi));
+                                const double mi = DFMA(A[j].x, bi, DMUL(A[j].y, br));
+                                Ga[c2].x = DFMA(ga.x, mr, DFMA(-ga.y, mi, Ga[c2].x));
+                                Ga[c2].y = DFMA(ga.x, mi, DFMA(ga.y, mr, Ga[c2].y));
+                                Gb[c2].x = DFMA(gb.x, mr, DFMA(-gb.y, mi, Gb[c2].x));
+                                Gb[c2].y = DFMA(gb.x, mi, DFMA(gb.y, mr, Gb[c2].y));
+                            }
+                        }
                     }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&sm.empty_bar[slot]);     // four warps out = the producer warp may refill the slot
+                    if (++slot == NSLOTX) { slot = 0; phase ^= 1u; }
                 }
-                if (g == 0 && grp >= 2) mbar_wait(&sm.comb_empty[b], (uint32_t)((grp >> 1) - 1) & 1u);   // the FFT warps are done with step grp - 2's values
-                dst[g * 256] = Ga;
-                dst[g * 256 + 128] = Gb;
-                __syncwarp();
-                if (lane == 0 && atomicAdd(&sm.consumed[slot], 1u) == 4 - 1) {
-                    sm.consumed[slot] = 0;
-                    const int r2 = grp * 8 + g + NSLOTX;
-                    if (r2 < total_regs) {
-                        __threadfence_block();
-                        fence_proxy_async();
-                        fill(slot, r2);
+                if (pair == 0 && grp >= 2) {      // the FFT warps are done with step grp - 2's values
+                    mbar_wait(&sm.comb_empty[b], (uint32_t)((grp >> 1) - 1) & 1u);
+                    tb16k::tc_fence_after();
+                }
+                {
+                    uint32_t v[16];
+#pragma unroll
+                    for (int c2 = 0; c2 < 2; ++c2) {
+                        tb16k::pack_cplx(Ga[c2].x, Ga[c2].y, v, 2 * c2);
+                        tb16k::pack_cplx(Gb[c2].x, Gb[c2].y, v, 2 * c2 + 1);
                     }
+                    tmem_st16(comb_t + (uint32_t)(b * 64 + pair * 16), v);
                 }
-                if (++slot == NSLOTX) { slot = 0; phase ^= 1u; }
             }
+            tmem_wait_st();
+            tb16k::tc_fence_before();
             mbar_arrive(&sm.comb_full[b]);
         }
     } else {
@@ -395,26 +430,42 @@ pbs_multibit_kernel_v8x2(const uint64_t *__restrict__ lwe_small, const uint32_t 
                 for (int c = 0; c < 8; ++c) st_async_cluster(dst + (uint32_t)(c * 128 * 16), re[c], im[c], peer_bar + (uint32_t)(b * 8));
             }
             if (!mbar_try_wait(&sm.comb_full[b], par)) mbar_wait(&sm.comb_full[b], par);
-            const cplx *cg = sm.comb[b] + T;
+            tb16k::tc_fence_after();
+            const uint32_t cg = comb_t + (uint32_t)(b * 64);
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {         // the half of the product that needs only my own spectrum, while the partner's is in flight
-                const cplx Ga = cg[g * 256];
-                const double fr = re[g], fi = im[g];
-                re[g] = DFMA(-fi, Ga.y, DMUL(fr, Ga.x));
-                im[g] = DFMA(fi, Ga.x, DMUL(fr, Ga.y));
+            for (int gp = 0; gp < 4; ++gp) {      // the half of the product that needs only my own spectrum, while the partner's is in flight
+                uint32_t v[16];
+                tmem_ld16(cg + 16 * gp, v);
+                tmem_wait_ld();
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int g = 2 * gp + q;
+                    const cplx Ga = cplx_from_words(v, 2 * q);
+                    const double fr = re[g], fi = im[g];
+                    re[g] = DFMA(-fi, Ga.y, DMUL(fr, Ga.x));
+                    im[g] = DFMA(fi, Ga.x, DMUL(fr, Ga.y));
+                }
             }
             if (!mbar_try_wait(&sm.spec_full[b], par)) mbar_wait(&sm.spec_full[b], par);
             if (T == 0) mbar_expect_tx(&sm.spec_full[b], 8 * 128 * 16);     // re-armed for step grp + 2 (the partner sends that only after my step grp + 1)
             const cplx *fop = sm.recv[b] + T;
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {
-                const cplx Gb = cg[g * 256 + 128], F = fop[g * 128];
-                double orr = DFMA(F.x, Gb.x, re[g]);
-                orr = DFMA(-F.y, Gb.y, orr);
-                double oi = DFMA(F.x, Gb.y, im[g]);
-                oi = DFMA(F.y, Gb.x, oi);
-                re[g] = orr; im[g] = oi;
+            for (int gp = 0; gp < 4; ++gp) {
+                uint32_t v[16];
+                tmem_ld16(cg + 16 * gp, v);
+                tmem_wait_ld();
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int g = 2 * gp + q;
+                    const cplx Gb = cplx_from_words(v, 2 * q + 1), F = fop[g * 128];
+                    double orr = DFMA(F.x, Gb.x, re[g]);
+                    orr = DFMA(-F.y, Gb.y, orr);
+                    double oi = DFMA(F.x, Gb.y, im[g]);
+                    oi = DFMA(F.y, Gb.x, oi);
+                    re[g] = orr; im[g] = oi;
+                }
             }
+            tb16k::tc_fence_before();
             mbar_arrive(&sm.comb_empty[b]);
             fft8_inv(re, im, tile, twd, T, poly_sync);
 #pragma unroll
@@ -437,7 +488,9 @@ pbs_multibit_kernel_v8x2(const uint64_t *__restrict__ lwe_small, const uint32_t 
         }
     }
     // nobody leaves while the partner could still address its shared memory
+    tb16k::tc_fence_before();
     asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (threadIdx.x < 32) tb16k::tmem_dealloc<COMB_COLS>(sm.tmem_base);
 }
 
 // std multi-bit key [group][j 8][level 1][row r][col c][N] (entities/lwe_multi_bit_bootstrap_key.rs:11-62) -> ring layout
@@ -489,7 +542,7 @@ cudaError_t launch_pbs_multibit_v8(const uint64_t *lwe_small, const uint32_t *lu
                                    int base_log, int n_groups, int cluster_max, cudaStream_t stream) {
     if (batch <= 0) return cudaSuccess;
     if (batch <= cluster_max) {
-        tbm8::pbs_multibit_kernel_v8x2<<<2 * batch, 256, sizeof(tbm8::SmemX2), stream>>>(
+        tbm8::pbs_multibit_kernel_v8x2<<<2 * batch, 288, sizeof(tbm8::SmemX2), stream>>>(
             lwe_small, lut_idx, luts, reinterpret_cast<const tb::cplx *>(bskm8), reinterpret_cast<const tb::cplx *>(tbl8),
             reinterpret_cast<const tb::cplx *>(roots), out, out_slot, batch, n, base_log, n_groups);
         return cudaGetLastError();

@@ -274,10 +274,10 @@ struct SmemX2 {
     cplx tile[tb8::kTileCplx];
     cplx recv[2][PIECES_PER_ITER * 128];
     cplx ring[NBUFX][HALF_ITER_CPLX];
-    unsigned long long full_bar[NBUFX], spec_full[2];
+    unsigned long long full_bar[NBUFX], empty_bar[NBUFX], spec_full[2];
 };
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(160, 1)
 pbs_classic_kernel_v8x2(const uint64_t *__restrict__ lwe_small, const uint32_t *__restrict__ lut_idx, const uint64_t *__restrict__ luts,
                         const cplx *__restrict__ bskf8, const cplx *__restrict__ tbl8, uint64_t *__restrict__ out,
                         const uint32_t *__restrict__ out_slot, int batch, int n, int base_log, int n_iters, int small_is_u16) {
@@ -302,12 +302,29 @@ pbs_classic_kernel_v8x2(const uint64_t *__restrict__ lwe_small, const uint32_t *
             tma_load_1d(sm.ring[buf] + g * 256, bskf8 + bskf8_index(it, g, w, 0), 256 * 16, &sm.full_bar[buf]);
     };
     if (T == 0) {
-        for (int s = 0; s < NBUFX; ++s) mbar_init(&sm.full_bar[s], 1);
+        for (int s = 0; s < NBUFX; ++s) { mbar_init(&sm.full_bar[s], 1); mbar_init(&sm.empty_bar[s], 4); }
         for (int s = 0; s < 2; ++s) { mbar_init(&sm.spec_full[s], 1); mbar_expect_tx(&sm.spec_full[s], SPEC_BYTES); }   // armed for iterations 0 and 1
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_proxy_async();
-        for (int g = 0; g < NBUFX && g < n_iters; ++g) fill(g);
     }
+    cluster_sync_all();     // both CTAs are resident and their barriers initialised before anyone stores into the partner's shared memory
+
+    if (threadIdx.x >= 128) {
+        // producer warp: one lane keeps the key ring full (eight bulk copies per iteration are ~100 single-lane instructions; on an FFT
+        // warp they sat on the iteration's critical path)
+        if (threadIdx.x == 128) {
+            for (int it = 0; it < n_iters; ++it) {
+                if (it >= NBUFX) {
+                    mbar_wait(&sm.empty_bar[it & (NBUFX - 1)], (uint32_t)(it / NBUFX - 1) & 1u);
+                    fence_proxy_async();
+                }
+                fill(it);
+            }
+        }
+        cluster_sync_all();
+        return;
+    }
+
     cplx twr[24];
     uint64_t accr[16];
     const RegTw8 twd_r{twr};
@@ -334,15 +351,9 @@ pbs_classic_kernel_v8x2(const uint64_t *__restrict__ lwe_small, const uint32_t *
             accr[2 * m] = v0; accr[2 * m + 1] = v1;
         }
     }
-    cluster_sync_all();     // both CTAs are resident and their barriers initialised before anyone stores into the partner's shared memory
-
     for (int i = 0; i < n_iters; ++i) {
         const uint32_t a = (small_is_u16 ? (uint32_t)__ldg(lwe16 + i) : modulus_switch_2n(__ldg(lwe + i))) & (2 * kN - 1);
-        poly_sync();    // the accumulator polynomial is complete in shared memory; everyone is past the previous iteration's MAC
-        if (T == 0 && i >= 1 && i - 1 + NBUFX < n_iters) {     // so the ring buffer of iteration i - 1 can take GGSW i - 1 + NBUFX
-            fence_proxy_async();
-            fill(i - 1 + NBUFX);
-        }
+        poly_sync();    // the accumulator polynomial is complete in shared memory
 #pragma unroll
         for (int m = 0; m < 8; ++m) {
             const int j = T + 128 * m;
@@ -358,10 +369,9 @@ pbs_classic_kernel_v8x2(const uint64_t *__restrict__ lwe_small, const uint32_t *
         fft8_fwd(re, im, tile, twd_r, T, poly_sync);
 
         // my spectrum -> the partner's receive buffer i & 1: the partner read that buffer last in iteration i - 2, i.e. before it sent
-        // me the spectrum of iteration i - 1 (its arrivals are releases), which I have waited for
+        // me the spectrum of iteration i - 1, which I have waited for
         {
             const uint32_t dst = peer_recv + (uint32_t)((i & 1) * PIECES_PER_ITER * 128 * 16);
-#pragma unroll
             const uint32_t bar = peer_bar + (uint32_t)((i & 1) * 8);      // every store reports its 16 bytes there: 16 KiB = the spectrum has landed
 #pragma unroll
             for (int c = 0; c < PIECES_PER_ITER; ++c) st_async_cluster(dst + (uint32_t)(c * 128 * 16), re[c], im[c], bar);
@@ -394,6 +404,8 @@ pbs_classic_kernel_v8x2(const uint64_t *__restrict__ lwe_small, const uint32_t *
                 oi = DFMA(F.y, B.x, oi);
                 re[c] = orr; im[c] = oi;
             }
+            __syncwarp();
+            if ((T & 31) == 0) mbar_arrive(&sm.empty_bar[buf]);      // four warps out = the producer may refill this ring buffer
         }
         fft8_inv(re, im, tile, twd_r, T, poly_sync);
         poly_sync();    // everyone has read the last exchange: the tile becomes the accumulator polynomial again
@@ -470,7 +482,7 @@ cudaError_t launch_pbs_classic_v8(const uint64_t *lwe_small, const uint32_t *lut
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const tb::cplx *bk = reinterpret_cast<const tb::cplx *>(bskf8), *tb = reinterpret_cast<const tb::cplx *>(tbl8);
     if (batch <= cluster_max && batch <= sms / 2)      // one ciphertext per two-SM cluster
-        tb8k::pbs_classic_kernel_v8x2<<<2 * batch, 128, sizeof(tb8k::SmemX2), stream>>>(lwe_small, lut_idx, luts, bk, tb, out, out_slot, batch, n,
+        tb8k::pbs_classic_kernel_v8x2<<<2 * batch, 160, sizeof(tb8k::SmemX2), stream>>>(lwe_small, lut_idx, luts, bk, tb, out, out_slot, batch, n,
                                                                                      base_log, n_iters, small_is_u16);
     else if (batch <= sms)
         tb8k::pbs_classic_kernel_v8<1><<<batch, 256, sizeof(tb8k::Smem<1>), stream>>>(lwe_small, lut_idx, luts, bk, tb, out, out_slot, batch, n,
