@@ -206,6 +206,7 @@ int tfhe_b200_ctx_create(int cuda_device, const tfhe_b200_params *params, tfhe_b
     TB_CUDA(tbk::pbs_v4_configure());
     TB_CUDA(tbk::pbs_v8_configure());
     if (const char *e = std::getenv("TFHE_B200_NARROW_KERNEL")) c->narrow_kernel = (e[0] == '8') ? 8 : 0;
+    if (const char *e = std::getenv("TFHE_B200_NARROW_CLUSTER")) c->narrow_cluster = (e[0] == '0') ? 0 : 1;
     if (const char *e = std::getenv("TFHE_B200_NARROW_MAX")) c->narrow_max = atoi(e);
     TB_CUDA(cudaDeviceGetAttribute(&c->sms, cudaDevAttrMultiProcessorCount, cuda_device));
     TB_CUDA(tbk::pbs_multibit_v4_configure());

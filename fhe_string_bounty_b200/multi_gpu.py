@@ -60,6 +60,11 @@ class HostComm:
     def zeros(self, rows: int, lwe_len: int):
         return np.zeros((rows, lwe_len), dtype=np.uint64)
 
+    def padded(self, blocks, rows: int, lwe_len: int):
+        out = np.zeros((rows, lwe_len), dtype=np.uint64)
+        out[:len(blocks)] = blocks
+        return out
+
     def all_reduce(self, blocks):
         """sum of LWE ciphertexts over ranks == homomorphic addition (wrapping u64 via two's-complement int64)"""
         if self.world == 1:
@@ -270,6 +275,15 @@ class DeviceComm:
     def zeros(self, rows: int, lwe_len: int):
         return torch.zeros((rows, lwe_len), dtype=torch.int64, device=self.dev)
 
+    @_on_own_stream
+    def padded(self, blocks, rows: int, lwe_len: int):
+        """`blocks` followed by zero rows up to `rows` (equal shares for an all-gather), enqueued on the comm's stream like the program
+        that produces `blocks` (a slice assignment on torch's current stream would not wait for it)"""
+        out = torch.zeros((rows, lwe_len), dtype=torch.int64, device=self.dev)
+        if blocks.shape[0]:
+            out[:blocks.shape[0]].copy_(blocks)
+        return out
+
     def _stage_for_peer(self, blocks) -> int:
         """rows that are not already in the send area (a rank without a share contributes zeros) are copied there"""
         if blocks is None:
@@ -463,8 +477,7 @@ def sharded_case(comm, params: dict, op: str, s, n_chars: int, rank: int | None 
     conv = comm.run(comm.program("string_" + op, (c1 - c0,), params), s[4 * c0:4 * c1]) if c1 > c0 else comm.zeros(0, L)
     if not gather:
         return comm.to_host(conv) if c1 > c0 else np.zeros((0, L), dtype=np.uint64)
-    mine = comm.zeros(4 * per, L)
-    mine[:4 * (c1 - c0)] = conv
+    mine = comm.padded(conv, 4 * per, L)      # on the comm's stream: `conv` is still being computed there
     parts = comm.to_host(comm.all_gather(mine).reshape(world * 4 * per, L)).reshape(world, 4 * per, L)
     out = []
     for r in range(active):
