@@ -209,7 +209,9 @@ int tfhe_b200_exchange_destroy(tfhe_b200_exchange *ex);
 /* Kernel selection (A/B comparisons and the parity tests that pin one kernel instance); the same keys are read from the environment at
  * context creation as TFHE_B200_<KEY>.  Keys: "narrow_kernel" (8 = pbs_v8.cu / pbs_multibit_v8.cu serve levels of at most narrow_max
  * ciphertexts and level tails, 0 = the 1- / 2-ciphertext instances of the wide kernels), "narrow_max" (0 = default: 2 x SM count
- * classic, SM count multi-bit), "ks_kernel" (2 = keyswitch on tcgen05.mma kind::i8 [default], 1 = on mma.sync, 0 = IMAD keyswitch; all three are bit-identical). */
+ * classic, SM count multi-bit), "ks_kernel" (2 = keyswitch on tcgen05.mma kind::i8 [default], 1 = on mma.sync, 0 = IMAD keyswitch; all three are
+ * bit-identical), "narrow_cluster" (1 [default] = levels of at most SM count / 2 ciphertexts put one ciphertext on a two-SM thread-block
+ * cluster, pbs_classic_kernel_v8x2 / pbs_multibit_kernel_v8x2; 0 = one SM per ciphertext; identical output words either way). */
 int tfhe_b200_set_tuning(tfhe_b200_ctx *ctx, const char *key, int value);
 
 /* Instrumentation. */
