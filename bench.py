@@ -330,6 +330,8 @@ def bench_string_ops(eng, wl: Workload, rank, world, exchange):
     out["contains_256_16_ops_per_s"] = _timed_ops(lambda: MG.sharded_contains(comm, params, hay, pat, 256, 16), 3, world)
     r = MG.sharded_find(comm, params, hay, pat, 256, 16)
     checks["find_256_16"] = (dec(r[0]), R.decrypt_radix(ck, r[1:])) == (1, hs.find(ps))
+    if not checks["find_256_16"]:
+        out["find_256_16_got_want"] = [[int(dec(r[0])), int(R.decrypt_radix(ck, r[1:]))], [1, hs.find(ps)]]
     out["find_256_16_ops_per_s"] = _timed_ops(lambda: MG.sharded_find(comm, params, hay, pat, 256, 16), 3, world)
     # config 4: case conversion of a 1024-char string (each rank keeps its own converted chars: no exchange on the path)
     s1k = bytes(rng.integers(0x20, 0x7F, size=1024).tolist())

@@ -323,7 +323,9 @@ class DeviceComm:
                 self._group_exchange(rows, out, False)
             else:
                 self.peer.all_gather(rows, out.data_ptr(), self._stream())
-            return out[:, : rows * self.L].reshape(self.world, rows, self.L)
+            # rows * L odd: every rank's part is padded to an even word count, so this slice is strided and reshape() would return a VIEW;
+            # the copy a caller's later reshape then makes would run on whatever stream is current there.  Materialise it here.
+            return out[:, : rows * self.L].reshape(self.world, rows, self.L).contiguous()
         t = blocks.contiguous()
         out = torch.empty((self.world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=self.dev)
         dist.all_gather_into_tensor(out, t)
@@ -367,6 +369,24 @@ def _tensor_from_ptr(ptr: int, n_words: int, dev: torch.device) -> torch.Tensor:
     return torch.as_tensor(o, device=dev)
 
 
+def _on_comm_stream(fn):
+    """a sharded operation in full -- including the incidental tensor views / copies between the comm's calls -- with the comm's
+    stream as torch's current stream (a copy enqueued on another stream would not wait for the kernels before it)"""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(comm, *args, **kwargs):
+        comm = _comm(comm)
+        if isinstance(comm, DeviceComm):
+            cur = torch.cuda.current_stream(comm.dev)
+            if cur != comm.stream:
+                comm.stream.wait_stream(cur)
+            with torch.cuda.stream(comm.stream):
+                return fn(comm, *args, **kwargs)
+        return fn(comm, *args, **kwargs)
+    return wrapper
+
+
 def _comm(x):
     """the CPU tests pass a bare `execute(program, inputs)` callable"""
     return x if isinstance(x, (HostComm, DeviceComm)) else HostComm(x)
@@ -388,6 +408,7 @@ def _worth_sharding(comm, first_level_width: int) -> bool:
 # `comm` is a DeviceComm / HostComm (or a bare execute callable -> HostComm).  hay / pat / a / b / s are the encrypted blocks, 4 per
 # char, as host arrays (numpy or pinned tensors); only a rank's own share is uploaded.  The result is returned as a host array.
 
+@_on_comm_stream
 def sharded_contains(comm, params: dict, hay, pat, hay_len: int, pat_len: int, rank: int | None = None, world: int | None = None,
                      device: str | None = None) -> np.ndarray:
     """contains(hay, pat) with the windows split over the ranks.  Every rank returns the same boolean block."""
@@ -409,6 +430,7 @@ def sharded_contains(comm, params: dict, hay, pat, hay_len: int, pat_len: int, r
     return comm.to_host(comm.run(comm.program("bool_sum_finish", (active, 0), params), total))[0]
 
 
+@_on_comm_stream
 def sharded_eq(comm, params: dict, a, b, n_chars: int, rank: int | None = None, world: int | None = None,
                device: str | None = None) -> np.ndarray:
     """eq of two equal-length strings with the chars split over ranks: per-rank eq of its slice, sum, x == active."""
@@ -432,6 +454,7 @@ def sharded_eq(comm, params: dict, a, b, n_chars: int, rank: int | None = None, 
 _CMP = {"lt": (1, 0), "le": (1, 1), "gt": (0, 0), "ge": (0, 1)}     # (want_less, or_equal) of strings.h cmp()
 
 
+@_on_comm_stream
 def sharded_compare(comm, params: dict, op: str, a, b, n_chars: int, rank: int | None = None, world: int | None = None,
                     device: str | None = None) -> np.ndarray:
     """lt / le / gt / ge of two equal-length strings with the chars split over ranks (lexicographic tree): every rank
@@ -454,6 +477,7 @@ def sharded_compare(comm, params: dict, op: str, a, b, n_chars: int, rank: int |
     return comm.to_host(comm.run(comm.program("signs_finish", (active, want_less, or_equal), params), comm.rows(signs, order)))[0]
 
 
+@_on_comm_stream
 def sharded_case(comm, params: dict, op: str, s, n_chars: int, rank: int | None = None, world: int | None = None,
                  device: str | None = None, gather: bool = True) -> np.ndarray:
     """to_lowercase / to_uppercase with the chars split over ranks: elementwise, so there is no exchange on the path.  With
@@ -486,6 +510,7 @@ def sharded_case(comm, params: dict, op: str, s, n_chars: int, rank: int | None 
     return np.concatenate(out)
 
 
+@_on_comm_stream
 def sharded_find(comm, params: dict, hay, pat, hay_len: int, pat_len: int, rank: int | None = None, world: int | None = None,
                  device: str | None = None) -> np.ndarray:
     """find(hay, pat) with the windows split over ranks: every rank finds the first match inside its window range (reported as a
