@@ -20,7 +20,9 @@ namespace tbh {
 
 class PaddedStringServerKey {
   public:
-    explicit PaddedStringServerKey(Program &prog) : pg(prog), isk(prog), ssk(prog), p(prog.params()) {}
+    explicit PaddedStringServerKey(Program &prog) : pg(prog), isk(prog), ssk(prog), p(prog.params()) {
+        ssk.require_two_bit_blocks("null-padded strings");
+    }
 
     // ---- chars -----------------------------------------------------------------------------------------------------------------
     Radix trivial_char(unsigned char ch) {

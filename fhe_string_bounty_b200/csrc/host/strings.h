@@ -20,13 +20,30 @@ class StringServerKey {
   public:
     explicit StringServerKey(Program &prog, bool packed_eq = false) : pg(prog), isk(prog), p(prog.params()), packed(packed_eq) {}
 
-    static constexpr size_t BLOCKS_PER_CHAR = 4;
+    // a char is an FheUint8: ceil(8 / log2(message_modulus)) little-endian blocks (integer/encryption.rs:69-83) -- 4 blocks of 2 bits for
+    // the *_2_CARRY_* sets every config of BASELINE.json uses, 8 of 1 bit for MESSAGE_1, 3 (3 + 3 + 2 bits) for MESSAGE_3, 2 for MESSAGE_4
+    static size_t blocks_per_char(const Params &q) {
+        unsigned bits = 0;
+        while ((uint64_t(1) << (bits + 1)) <= q.msg_mod) ++bits;
+        if (bits == 0 || (uint64_t(1) << bits) != q.msg_mod) throw std::invalid_argument("strings: the message modulus must be a power of two >= 2");
+        return (8 + bits - 1) / bits;
+    }
+    size_t blocks_per_char() const { return blocks_per_char(p); }
+    uint64_t char_block(unsigned char ch, size_t b) const {
+        unsigned bits = 0;
+        while ((uint64_t(1) << (bits + 1)) <= p.msg_mod) ++bits;
+        return (uint64_t(ch) >> (bits * b)) & (p.msg_mod - 1);
+    }
+    // the fused case conversion, the find index arithmetic and the null-padded model are written for 2-bit blocks (message modulus 4)
+    void require_two_bit_blocks(const char *what) const {
+        if (p.msg_mod != 4) throw std::invalid_argument(std::string(what) + ": implemented for message modulus 4 (2-bit blocks) only");
+    }
 
     FheString input_string(size_t n_chars) {
         FheString s;
         for (size_t i = 0; i < n_chars; ++i) {
             Radix c;
-            for (size_t b = 0; b < BLOCKS_PER_CHAR; ++b) c.push_back(pg.input());
+            for (size_t b = 0; b < blocks_per_char(); ++b) c.push_back(pg.input());
             s.chars.push_back(c);
         }
         return s;
@@ -36,7 +53,7 @@ class StringServerKey {
         FheString s;
         for (unsigned char ch : clear) {
             Radix c;
-            for (size_t b = 0; b < BLOCKS_PER_CHAR; ++b) c.push_back(pg.create_trivial((ch >> (2 * b)) & 3));
+            for (size_t b = 0; b < blocks_per_char(); ++b) c.push_back(pg.create_trivial(char_block(ch, b)));
             s.chars.push_back(c);
         }
         return s;
@@ -179,6 +196,7 @@ class StringServerKey {
     }
     // the same over the windows [w0, w1) only (the multi-GPU split): first match inside the range, reported as its GLOBAL window index
     std::pair<BooleanBlock, Radix> find_range(const FheString &hay, const FheString &pat, size_t w0, size_t w1, bool last = false) {
+        require_two_bit_blocks("find");
         const size_t W_all = pat.len() <= hay.len() ? hay.len() - pat.len() + 1 : 0;
         const size_t idx_blocks = index_blocks(hay.len(), pat.len());
         Radix zero_idx;
@@ -285,6 +303,7 @@ class StringServerKey {
         });
     }
     FheString change_case(const FheString &s, bool to_lower) {
+        require_two_bit_blocks("case conversion");
         FheString out = s;
         for (size_t i = 0; i < s.len(); ++i) {
             Ct flag = is_letter_of_case(s.chars[i], /*upper=*/to_lower);

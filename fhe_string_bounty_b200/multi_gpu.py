@@ -399,6 +399,12 @@ def _share(comm, prog, inputs):
     return comm.run(prog, inputs)
 
 
+def _bpc(params: dict) -> int:
+    """blocks per char: ceil(8 / log2(message_modulus)); 4 for the 2-bit sets"""
+    bits = int(params["msg_mod"]).bit_length() - 1
+    return -(-8 // bits)
+
+
 def _worth_sharding(comm, first_level_width: int) -> bool:
     """shard only when the widest (first) level of the tree is wider than what one GPU runs as a single narrow-level launch"""
     return comm.world > 1 and first_level_width > comm.min_shard_width
@@ -415,7 +421,7 @@ def sharded_contains(comm, params: dict, hay, pat, hay_len: int, pat_len: int, r
     comm = _comm(comm)
     rank, world = comm.rank, comm.world
     n_win = hay_len - pat_len + 1
-    if n_win <= 0 or pat_len == 0 or not _worth_sharding(comm, n_win * 4 * pat_len):   # nothing to split: the plain single-GPU program
+    if n_win <= 0 or pat_len == 0 or not _worth_sharding(comm, n_win * _bpc(params) * pat_len):   # nothing to split: the plain single-GPU program
         return comm.to_host(comm.run(comm.program("string_contains", (hay_len, pat_len), params), [hay, pat]))[0]
     total_mod = params["msg_mod"] * params["carry_mod"]
     active = min(world, n_win, total_mod - 1)       # the summed flags must stay below the padding bit; surplus ranks contribute zero
@@ -423,7 +429,7 @@ def sharded_contains(comm, params: dict, hay, pat, hay_len: int, pat_len: int, r
         w0, w1 = shard_range(n_win, rank, active)
         # a rank only needs the haystack chars its windows touch: upload hay[w0 : w1 - 1 + pat_len] and the pattern
         lo, hi = w0, w1 - 1 + pat_len
-        mine = _share(comm, comm.program("string_contains_windows", (hi - lo, pat_len, 0, w1 - w0), params), [hay[4 * lo:4 * hi], pat])
+        mine = _share(comm, comm.program("string_contains_windows", (hi - lo, pat_len, 0, w1 - w0), params), [hay[_bpc(params) * lo:_bpc(params) * hi], pat])
     else:
         mine = comm.zeros(1, hay.shape[1])
     total = comm.all_reduce(mine)
@@ -438,13 +444,13 @@ def sharded_eq(comm, params: dict, a, b, n_chars: int, rank: int | None = None, 
     rank, world = comm.rank, comm.world
     if n_chars == 0:
         return comm.to_host(comm.run(comm.program("string_eq", (0, 0), params), np.zeros((0, 1), dtype=np.uint64)))[0]
-    if not _worth_sharding(comm, 4 * n_chars):
+    if not _worth_sharding(comm, _bpc(params) * n_chars):
         return comm.to_host(comm.run(comm.program("string_eq", (n_chars, n_chars), params), [a, b]))[0]
     total_mod = params["msg_mod"] * params["carry_mod"]
     active = max(1, min(world, n_chars, total_mod - 1))
     if rank < active:
         c0, c1 = shard_range(n_chars, rank, active)
-        mine = _share(comm, comm.program("string_eq", (c1 - c0, c1 - c0), params), [a[4 * c0:4 * c1], b[4 * c0:4 * c1]])
+        mine = _share(comm, comm.program("string_eq", (c1 - c0, c1 - c0), params), [a[_bpc(params) * c0:_bpc(params) * c1], b[_bpc(params) * c0:_bpc(params) * c1]])
     else:
         mine = comm.zeros(1, a.shape[1])
     total = comm.all_reduce(mine)
@@ -468,7 +474,7 @@ def sharded_compare(comm, params: dict, op: str, a, b, n_chars: int, rank: int |
         return comm.to_host(comm.run(comm.program("string_" + op, (n_chars, n_chars), params), [a, b]))[0]
     if rank < active:
         c0, c1 = shard_range(n_chars, rank, active)
-        mine = _share(comm, comm.program("string_cmp_sign", (c1 - c0, c1 - c0), params), [a[4 * c0:4 * c1], b[4 * c0:4 * c1]])
+        mine = _share(comm, comm.program("string_cmp_sign", (c1 - c0, c1 - c0), params), [a[_bpc(params) * c0:_bpc(params) * c1], b[_bpc(params) * c0:_bpc(params) * c1]])
     else:
         mine = comm.zeros(1, a.shape[1])
     signs = comm.all_gather(mine)[:active, 0]
@@ -491,22 +497,22 @@ def sharded_case(comm, params: dict, op: str, s, n_chars: int, rank: int | None 
         if gather or world == 1:
             return out
         c0, c1 = shard_range(n_chars, rank, min(world, n_chars)) if rank < min(world, n_chars) else (0, 0)
-        return out[4 * c0:4 * c1]
+        return out[_bpc(params) * c0:_bpc(params) * c1]
     active = min(world, n_chars)
     per = -(-n_chars // active)                                  # padded share, in chars
     c0 = c1 = 0
     if rank < active:
         c0, c1 = shard_range(n_chars, rank, active)
     L = s.shape[1]
-    conv = comm.run(comm.program("string_" + op, (c1 - c0,), params), s[4 * c0:4 * c1]) if c1 > c0 else comm.zeros(0, L)
+    conv = comm.run(comm.program("string_" + op, (c1 - c0,), params), s[_bpc(params) * c0:_bpc(params) * c1]) if c1 > c0 else comm.zeros(0, L)
     if not gather:
         return comm.to_host(conv) if c1 > c0 else np.zeros((0, L), dtype=np.uint64)
-    mine = comm.padded(conv, 4 * per, L)      # on the comm's stream: `conv` is still being computed there
-    parts = comm.to_host(comm.all_gather(mine).reshape(world * 4 * per, L)).reshape(world, 4 * per, L)
+    mine = comm.padded(conv, _bpc(params) * per, L)      # on the comm's stream: `conv` is still being computed there
+    parts = comm.to_host(comm.all_gather(mine).reshape(world * _bpc(params) * per, L)).reshape(world, _bpc(params) * per, L)
     out = []
     for r in range(active):
         r0, r1 = shard_range(n_chars, r, active)
-        out.append(parts[r, :4 * (r1 - r0)])
+        out.append(parts[r, :_bpc(params) * (r1 - r0)])
     return np.concatenate(out)
 
 
@@ -520,7 +526,7 @@ def sharded_find(comm, params: dict, hay, pat, hay_len: int, pat_len: int, rank:
     rank, world = comm.rank, comm.world
     n_win = hay_len - pat_len + 1
     inputs = [hay, pat]
-    if n_win <= 1 or pat_len == 0 or not _worth_sharding(comm, n_win * 4 * pat_len):
+    if n_win <= 1 or pat_len == 0 or not _worth_sharding(comm, n_win * _bpc(params) * pat_len):
         return comm.to_host(comm.run(comm.program("string_find", (hay_len, pat_len), params), inputs))
     total_mod = params["msg_mod"] * params["carry_mod"]
     active = min(world, n_win, total_mod // 2)

@@ -159,7 +159,8 @@ int tfhe_b200_pbs_batch_partial(tfhe_b200_ctx *ctx, const uint64_t *lwe_small, c
  * Appending "_packed" to a string op (or radix_eq) selects packed block equalities: one PBS per PAIR of blocks built from
  * pack_block_chunk + lwe_sub + LUT[x == 0] (the Comparator's own trick, comparator.rs:193-221); same decrypted results.
  * With clear_operand != NULL the second string operand is that clear (trivial) string instead of an input.
- * Inputs are fresh shortint blocks (degree msg_mod-1); a char is 4 little-endian 2-bit blocks. */
+ * Inputs are fresh shortint blocks (degree msg_mod-1); a char is ceil(8 / log2(msg_mod)) little-endian blocks (4 two-bit blocks for the
+ * MESSAGE_2 sets).  to_lowercase / to_uppercase / eq_ignore_case / find and the pstring_* operations require msg_mod = 4. */
 typedef struct tfhe_b200_program tfhe_b200_program;
 int tfhe_b200_program_build(const tfhe_b200_params *params, const char *op, const uint64_t *args, size_t n_args,
                             const char *clear_operand, tfhe_b200_program **out);

@@ -207,11 +207,20 @@ def encrypt_radix(ck: O.ClientKey, value: int, n_blocks: int) -> list[np.ndarray
     return out
 
 
+def blocks_per_char(msg_mod: int) -> int:
+    """a char is an FheUint8: ceil(8 / log2(message_modulus)) blocks (integer/encryption.rs:69-83); 4 for the 2-bit sets"""
+    bits = int(msg_mod).bit_length() - 1
+    assert bits >= 1 and (1 << bits) == msg_mod
+    return -(-8 // bits)
+
+
 def encrypt_string(ck: O.ClientKey, s: bytes) -> np.ndarray:
-    """4 little-endian 2-bit blocks per char (examples/regex_engine/ciphertext.rs:19-22)"""
+    """little-endian blocks of log2(message_modulus) bits per char: 4 2-bit blocks for the MESSAGE_2 sets
+    (examples/regex_engine/ciphertext.rs:19-22)"""
     blocks = []
+    n = blocks_per_char(ck.p.msg_mod)
     for ch in s:
-        blocks.extend(encrypt_radix(ck, ch, 4))
+        blocks.extend(encrypt_radix(ck, ch, n))
     return np.stack(blocks) if blocks else np.zeros((0, ck.p.big_dim + 1), dtype=U64)
 
 
@@ -224,4 +233,5 @@ def decrypt_radix(ck: O.ClientKey, blocks) -> int:
 
 
 def decrypt_string(ck: O.ClientKey, blocks) -> bytes:
-    return bytes(decrypt_radix(ck, blocks[i:i + 4]) for i in range(0, len(blocks), 4))
+    n = blocks_per_char(ck.p.msg_mod)
+    return bytes(decrypt_radix(ck, blocks[i:i + n]) & 0xFF for i in range(0, len(blocks), n))

@@ -178,3 +178,30 @@ def test_generic_multi_bit_agrees_with_tuned_kernel(orc, keys_multibit, monkeypa
     assert list(ck.decrypt_batch(gen.ks_pbs_batch(cts, None))) == want
     tuned.close()
     gen.close()
+
+
+@pytest.mark.parametrize("name", ["1_3", "3_3"])
+def test_string_ops_on_other_message_moduli_gpu(orc, name):
+    """String programs on parameter sets whose message modulus is not 4: PARAM_MESSAGE_1_CARRY_3 (8 one-bit blocks per char, runs on
+    the tuned N = 2048 kernels) and PARAM_MESSAGE_3_CARRY_3 (3 blocks per char, generic kernel, N = 8192); decrypted results against
+    Python's bytes semantics."""
+    import fhe_string_bounty_b200 as F
+    from fhe_string_bounty_b200.host import Program
+    from oracle import radix as R
+    from helpers import engine_params
+    p = orc.params(name)
+    ck = orc.ClientKey(p, 0xB230)
+    sk = orc.ServerKey(ck, 0xB231)
+    eng = F.Engine(engine_params(p))
+    eng.upload_ksk(sk.ksk)
+    eng.upload_bsk_std(sk.bsk)
+    cases = [(b"Zama", b"Zama"), (b"Zama", b"Zamb"), (b"abcab", b"ca")] if name == "3_3" else \
+        [(b"hello", b"hello"), (b"hello", b"hellp"), (b"abd", b"abc"), (b"abcabd", b"abd"), (b"zz~", b"zz")]
+    for a, b in cases:
+        ins = np.concatenate([R.encrypt_string(ck, a), R.encrypt_string(ck, b)])
+        want = {"eq": a == b, "ne": a != b, "lt": a < b, "ge": a >= b, "contains": b in a, "starts_with": a.startswith(b)}
+        for op, w in want.items():
+            P = Program("string_" + op, (len(a), len(b)), params=engine_params(p))
+            out = P.run(eng, ins)
+            assert ck.decrypt_message_and_carry(out[0]) == int(w), (name, op, a, b)
+    eng.close()

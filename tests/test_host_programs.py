@@ -299,3 +299,32 @@ def test_default_comparisons_on_dirty_carries(degree):
     # fresh operands take the no-propagation branch (comparison.rs:213-214): same program as the unchecked form
     assert Program("radix_default_lt", (nb, 3)).n_pbs == Program("radix_lt", (nb,)).n_pbs
     assert Program("radix_default_lt", (nb, 6)).n_pbs > Program("radix_lt", (nb,)).n_pbs
+
+
+@pytest.mark.parametrize("msg_mod,carry_mod", [(2, 8), (8, 8), (16, 16)])
+def test_string_ops_on_other_message_moduli(orc, msg_mod, carry_mod):
+    """A char is an FheUint8 = ceil(8 / log2(message_modulus)) blocks (integer/encryption.rs:69-83): 8 one-bit blocks for the MESSAGE_1
+    sets, 3 for MESSAGE_3, 2 for MESSAGE_4.  eq / ne / the comparator (needs >= 4 bits of message + carry, comparator.rs:51-60) /
+    contains / starts_with / ends_with are composed from the radix methods and do not care; the fused case conversion, find and the
+    null-padded model are written for 2-bit blocks and say so."""
+    from oracle import radix as R
+    p = orc.params("toy")
+    p.msg_mod, p.carry_mod = msg_mod, carry_mod
+    p.poly_size = max(256, 16 * msg_mod * carry_mod)    # a box of the lookup table must stay wider than the modulus-switch rounding
+    ck = orc.ClientKey(p, 0xB210 + msg_mod)
+    sk = orc.ServerKey(ck, 0xB220 + msg_mod)
+    keys = (p, ck, sk)
+    bpc = R.blocks_per_char(msg_mod)
+    assert bpc == {2: 8, 8: 3, 16: 2}[msg_mod]
+    assert R.decrypt_string(ck, R.encrypt_string(ck, b"Az~\x00\x7f")) == b"Az~\x00\x7f"
+    for a, b in [(b"hello", b"hello"), (b"hello", b"hellp"), (b"abd", b"abc"), (b"ab", b"abc"), (b"zz~", b"zz"), (b"abcabd", b"abd")]:
+        ins = np.concatenate([R.encrypt_string(ck, a), R.encrypt_string(ck, b)])
+        want = {"eq": a == b, "ne": a != b, "lt": a < b, "le": a <= b, "gt": a > b, "ge": a >= b,
+                "starts_with": a.startswith(b), "ends_with": a.endswith(b), "contains": b in a}
+        for op, w in want.items():
+            out, P = _run(orc, keys, "string_" + op, (len(a), len(b)), ins)
+            assert P.n_inputs == bpc * (len(a) + len(b))
+            assert _dec_bool(ck, out[0]) == int(w), (msg_mod, op, a, b)
+    for op, args in (("string_to_lowercase", (3,)), ("string_find", (4, 2)), ("pstring_len", (4,))):
+        with pytest.raises(Exception, match="message modulus 4"):
+            Program(op, args, params=engine_params(p))
