@@ -96,6 +96,12 @@ static int do_pbs_kernels(tfhe_b200_ctx *c, const uint64_t *d_small, const uint3
     if (fused && !fused_supported(c)) return fail("internal: fused PBS input requested on an unsupported configuration");
     if (!c->have_bsk) return fail("bootstrap key not uploaded");
     if (!d_luts) return fail("no lookup tables uploaded");
+    if (c->tuned512 && batch >= (size_t)(c->tuned512_min ? c->tuned512_min : c->sms)) {
+        TB_CUDA(tbk::launch_pbs_n512(d_small, d_idx, d_luts, c->bskf8.p, c->tbl16.p, d_out, out_slot, (int)batch, (int)c->p.lwe_dim,
+                                     (int)c->p.pbs_base_log, (int)(n_iters < c->p.lwe_dim ? n_iters : c->p.lwe_dim), s));
+        c->launches += 1;
+        return 0;
+    }
     if (c->generic) {
         const uint32_t steps = c->p.grouping_factor ? c->p.lwe_dim / c->p.grouping_factor : c->p.lwe_dim;
         TB_CUDA(tbk::launch_pbs_generic(d_small, d_idx, d_luts, c->bskf.p, c->tw_generic.p, d_out, out_slot, (int)batch, (int)c->p.lwe_dim,
@@ -203,6 +209,9 @@ int tfhe_b200_ctx_create(int cuda_device, const tfhe_b200_params *params, tfhe_b
         TB_CUDA(c->tw_generic.reserve(tw.size() * 8));
         TB_CUDA(cudaMemcpy(c->tw_generic.p, tw.data(), tw.size() * 8, cudaMemcpyHostToDevice));
     }
+    c->tuned512 = c->generic && tbk::pbs_n512_supported((int)params->poly_size, (int)params->glwe_dim, (int)params->pbs_level, (int)params->grouping_factor);
+    if (const char *e = std::getenv("TFHE_B200_TUNED512")) if (e[0] == '0') c->tuned512 = false;
+    if (c->tuned512) TB_CUDA(tbk::pbs_n512_configure());
     TB_CUDA(tbk::pbs_v4_configure());
     TB_CUDA(tbk::pbs_v8_configure());
     if (const char *e = std::getenv("TFHE_B200_NARROW_KERNEL")) c->narrow_kernel = (e[0] == '8') ? 8 : 0;
@@ -221,7 +230,8 @@ int tfhe_b200_ctx_create(int cuda_device, const tfhe_b200_params *params, tfhe_b
     TB_CUDA(tbk::ks_configure((int)params->ks_level));
     // twiddle tables of the 16- and 8-points-per-thread FFTs
     std::vector<double> tbl16(2 * (tb::kM + 64));
-    tb16_make_tables(tbl16.data(), tbl16.data() + 2 * tb::kM);
+    if (c->tuned512) tbk::pbs_n512_make_table(tbl16.data());      // this context never runs the N = 2048 kernels: the buffer holds pbs_n512.cu's table
+    else tb16_make_tables(tbl16.data(), tbl16.data() + 2 * tb::kM);
     TB_CUDA(c->tbl16.reserve(tbl16.size() * sizeof(double)));
     TB_CUDA(cudaMemcpyAsync(c->tbl16.p, tbl16.data(), tbl16.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     std::vector<double> tbl8(2 * 24 * 128);
@@ -251,6 +261,9 @@ int tfhe_b200_set_tuning(tfhe_b200_ctx *c, const char *key, int value) {
     } else if (k == "narrow_max") {
         if (value < 0) return fail("narrow_max must be >= 0");
         c->narrow_max = value;
+    } else if (k == "tuned512_min") {
+        if (value < 0) return fail("tuned512_min must be >= 0");
+        c->tuned512_min = value;
     } else if (k == "narrow_cluster") {
         if (value != 0 && value != 1) return fail("narrow_cluster must be 0 or 1");
         c->narrow_cluster = value;
@@ -310,9 +323,14 @@ static size_t bsk_poly_count(const tfhe_b200_ctx *c) {
 static int finish_bsk(tfhe_b200_ctx *c, const tbc::DevBuf &raw) {
     const size_t n_polys = bsk_poly_count(c);
     TB_CUDA(c->bskf.reserve(n_polys * (c->p.poly_size / 2) * sizeof(double) * 2));
-    if (c->generic)
+    if (c->generic) {
         TB_CUDA(tbk::launch_bsk_convert_generic((const uint64_t *)raw.p, c->bskf.p, c->tw_generic.p, n_polys, (int)c->p.poly_size, c->stream));
-    else if (c->p.grouping_factor == 3) {
+        if (c->tuned512) {     // second copy of the key in pbs_n512.cu's ring order
+            TB_CUDA(c->bskf8.reserve(n_polys * (c->p.poly_size / 2) * sizeof(double) * 2));
+            TB_CUDA(tbk::launch_bsk_convert_n512((const uint64_t *)raw.p, c->bskf8.p, c->tbl16.p, (int)n_polys, c->stream));
+            c->launches += 1;
+        }
+    } else if (c->p.grouping_factor == 3) {
         TB_CUDA(tbk::launch_bsk_convert_multibit_v4((const uint64_t *)raw.p, c->bskf.p, c->tbl16.p, (int)n_polys, c->stream));
         // second copy of the key for the narrow-level kernel (always built: the narrow-kernel choice can change per context at run time)
         TB_CUDA(c->bskf8.reserve(n_polys * tb::kM * sizeof(double) * 2));
