@@ -212,7 +212,9 @@ int tfhe_b200_exchange_destroy(tfhe_b200_exchange *ex);
  * ciphertexts and level tails, 0 = the 1- / 2-ciphertext instances of the wide kernels), "narrow_max" (0 = default: 2 x SM count
  * classic, SM count multi-bit), "ks_kernel" (2 = keyswitch on tcgen05.mma kind::i8 [default], 1 = on mma.sync, 0 = IMAD keyswitch; all three are
  * bit-identical), "narrow_cluster" (1 [default] = levels of at most SM count / 2 ciphertexts put one ciphertext on a two-SM thread-block
- * cluster, pbs_classic_kernel_v8x2 / pbs_multibit_kernel_v8x2; 0 = one SM per ciphertext; identical output words either way). */
+ * cluster, pbs_classic_kernel_v8x2 / pbs_multibit_kernel_v8x2; 0 = one SM per ciphertext; identical output words either way),
+ * "tuned512_min" (N = 512, k = 3 contexts: batches of at least this many ciphertexts run on pbs_n512.cu, smaller ones on the generic
+ * kernel; 0 = default: SM count). */
 int tfhe_b200_set_tuning(tfhe_b200_ctx *ctx, const char *key, int value);
 
 /* Instrumentation. */
