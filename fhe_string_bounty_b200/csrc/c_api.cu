@@ -102,6 +102,12 @@ static int do_pbs_kernels(tfhe_b200_ctx *c, const uint64_t *d_small, const uint3
         c->launches += 1;
         return 0;
     }
+    if (c->tuned8192) {
+        TB_CUDA(tbk::launch_pbs_n8192(d_small, d_idx, d_luts, c->bskf8.p, c->tbl16.p, d_out, out_slot, (int)batch, (int)c->p.lwe_dim,
+                                      (int)c->p.pbs_base_log, (int)(n_iters < c->p.lwe_dim ? n_iters : c->p.lwe_dim), (int)c->p.lwe_dim, s));
+        c->launches += 1;
+        return 0;
+    }
     if (c->generic) {
         const uint32_t steps = c->p.grouping_factor ? c->p.lwe_dim / c->p.grouping_factor : c->p.lwe_dim;
         TB_CUDA(tbk::launch_pbs_generic(d_small, d_idx, d_luts, c->bskf.p, c->tw_generic.p, d_out, out_slot, (int)batch, (int)c->p.lwe_dim,
@@ -212,6 +218,9 @@ int tfhe_b200_ctx_create(int cuda_device, const tfhe_b200_params *params, tfhe_b
     c->tuned512 = c->generic && tbk::pbs_n512_supported((int)params->poly_size, (int)params->glwe_dim, (int)params->pbs_level, (int)params->grouping_factor);
     if (const char *e = std::getenv("TFHE_B200_TUNED512")) if (e[0] == '0') c->tuned512 = false;
     if (c->tuned512) TB_CUDA(tbk::pbs_n512_configure());
+    c->tuned8192 = c->generic && tbk::pbs_n8192_supported((int)params->poly_size, (int)params->glwe_dim, (int)params->pbs_level, (int)params->grouping_factor);
+    if (const char *e = std::getenv("TFHE_B200_TUNED8192")) if (e[0] == '0') c->tuned8192 = false;
+    if (c->tuned8192) TB_CUDA(tbk::pbs_n8192_configure());
     TB_CUDA(tbk::pbs_v4_configure());
     TB_CUDA(tbk::pbs_v8_configure());
     if (const char *e = std::getenv("TFHE_B200_NARROW_KERNEL")) c->narrow_kernel = (e[0] == '8') ? 8 : 0;
@@ -229,8 +238,9 @@ int tfhe_b200_ctx_create(int cuda_device, const tfhe_b200_params *params, tfhe_b
     }
     TB_CUDA(tbk::ks_configure((int)params->ks_level));
     // twiddle tables of the 16- and 8-points-per-thread FFTs
-    std::vector<double> tbl16(2 * (tb::kM + 64));
-    if (c->tuned512) tbk::pbs_n512_make_table(tbl16.data());      // this context never runs the N = 2048 kernels: the buffer holds pbs_n512.cu's table
+    std::vector<double> tbl16(c->tuned8192 ? 2 * 4352 : 2 * (tb::kM + 64));
+    if (c->tuned8192) tbk::pbs_n8192_make_table(tbl16.data());
+    else if (c->tuned512) tbk::pbs_n512_make_table(tbl16.data());      // this context never runs the N = 2048 kernels: the buffer holds pbs_n512.cu's table
     else tb16_make_tables(tbl16.data(), tbl16.data() + 2 * tb::kM);
     TB_CUDA(c->tbl16.reserve(tbl16.size() * sizeof(double)));
     TB_CUDA(cudaMemcpyAsync(c->tbl16.p, tbl16.data(), tbl16.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
@@ -261,6 +271,11 @@ int tfhe_b200_set_tuning(tfhe_b200_ctx *c, const char *key, int value) {
     } else if (k == "narrow_max") {
         if (value < 0) return fail("narrow_max must be >= 0");
         c->narrow_max = value;
+    } else if (k == "tuned8192") {
+        if (value != 0 && value != 1) return fail("tuned8192 must be 0 or 1");
+        if (value == 1 && !(c->bskf8.p && tbk::pbs_n8192_supported((int)c->p.poly_size, (int)c->p.glwe_dim, (int)c->p.pbs_level, (int)c->p.grouping_factor)))
+            return fail("tuned8192: not this parameter shape, or the key was uploaded without the tuned copy");
+        c->tuned8192 = value;
     } else if (k == "tuned512_min") {
         if (value < 0) return fail("tuned512_min must be >= 0");
         c->tuned512_min = value;
@@ -325,6 +340,11 @@ static int finish_bsk(tfhe_b200_ctx *c, const tbc::DevBuf &raw) {
     TB_CUDA(c->bskf.reserve(n_polys * (c->p.poly_size / 2) * sizeof(double) * 2));
     if (c->generic) {
         TB_CUDA(tbk::launch_bsk_convert_generic((const uint64_t *)raw.p, c->bskf.p, c->tw_generic.p, n_polys, (int)c->p.poly_size, c->stream));
+        if (c->tuned8192) {    // second copy of the key, per output polynomial, in pbs_n8192.cu's ring order
+            TB_CUDA(c->bskf8.reserve(n_polys * (c->p.poly_size / 2) * sizeof(double) * 2));
+            TB_CUDA(tbk::launch_bsk_convert_n8192((const uint64_t *)raw.p, c->bskf8.p, c->tbl16.p, (int)c->p.lwe_dim, c->stream));
+            c->launches += 1;
+        }
         if (c->tuned512) {     // second copy of the key in pbs_n512.cu's ring order
             TB_CUDA(c->bskf8.reserve(n_polys * (c->p.poly_size / 2) * sizeof(double) * 2));
             TB_CUDA(tbk::launch_bsk_convert_n512((const uint64_t *)raw.p, c->bskf8.p, c->tbl16.p, (int)n_polys, c->stream));

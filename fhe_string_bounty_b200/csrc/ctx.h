@@ -77,6 +77,7 @@ struct tfhe_b200_ctx {
     int log2_q = 64;         // ciphertext modulus 2^log2_q; < 64: PBS outputs are rounded to multiples of 2^(64 - log2_q) (bootstrap.rs:318-330)
     int sms = 148;
     bool tuned512 = false;   // N = 512, k = 3, one level: pbs_n512.cu serves batches of at least tuned512_min ciphertexts (key copy in bskf8, table in tbl16)
+    bool tuned8192 = false;  // N = 8192, k = 1, two levels: pbs_n8192.cu (one ciphertext per two-SM cluster; key copy in bskf8, table in tbl16)
     int tuned512_min = 0;    // 0 = default (SM count); smaller batches stay on the generic kernel
     int narrow_cluster = 1;  // classic levels of at most SM count / 2 ciphertexts: one ciphertext per two-SM cluster (pbs_classic_kernel_v8x2)
     int narrow_max = 0;      // widest level the narrow kernel takes (0 = 2 * SM count); env TFHE_B200_NARROW_MAX

@@ -257,3 +257,55 @@ def test_tuned_n512_kernel(orc):
         assert err.max() < 2**63 // space // 8
     print(f"pbs_n512: one / two CMUX max|delta| 2^{np.log2(max(worst, 1)):.1f}")
     eng.close()
+
+
+def test_tuned_n8192_kernel(orc):
+    """PARAM_MESSAGE_3_CARRY_3_KS_PBS (N = 8192, k = 1, two levels) on pbs_n8192.cu -- one ciphertext per two-SM cluster, 16 x 16 x 16 FFT,
+    spectra swapped per level with st.async -- against the oracle (LUT rotation bit-exact, one CMUX within 2^44 with the
+    maximum stated) and against the generic kernel; every message through three LUTs decrypts; identical words on re-run; a batch wider
+    than the number of clusters that fit the GPU."""
+    import torch
+    import fhe_string_bounty_b200 as F
+    p = orc.params("3_3")
+    ck = orc.ClientKey(p, 0xB200 + 42)
+    sk = orc.ServerKey(ck, 0xB300 + 42)
+    space = p.msg_mod * p.carry_mod
+    fs = [lambda x: x, lambda x: (3 * x + 1) % space, lambda x: int(x >= space // 2)]
+    luts = np.stack([sk.generate_lookup_table(f)[0] for f in fs])
+    eng = F.Engine(engine_params(p))
+    eng.upload_ksk(sk.ksk)
+    eng.upload_bsk_std(sk.bsk)
+    eng.upload_luts(luts)
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    base_vals = np.array([(v * 5) % space for v in range(48)])
+    base_idx = (np.arange(48) % 3).astype(np.uint32)
+    base = ck.encrypt_batch(base_vals)
+    worst = 0
+    for batch in (3, sms // 2 + 7):
+        reps = -(-batch // len(base))
+        cts = np.tile(base, (reps, 1))[:batch]
+        vals, idx = np.tile(base_vals, reps)[:batch], np.tile(base_idx, reps)[:batch]
+        small = eng.keyswitch_batch(cts)
+        eng.set_tuning("tuned8192", 1)
+        part = [eng.pbs_batch(small, idx, n_iters=k) for k in (0, 1)]
+        out = eng.ks_pbs_batch(cts, idx)
+        assert np.array_equal(out, eng.ks_pbs_batch(cts, idx)), "deterministic"
+        eng.set_tuning("tuned8192", 0)                          # generic kernel
+        gen = [eng.pbs_batch(small, idx, n_iters=k) for k in (0, 1)]
+        assert np.array_equal(part[0], gen[0])
+        assert np.abs((part[1] - gen[1]).view(np.int64)).max() <= 2**44
+        for b in (0, 1, batch - 1):
+            for k in (0, 1):     # (after two CMUXes a 2^33 rounding difference flips level-2 digits, boundaries 2^34 apart: DESIGN section 4)
+                want = oracle_partial_pbs(orc, sk, small[b], luts[idx[b]], k)
+                d = int(np.abs((part[k][b] - want).view(np.int64)).max())
+                if k == 0:
+                    assert d == 0, (batch, b, "LUT rotation / sample extraction must be bit-exact")
+                else:
+                    worst = max(worst, d)
+                    assert d <= 2**44, (batch, b, k, np.log2(max(d, 1)))
+        want = np.array([fs[i](int(v)) for v, i in zip(vals, idx)])
+        assert np.array_equal(ck.decrypt_batch(out), want), batch
+        err = _phase_error(ck, p, out[:48], want[:48])
+        assert err.max() < 2**63 // space // 8
+    print(f"pbs_n8192: one CMUX max|delta| 2^{np.log2(max(worst, 1)):.1f}")
+    eng.close()
