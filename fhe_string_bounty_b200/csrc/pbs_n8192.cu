@@ -58,18 +58,20 @@ __device__ __forceinline__ uint32_t mod_switch(uint64_t x) { return (uint32_t)((
 
 // the two signed digits of x (level 2 = least significant first in the carry chain): decomposer.rs:98-118, iter.rs:120-127
 __device__ __forceinline__ void signed_digits2(uint64_t x, int base_log, int &d2, int &d1) {
-    const int shift = 64 - base_log * LEVELS - 1;
-    uint64_t state = (((x >> shift) + 1) & ~(uint64_t)1) >> 1;
-    const uint64_t mask = ((uint64_t)1 << base_log) - 1;
-    uint64_t digit = state & mask;
+    // base_log * LEVELS <= 31: everything the decomposition looks at sits in the top 32 bits (+ the rounding bit below), 32-bit arithmetic
+    const int bits = base_log * LEVELS;
+    const uint32_t hi = (uint32_t)(x >> 32);
+    uint32_t state = (((hi >> (31 - bits)) + 1u) >> 1) & (bits == 31 ? 0x7FFFFFFFu : ((1u << bits) - 1u));   // closest representable, as an integer
+    const uint32_t mask = (1u << base_log) - 1u;
+    uint32_t digit = state & mask;
     state >>= base_log;
-    uint64_t carry = (((digit - 1) | state) & digit) >> (base_log - 1);
+    uint32_t carry = (((digit - 1u) | state) & digit) >> (base_log - 1);
     state += carry;
-    d2 = (int)(int64_t)(digit - (carry << base_log));
+    d2 = (int)(digit - (carry << base_log));
     digit = state & mask;
     state >>= base_log;
-    carry = (((digit - 1) | state) & digit) >> (base_log - 1);
-    d1 = (int)(int64_t)(digit - (carry << base_log));
+    carry = (((digit - 1u) | state) & digit) >> (base_log - 1);
+    d1 = (int)(digit - (carry << base_log));
 }
 
 template <class Tw>

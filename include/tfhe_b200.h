@@ -214,7 +214,8 @@ int tfhe_b200_exchange_destroy(tfhe_b200_exchange *ex);
  * bit-identical), "narrow_cluster" (1 [default] = levels of at most SM count / 2 ciphertexts put one ciphertext on a two-SM thread-block
  * cluster, pbs_classic_kernel_v8x2 / pbs_multibit_kernel_v8x2; 0 = one SM per ciphertext; identical output words either way),
  * "tuned512_min" (N = 512, k = 3 contexts: batches of at least this many ciphertexts run on pbs_n512.cu, smaller ones on the generic
- * kernel; 0 = default: SM count). */
+ * kernel; 0 = default: SM count), "tuned8192" (N = 8192, k = 1, two-level contexts: 1 [default] = pbs_n8192.cu, one ciphertext per two-SM
+ * cluster; 0 = generic kernel). */
 int tfhe_b200_set_tuning(tfhe_b200_ctx *ctx, const char *key, int value);
 
 /* Instrumentation. */
