@@ -23,12 +23,14 @@
 
 #include "kernels.h"
 #include "pbs16_common.cuh"
+#include "fft16x_slots.cuh"
 
 namespace tb512 {
 using namespace tb16k;
+using namespace tb16x;
 
 constexpr int LOGN = 9, N = 1 << LOGN, M = N / 2, K1 = 4;
-constexpr int TILE = 16 * 17;                       // complex elements per polynomial tile (>= N u64 words for the rotated gather)
+constexpr int TILE = kTile256;                      // complex elements per polynomial tile (>= N u64 words for the rotated gather)
 constexpr int QPP = 4;                              // frequencies (registers) per ring piece
 constexpr int PIECE_CPLX = QPP * K1 * K1 * 16;      // [q 4][out poly c 4][in poly r 4][thread 16] = 1024 complex = 16 KiB
 constexpr int PIECE_BYTES = PIECE_CPLX * 16;
@@ -61,10 +63,10 @@ struct Fft256 {
         twd.template apply<false>(re, im);
         __syncwarp();          // the half-warp is done with the tile (rotated gather / previous exchange)
 #pragma unroll
-        for (int p = 0; p < 16; ++p) { cplx v; v.x = re[p]; v.y = im[p]; tile[p * 17 + T] = v; }
+        for (int p = 0; p < 16; ++p) { cplx v; v.x = re[p]; v.y = im[p]; tile[s256_write(T, p)] = v; }
         __syncwarp();
 #pragma unroll
-        for (int u = 0; u < 16; ++u) { const cplx v = tile[T * 17 + u]; re[u] = v.x; im[u] = v.y; }
+        for (int u = 0; u < 16; ++u) { const cplx v = tile[s256_read(T, u)]; re[u] = v.x; im[u] = v.y; }
         radix16_dif(re, im);
     }
     // inverse, scaled by 256
@@ -72,10 +74,10 @@ struct Fft256 {
     __device__ __forceinline__ static void inv(double (&re)[16], double (&im)[16], cplx *tile, const Tw &twd, int T) {
         radix16_dit_inv(re, im);
 #pragma unroll
-        for (int u = 0; u < 16; ++u) { cplx v; v.x = re[u]; v.y = im[u]; tile[T * 17 + u] = v; }
+        for (int u = 0; u < 16; ++u) { cplx v; v.x = re[u]; v.y = im[u]; tile[s256_read(T, u)] = v; }
         __syncwarp();
 #pragma unroll
-        for (int p = 0; p < 16; ++p) { const cplx v = tile[p * 17 + T]; re[p] = v.x; im[p] = v.y; }
+        for (int p = 0; p < 16; ++p) { const cplx v = tile[s256_write(T, p)]; re[p] = v.x; im[p] = v.y; }
         twd.template apply<true>(re, im);
         radix16_dit_inv(re, im);
         posttwist16_inv(re, im);
@@ -224,7 +226,7 @@ pbs_n512_kernel(const uint64_t *__restrict__ lwe_small, const uint32_t *__restri
         Fft256::fwd(re, im, tile, twd, T);
         // park my spectrum in my own reader row of the tile (nobody else reads that row during the FFT)
 #pragma unroll
-        for (int g = 0; g < 16; ++g) { cplx v; v.x = re[g]; v.y = im[g]; tile[T * 17 + g] = v; }
+        for (int g = 0; g < 16; ++g) { cplx v; v.x = re[g]; v.y = im[g]; tile[s256_read(T, g)] = v; }
         bar_sync(ct_bar, 64);
 
         // out_fft[c = r] = sum over the four input polynomials r' of F_r' * G[r'][c]
@@ -349,17 +351,7 @@ bool pbs_n512_supported(int poly_size, int glwe_dim, int pbs_level, int grouping
     return poly_size == tb512::N && glwe_dim == tb512::K1 - 1 && pbs_level == 1 && grouping_factor == 0;
 }
 
-// T1[p * 16 + T] = exp(i pi T (1 - 4 brev4(p)) / 512): 256 complex values
-void pbs_n512_make_table(double *t) {
-    const long double pi = 3.14159265358979323846264338327950288L;
-    for (int p = 0; p < 16; ++p)
-        for (int T = 0; T < 16; ++T) {
-            long e = ((long)T * (1 - 4 * (long)tb16::brev4(p))) % 1024;
-            if (e < 0) e += 1024;
-            t[2 * (p * 16 + T)] = (double)cosl(pi * (long double)e / 512.0L);
-            t[2 * (p * 16 + T) + 1] = (double)sinl(pi * (long double)e / 512.0L);
-        }
-}
+void pbs_n512_make_table(double *t) { tb16x_make_table_512(t); }
 
 cudaError_t pbs_n512_configure() {
     cudaError_t e = cudaFuncSetAttribute(tb512::pbs_n512_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tb512::Smem<8>));

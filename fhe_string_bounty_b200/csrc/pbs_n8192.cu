@@ -29,13 +29,15 @@
 
 #include "kernels.h"
 #include "pbs16_common.cuh"
+#include "fft16x_slots.cuh"
 
 namespace tb8192 {
 using namespace tb16k;
+using namespace tb16x;
 
 constexpr int LOGN = 13, N = 1 << LOGN, M = N / 2, LEVELS = 2;
 constexpr int THREADS = 256;
-constexpr int TILE = 16 * 272;                       // 4352 complex = 68 KiB (>= N u64 words for the rotated gather)
+constexpr int TILE = kTile4096;                      // 4352 complex = 68 KiB (>= N u64 words for the rotated gather)
 constexpr int QPP = 4;
 constexpr int PIECE_CPLX = QPP * THREADS;            // [q 4][thread 256] = 16 KiB
 constexpr int PIECE_BYTES = PIECE_CPLX * 16;
@@ -84,39 +86,37 @@ struct Fft4096 {
         twd.template apply1<false>(re, im);
         sync();
 #pragma unroll
-        for (int p = 0; p < 16; ++p) { cplx v; v.x = re[p]; v.y = im[p]; tile[272 * p + T] = v; }
+        for (int p = 0; p < 16; ++p) { cplx v; v.x = re[p]; v.y = im[p]; tile[s4096_a_write(T, p)] = v; }
         sync();
-        const int base = 272 * (T >> 4), u = T & 15;
 #pragma unroll
-        for (int v = 0; v < 16; ++v) { const cplx x = tile[base + u + 16 * v]; re[v] = x.x; im[v] = x.y; }
+        for (int v = 0; v < 16; ++v) { const cplx x = tile[s4096_a_read(T, v)]; re[v] = x.x; im[v] = x.y; }
         radix16_dif(re, im);
         twd.template apply2<false>(re, im);
         __syncwarp();        // everything below stays inside the half-warp's region of the tile
 #pragma unroll
-        for (int p = 0; p < 16; ++p) { cplx v; v.x = re[p]; v.y = im[p]; tile[base + 17 * p + u] = v; }
+        for (int p = 0; p < 16; ++p) { cplx v; v.x = re[p]; v.y = im[p]; tile[s4096_b_write(T, p)] = v; }
         __syncwarp();
 #pragma unroll
-        for (int q = 0; q < 16; ++q) { const cplx x = tile[base + 17 * u + q]; re[q] = x.x; im[q] = x.y; }
+        for (int q = 0; q < 16; ++q) { const cplx x = tile[s4096_b_read(T, q)]; re[q] = x.x; im[q] = x.y; }
         radix16_dif(re, im);
     }
     // inverse, scaled by 4096; on entry nobody may still be reading the tile, on exit it may still be read by other threads
     template <class Sync>
     __device__ __forceinline__ static void inv(double (&re)[16], double (&im)[16], cplx *tile, const Tw &twd, int T, Sync sync) {
-        const int base = 272 * (T >> 4), u = T & 15;
         radix16_dit_inv(re, im);
 #pragma unroll
-        for (int q = 0; q < 16; ++q) { cplx v; v.x = re[q]; v.y = im[q]; tile[base + 17 * u + q] = v; }
+        for (int q = 0; q < 16; ++q) { cplx v; v.x = re[q]; v.y = im[q]; tile[s4096_b_read(T, q)] = v; }
         __syncwarp();
 #pragma unroll
-        for (int p = 0; p < 16; ++p) { const cplx x = tile[base + 17 * p + u]; re[p] = x.x; im[p] = x.y; }
+        for (int p = 0; p < 16; ++p) { const cplx x = tile[s4096_b_write(T, p)]; re[p] = x.x; im[p] = x.y; }
         twd.template apply2<true>(re, im);
         radix16_dit_inv(re, im);
         __syncwarp();
 #pragma unroll
-        for (int v = 0; v < 16; ++v) { cplx x; x.x = re[v]; x.y = im[v]; tile[base + u + 16 * v] = x; }
+        for (int v = 0; v < 16; ++v) { cplx x; x.x = re[v]; x.y = im[v]; tile[s4096_a_read(T, v)] = x; }
         sync();
 #pragma unroll
-        for (int p = 0; p < 16; ++p) { const cplx x = tile[272 * p + T]; re[p] = x.x; im[p] = x.y; }
+        for (int p = 0; p < 16; ++p) { const cplx x = tile[s4096_a_write(T, p)]; re[p] = x.x; im[p] = x.y; }
         twd.template apply1<true>(re, im);
         radix16_dit_inv(re, im);
         posttwist16_inv(re, im);
@@ -436,23 +436,7 @@ bool pbs_n8192_supported(int poly_size, int glwe_dim, int pbs_level, int groupin
     return poly_size == tb8192::N && glwe_dim == 1 && pbs_level == tb8192::LEVELS && grouping_factor == 0;
 }
 
-// T1[p1 * 256 + T] = exp(i pi T (1 - 4 brev4(p1)) / 8192) (4096 entries), then T2[p2 * 16 + u] = exp(-2 pi i u brev4(p2) / 256) (256 entries)
-void pbs_n8192_make_table(double *t) {
-    const long double pi = 3.14159265358979323846264338327950288L;
-    for (int p = 0; p < 16; ++p)
-        for (int T = 0; T < 256; ++T) {
-            long e = ((long)T * (1 - 4 * (long)tb16::brev4(p))) % 16384;
-            if (e < 0) e += 16384;
-            t[2 * (p * 256 + T)] = (double)cosl(pi * (long double)e / 8192.0L);
-            t[2 * (p * 256 + T) + 1] = (double)sinl(pi * (long double)e / 8192.0L);
-        }
-    for (int p = 0; p < 16; ++p)
-        for (int u = 0; u < 16; ++u) {
-            const int e = (u * tb16::brev4(p)) % 256;
-            t[2 * (4096 + p * 16 + u)] = (double)cosl(-2.0L * pi * e / 256.0L);
-            t[2 * (4096 + p * 16 + u) + 1] = (double)sinl(-2.0L * pi * e / 256.0L);
-        }
-}
+void pbs_n8192_make_table(double *t) { tb16x_make_table_8192(t); }
 
 cudaError_t pbs_n8192_configure() {
     cudaError_t e = cudaFuncSetAttribute(tb8192::bsk_convert_n8192_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tb8192::TILE * 16);

@@ -103,3 +103,15 @@ def test_parameter_tables_match_the_oracle_and_the_engine_envelope():
     for name, t in list(_CLASSIC_SETS.items()) + list(_MULTI_BIT_SETS.items()):
         n, k, N, pb, pl, kb, kl = t[:7]
         assert (N, k) in shapes and 2 <= kb <= 7 and kb * kl <= 31 and 2 <= pb <= 30 and pb * pl <= 52 and n <= 4096, name
+
+
+def test_cpu_mirror_of_the_16x16_and_16x16x16_ffts(tmp_path):
+    """tests/cpu_mirror/fft16x_mirror.cpp: the 256-point FFT of pbs_n512.cu (16 threads) and the 4096-point FFT of pbs_n8192.cu (256
+    threads), emulated thread by thread from the slot functions and twiddle tables the kernels use (csrc/fft16x_slots.cuh): forward ==
+    definition at the documented frequency map, inverse(forward) == M x, exchanges injective and bank-conflict free."""
+    import subprocess
+    exe = tmp_path / "fft16x_mirror"
+    subprocess.run(["g++", "-O1", "-std=c++17", "-ffp-contract=off", str(ROOT / "tests/cpu_mirror/fft16x_mirror.cpp"), "-o", str(exe)],
+                   check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip().endswith("OK"), out.stdout + out.stderr
