@@ -295,6 +295,24 @@ class PaddedStringServerKey {
         for (size_t w = 0; w < std::max<size_t>(hay.len(), 1); ++w) m.push_back(window_match(hay, pat, w, pz));
         return isk.is_at_least_one_comparisons_block_true(m);
     }
+    // find / rfind with a padded pattern (str::find / str::rfind: byte index of the first / last match; the empty pattern matches at 0 and,
+    // for rfind, at len).  Window w = 0 .. capacity: a match must start inside the string or right at its end (w == 0 or hay[w - 1] != 0),
+    // which only matters for the empty pattern -- a non-empty one cannot match in the padding.  Index: radix digits of w, as string_find.
+    std::pair<BooleanBlock, Radix> find(const FheString &hay, const FheString &pat, bool last) {
+        const size_t n = hay.len();
+        size_t idx_blocks = 1;
+        while ((size_t(1) << (2 * idx_blocks)) < n + 1) ++idx_blocks;
+        std::vector<Ct> pz = zero_flags(pat), m;
+        for (size_t w = 0; w <= n; ++w) {
+            Ct mw = w < n || pat.len() == 0 ? (pat.len() == 0 ? pg.create_trivial(1) : window_match(hay, pat, w, pz))
+                                            : isk.are_all_comparisons_block_true(pz);            // w == n: only the empty pattern fits
+            if (w > 0) mw = isk.boolean_bitand(mw, nonzero(hay.chars[w - 1]));
+            m.push_back(mw);
+        }
+        if (last) std::reverse(m.begin(), m.end());
+        return ssk.first_true(m, [=](size_t w) { return last ? n - w : w; }, idx_blocks);
+    }
+
     // some suffix of the haystack equals the pattern as padded strings (the empty suffix included)
     BooleanBlock ends_with(const FheString &hay, const FheString &pat) {
         const size_t n = hay.len(), m = pat.len();

@@ -210,10 +210,16 @@ class StringServerKey {
             for (size_t b = 0; b < idx_blocks; ++b) idx.push_back(pg.create_trivial(w1 == W_all ? ((W_all - 1) >> (2 * b)) & 3 : 0));
             return {pg.create_trivial(w1 == W_all ? 1 : 0), idx};
         }
-        const size_t W = w1 - w0;            // local window count; local window w is global window w0 + w (w1 - 1 - w for rfind)
+        // local window w is global window w0 + w (w1 - 1 - w for rfind)
         std::vector<Ct> m = window_matches(hay, pat, w0, w1);
         if (last) std::reverse(m.begin(), m.end());
-        const auto global = [=](size_t w) { return last ? w1 - 1 - w : w0 + w; };
+        return first_true(m, [=](size_t w) { return last ? w1 - 1 - w : w0 + w; }, idx_blocks);
+    }
+    // (found, index) of the FIRST true flag of m, reported as global(w) in idx_blocks radix digits (zero when nothing is true)
+    template <class Global>
+    std::pair<BooleanBlock, Radix> first_true(const std::vector<Ct> &m, Global global, size_t idx_blocks) {
+        require_two_bit_blocks("find");
+        const size_t W = m.size();
         // one-hot first match in THREE levels instead of a log-depth prefix OR.  Windows are cut into blocks of 14:
         //   level 1   any_k   = [sum of the block's match flags != 0]                (leveled sum of <= 14 booleans + 1 PBS per block)
         //   level 2   before_k = [sum_{k' < k} any_k' != 0]                         (leveled prefix sums, chunks of <= 15, 1 PBS per block)

@@ -220,6 +220,7 @@ bool record(tfhe_b200_program &h, const std::string &op_in, const uint64_t *a, s
         else if (f == "starts_with") pg.output(psk.starts_with(s, t));
         else if (f == "ends_with") pg.output(psk.ends_with(s, t));
         else if (f == "concat") output_string(pg, psk.concat(s, t));
+        else if (f == "find" || f == "rfind") { auto r = psk.find(s, t, f == "rfind"); pg.output(r.first); output_radix(pg, r.second); }
         else { err = "unknown padded string op: " + op; return false; }
         return true;
     }

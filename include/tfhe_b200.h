@@ -153,7 +153,7 @@ int tfhe_b200_pbs_batch_partial(tfhe_b200_ctx *ctx, const uint64_t *lwe_small, c
  *   string_{to_lowercase,to_uppercase} {len}     string_contains_windows {len_a, len_b, w0, w1}
  *   string_{eq,ne,lt,le,contains}_many {len_a, len_b, count}   (count independent pairs in one program)
  *   pstring_{len,is_empty,trim_start,trim_end,trim} {capacity}     pstring_{strip_prefix,strip_suffix} {capacity} + clear pattern
- *   pstring_{eq,ne,lt,le,gt,ge,contains,starts_with,ends_with,concat} {capacity_a, capacity_b}     pstring_repeat {capacity, count}
+ *   pstring_{eq,ne,lt,le,gt,ge,contains,starts_with,ends_with,find,rfind,concat} {capacity_a, capacity_b}     pstring_repeat {capacity, count}
  *     -- NULL-PADDED strings: public capacity, secret length, content followed by zero bytes (host/padded.h); len returns a radix of
  *        ceil(log4(capacity + 1)) blocks, the string-valued ops return 4 blocks per char of the result capacity
  * Appending "_packed" to a string op (or radix_eq) selects packed block equalities: one PBS per PAIR of blocks built from

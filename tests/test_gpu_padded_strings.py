@@ -40,13 +40,16 @@ def test_padded_string_ops_gpu(orc, keys_2_2):
             assert dec(out[0]) == int(s.endswith(pat)) and R.decrypt_string(ck, out[1:]) == pad(want, cap), (s, pat)
     print(f"trim, capacity {cap}: {P.n_pbs} PBS in {len(P.level_widths)} levels, {P.last_ms():.1f} ms on device")
     ca, cb = 12, 8
-    for a, b in ((b"encrypted", b"crypt"), (b"encrypted", b"ted"), (b"abc", b"abd"), (b"", b""), (b"same", b"same"), (b"xy", b"xyz")):
+    for a, b in ((b"abcabcab", b"ab"), (b"encrypted", b"crypt"), (b"encrypted", b"ted"), (b"abc", b"abd"), (b"", b""), (b"same", b"same"), (b"xy", b"xyz")):
         enc = np.concatenate([R.encrypt_string(ck, pad(a, ca)), R.encrypt_string(ck, pad(b, cb))])
         want = {"eq": a == b, "ne": a != b, "lt": a < b, "le": a <= b, "gt": a > b, "ge": a >= b, "contains": b in a,
                 "starts_with": a.startswith(b), "ends_with": a.endswith(b)}
         for op, w in want.items():
             assert dec(Program("pstring_" + op, (ca, cb), params=prm).run(eng, enc)[0]) == int(w), (op, a, b)
         assert R.decrypt_string(ck, Program("pstring_concat", (ca, cb), params=prm).run(eng, enc)) == pad(a + b, ca + cb)
+        for op, pos in (("find", a.find(b)), ("rfind", a.rfind(b))):
+            out = Program("pstring_" + op, (ca, cb), params=prm).run(eng, enc)
+            assert (dec(out[0]), R.decrypt_radix(ck, out[1:])) == (int(pos >= 0), max(pos, 0)), (op, a, b)
     enc = R.encrypt_string(ck, pad(b"ab", 4))
     assert R.decrypt_string(ck, Program("pstring_repeat", (4, 3), params=prm).run(eng, enc)) == pad(b"ababab", 12)
     eng.close()

@@ -51,7 +51,8 @@ def test_len_trim_strip_clear_simulation(s):
         assert int(out[0]) == int(s.endswith(pat)) and blocks_to_bytes(out[1:]) == pad(want, cap), (s, pat)
 
 
-BINARY = [(b"hello", b"hello"), (b"hello", b"hell"), (b"", b""), (b"abc", b"abd"), (b"b", b"abc"), (b"abcdefgh", b"efgh"),
+BINARY = [(b"abababab", b"ab"), (b"abababab", b""), (b"aaaa", b"aa"), (b"xaxbxc", b"xc"),
+          (b"hello", b"hello"), (b"hello", b"hell"), (b"", b""), (b"abc", b"abd"), (b"b", b"abc"), (b"abcdefgh", b"efgh"),
           (b"abcab", b"ab"), (b"abcab", b""), (b"", b"x"), (b"xyz", b"yz"), (b"xyzxyz", b"zx"), (b"abcdefgh", b"abcdef"), (b"aab", b"ab")]
 
 
@@ -66,6 +67,11 @@ def test_padded_binary_ops_clear_simulation(a, b):
         assert int(out[0]) == int(w), (op, a, b)
     out, _ = run_clear("pstring_concat", (ca, cb), ins)
     assert blocks_to_bytes(out) == pad(a + b, ca + cb), (a, b)
+    # str::find / str::rfind: (found, byte index); the empty pattern is found at 0 / at len
+    for op, pos in (("find", a.find(b)), ("rfind", a.rfind(b))):
+        out, _ = run_clear("pstring_" + op, (ca, cb), ins)
+        got = (int(out[0]), sum(int(d) << (2 * i) for i, d in enumerate(out[1:])))
+        assert got == (int(pos >= 0), max(pos, 0)), (op, a, b, got)
 
 
 def test_repeat_and_shapes():
