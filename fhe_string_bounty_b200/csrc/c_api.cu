@@ -150,11 +150,25 @@ static int do_pbs_kernels(tfhe_b200_ctx *c, const uint64_t *d_small, const uint3
         const size_t wave = (size_t)4 * c->sms, narrow = c->narrow_kernel == 8 ? (size_t)(c->narrow_max ? c->narrow_max : 2 * c->sms) : 0;
         const size_t rem = batch % wave;
         const size_t tail = batch <= narrow ? batch : (rem != 0 && rem <= narrow) ? rem : 0;
-        const size_t wide = batch - tail;
+        size_t wide = batch - tail;
+        // a remainder of more than two but at most three ciphertexts per SM: its own launch on the 3-per-SM instance (5.5 ms) instead of
+        // a fourth-empty last wave of the 4-per-SM instance (7.25 ms); launch_pbs_classic_v4 picks the instance from the batch size
+        const size_t mid = (tail == 0 && wide > wave && rem > (size_t)2 * c->sms && rem <= (size_t)3 * c->sms) ? rem : 0;
+        wide -= mid;
+        const size_t in_stride_all = (size_t)(c->p.lwe_dim + 1) * (fused ? 2 : 8), out_stride_all = (size_t)c->p.glwe_dim * c->p.poly_size + 1;
         if (wide) {
             TB_CUDA(tbk::launch_pbs_classic_v4(d_small, d_idx, d_luts, c->bskf.p, c->tbl16.p, d_out, out_slot, (int)wide, (int)c->p.lwe_dim,
                                                (int)c->p.pbs_base_log, (int)n_iters, fused ? 1 : 0, s));
             c->launches += 1;
+        }
+        if (mid) {
+            const uint64_t *m_small = reinterpret_cast<const uint64_t *>(reinterpret_cast<const char *>(d_small) + wide * in_stride_all);
+            uint64_t *m_out = out_slot ? d_out : d_out + wide * out_stride_all;
+            TB_CUDA(tbk::launch_pbs_classic_v4(m_small, d_idx ? d_idx + wide : nullptr, d_luts, c->bskf.p, c->tbl16.p, m_out,
+                                               out_slot ? out_slot + wide : nullptr, (int)mid, (int)c->p.lwe_dim, (int)c->p.pbs_base_log,
+                                               (int)n_iters, fused ? 1 : 0, s));
+            c->launches += 1;
+            wide += mid;     // the narrow tail below (none in this case) starts after it
         }
         if (tail) {
             const size_t in_stride = (size_t)(c->p.lwe_dim + 1) * (fused ? 2 : 8);

@@ -314,7 +314,9 @@ cudaError_t launch_pbs_classic_v4(const uint64_t *lwe_small, const uint32_t *lut
     else if (batch <= 2 * sms)
         tb4::pbs_classic_kernel_v4<2><<<(batch + 1) / 2, 256, sizeof(tb4::Smem<2>), stream>>>(lwe_small, lut_idx, luts, bk, tb, out, out_slot,
                                                                                             batch, n, base_log, n_iters, small_is_u16);
-    else if (std::getenv("TFHE_B200_WIDE_CTS") && std::getenv("TFHE_B200_WIDE_CTS")[0] == '3')   // experiment: 3 ciphertexts x 168 registers
+    else if (batch <= 3 * sms || (std::getenv("TFHE_B200_WIDE_CTS") && std::getenv("TFHE_B200_WIDE_CTS")[0] == '3'))
+        // one wave of three ciphertexts per SM (152 registers, 7-slot ring) takes 5.5 ms against 7.25 ms for a -- then mostly empty -- wave
+        // of four; TFHE_B200_WIDE_CTS=3 runs every width on this instance (the A/B that showed equal throughput from 12 and 16 warps)
         tb4::pbs_classic_kernel_v4<3><<<(batch + 2) / 3, 384, sizeof(tb4::Smem<3>), stream>>>(lwe_small, lut_idx, luts, bk, tb, out, out_slot,
                                                                                             batch, n, base_log, n_iters, small_is_u16);
     else

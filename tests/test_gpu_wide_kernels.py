@@ -117,6 +117,23 @@ def test_classic_v4_four_per_sm(orc, classic):
         assert np.array_equal(out[b], out[b % 64]), f"row {b} differs from row {b % 64} (same input, same LUT)"
 
 
+def test_classic_v4_three_per_sm(orc, classic):
+    """Levels (and remainders of wider levels) of more than two but at most three ciphertexts per SM run pbs_classic_kernel_v4<3> (12 warps,
+    152 registers, 7-slot ring): batch = 3 * SMs - 1 on its own, and 4 * SMs + 3 * SMs - 2 = one full wave of <4> followed by <3>."""
+    p, ck, sk, luts, eng = classic
+    sms = _sms()
+    for batch, label in ((3 * sms - 1, "pbs_classic_kernel_v4<3>"), (7 * sms - 2, "pbs_classic_kernel_v4<4> + <3> remainder")):
+        cts, vals, idx = _batch(ck, batch, len(FS), 300 + batch)
+        small = eng.keyswitch_batch(cts)
+        rows = _probe_rows(batch, 3, n=12) + ([4 * sms - 1, 4 * sms, 4 * sms + 1] if batch > 4 * sms else [])
+        _check_partial(eng, sk, small, idx, luts, rows, label)
+        out = _check_full(eng, ck, sk, cts, vals, idx, luts, FS, rows[:24], label)
+        assert np.array_equal(out, eng.pbs_batch(small, idx)), "fused KS->PBS hand-off differs from keyswitch_batch + pbs_batch"
+        same = [b for b in range(64, batch) if idx[b] == idx[b % 64]][:16]
+        for b in same:
+            assert np.array_equal(out[b], out[b % 64]), f"{label}: row {b} differs from row {b % 64} (same input, same LUT)"
+
+
 @pytest.mark.parametrize("per_cta", [2, 1])
 def test_classic_v4_narrow_instances(orc, classic, per_cta):
     """narrow_kernel = 0 keeps levels of <= 2 x SMs on pbs_v4.cu: <2> for SMs < batch <= 2 SMs, <1> for batch <= SMs (ragged tails)"""
