@@ -203,6 +203,7 @@ EXPORTS = {
     "tfhe_b200_time_last_kernels": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "tfhe_b200_probe_fp64_tflops": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
     "tfhe_b200_version": (C.c_char_p, []),
+    "tfhe_b200_plan_classic_level": (None, [C.c_size_t, C.c_uint32, C.c_size_t, C.c_int, C.POINTER(C.c_size_t)]),
     "tfhe_b200_program_build": (C.c_int, [C.POINTER(Params), C.c_char_p, C.c_void_p, C.c_size_t, C.c_char_p, C.POINTER(C.c_void_p)]),
     "tfhe_b200_program_destroy": (C.c_int, [C.c_void_p]),
     "tfhe_b200_program_counts": (C.c_int, [C.c_void_p, C.c_void_p]),

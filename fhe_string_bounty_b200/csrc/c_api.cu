@@ -48,6 +48,31 @@ int check_params(const tfhe_b200_params &p) {
 
 namespace tbc {
 
+// How a tree level of `batch` ciphertexts of the headline set is cut into launches.  Wave times in ms, measured on B200 with
+// scripts/level_width_probe.py (n = 742): a wave of 4 per SM 7.2, of 3 per SM 5.49, the narrow kernels 4.37 (<= 2 per SM), 2.75 (<= 1
+// per SM) and 1.84 (<= 1 per two-SM cluster).  Only their ratios matter.  narrow = the widest tail the narrow kernels may take (0: none,
+// then everything goes to pbs_v4.cu and its launcher picks the instance from the batch size).
+struct LevelPlan { size_t four_per_sm, three_per_sm, tail; bool auto_instance; };
+LevelPlan plan_classic_level(size_t batch, size_t sms, size_t narrow, bool cluster) {
+    if (narrow == 0) return {batch, 0, 0, true};
+    const double c4 = 7.2, c3 = 5.49, c2 = 4.37, c1 = 2.75, cx = 1.84;
+    const size_t w4 = 4 * sms, w3 = 3 * sms;
+    LevelPlan best{batch, 0, 0, false};
+    double best_cost = 1e30;
+    for (size_t a = 0; a * w4 < batch + w4; ++a) {
+        for (size_t b = 0; b <= 3; ++b) {
+            const size_t n4 = a * w4 < batch ? a * w4 : batch, left = batch - n4, n3 = b * w3 < left ? b * w3 : left, r = left - n3;
+            if ((a && n4 <= (a - 1) * w4) || (b && n3 <= (b - 1) * w3)) continue;      // an empty wave
+            double cost = a * c4 + b * c3;
+            if (r > narrow || r > 2 * sms) continue;
+            if (r) cost += (cluster && r <= sms / 2) ? cx : r <= sms ? c1 : c2;
+            cost += 0.02 * ((a != 0) + (b != 0) + (r != 0));                          // ties: fewer launches
+            if (cost < best_cost) { best_cost = cost; best = {n4, n3, r, false}; }
+        }
+    }
+    return best;
+}
+
 bool fused_supported(const tfhe_b200_ctx *c) { return c->ks_kernel >= 1 && c->p.grouping_factor == 0 && !c->generic; }
 
 int do_keyswitch(tfhe_b200_ctx *c, const uint64_t *d_in, uint64_t *d_small, size_t batch, cudaStream_t s, const uint32_t *in_slot,
@@ -145,38 +170,30 @@ static int do_pbs_kernels(tfhe_b200_ctx *c, const uint64_t *d_small, const uint3
         return 0;
     }
     {
-        // Wide part: whole waves of 4 ciphertexts per SM on pbs_v4.cu.  What is left over, if it fits two ciphertexts per SM, runs on
-        // the narrow-level kernel pbs_v8.cu (2.9 ms for <= SM count, 4.4 ms for <= 2 x SM count) instead of a mostly empty 7.8 ms wave.
-        const size_t wave = (size_t)4 * c->sms, narrow = c->narrow_kernel == 8 ? (size_t)(c->narrow_max ? c->narrow_max : 2 * c->sms) : 0;
-        const size_t rem = batch % wave;
-        const size_t tail = batch <= narrow ? batch : (rem != 0 && rem <= narrow) ? rem : 0;
-        size_t wide = batch - tail;
-        // a remainder of more than two but at most three ciphertexts per SM: its own launch on the 3-per-SM instance (5.5 ms) instead of
-        // a fourth-empty last wave of the 4-per-SM instance (7.25 ms); launch_pbs_classic_v4 picks the instance from the batch size
-        const size_t mid = (tail == 0 && wide > wave && rem > (size_t)2 * c->sms && rem <= (size_t)3 * c->sms) ? rem : 0;
-        wide -= mid;
-        const size_t in_stride_all = (size_t)(c->p.lwe_dim + 1) * (fused ? 2 : 8), out_stride_all = (size_t)c->p.glwe_dim * c->p.poly_size + 1;
-        if (wide) {
-            TB_CUDA(tbk::launch_pbs_classic_v4(d_small, d_idx, d_luts, c->bskf.p, c->tbl16.p, d_out, out_slot, (int)wide, (int)c->p.lwe_dim,
-                                               (int)c->p.pbs_base_log, (int)n_iters, fused ? 1 : 0, s));
+        // A level is cut into at most three launches over contiguous ranges: whole waves of 4 ciphertexts per SM (pbs_v4.cu), waves of 3
+        // per SM (the same kernel's 152-register instance), and a tail of at most 2 per SM on the narrow-level kernels (pbs_v8.cu);
+        // plan_classic_level picks the cheapest cut from the measured wave times.
+        const size_t narrow = c->narrow_kernel == 8 ? (size_t)(c->narrow_max ? c->narrow_max : 2 * c->sms) : 0;
+        const LevelPlan plan = plan_classic_level(batch, (size_t)c->sms, narrow, c->narrow_cluster != 0);
+        const size_t in_stride = (size_t)(c->p.lwe_dim + 1) * (fused ? 2 : 8), out_stride = (size_t)c->p.glwe_dim * c->p.poly_size + 1;
+        size_t done = 0;
+        auto wide_launch = [&](size_t count, int cts) -> int {
+            const uint64_t *w_small = reinterpret_cast<const uint64_t *>(reinterpret_cast<const char *>(d_small) + done * in_stride);
+            TB_CUDA(tbk::launch_pbs_classic_v4(w_small, d_idx ? d_idx + done : nullptr, d_luts, c->bskf.p, c->tbl16.p,
+                                               out_slot ? d_out : d_out + done * out_stride, out_slot ? out_slot + done : nullptr, (int)count,
+                                               (int)c->p.lwe_dim, (int)c->p.pbs_base_log, (int)n_iters, fused ? 1 : 0, cts, s));
             c->launches += 1;
-        }
-        if (mid) {
-            const uint64_t *m_small = reinterpret_cast<const uint64_t *>(reinterpret_cast<const char *>(d_small) + wide * in_stride_all);
-            uint64_t *m_out = out_slot ? d_out : d_out + wide * out_stride_all;
-            TB_CUDA(tbk::launch_pbs_classic_v4(m_small, d_idx ? d_idx + wide : nullptr, d_luts, c->bskf.p, c->tbl16.p, m_out,
-                                               out_slot ? out_slot + wide : nullptr, (int)mid, (int)c->p.lwe_dim, (int)c->p.pbs_base_log,
-                                               (int)n_iters, fused ? 1 : 0, s));
-            c->launches += 1;
-            wide += mid;     // the narrow tail below (none in this case) starts after it
-        }
-        if (tail) {
-            const size_t in_stride = (size_t)(c->p.lwe_dim + 1) * (fused ? 2 : 8);
-            const uint64_t *t_small = reinterpret_cast<const uint64_t *>(reinterpret_cast<const char *>(d_small) + wide * in_stride);
-            uint64_t *t_out = out_slot ? d_out : d_out + wide * ((size_t)c->p.glwe_dim * c->p.poly_size + 1);
-            TB_CUDA(tbk::launch_pbs_classic_v8(t_small, d_idx ? d_idx + wide : nullptr, d_luts, c->bskf8.p, c->tbl8.p, t_out,
-                                               out_slot ? out_slot + wide : nullptr, (int)tail, (int)c->p.lwe_dim, (int)c->p.pbs_base_log,
-                                               (int)n_iters, fused ? 1 : 0, c->narrow_cluster ? c->sms / 2 : 0, s));
+            done += count;
+            return 0;
+        };
+        if (plan.four_per_sm && wide_launch(plan.four_per_sm, plan.auto_instance ? 0 : 4)) return -1;
+        if (plan.three_per_sm && wide_launch(plan.three_per_sm, 3)) return -1;
+        if (plan.tail) {
+            const uint64_t *t_small = reinterpret_cast<const uint64_t *>(reinterpret_cast<const char *>(d_small) + done * in_stride);
+            TB_CUDA(tbk::launch_pbs_classic_v8(t_small, d_idx ? d_idx + done : nullptr, d_luts, c->bskf8.p, c->tbl8.p,
+                                               out_slot ? d_out : d_out + done * out_stride, out_slot ? out_slot + done : nullptr, (int)plan.tail,
+                                               (int)c->p.lwe_dim, (int)c->p.pbs_base_log, (int)n_iters, fused ? 1 : 0,
+                                               c->narrow_cluster ? c->sms / 2 : 0, s));
             c->launches += 1;
         }
         return 0;
@@ -273,6 +290,11 @@ int tfhe_b200_set_ciphertext_modulus_log2(tfhe_b200_ctx *c, uint32_t log2_q) {
     std::lock_guard<std::mutex> lk(c->mu);
     c->log2_q = (int)log2_q;
     return 0;
+}
+
+void tfhe_b200_plan_classic_level(size_t batch, uint32_t sms, size_t narrow_max, int cluster, size_t counts[3]) {
+    const tbc::LevelPlan plan = tbc::plan_classic_level(batch, sms, narrow_max, cluster != 0);
+    counts[0] = plan.four_per_sm; counts[1] = plan.three_per_sm; counts[2] = plan.tail;
 }
 
 int tfhe_b200_set_tuning(tfhe_b200_ctx *c, const char *key, int value) {

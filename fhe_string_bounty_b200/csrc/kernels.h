@@ -34,7 +34,7 @@ cudaError_t launch_keyswitch_tc(const uint64_t *lwe_in, const uint32_t *in_slot,
 cudaError_t pbs_v4_configure();
 cudaError_t launch_pbs_classic_v4(const uint64_t *lwe_small, const uint32_t *lut_idx, const uint64_t *luts, const void *bskf4,
                                   const void *tbl16, uint64_t *out, const uint32_t *out_slot, int batch, int n, int base_log,
-                                  int n_iters, int small_is_u16, cudaStream_t stream);
+                                  int n_iters, int small_is_u16, int cts, cudaStream_t stream);
 cudaError_t launch_bsk_convert_v4(const uint64_t *bsk_std, void *bskf4, const void *tbl16, int n_polys, cudaStream_t stream);
 // probe.cu
 cudaError_t launch_fp64_peak(double *sink, int blocks, int iters, cudaStream_t stream);

@@ -302,21 +302,24 @@ cudaError_t pbs_v4_configure() {
 
 cudaError_t launch_pbs_classic_v4(const uint64_t *lwe_small, const uint32_t *lut_idx, const uint64_t *luts, const void *bskf4,
                                   const void *tbl16, uint64_t *out, const uint32_t *out_slot, int batch, int n, int base_log,
-                                  int n_iters, int small_is_u16, cudaStream_t stream) {
+                                  int n_iters, int small_is_u16, int cts, cudaStream_t stream) {
     if (batch <= 0) return cudaSuccess;
     int sms = 148, dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const tb::cplx *bk = reinterpret_cast<const tb::cplx *>(bskf4), *tb = reinterpret_cast<const tb::cplx *>(tbl16);
-    if (batch <= sms)
+    // cts: ciphertexts per SM the caller planned for (3 or 4), 0 = pick the instance from the batch size
+    if (cts == 0 && std::getenv("TFHE_B200_WIDE_CTS") && std::getenv("TFHE_B200_WIDE_CTS")[0] == '3' && batch > 2 * sms) cts = 3;
+    if (cts == 0) cts = batch <= sms ? 1 : batch <= 2 * sms ? 2 : batch <= 3 * sms ? 3 : 4;
+    if (cts == 1)
         tb4::pbs_classic_kernel_v4<1><<<batch, 128, sizeof(tb4::Smem<1>), stream>>>(lwe_small, lut_idx, luts, bk, tb, out, out_slot, batch, n,
                                                                                   base_log, n_iters, small_is_u16);
-    else if (batch <= 2 * sms)
+    else if (cts == 2)
         tb4::pbs_classic_kernel_v4<2><<<(batch + 1) / 2, 256, sizeof(tb4::Smem<2>), stream>>>(lwe_small, lut_idx, luts, bk, tb, out, out_slot,
                                                                                             batch, n, base_log, n_iters, small_is_u16);
-    else if (batch <= 3 * sms || (std::getenv("TFHE_B200_WIDE_CTS") && std::getenv("TFHE_B200_WIDE_CTS")[0] == '3'))
+    else if (cts == 3)
         // one wave of three ciphertexts per SM (152 registers, 7-slot ring) takes 5.5 ms against 7.25 ms for a -- then mostly empty -- wave
-        // of four; TFHE_B200_WIDE_CTS=3 runs every width on this instance (the A/B that showed equal throughput from 12 and 16 warps)
+        // of four; TFHE_B200_WIDE_CTS=3 runs every wide batch on this instance (the A/B that showed equal throughput from 12 and 16 warps)
         tb4::pbs_classic_kernel_v4<3><<<(batch + 2) / 3, 384, sizeof(tb4::Smem<3>), stream>>>(lwe_small, lut_idx, luts, bk, tb, out, out_slot,
                                                                                             batch, n, base_log, n_iters, small_is_u16);
     else

@@ -223,6 +223,10 @@ uint64_t tfhe_b200_kernel_launches(const tfhe_b200_ctx *ctx);   /* kernels launc
 int tfhe_b200_time_last_kernels(tfhe_b200_ctx *ctx, float *ks_ms, float *pbs_ms); /* CUDA-event ms of the last ks_pbs call */
 int tfhe_b200_probe_fp64_tflops(int cuda_device, double *tflops);  /* dependent-FMA microbenchmark */
 const char *tfhe_b200_version(void);
+/* How the classic-PBS dispatcher cuts a tree level of `batch` ciphertexts of the headline set into launches on a device with `sms` SMs:
+ * counts[0] ciphertexts on the 4-per-SM instance of the wide kernel, then counts[1] on its 3-per-SM instance, then counts[2] on the
+ * narrow-level kernels; narrow_max = the widest tail those may take, cluster = two-SM clusters allowed.  Pure host arithmetic. */
+void tfhe_b200_plan_classic_level(size_t batch, uint32_t sms, size_t narrow_max, int cluster, size_t counts[3]);
 
 #ifdef __cplusplus
 }

@@ -10,7 +10,7 @@ eng.upload_ksk(rng.integers(0, 2**64, size=p.ksk_len, dtype=np.uint64))
 eng.upload_bsk_std(rng.integers(0, 2**64, size=p.bsk_len, dtype=np.uint64))
 eng.upload_luts(rng.integers(0, 2**64, size=(4, p.lut_len), dtype=np.uint64))
 s = torch.cuda.Stream()
-for batch in (74, 148, 296, 297, 400, 444, 445, 592, 700, 888, 1024, 1036, 1184):
+for batch in [int(a) for a in sys.argv[1:]] or (74, 148, 296, 297, 400, 444, 445, 592, 700, 888, 1024, 1036, 1184):
     d_in = torch.from_numpy(rng.integers(0, 2**63, size=(batch, p.big_len), dtype=np.int64)).cuda()
     d_out = torch.empty_like(d_in)
     idx = torch.zeros(batch, dtype=torch.int32, device="cuda")

@@ -47,6 +47,41 @@ def test_rejects_unsupported_params(native):
     assert lib.tfhe_b200_ctx_create(0, C.byref(p), None) != 0
 
 
+def test_level_planner_covers_every_width(native):
+    """the dispatcher's cut of a level into (4 per SM, 3 per SM, narrow tail) launches: every ciphertext exactly once, each part within
+    what its kernel takes, never more waves than the all-4-per-SM cut, and the cuts the measured wave times favour"""
+    import ctypes as C
+    lib = native.load_native()
+    sms = 148
+
+    def plan(batch, narrow=2 * sms, cluster=1):
+        out = (C.c_size_t * 3)()
+        lib.tfhe_b200_plan_classic_level(batch, sms, narrow, cluster, out)
+        return tuple(out)
+
+    cost = {4: 7.2, 3: 5.49}
+    for batch in list(range(1, 1400)) + [1920, 1984, 4096, 8192, 16384, 65536, 65537]:
+        n4, n3, tail = plan(batch)
+        assert n4 + n3 + tail == batch
+        assert tail <= 2 * sms
+        assert n4 % (4 * sms) == 0 or n3 + tail == 0          # only the last part may end inside a wave
+        assert n3 % (3 * sms) == 0 or tail == 0
+        waves = lambda n, per: -(-n // (per * sms))
+        t = waves(n4, 4) * cost[4] + waves(n3, 3) * cost[3] + (0 if tail == 0 else 1.84 if tail <= sms // 2 else 2.75 if tail <= sms else 4.37)
+        assert t <= waves(batch, 4) * cost[4] + 1e-9, (batch, n4, n3, tail)
+    assert plan(74) == (0, 0, 74) and plan(296) == (0, 0, 296)
+    assert plan(297) == (0, 297, 0) and plan(444) == (0, 444, 0)
+    assert plan(445) == (445, 0, 0) and plan(592) == (592, 0, 0)
+    assert plan(592 + 30) == (592, 0, 30)
+    assert plan(592 + 200) == (0, 792, 0)                        # two waves of three beat a wave of four plus a two-per-SM tail
+    assert plan(1024) == (592, 432, 0)
+    assert plan(8192) == (8192, 0, 0)
+    # no narrow kernels: everything to the wide kernel, whose launcher picks the instance
+    assert plan(100, narrow=0) == (100, 0, 0) and plan(1000, narrow=0) == (1000, 0, 0)
+    # a narrow kernel limited to one ciphertext per SM
+    assert plan(200, narrow=sms) == (0, 200, 0) and plan(592 + 100, narrow=sms) == (592, 0, 100)
+
+
 def test_cpu_mirror_of_warp_fft(tmp_path):
     """tests/cpu_mirror/fft_mirror.cpp emulates the 32 lanes of the warp FFT from the SAME header the
     kernels compile (fft_core.cuh) and checks it against the DFT definition."""
