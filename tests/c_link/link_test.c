@@ -24,9 +24,13 @@ int main(void) {
     ADDR(tfhe_b200_exchange_send_rows); ADDR(tfhe_b200_exchange_gather_stride); ADDR(tfhe_b200_exchange_all_gather);
     ADDR(tfhe_b200_exchange_all_reduce_sum); ADDR(tfhe_b200_exchange_group_run); ADDR(tfhe_b200_exchange_destroy);
     ADDR(tfhe_b200_set_tuning); ADDR(tfhe_b200_kernel_launches); ADDR(tfhe_b200_time_last_kernels); ADDR(tfhe_b200_probe_fp64_tflops);
-    ADDR(tfhe_b200_version);
+    ADDR(tfhe_b200_version); ADDR(tfhe_b200_plan_classic_level);
 
     printf("version: %s\n", tfhe_b200_version());
+    size_t cut[3];
+    tfhe_b200_plan_classic_level(1024, 148, 296, 1, cut);
+    printf("level of 1024 ciphertexts: %zu + %zu + %zu\n", cut[0], cut[1], cut[2]);
+    if (cut[0] + cut[1] + cut[2] != 1024) return 2;
     /* PARAM_MESSAGE_2_CARRY_2_KS_PBS, shortint/parameters/mod.rs:703-717 */
     tfhe_b200_params p = {742, 1, 2048, 23, 1, 3, 5, 0, 4, 4};
     tfhe_b200_program *prog = NULL;
