@@ -186,7 +186,19 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "PBS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
+
+
+_JSON_FD = None
+
+
+def emit(line: dict):
+    """the JSON line, on the process's original stdout (see main)"""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
 
 
 def run_param_sweep(args):
@@ -194,7 +206,7 @@ def run_param_sweep(args):
     Device-resident inputs, CUDA events on the launching stream, random key words (timing only: parity of these sets is
     tests/test_gpu_param_sets.py).  One JSON line; not the headline metric."""
     rows = param_sweep_rows(args.param_sweep.split(","), args.cpu_sample != 0, 0)
-    print(json.dumps({"metric": "KS-PBS throughput per classic parameter set (1 GPU, device-resident)", "unit": "PBS/s", "sets": rows}))
+    emit({"metric": "KS-PBS throughput per classic parameter set (1 GPU, device-resident)", "unit": "PBS/s", "sets": rows})
 
 
 def param_sweep_rows(names, with_cpu: bool, device: int):
@@ -616,7 +628,7 @@ def run_b200(args):
                 string_ops["cpu_port_ops_per_s_derived"] = {
                     "eq_8char": cpu_rate / 36.0, "contains_256_16": cpu_rate / 16890.0, "find_256_16": cpu_rate / 17916.0,
                     "to_lowercase_1024": cpu_rate / 4096.0, "note": "derived: CPU KS-PBS/s of cpu_baseline / PBS count of the reference-shaped tree"}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -638,6 +650,12 @@ def main():
     ap.add_argument("--other-sets", default="1_1,3_3", help="classic sets measured briefly after the headline and reported as other_parameter_sets ('' = skip)")
     ap.add_argument("--cpu-sample", type=int, default=-1, help="KS-PBS evaluated by the CPU baseline leg (-1 = host cores x 320, about 10 s; 0 = skip)")
     args = ap.parse_args()
+    # stdout carries the one JSON line and nothing else: libraries that write to file descriptor 1 behind Python's back (NCCL's version
+    # banner and warnings, OpenMP runtime notices) are sent to stderr; emit() writes the line to the saved descriptor
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.param_sweep:
         run_param_sweep(args)
     elif args.impl == "reference":
