@@ -134,6 +134,32 @@ def test_classic_v4_three_per_sm(orc, classic):
             assert np.array_equal(out[b], out[b % 64]), f"{label}: row {b} differs from row {b % 64} (same input, same LUT)"
 
 
+def test_planned_level_cuts(orc, classic):
+    """Cuts of plan_classic_level (c_api.cu) that no other test reaches: 4 SMs + 200 = two waves of the 3-per-SM instance in ONE launch
+    (more CTAs than SMs), 5 SMs = a wave of three followed by a two-per-SM tail on pbs_v8.cu.  Same checks as the pinned instances, and the
+    planner's cut is the one the test expects."""
+    import ctypes as C
+    import fhe_string_bounty_b200 as F
+    p, ck, sk, luts, eng = classic
+    sms = _sms()
+    lib = F.load_native()
+    for batch, want_cut in ((4 * sms + 200, (0, 4 * sms + 200, 0)), (5 * sms, (0, 3 * sms, 2 * sms))):
+        cut = (C.c_size_t * 3)()
+        lib.tfhe_b200_plan_classic_level(batch, sms, 2 * sms, 1, cut)
+        assert tuple(cut) == want_cut, tuple(cut)
+        label = f"level of {batch} cut {want_cut}"
+        cts, vals, idx = _batch(ck, batch, len(FS), 500 + batch)
+        small = eng.keyswitch_batch(cts)
+        rows = _probe_rows(batch, 3, n=12) + [3 * sms - 1, 3 * sms, 3 * sms + 1]
+        _check_partial(eng, sk, small, idx, luts, rows, label)
+        out = _check_full(eng, ck, sk, cts, vals, idx, luts, FS, rows[:24], label)
+        assert np.array_equal(out, eng.pbs_batch(small, idx)), "fused KS->PBS hand-off differs from keyswitch_batch + pbs_batch"
+        wide_rows = want_cut[0] + want_cut[1]
+        same = [b for b in range(64, wide_rows) if idx[b] == idx[b % 64]][:16]
+        for b in same:
+            assert np.array_equal(out[b], out[b % 64]), f"{label}: row {b} differs from row {b % 64} (same input, same LUT)"
+
+
 @pytest.mark.parametrize("per_cta", [2, 1])
 def test_classic_v4_narrow_instances(orc, classic, per_cta):
     """narrow_kernel = 0 keeps levels of <= 2 x SMs on pbs_v4.cu: <2> for SMs < batch <= 2 SMs, <1> for batch <= SMs (ragged tails)"""
