@@ -3,7 +3,9 @@ from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import numpy as np, torch
 import fhe_string_bounty_b200 as F
-p = F.Params(**F.PARAM_MESSAGE_2_CARRY_2_KS_PBS)
+MB = "--mb" in sys.argv        # multi-bit GROUP_3 set instead of the classic headline set
+if MB: sys.argv.remove("--mb")
+p = F.Params(**(F.PARAM_MULTI_BIT_MESSAGE_2_CARRY_2_GROUP_3_KS_PBS if MB else F.PARAM_MESSAGE_2_CARRY_2_KS_PBS))
 eng = F.Engine(p)
 rng = np.random.default_rng(1)
 eng.upload_ksk(rng.integers(0, 2**64, size=p.ksk_len, dtype=np.uint64))
