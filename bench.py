@@ -382,7 +382,10 @@ def bench_string_ops(eng, wl: Workload, rank, world, exchange):
         checks["eq_ignore_case_1024"] = dec(run_pinned(eic, two)[0]) == 1
         out["eq_ignore_case_1024_ops_per_s"] = _timed_ops(lambda: run_pinned(eic, two), 2, world)
         out["eq_ignore_case_1024_pbs"] = eic.n_pbs
-    out["pbs_counts"] = {"eq_8char": 36, "contains_256_16": 16890, "find_256_16": 17916, "to_lowercase_1024": 4096}
+    out["pbs_counts"] = {"eq_8char": Program("string_eq", (8, 8), params=params).n_pbs,
+                         "contains_256_16": Program("string_contains", (256, 16), params=params).n_pbs,
+                         "find_256_16": Program("string_find", (256, 16), params=params).n_pbs,
+                         "to_lowercase_1024": Program("string_to_lowercase", (1024,), params=params).n_pbs}
     out["decrypted_results_correct"] = {k: bool(v) for k, v in checks.items()}
     out["exchange"] = "none (1 rank)" if world == 1 else ("engine peer-memory kernel over CUDA IPC / NVLink (csrc/exchange.cu)" if comm.peer is not None else "NCCL")
     out["note"] = ("page-locked host buffers in, result block out; eq shards chars, contains / find shard windows, to_lowercase shards chars "
@@ -625,9 +628,10 @@ def run_b200(args):
                                     "sample": f"{n_cpu} KS-PBS (same keys and ciphertexts as the GPU arm), {cpu_dt:.1f} s", "outputs_decrypt_correctly": cpu_ok}
             if string_ops is not None:
                 # the CPU path has no batching effect beyond its cores: a string op costs (its PBS count) / (CPU KS-PBS rate)
+                counts = string_ops["pbs_counts"]
                 string_ops["cpu_port_ops_per_s_derived"] = {
-                    "eq_8char": cpu_rate / 36.0, "contains_256_16": cpu_rate / 16890.0, "find_256_16": cpu_rate / 17916.0,
-                    "to_lowercase_1024": cpu_rate / 4096.0, "note": "derived: CPU KS-PBS/s of cpu_baseline / PBS count of the reference-shaped tree"}
+                    **{k: cpu_rate / float(v) for k, v in counts.items()},
+                    "note": "derived: CPU KS-PBS/s of cpu_baseline / PBS count of the unsharded tree (pbs_counts)"}
         emit(line)
     if world > 1:
         dist.barrier()

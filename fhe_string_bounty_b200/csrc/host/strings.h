@@ -224,7 +224,8 @@ class StringServerKey {
         //   level 1   any_k   = [sum of the block's match flags != 0]                (leveled sum of <= 14 booleans + 1 PBS per block)
         //   level 2   before_k = [sum_{k' < k} any_k' != 0]                         (leveled prefix sums, chunks of <= 15, 1 PBS per block)
         //   level 3   first_w = [ (#matches before w inside its block) + before_k + (1 - m_w) == 0 ]
-        //             -- the in-block prefix count is a leveled sum (<= 13), so the argument stays <= 15 and needs one PBS per window.
+        //             -- the in-block prefix count is a leveled sum (<= 13), so the argument stays <= 15; the same PBS multiplies by
+        //             the window's index digit (one PBS per window and non-zero digit).
         // found = OR of the blocks' any flags (same count-tree as contains).
         constexpr size_t BLK = 14;
         const size_t n_blk = (W + BLK - 1) / BLK;
@@ -253,15 +254,15 @@ class StringServerKey {
                 g0 = g1;
             }
         }
-        std::vector<Ct> first(W);
+        // y_w = (matches before w in the block) + before_k + 1 - m_w   in [0, 15];  first_w = [y_w == 0] is never materialised: the
+        // index digits are selected straight from y_w (one LUT per non-zero digit value), which saves a tree level and W PBS
+        std::vector<Ct> y(W);
         for (size_t w = 0; w < W; ++w) {
             const size_t k = w / BLK;
-            // y = (matches before w in the block) + before_k + 1 - m_w   in [0, 15]
-            Ct y = pg.unchecked_scalar_add(pg.unchecked_scalar_mul(m[w], uint64_t(-1)), 1);
-            y.degree = 1;
-            for (size_t i = k * BLK; i < w; ++i) y = pg.unchecked_add(y, m[i]);
-            y = pg.unchecked_add(y, before[k]);
-            first[w] = pg.pbs(y, [](uint64_t x) { return uint64_t(x == 0); });
+            Ct t = pg.unchecked_scalar_add(pg.unchecked_scalar_mul(m[w], uint64_t(-1)), 1);
+            t.degree = 1;
+            for (size_t i = k * BLK; i < w; ++i) t = pg.unchecked_add(t, m[i]);
+            y[w] = pg.unchecked_add(t, before[k]);
         }
         Ct found = isk.is_at_least_one_comparisons_block_true(any);
         // index digit b = sum_w ((w >> 2b) & 3) * first_w: select with a LUT (clean, noise NOMINAL), then sum in
@@ -273,7 +274,7 @@ class StringServerKey {
             for (size_t w = 0; w < W; ++w) {
                 const uint64_t digit = (global(w) >> (2 * b)) & 3;
                 if (digit == 0) continue;
-                terms.push_back(pg.pbs(first[w], [digit](uint64_t x) { return (x & 1) ? digit : uint64_t(0); }));
+                terms.push_back(pg.pbs(y[w], [digit](uint64_t x) { return x == 0 ? digit : uint64_t(0); }));
             }
             if (terms.empty()) { index.push_back(pg.create_trivial(0)); continue; }
             while (terms.size() > 1) {
