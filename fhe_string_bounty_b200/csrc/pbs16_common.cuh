@@ -117,8 +117,7 @@ struct GlobalTwiddles {
 // register pv = frequency freq_of16(T2, pv) and nobody but T2 itself touches its exchange-B reader slots.
 template <class Tw, class Sync>
 __device__ __forceinline__ void fft16_fwd(double (&re)[16], double (&im)[16], cplx *tile, const Tw &twd, int T, Sync sync) {
-    pretwist16_fwd(re, im);
-    radix16_dif(re, im);
+    radix16_twisted_fwd(re, im);
     twd.template apply16<false>(re, im);
     sync();
     {
@@ -150,7 +149,7 @@ __device__ __forceinline__ void fft16_fwd(double (&re)[16], double (&im)[16], cp
 #pragma unroll
         for (int u = 0; u < 16; ++u) { const cplx v = rp[xb_roff(u)]; re[u] = v.x; im[u] = v.y; }
     }
-    radix16_dif(re, im);
+    radix16_fwd(re, im);
 }
 
 // inverse (scaled by 1024): on entry nobody else may be reading this thread's exchange-B reader slots; on exit the tile may

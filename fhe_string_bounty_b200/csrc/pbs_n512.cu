@@ -58,8 +58,7 @@ __device__ __forceinline__ uint32_t mod_switch(uint64_t x) { return (uint32_t)((
 struct Fft256 {
     template <class Tw>
     __device__ __forceinline__ static void fwd(double (&re)[16], double (&im)[16], cplx *tile, const Tw &twd, int T) {
-        pretwist16_fwd(re, im);
-        radix16_dif(re, im);
+        radix16_twisted_fwd(re, im);
         twd.template apply<false>(re, im);
         __syncwarp();          // the half-warp is done with the tile (rotated gather / previous exchange)
 #pragma unroll
@@ -67,7 +66,7 @@ struct Fft256 {
         __syncwarp();
 #pragma unroll
         for (int u = 0; u < 16; ++u) { const cplx v = tile[s256_read(T, u)]; re[u] = v.x; im[u] = v.y; }
-        radix16_dif(re, im);
+        radix16_fwd(re, im);
     }
     // inverse, scaled by 256
     template <class Tw>

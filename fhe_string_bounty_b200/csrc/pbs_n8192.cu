@@ -81,8 +81,7 @@ struct Fft4096 {
     // forward: on entry the tile may still be read by other threads (the first barrier covers that)
     template <class Sync>
     __device__ __forceinline__ static void fwd(double (&re)[16], double (&im)[16], cplx *tile, const Tw &twd, int T, Sync sync) {
-        pretwist16_fwd(re, im);
-        radix16_dif(re, im);
+        radix16_twisted_fwd(re, im);
         twd.template apply1<false>(re, im);
         sync();
 #pragma unroll
@@ -90,7 +89,7 @@ struct Fft4096 {
         sync();
 #pragma unroll
         for (int v = 0; v < 16; ++v) { const cplx x = tile[s4096_a_read(T, v)]; re[v] = x.x; im[v] = x.y; }
-        radix16_dif(re, im);
+        radix16_fwd(re, im);
         twd.template apply2<false>(re, im);
         __syncwarp();        // everything below stays inside the half-warp's region of the tile
 #pragma unroll
@@ -98,7 +97,7 @@ struct Fft4096 {
         __syncwarp();
 #pragma unroll
         for (int q = 0; q < 16; ++q) { const cplx x = tile[s4096_b_read(T, q)]; re[q] = x.x; im[q] = x.y; }
-        radix16_dif(re, im);
+        radix16_fwd(re, im);
     }
     // inverse, scaled by 4096; on entry nobody may still be reading the tile, on exit it may still be read by other threads
     template <class Sync>

@@ -76,7 +76,7 @@ int main() {
 
     // forward
     for (int t = 0; t < 64; ++t) {
-        pretwist16_fwd(w.re[t], w.im[t]); radix16_dif(w.re[t], w.im[t]);
+        radix16_twisted_fwd(w.re[t], w.im[t]);
         twiddle16_fwd(w.re[t], w.im[t], [&](int p) { return t1[p * 64 + t]; });
     }
     if (!exchange(w, xaw, xar, false)) { printf("FAIL exchange A\n"); return 1; }
@@ -86,7 +86,7 @@ int main() {
         twiddle4_fwd(w.re[t], w.im[t], tw);
     }
     if (!exchange(w, xbw, xbr, false)) { printf("FAIL exchange B\n"); return 1; }
-    for (int t = 0; t < 64; ++t) radix16_dif(w.re[t], w.im[t]);
+    for (int t = 0; t < 64; ++t) radix16_fwd(w.re[t], w.im[t]);
 
     long double max_err = 0, max_mag = 0;
     std::set<int> seen;

@@ -71,20 +71,20 @@ static int check(int M, int n_threads) {
 
     // ---- forward ----
     for (int t = 0; t < n_threads; ++t) {
-        pretwist16_fwd(th[t].re, th[t].im); radix16_dif(th[t].re, th[t].im);
+        radix16_twisted_fwd(th[t].re, th[t].im);
         for (int p = 0; p < 16; ++p) mul(th[t], p, tbl[p * n_threads + t], false);
     }
     if (M == 256) {
         if (!exchange(th, kTile256, s256_write, s256_read, false)) { printf("FAIL 256 exchange\n"); return 1; }
-        for (int t = 0; t < n_threads; ++t) radix16_dif(th[t].re, th[t].im);
+        for (int t = 0; t < n_threads; ++t) radix16_fwd(th[t].re, th[t].im);
     } else {
         if (!exchange(th, kTile4096, s4096_a_write, s4096_a_read, false)) { printf("FAIL 4096 exchange A\n"); return 1; }
         for (int t = 0; t < n_threads; ++t) {
-            radix16_dif(th[t].re, th[t].im);
+            radix16_fwd(th[t].re, th[t].im);
             for (int p = 0; p < 16; ++p) mul(th[t], p, tbl[4096 + p * 16 + (t & 15)], false);
         }
         if (!exchange(th, kTile4096, s4096_b_write, s4096_b_read, false)) { printf("FAIL 4096 exchange B\n"); return 1; }
-        for (int t = 0; t < n_threads; ++t) radix16_dif(th[t].re, th[t].im);
+        for (int t = 0; t < n_threads; ++t) radix16_fwd(th[t].re, th[t].im);
     }
     // against the definition, on a sample of frequencies (the full check is O(M^2) = fine for 256, sampled for 4096)
     std::set<int> seen;
